@@ -1,0 +1,701 @@
+// b2b.cu -- C ABI (include/b2b.h) over the sm_100a kernels.  No CPU fallback anywhere: every
+// transform, LZ4 block and frame is produced by the kernels in this directory.
+#include "../../include/b2b.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "filter_kernels.cuh"
+#include "lz4_kernels.cuh"
+#include "scan.cuh"
+
+using namespace b2b;
+
+struct b2b_ctx {
+    int device = 0;
+    int sm_count = 148;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;     // for the host-pointer entry points
+    uint8_t *arena = nullptr;          // device scratch, grow-only
+    size_t arena_cap = 0;
+    int opt_quirk = 0;
+    int opt_filter_ctas_per_sm = 0;
+    uint64_t opt_stage_bytes = 256ull << 20;
+    uint64_t launches = 0;
+    std::string last_err;
+};
+
+namespace {
+
+#define CU(ctx, call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (ctx)->last_err = std::string(#call) + ": " + cudaGetErrorString(e__);            \
+            return B2B_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// bump allocator over the ctx arena
+struct Arena {
+    b2b_ctx *ctx;
+    uint64_t used = 0;
+    explicit Arena(b2b_ctx *c) : ctx(c) {}
+    template <typename T> T *take(uint64_t count) {
+        used = align_up(used, 256);
+        T *p = reinterpret_cast<T *>(ctx->arena + used);
+        used += count * sizeof(T);
+        return p;
+    }
+};
+
+int ensure_arena(b2b_ctx *ctx, uint64_t bytes) {
+    bytes = align_up(bytes + 4096, 1 << 20);
+    if (bytes <= ctx->arena_cap) return B2B_OK;
+    CU(ctx, cudaDeviceSynchronize());
+    if (ctx->arena) CU(ctx, cudaFree(ctx->arena));
+    ctx->arena = nullptr; ctx->arena_cap = 0;
+    CU(ctx, cudaMalloc(&ctx->arena, bytes));
+    ctx->arena_cap = bytes;
+    return B2B_OK;
+}
+
+uint32_t tiles_for(uint64_t max_len, uint32_t nframes, const b2b_ctx *ctx) {
+    uint64_t t = (max_len + kTileBytes - 1) / kTileBytes;
+    if (t < 1) t = 1;
+    if (ctx->opt_filter_ctas_per_sm > 0) {  // persistent-style grid: CTAs stride over tiles
+        uint64_t want = (uint64_t)ctx->sm_count * ctx->opt_filter_ctas_per_sm;
+        uint64_t per = (want + nframes - 1) / nframes;
+        if (per < 1) per = 1;
+        t = std::min(t, per);
+    }
+    const uint64_t cap = (1ull << 30) / std::max<uint32_t>(nframes, 1);
+    t = std::min<uint64_t>(t, std::max<uint64_t>(cap, 1));
+    return (uint32_t)t;
+}
+
+uint64_t scan_scratch_bytes(uint32_t n) {
+    const uint64_t tiles = ((uint64_t)n + kScanTile - 1) / kScanTile;
+    return align_up(tiles * 8 + 8, 256) + 256;
+}
+
+// exclusive scan on `s`; `work` points at scan_scratch_bytes(n) of scratch
+int launch_scan(b2b_ctx *ctx, const uint32_t *d_len, uint32_t n, uint64_t *d_off, uint64_t *d_total,
+                int op, uint8_t *work, cudaStream_t s) {
+    if (n == 0) {
+        if (d_total) CU(ctx, cudaMemsetAsync(d_total, 0, 8, s));
+        return B2B_OK;
+    }
+    const uint32_t tiles = (n + kScanTile - 1) / kScanTile;
+    const uint64_t wbytes = align_up((uint64_t)tiles * 8 + 8, 256);
+    CU(ctx, cudaMemsetAsync(work, 0, wbytes, s));
+    ScanWork w;
+    w.tile_state = reinterpret_cast<uint64_t *>(work);
+    w.ticket = reinterpret_cast<uint32_t *>(work + (uint64_t)tiles * 8);
+    scan_offsets_kernel<<<tiles, kScanThreads, 0, s>>>(d_len, n, d_off, d_total, w, op);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    return B2B_OK;
+}
+
+int launch_filter(b2b_ctx *ctx, const uint8_t *src, uint8_t *dst, const uint64_t *off,
+                  const uint32_t *len, uint64_t uniform_len, uint32_t nframes, uint64_t max_len,
+                  const FrameMeta *meta, FrameMeta uniform, const uint32_t *status, int inverse,
+                  cudaStream_t s) {
+    if (nframes == 0) return B2B_OK;
+    FilterArgs a;
+    a.src = src; a.dst = dst;
+    a.ft.off = off; a.ft.len = len; a.ft.uniform_len = uniform_len; a.ft.nframes = nframes;
+    a.ft.tiles_per_frame = tiles_for(max_len, nframes, ctx);
+    a.meta = meta; a.uniform = uniform; a.status = status; a.inverse = inverse;
+    a.copy_inactive = 1;
+    const uint64_t grid = (uint64_t)nframes * a.ft.tiles_per_frame;
+    filter_batch_kernel<<<(unsigned)grid, kFilterThreads, 0, s>>>(a);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    return B2B_OK;
+}
+
+FrameMeta uniform_meta(int mode, int64_t typesize) {
+    FrameMeta m; m.mode = 0; m.typesize = 0;
+    if ((mode == B2B_SHUFFLE || mode == B2B_BITSHUFFLE) && typesize > 1 &&
+        typesize <= 0xFFFFFFFFll) {
+        m.mode = (uint32_t)mode; m.typesize = (uint32_t)typesize;
+    }
+    return m;
+}
+
+// ---- device-pointer cores (ctx->mu held by the caller) ----------------------------------
+int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d_src_off,
+                              const uint32_t *d_src_len, uint32_t nframes, uint64_t total_src,
+                              uint32_t max_len, int shuffle, int64_t typesize, void *d_dst,
+                              uint64_t dst_cap, uint64_t *d_frame_off, uint32_t *d_frame_len,
+                              uint32_t *d_status, uint64_t *d_total_out, cudaStream_t s) {
+    if (nframes == 0) {
+        if (d_total_out) CU(ctx, cudaMemsetAsync(d_total_out, 0, 8, s));
+        return B2B_OK;
+    }
+    if (!d_src || !d_src_off || !d_src_len || !d_dst || !d_frame_off || !d_frame_len || !d_status)
+        return B2B_EINVAL;
+    if (((uintptr_t)d_dst & 15u) != 0) return B2B_EINVAL;
+    if (dst_cap < total_src + 16ull * nframes + 15ull * nframes) return B2B_EDST_TOO_SMALL;
+    if (typesize <= 0) typesize = 1;                                   // blosc.go:274-276
+    const FrameMeta fm = uniform_meta(shuffle, typesize);
+    const bool filtered = fm.mode != 0;
+    const uint32_t shuffle_flag = shuffle == B2B_SHUFFLE ? B2B_FLAG_SHUFFLE
+                                : shuffle == B2B_BITSHUFFLE ? B2B_FLAG_BITSHUFFLE : 0;  // blosc.go:348-353
+
+    // scratch layout
+    const uint64_t comp_bytes = total_src + total_src / 255 + 48ull * nframes + 256;
+    const uint64_t need = (filtered ? align_up(total_src + 64, 256) : 0) + align_up(comp_bytes, 256) +
+                          3 * align_up(8ull * nframes, 256) + 2 * scan_scratch_bytes(nframes) + 4096;
+    int rc = ensure_arena(ctx, need);
+    if (rc) return rc;
+    Arena ar(ctx);
+    uint8_t *d_shuf = filtered ? ar.take<uint8_t>(total_src + 64) : nullptr;
+    uint8_t *d_comp = ar.take<uint8_t>(comp_bytes);
+    uint64_t *d_comp_off = ar.take<uint64_t>(nframes);
+    uint32_t *d_comp_len = ar.take<uint32_t>(nframes);
+    uint32_t *d_flags = ar.take<uint32_t>(nframes);
+    uint8_t *scan_a = ar.take<uint8_t>(scan_scratch_bytes(nframes));
+    uint8_t *scan_b = ar.take<uint8_t>(scan_scratch_bytes(nframes));
+
+    const uint8_t *in = static_cast<const uint8_t *>(d_src);
+    if (filtered) {
+        rc = launch_filter(ctx, in, d_shuf, d_src_off, d_src_len, 0, nframes, max_len, nullptr, fm,
+                           nullptr, 0, s);
+        if (rc) return rc;
+        in = d_shuf;
+    }
+    rc = launch_scan(ctx, d_src_len, nframes, d_comp_off, nullptr, kScanLz4Slot, scan_a, s);
+    if (rc) return rc;
+
+    EncodeArgs e;
+    e.in = in; e.src_off = d_src_off; e.src_len = d_src_len; e.nframes = nframes;
+    e.comp = d_comp; e.comp_off = d_comp_off; e.comp_len = d_comp_len; e.frame_len = d_frame_len;
+    e.flags = d_flags; e.status = d_status; e.shuffle_flag = shuffle_flag; e.keep_raw = 0;
+    lz4_encode_kernel<<<(nframes + kCodecWarps - 1) / kCodecWarps, kCodecThreads, 0, s>>>(e);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+
+    rc = launch_scan(ctx, d_frame_len, nframes, d_frame_off, d_total_out, kScanAlign16, scan_b, s);
+    if (rc) return rc;
+
+    PackArgs p;
+    p.comp = d_comp; p.comp_off = d_comp_off;
+    p.raw = ctx->opt_quirk ? static_cast<const uint8_t *>(d_src) : in;   // SURVEY F4 policy
+    p.src_off = d_src_off; p.src_len = d_src_len; p.comp_len = d_comp_len; p.flags = d_flags;
+    p.status = d_status; p.frame_off = d_frame_off; p.dst = static_cast<uint8_t *>(d_dst);
+    p.nframes = nframes; p.tiles_per_frame = tiles_for((uint64_t)max_len + 16, nframes, ctx);
+    p.codec = B2B_LZ4; p.typesize_u8 = (uint32_t)(uint8_t)typesize;     // blosc.go:362
+    pack_frames_kernel<<<(unsigned)((uint64_t)nframes * p.tiles_per_frame), kFilterThreads, 0, s>>>(p);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    return B2B_OK;
+}
+
+int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64_t *d_frame_off,
+                                const uint32_t *d_frame_len, uint32_t nframes,
+                                int64_t typesize_override, void *d_dst, const uint64_t *d_dst_off,
+                                const uint32_t *d_dst_cap, uint64_t total_dst, uint32_t max_orig,
+                                uint32_t *d_out_len, uint32_t *d_status, cudaStream_t s) {
+    if (nframes == 0) return B2B_OK;
+    if (!d_frames || !d_frame_off || !d_frame_len || !d_dst || !d_dst_off || !d_dst_cap ||
+        !d_out_len || !d_status)
+        return B2B_EINVAL;
+    const uint64_t need = align_up(total_dst + 64, 256) + align_up(8ull * nframes, 256) + 4096;
+    int rc = ensure_arena(ctx, need);
+    if (rc) return rc;
+    Arena ar(ctx);
+    uint8_t *d_stage = ar.take<uint8_t>(total_dst + 64);
+    FrameMeta *d_meta = ar.take<FrameMeta>(nframes);
+
+    DecodeArgs a;
+    a.frames = static_cast<const uint8_t *>(d_frames); a.frame_off = d_frame_off;
+    a.frame_len = d_frame_len; a.nframes = nframes; a.typesize_override = typesize_override;
+    a.dst = static_cast<uint8_t *>(d_dst); a.scratch = d_stage; a.dst_off = d_dst_off;
+    a.dst_cap = d_dst_cap; a.out_len = d_out_len; a.status = d_status; a.meta = d_meta;
+    lz4_decode_kernel<<<(nframes + kCodecWarps - 1) / kCodecWarps, kCodecThreads, 0, s>>>(a);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+
+    // unshuffle the frames that asked for it: stage -> dst (frames with mode 0 were decoded
+    // straight into dst and are skipped because src != dst is only copied for mode != 0)
+    FilterArgs fa;
+    fa.src = d_stage; fa.dst = static_cast<uint8_t *>(d_dst);
+    fa.ft.off = d_dst_off; fa.ft.len = d_out_len; fa.ft.uniform_len = 0; fa.ft.nframes = nframes;
+    fa.ft.tiles_per_frame = tiles_for(max_orig, nframes, ctx);
+    fa.meta = d_meta; fa.uniform = FrameMeta{0, 0}; fa.status = d_status; fa.inverse = 1;
+    fa.copy_inactive = 0;  // mode 0 frames are already in dst
+    filter_batch_kernel<<<(unsigned)((uint64_t)nframes * fa.ft.tiles_per_frame), kFilterThreads, 0, s>>>(fa);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    return B2B_OK;
+}
+
+int shuffle_dev_locked(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, const void *d_src,
+                       void *d_dst, size_t n, cudaStream_t s) {
+    if (n == 0) return B2B_OK;
+    if (!d_src || !d_dst) return B2B_EINVAL;
+    if (typesize > 0xFFFFFFFFll && (uint64_t)n >= (uint64_t)typesize) return B2B_EUNSUPPORTED;
+    const FrameMeta fm = uniform_meta(mode, typesize);
+    const uint8_t *src = static_cast<const uint8_t *>(d_src);
+    uint8_t *dst = static_cast<uint8_t *>(d_dst);
+    const bool identity = fm.mode == 0 || (uint64_t)n < fm.typesize;
+    if (identity) {
+        if (src != dst) CU(ctx, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s));
+        return B2B_OK;
+    }
+    uint8_t *out = dst;
+    if (src == dst) {  // in place (ShuffleBuffer semantics): transform into scratch, copy back
+        int rc = ensure_arena(ctx, n + 4096);
+        if (rc) return rc;
+        out = ctx->arena;
+    }
+    int rc = launch_filter(ctx, src, out, nullptr, nullptr, n, 1, n, nullptr, fm, nullptr, inverse ? 1 : 0, s);
+    if (rc) return rc;
+    if (out != dst) CU(ctx, cudaMemcpyAsync(dst, out, n, cudaMemcpyDeviceToDevice, s));
+    return B2B_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// extern "C"
+// =========================================================================================
+extern "C" {
+
+const char *b2b_version(void) { return "b2b 0.1.0 (sm_100a; go-blosc v1.0.2 frame format)"; }
+
+const char *b2b_strerror(int st) {
+    switch (st) {
+        case B2B_OK: return "ok";
+        case B2B_EINVALID_DATA: return "blosc: invalid compressed data";
+        case B2B_EINVALID_HEADER: return "blosc: invalid header";
+        case B2B_EINVALID_VERSION: return "blosc: unsupported format version";
+        case B2B_EINVALID_CODEC: return "blosc: unsupported codec";
+        case B2B_ESIZE_MISMATCH: return "blosc: decompressed size mismatch";
+        case B2B_EDATA_TOO_LARGE: return "blosc: data too large";
+        case B2B_ECOMPRESSION_FAILED: return "blosc: compression failed";
+        case B2B_EDECOMPRESSION_FAILED: return "blosc: decompression failed";
+        case B2B_ECUDA: return "b2b: CUDA error";
+        case B2B_EUNSUPPORTED: return "b2b: codec outside the GPU path";
+        case B2B_EDST_TOO_SMALL: return "b2b: destination too small";
+        case B2B_EINVAL: return "b2b: invalid argument";
+        default: return "b2b: unknown status";
+    }
+}
+
+int b2b_init(int device, b2b_ctx **out) {
+    if (!out) return B2B_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+        return B2B_ECUDA;  // no CPU fallback: fail loudly
+    b2b_ctx *ctx = new (std::nothrow) b2b_ctx();
+    if (!ctx) return B2B_ECUDA;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return B2B_ECUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return B2B_ECUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx; return B2B_ECUDA;
+    }
+    *out = ctx;
+    return B2B_OK;
+}
+
+void b2b_destroy(b2b_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *b2b_last_error(b2b_ctx *ctx) { return ctx ? ctx->last_err.c_str() : ""; }
+
+int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
+    if (!ctx) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    switch (option) {
+        case B2B_OPT_REF_MEMCPY_QUIRK: ctx->opt_quirk = value != 0; return B2B_OK;
+        case B2B_OPT_FILTER_CTAS_PER_SM: ctx->opt_filter_ctas_per_sm = (int)std::max<int64_t>(0, value); return B2B_OK;
+        case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (256ull << 20); return B2B_OK;
+        default: return B2B_EINVAL;
+    }
+}
+
+int b2b_reserve(b2b_ctx *ctx, uint64_t total, uint32_t nframes) {
+    if (!ctx) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t need = 2 * align_up(total + 64, 256) + total / 255 + 64ull * nframes +
+                          8 * align_up(8ull * nframes, 256) + 2 * scan_scratch_bytes(nframes) + (1 << 20);
+    return ensure_arena(ctx, need);
+}
+
+uint64_t b2b_launch_count(b2b_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+size_t b2b_max_frame_size(size_t n) { return n + B2B_HEADER_SIZE; }
+size_t b2b_lz4_bound(size_t n) { return n + n / 255 + 16; }
+
+int b2b_parse_header(const void *frame, size_t len, b2b_header *h) {
+    if (!h || (!frame && len)) return B2B_EINVAL;
+    if (len < B2B_HEADER_SIZE) return B2B_EINVALID_HEADER;             // blosc.go:166-168
+    const uint8_t *p = static_cast<const uint8_t *>(frame);
+    auto rd = [&](int o) { return (uint32_t)p[o] | ((uint32_t)p[o + 1] << 8) | ((uint32_t)p[o + 2] << 16) | ((uint32_t)p[o + 3] << 24); };
+    h->version = p[0]; h->versionlz = p[1]; h->flags = p[2]; h->typesize = p[3];
+    h->nbytes_orig = rd(4); h->blocksize = rd(8); h->nbytes_comp = rd(12);
+    if (h->version != B2B_FORMAT_VERSION) return B2B_EINVALID_VERSION; // blosc.go:180-182
+    return B2B_OK;
+}
+
+void b2b_header_bytes(const b2b_header *h, uint8_t out[16]) {
+    out[0] = h->version; out[1] = h->versionlz; out[2] = h->flags; out[3] = h->typesize;
+    const uint32_t v[3] = {h->nbytes_orig, h->blocksize, h->nbytes_comp};
+    for (int k = 0; k < 3; k++)
+        for (int b = 0; b < 4; b++) out[4 + 4 * k + b] = (uint8_t)(v[k] >> (8 * b));
+}
+
+// ---- device-pointer entry points --------------------------------------------------------
+int b2b_shuffle_dev(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, const void *d_src,
+                    void *d_dst, size_t n, void *stream) {
+    if (!ctx) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    return shuffle_dev_locked(ctx, mode, inverse, typesize, d_src, d_dst, n, (cudaStream_t)stream);
+}
+
+int b2b_compress_batch_dev(b2b_ctx *ctx, const void *d_src, const uint64_t *d_src_off,
+                           const uint32_t *d_src_len, uint32_t nframes, uint64_t total_src_bytes,
+                           uint32_t max_frame_len, int shuffle, int64_t typesize, void *d_dst,
+                           uint64_t dst_cap, uint64_t *d_frame_off, uint32_t *d_frame_len,
+                           uint32_t *d_status, uint64_t *d_total_out, void *stream) {
+    if (!ctx) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    return compress_batch_dev_locked(ctx, d_src, d_src_off, d_src_len, nframes, total_src_bytes,
+                                     max_frame_len, shuffle, typesize, d_dst, dst_cap, d_frame_off,
+                                     d_frame_len, d_status, d_total_out, (cudaStream_t)stream);
+}
+
+int b2b_frame_info_batch_dev(b2b_ctx *ctx, const void *d_frames, const uint64_t *d_frame_off,
+                             const uint32_t *d_frame_len, uint32_t nframes, uint32_t *d_orig_len,
+                             uint64_t *d_dst_off, uint64_t *d_total, uint32_t *d_status, void *stream) {
+    if (!ctx) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nframes == 0) { if (d_total) CU(ctx, cudaMemsetAsync(d_total, 0, 8, s)); return B2B_OK; }
+    if (!d_frames || !d_frame_off || !d_frame_len || !d_orig_len || !d_dst_off || !d_status) return B2B_EINVAL;
+    int rc = ensure_arena(ctx, scan_scratch_bytes(nframes) + 4096);
+    if (rc) return rc;
+    frame_info_kernel<<<(nframes + 255) / 256, 256, 0, s>>>(static_cast<const uint8_t *>(d_frames),
+                                                            d_frame_off, d_frame_len, nframes,
+                                                            d_orig_len, d_status);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    return launch_scan(ctx, d_orig_len, nframes, d_dst_off, d_total, kScanAlign16, ctx->arena, s);
+}
+
+int b2b_decompress_batch_dev(b2b_ctx *ctx, const void *d_frames, const uint64_t *d_frame_off,
+                             const uint32_t *d_frame_len, uint32_t nframes, int64_t typesize_override,
+                             void *d_dst, const uint64_t *d_dst_off, const uint32_t *d_dst_cap,
+                             uint64_t total_dst_bytes, uint32_t max_orig_len, uint32_t *d_out_len,
+                             uint32_t *d_status, void *stream) {
+    if (!ctx) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    return decompress_batch_dev_locked(ctx, d_frames, d_frame_off, d_frame_len, nframes,
+                                       typesize_override, d_dst, d_dst_off, d_dst_cap,
+                                       total_dst_bytes, max_orig_len, d_out_len, d_status,
+                                       (cudaStream_t)stream);
+}
+
+int b2b_scan_offsets_dev(b2b_ctx *ctx, const uint32_t *d_len, uint32_t n, uint64_t *d_off,
+                         uint64_t *d_total, void *stream) {
+    if (!ctx) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n && (!d_len || !d_off)) return B2B_EINVAL;
+    int rc = ensure_arena(ctx, scan_scratch_bytes(n) + 4096);
+    if (rc) return rc;
+    return launch_scan(ctx, d_len, n, d_off, d_total, kScanIdentity, ctx->arena, (cudaStream_t)stream);
+}
+
+// ---- host-pointer entry points ----------------------------------------------------------
+int b2b_shuffle(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, const void *src, void *dst,
+                size_t n) {
+    if (!ctx) return B2B_EINVAL;
+    if (n == 0) return B2B_OK;
+    if (!src || !dst) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    // stage buffers live outside the arena (shuffle_dev may use the arena for in-place)
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    CU(ctx, cudaMalloc(&d_in, n + 64));
+    if (cudaMalloc(&d_out, n + 64) != cudaSuccess) { cudaFree(d_in); ctx->last_err = "cudaMalloc"; return B2B_ECUDA; }
+    int rc = B2B_OK;
+    cudaError_t e = cudaMemcpyAsync(d_in, src, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) rc = shuffle_dev_locked(ctx, mode, inverse, typesize, d_in, d_out, n, ctx->stream);
+    if (e == cudaSuccess && rc == B2B_OK) e = cudaMemcpyAsync(dst, d_out, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return B2B_ECUDA; }
+    return rc;
+}
+
+int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, const uint32_t *src_len,
+                       uint32_t nframes, int shuffle, int64_t typesize, void *dst, uint64_t dst_cap,
+                       uint64_t *frame_off, uint32_t *frame_len, uint32_t *status, uint64_t *total_out) {
+    if (!ctx) return B2B_EINVAL;
+    if (nframes == 0) { if (total_out) *total_out = 0; return B2B_OK; }
+    if (!src || !src_off || !src_len || !dst || !frame_off || !frame_len || !status) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    // extent of the source region that the frames cover, and host-known bounds
+    uint64_t lo = ~0ull, hi = 0, total = 0; uint32_t max_len = 0;
+    for (uint32_t f = 0; f < nframes; f++) {
+        lo = std::min(lo, src_off[f]); hi = std::max(hi, src_off[f] + src_len[f]);
+        total += src_len[f]; max_len = std::max(max_len, src_len[f]);
+    }
+    const uint64_t span = hi - lo;
+    std::vector<uint64_t> rel(nframes);
+    for (uint32_t f = 0; f < nframes; f++) rel[f] = src_off[f] - lo;
+    // for the filter scratch the frames are addressed by rel offsets inside [0, span)
+    const uint64_t out_cap = span + 31ull * nframes + 64;
+    uint8_t *d_in = nullptr, *d_out = nullptr, *d_tab = nullptr;
+    const uint64_t tab_bytes = align_up(8ull * nframes, 256) * 2 + align_up(4ull * nframes, 256) * 3 + 256;
+    cudaStream_t s = ctx->stream;
+    int rc = B2B_OK;
+    cudaError_t e = cudaMalloc(&d_in, span + 64);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, out_cap);
+    if (e == cudaSuccess) e = cudaMalloc(&d_tab, tab_bytes);
+    uint64_t *d_src_off = nullptr, *d_frame_off = nullptr, *d_total = nullptr;
+    uint32_t *d_src_len = nullptr, *d_frame_len = nullptr, *d_status = nullptr;
+    uint64_t h_total = 0;
+    if (e == cudaSuccess) {
+        uint8_t *t = d_tab;
+        d_src_off = (uint64_t *)t; t += align_up(8ull * nframes, 256);
+        d_frame_off = (uint64_t *)t; t += align_up(8ull * nframes, 256);
+        d_src_len = (uint32_t *)t; t += align_up(4ull * nframes, 256);
+        d_frame_len = (uint32_t *)t; t += align_up(4ull * nframes, 256);
+        d_status = (uint32_t *)t; t += align_up(4ull * nframes, 256);
+        d_total = (uint64_t *)t;
+        e = cudaMemcpyAsync(d_in, static_cast<const uint8_t *>(src) + lo, span, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_src_off, rel.data(), 8ull * nframes, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_src_len, src_len, 4ull * nframes, cudaMemcpyHostToDevice, s);
+    }
+    if (e == cudaSuccess) {
+        // the shuffle scratch is addressed with the same offsets as the source: size it by span
+        rc = compress_batch_dev_locked(ctx, d_in, d_src_off, d_src_len, nframes, span, max_len, shuffle,
+                                       typesize, d_out, out_cap, d_frame_off, d_frame_len, d_status,
+                                       d_total, s);
+        (void)total;
+    }
+    if (e == cudaSuccess && rc == B2B_OK) {
+        e = cudaMemcpyAsync(frame_off, d_frame_off, 8ull * nframes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(frame_len, d_frame_len, 4ull * nframes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, 4ull * nframes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_total, d_total, 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) {
+            if (h_total > dst_cap) rc = B2B_EDST_TOO_SMALL;
+            else {
+                e = cudaMemcpyAsync(dst, d_out, h_total, cudaMemcpyDeviceToHost, s);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+                if (total_out) *total_out = h_total;
+            }
+        }
+    }
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_tab);
+    if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return B2B_ECUDA; }
+    return rc;
+}
+
+int b2b_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame_off,
+                         const uint32_t *frame_len, uint32_t nframes, int64_t typesize_override,
+                         void *dst, uint64_t dst_cap, const uint64_t *dst_off, uint32_t *out_len,
+                         uint32_t *status) {
+    if (!ctx) return B2B_EINVAL;
+    if (nframes == 0) return B2B_OK;
+    if (!frames || !frame_off || !frame_len || !dst_off || !out_len || !status) return B2B_EINVAL;
+    if (!dst && dst_cap) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint8_t *hf = static_cast<const uint8_t *>(frames);
+    uint64_t lo = ~0ull, hi = 0; uint32_t max_orig = 0;
+    std::vector<uint64_t> rel(nframes);
+    std::vector<uint32_t> cap(nframes);
+    for (uint32_t f = 0; f < nframes; f++) { lo = std::min(lo, frame_off[f]); hi = std::max(hi, frame_off[f] + frame_len[f]); }
+    const uint64_t span = hi - lo;
+    for (uint32_t f = 0; f < nframes; f++) {
+        rel[f] = frame_off[f] - lo;
+        // capacity of slot f: what the header announces, clipped to the caller's buffer
+        uint32_t norig = 0;
+        if (frame_len[f] >= 16) {
+            const uint8_t *p = hf + frame_off[f];
+            norig = (uint32_t)p[4] | ((uint32_t)p[5] << 8) | ((uint32_t)p[6] << 16) | ((uint32_t)p[7] << 24);
+        }
+        uint64_t room = dst_off[f] <= dst_cap ? dst_cap - dst_off[f] : 0;
+        // an LZ4 block cannot expand by more than 255x: never allocate beyond that
+        const uint64_t reach = 255ull * frame_len[f] + 64;
+        cap[f] = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(norig, room), reach);
+        max_orig = std::max(max_orig, cap[f]);
+    }
+    uint64_t dst_span = 0;
+    for (uint32_t f = 0; f < nframes; f++) dst_span = std::max(dst_span, dst_off[f] + cap[f]);
+    uint8_t *d_in = nullptr, *d_out = nullptr, *d_tab = nullptr;
+    const uint64_t tab_bytes = align_up(8ull * nframes, 256) * 2 + align_up(4ull * nframes, 256) * 4;
+    cudaStream_t s = ctx->stream;
+    int rc = B2B_OK;
+    cudaError_t e = cudaMalloc(&d_in, span + 64);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, dst_span + 64);
+    if (e == cudaSuccess) e = cudaMalloc(&d_tab, tab_bytes);
+    if (e == cudaSuccess) {
+        uint8_t *t = d_tab;
+        uint64_t *d_frame_off = (uint64_t *)t; t += align_up(8ull * nframes, 256);
+        uint64_t *d_dst_off = (uint64_t *)t; t += align_up(8ull * nframes, 256);
+        uint32_t *d_frame_len = (uint32_t *)t; t += align_up(4ull * nframes, 256);
+        uint32_t *d_cap = (uint32_t *)t; t += align_up(4ull * nframes, 256);
+        uint32_t *d_out_len = (uint32_t *)t; t += align_up(4ull * nframes, 256);
+        uint32_t *d_status = (uint32_t *)t;
+        e = cudaMemcpyAsync(d_in, hf + lo, span, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_frame_off, rel.data(), 8ull * nframes, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dst_off, dst_off, 8ull * nframes, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_frame_len, frame_len, 4ull * nframes, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_cap, cap.data(), 4ull * nframes, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess)
+            rc = decompress_batch_dev_locked(ctx, d_in, d_frame_off, d_frame_len, nframes, typesize_override,
+                                             d_out, d_dst_off, d_cap, dst_span, max_orig, d_out_len,
+                                             d_status, s);
+        if (e == cudaSuccess && rc == B2B_OK) {
+            e = cudaMemcpyAsync(out_len, d_out_len, 4ull * nframes, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, 4ull * nframes, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && dst_span) e = cudaMemcpyAsync(dst, d_out, dst_span, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        }
+    }
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_tab);
+    if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return B2B_ECUDA; }
+    return rc;
+}
+
+int b2b_compress(b2b_ctx *ctx, const void *src, size_t n, int codec, int level, int shuffle,
+                 int64_t typesize, void *dst, size_t cap, size_t *out_len) {
+    (void)level;  // clamped at blosc.go:277-282, never read by the LZ4 adapter (codec.go:63)
+    if (!ctx || !out_len) return B2B_EINVAL;
+    if (n == 0) return B2B_EINVALID_DATA;                                  // blosc.go:269-271
+    if (codec <= B2B_BLOSCLZ || codec > B2B_ZSTD) return B2B_EINVALID_CODEC;  // blosc.go:322-325
+    if (codec != B2B_LZ4) return B2B_EUNSUPPORTED;
+    if (n > 0xFFFFFFFFull - 16ull) return B2B_EDATA_TOO_LARGE;
+    if (!src || !dst) return B2B_EINVAL;
+    const uint64_t off = 0; const uint32_t len = (uint32_t)n;
+    uint64_t foff = 0, total = 0; uint32_t flen = 0, st = 0;
+    std::vector<uint8_t> tmp;
+    void *out = dst; uint64_t out_cap = cap;
+    if (cap < n + 16 + 64) { tmp.resize(n + 16 + 64); out = tmp.data(); out_cap = tmp.size(); }
+    int rc = b2b_compress_batch(ctx, src, &off, &len, 1, shuffle, typesize, out, out_cap, &foff, &flen, &st, &total);
+    if (rc) return rc;
+    if (st) return (int)st;
+    if (flen > cap) return B2B_EDST_TOO_SMALL;
+    if (out != dst) memcpy(dst, tmp.data(), flen);
+    *out_len = flen;
+    return B2B_OK;
+}
+
+int b2b_decompress(b2b_ctx *ctx, const void *frame, size_t len, int64_t typesize_override, void *dst,
+                   size_t cap, size_t *out_len) {
+    if (!ctx || !out_len) return B2B_EINVAL;
+    b2b_header h;
+    if (len < B2B_HEADER_SIZE) return B2B_EINVALID_HEADER;                 // blosc.go:297-299
+    if (!frame) return B2B_EINVAL;
+    int rc = b2b_parse_header(frame, len, &h);
+    if (rc) return rc;
+    if ((uint64_t)h.nbytes_comp > len || h.nbytes_comp < B2B_HEADER_SIZE) return B2B_EINVALID_DATA;
+    if (len > 0xFFFFFFFFull) len = h.nbytes_comp;  // bytes past NBytesComp are ignored anyway
+    const uint64_t foff = 0, doff = 0; const uint32_t flen = (uint32_t)len;
+    uint32_t got = 0, st = 0;
+    // cap < NBytesOrig surfaces as EDST_TOO_SMALL from the kernel, after the reference's own checks
+    rc = b2b_decompress_batch(ctx, frame, &foff, &flen, 1, typesize_override, dst, cap, &doff, &got, &st);
+    if (rc) return rc;
+    if (st) return (int)st;
+    *out_len = got;
+    return B2B_OK;
+}
+
+int b2b_lz4_block_compress(b2b_ctx *ctx, const void *src, size_t n, void *dst, size_t cap, size_t *out_len) {
+    if (!ctx || !out_len || (!src && n) || !dst) return B2B_EINVAL;
+    if (n > 0xFFFFFFFFull - 16ull) return B2B_EDATA_TOO_LARGE;
+    if (cap < b2b_lz4_bound(n)) return B2B_EDST_TOO_SMALL;
+    if (n == 0) {  // an empty block is the single token 0x00
+        static_cast<uint8_t *>(dst)[0] = 0; *out_len = 1; return B2B_OK;
+    }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t slot = align_up(b2b_lz4_bound(n), 16);
+    int rc = ensure_arena(ctx, align_up(n + 64, 256) + slot + 4096);
+    if (rc) return rc;
+    Arena ar(ctx);
+    uint8_t *d_in = ar.take<uint8_t>(n + 64);
+    uint8_t *d_comp = ar.take<uint8_t>(slot);
+    uint64_t *d_off = ar.take<uint64_t>(2);
+    uint32_t *d_u32 = ar.take<uint32_t>(8);
+    cudaStream_t s = ctx->stream;
+    const uint64_t h_off[2] = {0, 0}; const uint32_t h_len = (uint32_t)n;
+    CU(ctx, cudaMemcpyAsync(d_in, src, n, cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemcpyAsync(d_off, h_off, 16, cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemcpyAsync(d_u32, &h_len, 4, cudaMemcpyHostToDevice, s));
+    // raw block: run the encoder warp directly, keep its true length (no memcpy substitution)
+    EncodeArgs e;
+    e.in = d_in; e.src_off = d_off; e.src_len = d_u32; e.nframes = 1; e.comp = d_comp;
+    e.comp_off = d_off + 1; e.comp_len = d_u32 + 1; e.frame_len = d_u32 + 2; e.flags = d_u32 + 3;
+    e.status = d_u32 + 4; e.shuffle_flag = 0; e.keep_raw = 1;
+    lz4_encode_kernel<<<1, kCodecThreads, 0, s>>>(e);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    uint32_t h_res[5] = {0, 0, 0, 0, 0};
+    CU(ctx, cudaMemcpyAsync(h_res, d_u32, sizeof h_res, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    if (h_res[4]) return (int)h_res[4];
+    const uint32_t c = h_res[1];
+    CU(ctx, cudaMemcpyAsync(dst, d_comp, c, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    *out_len = c;
+    return B2B_OK;
+}
+
+int b2b_lz4_block_decompress(b2b_ctx *ctx, const void *src, size_t n, void *dst, size_t expected,
+                             size_t *out_len) {
+    if (!ctx || !out_len || (!src && n) || (!dst && expected)) return B2B_EINVAL;
+    if (n > 0xFFFFFFFFull - 32ull || expected > 0xFFFFFFFFull) return B2B_EDATA_TOO_LARGE;
+    // wrap the block in a frame header and reuse the frame decoder
+    std::vector<uint8_t> fr(16 + n);
+    b2b_header h = {2, B2B_LZ4, 0, 1, (uint32_t)expected, (uint32_t)expected, (uint32_t)(16 + n)};
+    b2b_header_bytes(&h, fr.data());
+    if (n) memcpy(fr.data() + 16, src, n);
+    const uint64_t foff = 0, doff = 0; const uint32_t flen = (uint32_t)fr.size();
+    uint32_t got = 0, st = 0;
+    int rc = b2b_decompress_batch(ctx, fr.data(), &foff, &flen, 1, 0, dst, expected, &doff, &got, &st);
+    if (rc) return rc;
+    // codec.go:77-84 returns buf[:n]: a short decode is not an error at this level
+    if (st == B2B_ESIZE_MISMATCH) return B2B_ESIZE_MISMATCH;
+    if (st) return (int)st;
+    *out_len = got;
+    return B2B_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+/*
+ * b2b.h -- C ABI of the B200-native shuffle + LZ4 backend for go-blosc ("b2b" = blosc-to-B200).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no CUDA or torch types.  It is
+ * what the reference's own backend seam would bind through cgo:
+ *
+ *   reference (mrjoshuak/go-blosc v1.0.2)            entry point here
+ *   ------------------------------------------------  --------------------------------------
+ *   compressBackend      blosc.go:320-374            b2b_compress
+ *   decompressBackend    blosc.go:377-434            b2b_decompress
+ *   ShuffleBuffer        shuffle.go:298-309          b2b_shuffle(mode, inverse=0)
+ *   UnshuffleBuffer      shuffle.go:312-323          b2b_shuffle(mode, inverse=1)
+ *   shuffleBytes/unshuffleBytes/bitShuffle/bitUnshuffle and their amd64/arm64 assembly
+ *                        shuffle.go:16-295, shuffle_amd64.s, shuffle_arm64.s
+ *                                                     b2b_shuffle / b2b_shuffle_dev
+ *   lz4Codec.Compress / .Decompress  codec.go:63-84  inside b2b_compress / b2b_decompress
+ *                                                     (and b2b_lz4_block_* for the
+ *                                                     CodecInterface plugin seam, codec.go:15-38)
+ *   ParseHeader / Header.Bytes  blosc.go:165-198     b2b_parse_header / b2b_header_bytes
+ *   (no counterpart: the reference is one frame per call)
+ *                                                     *_batch and *_batch_dev: many independent
+ *                                                     frames per call + the packed-offsets table
+ *
+ * The Go side (go-blosc_b200/go/blosc) keeps every exported identifier of package blosc
+ * and maps the status codes below onto the reference's sentinels (blosc.go:125-149).
+ *
+ * Threading: a b2b_ctx serialises the calls made on it (internal mutex); use one ctx per
+ * concurrent caller (the Go package keeps a pool).  All functions return a B2B_* status.
+ * There is NO CPU fallback: without a usable CUDA device b2b_init fails with B2B_ECUDA.
+ */
+#ifndef B2B_H
+#define B2B_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B2B_API __attribute__((visibility("default")))
+#else
+#define B2B_API
+#endif
+
+/* ---- status codes: one per reference sentinel (blosc.go:125-149) -------------------- */
+enum {
+    B2B_OK = 0,
+    B2B_EINVALID_DATA = 1,         /* ErrInvalidData        (returned bare by the reference)  */
+    B2B_EINVALID_HEADER = 2,       /* ErrInvalidHeader      (bare)                             */
+    B2B_EINVALID_VERSION = 3,      /* ErrInvalidVersion     (wrapped)                          */
+    B2B_EINVALID_CODEC = 4,        /* ErrInvalidCodec       (wrapped)                          */
+    B2B_ESIZE_MISMATCH = 5,        /* ErrSizeMismatch       (wrapped)                          */
+    B2B_EDATA_TOO_LARGE = 6,       /* ErrDataTooLarge: n > 2^32-17 cannot be framed */
+    B2B_ECOMPRESSION_FAILED = 7,   /* ErrCompressionFailed  (wrapped)                          */
+    B2B_EDECOMPRESSION_FAILED = 8, /* ErrDecompressionFailed(wrapped)                          */
+    B2B_ECUDA = 9,                 /* CUDA runtime failure; see b2b_last_error                 */
+    B2B_EUNSUPPORTED = 10,         /* codec is registered in the reference (LZ4HC encode, Snappy,
+                                      ZLIB, ZSTD) but is outside this path: the Go host keeps
+                                      those on the reference codecs.  LZ4 never returns this.  */
+    B2B_EDST_TOO_SMALL = 11,       /* caller's dst capacity is insufficient                    */
+    B2B_EINVAL = 12                /* bad argument (null pointer, bad enum, ...)               */
+};
+
+/* ---- enums of the reference (blosc.go:55-64, 86-92, 110-115) ------------------------ */
+enum { B2B_BLOSCLZ = 0, B2B_LZ4 = 1, B2B_LZ4HC = 2, B2B_SNAPPY = 3, B2B_ZLIB = 4, B2B_ZSTD = 5 };
+enum { B2B_NOSHUFFLE = 0, B2B_SHUFFLE = 1, B2B_BITSHUFFLE = 2 };
+enum { B2B_FLAG_SHUFFLE = 0x1, B2B_FLAG_MEMCPY = 0x2, B2B_FLAG_BITSHUFFLE = 0x4 };
+#define B2B_HEADER_SIZE 16
+#define B2B_FORMAT_VERSION 2
+
+/* 16-byte frame header, little-endian on the wire (blosc.go:154-162) */
+typedef struct b2b_header {
+    uint8_t version;      /* 2 */
+    uint8_t versionlz;    /* Codec enum (go-blosc stores the codec id here) */
+    uint8_t flags;        /* B2B_FLAG_* */
+    uint8_t typesize;     /* uint8(opts.TypeSize) */
+    uint32_t nbytes_orig;
+    uint32_t blocksize;   /* always == nbytes_orig (one block per frame) */
+    uint32_t nbytes_comp; /* 16 + payload bytes */
+} b2b_header;
+
+/* ---- context ------------------------------------------------------------------------- */
+typedef struct b2b_ctx b2b_ctx;
+
+B2B_API int b2b_init(int device, b2b_ctx **out);
+B2B_API void b2b_destroy(b2b_ctx *ctx);
+B2B_API const char *b2b_strerror(int status);
+B2B_API const char *b2b_version(void);
+/* text of the last CUDA failure seen on this ctx ("" if none) */
+B2B_API const char *b2b_last_error(b2b_ctx *ctx);
+
+/* options */
+enum {
+    /* 0 (default): a memcpy frame stores the SHUFFLED bytes, so it round-trips through the
+     *    reference decoder (which un-shuffles memcpy payloads too, blosc.go:398-426);
+     * 1: store the original bytes exactly like blosc.go:342-345 (byte-identical frames, but
+     *    the reference itself cannot round-trip them when a shuffle flag is set). */
+    B2B_OPT_REF_MEMCPY_QUIRK = 1,
+    /* number of CTAs per SM for the persistent filter kernels (tuning; 0 = built-in default) */
+    B2B_OPT_FILTER_CTAS_PER_SM = 2,
+    /* host batch path: bytes of uncompressed data per pipeline stage (0 = default 256 MiB) */
+    B2B_OPT_HOST_STAGE_BYTES = 3
+};
+B2B_API int b2b_set_option(b2b_ctx *ctx, int option, int64_t value);
+/* pre-size the device scratch arena so that later calls do not allocate */
+B2B_API int b2b_reserve(b2b_ctx *ctx, uint64_t total_uncompressed_bytes, uint32_t nframes);
+/* number of kernel launches issued through this ctx since creation (bench's gpu_launches) */
+B2B_API uint64_t b2b_launch_count(b2b_ctx *ctx);
+
+/* ---- sizes and headers (host only; GetInfo / GetDecompressedSize never touch the GPU) -- */
+B2B_API size_t b2b_max_frame_size(size_t n); /* 16 + n: the memcpy frame bounds every frame */
+B2B_API int b2b_parse_header(const void *frame, size_t len, b2b_header *out);
+B2B_API void b2b_header_bytes(const b2b_header *h, uint8_t out[16]);
+
+/* ---- host-pointer, one frame: what compressBackend / decompressBackend bind ------------
+ * b2b_compress: options are taken as CompressWithOptions leaves them (blosc.go:268-286):
+ *   n == 0 -> B2B_EINVALID_DATA; typesize <= 0 -> 1; level is clamped and then unused by
+ *   LZ4 (codec.go:63); header typesize is uint8(typesize).  dst needs b2b_max_frame_size(n).
+ * b2b_decompress: check order of blosc.go:296-303,377-434; typesize_override as
+ *   DecompressWithSize; dst needs nbytes_orig bytes (b2b_parse_header gives it). */
+B2B_API int b2b_compress(b2b_ctx *ctx, const void *src, size_t n, int codec, int level, int shuffle,
+                         int64_t typesize, void *dst, size_t cap, size_t *out_len);
+B2B_API int b2b_decompress(b2b_ctx *ctx, const void *frame, size_t len, int64_t typesize_override,
+                           void *dst, size_t cap, size_t *out_len);
+/* whole-buffer filter, out of place or in place (src == dst), any n (64-bit), any typesize.
+ * mode: B2B_SHUFFLE | B2B_BITSHUFFLE (anything else: plain copy, like shuffle.go:300-307). */
+B2B_API int b2b_shuffle(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, const void *src,
+                        void *dst, size_t n);
+
+/* ---- CodecInterface plugin seam (codec.go:15-38): raw LZ4 block, host pointers ----------
+ * For RegisterCodec(LZ4, gpuCodec): Compress returns one LZ4 block (cap >= b2b_lz4_bound(n));
+ * Decompress decodes into exactly expected_size bytes and reports how many were produced. */
+B2B_API size_t b2b_lz4_bound(size_t n); /* n + n/255 + 16, as CompressBlockBound */
+B2B_API int b2b_lz4_block_compress(b2b_ctx *ctx, const void *src, size_t n, void *dst, size_t cap,
+                                   size_t *out_len);
+B2B_API int b2b_lz4_block_decompress(b2b_ctx *ctx, const void *src, size_t n, void *dst,
+                                     size_t expected_size, size_t *out_len);
+
+/* ---- host-pointer batches (pipelined H2D -> kernels -> D2H) ---------
+ * nframes independent frames; frame f is src[src_off[f] .. +src_len[f]).  Output frames are
+ * packed back to back into dst; frame_off/frame_len (host arrays, nframes entries) receive
+ * the packed-offsets table, status[f] the per-frame B2B_* status.  Pinned (cudaHostAlloc /
+ * cudaHostRegister) buffers are DMA'd directly, pageable ones are staged. */
+B2B_API int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off,
+                               const uint32_t *src_len, uint32_t nframes, int shuffle,
+                               int64_t typesize, void *dst, uint64_t dst_cap, uint64_t *frame_off,
+                               uint32_t *frame_len, uint32_t *status, uint64_t *total_out);
+B2B_API int b2b_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame_off,
+                                 const uint32_t *frame_len, uint32_t nframes,
+                                 int64_t typesize_override, void *dst, uint64_t dst_cap,
+                                 const uint64_t *dst_off, uint32_t *out_len, uint32_t *status);
+
+/* ---- device-pointer entry points (the measured path; `stream` is a cudaStream_t) ---------
+ * All pointers prefixed d_ are device pointers.  Work is enqueued on `stream`; nothing is
+ * synchronised unless the scratch arena has to grow (avoid with b2b_reserve). */
+B2B_API int b2b_shuffle_dev(b2b_ctx *ctx, int mode, int inverse, int64_t typesize,
+                            const void *d_src, void *d_dst, size_t n, void *stream);
+
+/* Compress nframes frames.  total_src_bytes / max_frame_len are host-known bounds used to
+ * size scratch (sum and max of d_src_len).  Output is PACKED: frame f is written at
+ * d_dst + d_frame_off[f] (exclusive scan of d_frame_len, built on the device by a
+ * single-pass decoupled-look-back scan), d_total_out[0] = total bytes.  dst_cap must be
+ * >= total_src_bytes + 16*nframes.  d_status[f] is a B2B_* code. */
+B2B_API int b2b_compress_batch_dev(b2b_ctx *ctx, const void *d_src, const uint64_t *d_src_off,
+                                   const uint32_t *d_src_len, uint32_t nframes,
+                                   uint64_t total_src_bytes, uint32_t max_frame_len, int shuffle,
+                                   int64_t typesize, void *d_dst, uint64_t dst_cap,
+                                   uint64_t *d_frame_off, uint32_t *d_frame_len,
+                                   uint32_t *d_status, uint64_t *d_total_out, void *stream);
+
+/* Parse nframes headers on the device: d_orig_len[f] = NBytesOrig (0 on a bad header),
+ * d_dst_off = exclusive scan of d_orig_len, d_total[0] = sum, d_status[f] = header status. */
+B2B_API int b2b_frame_info_batch_dev(b2b_ctx *ctx, const void *d_frames,
+                                     const uint64_t *d_frame_off, const uint32_t *d_frame_len,
+                                     uint32_t nframes, uint32_t *d_orig_len, uint64_t *d_dst_off,
+                                     uint64_t *d_total, uint32_t *d_status, void *stream);
+
+/* Decompress nframes frames; frame f's output goes to d_dst + d_dst_off[f] and must fit in
+ * d_dst_cap[f] bytes (pass the d_orig_len from b2b_frame_info_batch_dev).
+ * total_dst_bytes / max_orig_len are host-known bounds for scratch sizing. */
+B2B_API int b2b_decompress_batch_dev(b2b_ctx *ctx, const void *d_frames,
+                                     const uint64_t *d_frame_off, const uint32_t *d_frame_len,
+                                     uint32_t nframes, int64_t typesize_override, void *d_dst,
+                                     const uint64_t *d_dst_off, const uint32_t *d_dst_cap,
+                                     uint64_t total_dst_bytes, uint32_t max_orig_len,
+                                     uint32_t *d_out_len, uint32_t *d_status, void *stream);
+
+/* K5 on its own: d_off = exclusive scan of d_len (u32 -> u64), d_total[0] = sum. */
+B2B_API int b2b_scan_offsets_dev(b2b_ctx *ctx, const uint32_t *d_len, uint32_t n, uint64_t *d_off,
+                                 uint64_t *d_total, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2B_H */

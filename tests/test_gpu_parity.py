@@ -1,0 +1,366 @@
+"""GPU (-m gpu): parity of the CUDA path with the oracle, through the C ABI.
+
+  * the reference's own test cases (reference_suite.py) against the CUDA path;
+  * K1/K2 bit-exact vs the oracle over the reference's size / typesize grid, misaligned
+    buffers, in place, whole-buffer sizes, and the committed golden hashes;
+  * K3: GPU frames decode through the oracle (= reference Decompress) and through liblz4,
+    header fields equal the oracle's, compressed size within 1% of the oracle's;
+  * K4: oracle-produced frames (pierrec-style and liblz4 payloads, memcpy, LZ4HC id) decode
+    bit-exactly on the GPU; hostile streams are rejected with the reference's sentinel;
+  * K5 + batches: packed offsets table equals a numpy cumsum; ragged batches; per-frame status.
+"""
+import hashlib
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import datagen as dg
+import reference_suite as rs
+from adapters import GpuImpl
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden_v1.json")
+
+
+@pytest.fixture(scope="module")
+def impl(ctx, pkg):
+    return GpuImpl(ctx, pkg)
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+# ---- the reference's own cases ---------------------------------------------------------------
+@pytest.mark.parametrize("case", rs.ALL_CASES, ids=lambda c: c.__name__)
+def test_reference_case(case, impl):
+    case(impl)
+
+
+@pytest.mark.parametrize("case", rs.CASES_WITH_PKG, ids=lambda c: c.__name__)
+def test_reference_case_errors(case, impl, pkg):
+    case(impl, pkg)
+
+
+def test_package_level_api(pkg):
+    data = dg.f32_ramp(2500)
+    fr = pkg.compress(data, pkg.Codec.LZ4, 5, pkg.Shuffle.Shuffle1, 4)
+    assert pkg.decompress(fr) == data.tobytes()
+    assert pkg.get_decompressed_size(fr) == data.size and str(pkg.Codec(pkg.get_info(fr).versionlz)) == "lz4"
+    buf = bytearray(data.tobytes())
+    pkg.shuffle_buffer(buf, 4, pkg.Shuffle.Shuffle1)                  # shuffle_test.go:93-111, 224-282
+    assert bytes(buf) != data.tobytes()
+    pkg.unshuffle_buffer(buf, 4, pkg.Shuffle.Shuffle1)
+    assert bytes(buf) == data.tobytes()
+    pkg.shuffle_buffer(buf, 4, 99)                                     # unknown mode: untouched
+    assert bytes(buf) == data.tobytes()
+    for codec in (pkg.Codec.ZSTD, pkg.Codec.ZLIB, pkg.Codec.Snappy, pkg.Codec.LZ4HC):
+        with pytest.raises(pkg.ErrUnsupported):                        # stay on the reference's Go codecs
+            pkg.compress(data, codec, 5, pkg.Shuffle.Shuffle1, 4)
+
+
+# ---- K1 / K2 vs the oracle -------------------------------------------------------------------
+@pytest.mark.parametrize("T", dg.TYPESIZES)
+def test_filters_bit_exact_grid(ctx, orc, T):
+    for n in dg.SIZES:
+        src = dg.lcg_bytes(n, seed=n + T) if n <= 4096 else dg.random_bytes(n, n + T)
+        for mode, f, finv in ((1, orc.shuffle, orc.unshuffle), (2, orc.bitshuffle, orc.bitunshuffle)):
+            got = ctx.shuffle(src, T, mode)
+            assert np.array_equal(got, f(src, T)), (n, T, mode)
+            got = ctx.shuffle(src, T, mode, inverse=True)
+            assert np.array_equal(got, finv(src, T)), (n, T, mode, "inv")
+
+
+@pytest.mark.parametrize("T", [2, 4, 8, 16])
+@pytest.mark.parametrize("n", [16384 * T, 16384 * T + 16 * T, 3 * 16384 * T - 16 * T, (1 << 22) + 64, (1 << 22) + 7])
+def test_filters_tile_boundaries(ctx, orc, T, n):
+    src = dg.random_bytes(n, n % 1000 + T)
+    assert np.array_equal(ctx.shuffle(src, T, 1), orc.shuffle(src, T))
+    assert np.array_equal(ctx.shuffle(src, T, 1, True), orc.unshuffle(src, T))
+    assert np.array_equal(ctx.shuffle(src, T, 2), orc.bitshuffle(src, T))
+    assert np.array_equal(ctx.shuffle(src, T, 2, True), orc.bitunshuffle(src, T))
+
+
+def test_filters_device_misaligned_and_in_place(ctx, orc, torch_mod):
+    torch = torch_mod
+    n = 1 << 20
+    host = dg.random_bytes(n + 64, 77)
+    d_src = torch.from_numpy(host).cuda()
+    d_dst = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for so, do in ((0, 0), (1, 0), (0, 3), (5, 9), (16, 8)):
+        for mode in (1, 2):
+            for T in (2, 4, 8, 16, 3):
+                for inv in (False, True):
+                    d_dst.zero_()
+                    ctx.shuffle_dev(mode, inv, T, d_src.data_ptr() + so, d_dst.data_ptr() + do, n, s)
+                    torch.cuda.synchronize()
+                    got = d_dst.cpu().numpy()
+                    src = host[so:so + n]
+                    want = {(1, False): orc.shuffle, (1, True): orc.unshuffle, (2, False): orc.bitshuffle,
+                            (2, True): orc.bitunshuffle}[(mode, inv)](src, T)
+                    assert np.array_equal(got[do:do + n], want), (so, do, mode, T, inv)
+                    assert not got[:do].any() and not got[do + n:].any()
+    work = d_src[:n].clone()
+    ctx.shuffle_dev(1, False, 4, work, work, n, s)                    # in place, like ShuffleBuffer
+    torch.cuda.synchronize()
+    assert np.array_equal(work.cpu().numpy(), orc.shuffle(host[:n], 4))
+
+
+@pytest.mark.parametrize("T", [2, 4, 8, 16])
+def test_shuffle_whole_buffer_1gib_vs_torch(ctx, torch_mod, T):
+    """Config C2 shape (whole-buffer transform, 64-bit plane stride) at 1 GiB: the byte shuffle is
+    a [E, T] -> [T, E] transpose, which torch states independently; bit-exact, full size."""
+    torch = torch_mod
+    n = 1 << 30
+    g = torch.Generator(device="cuda"); g.manual_seed(T)
+    src = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    dst = torch.empty_like(src)
+    s = torch.cuda.current_stream().cuda_stream
+    ctx.shuffle_dev(1, False, T, src, dst, n, s)
+    torch.cuda.synchronize()
+    assert torch.equal(dst.view(T, n // T), src.view(n // T, T).t())
+    back = torch.empty_like(src)
+    ctx.shuffle_dev(1, True, T, dst, back, n, s)
+    torch.cuda.synchronize()
+    assert torch.equal(back, src)
+    ctx.shuffle_dev(2, False, T, src, dst, n, s)                       # bitshuffle: involution-based check
+    ctx.shuffle_dev(2, True, T, dst, back, n, s)
+    torch.cuda.synchronize()
+    assert torch.equal(back, src) and not torch.equal(dst, src)
+
+
+def test_golden_fixtures_on_gpu(ctx, orc):
+    import make_golden
+    with open(GOLDEN) as f:
+        g = json.load(f)
+    for item in g["filters"]:
+        data = make_golden.make_input(item["input"])
+        mode, inv = {"shuffle": (1, False), "unshuffle": (1, True), "bitshuffle": (2, False),
+                     "bitunshuffle": (2, True)}[item["op"]]
+        got = ctx.shuffle(data, item["typesize"], mode, inv)
+        assert hashlib.sha256(got.tobytes()).hexdigest() == item["sha256"], item
+    for item in g["frames"]:
+        data = make_golden.make_input(item["input"])
+        if "frame_hex" in item:                                          # oracle frame -> GPU decoder
+            fr = bytes.fromhex(item["frame_hex"])
+        else:
+            rc, fr = orc.compress(data, orc.LZ4, 5, item["shuffle"], item["typesize"], item["policy"])
+            fr = fr.tobytes()
+            assert hashlib.sha256(fr).hexdigest() == item["frame_sha256"]
+        out = ctx.decompress(fr)
+        assert hashlib.sha256(out).hexdigest() == item["decoded_sha256"], item
+        ctx.set_option(1, item["policy"])                                # GPU frame: same header fields
+        try:
+            mine = ctx.compress(data, 1, 5, item["shuffle"], item["typesize"])
+        finally:
+            ctx.set_option(1, 0)
+        assert mine[:12] == fr[:12], item
+        assert (mine[2] & 0x5) == (fr[2] & 0x5)
+        rc, back = orc.decompress(np.frombuffer(mine, dtype=np.uint8))
+        assert rc == 0 and hashlib.sha256(back.tobytes()).hexdigest() == item["decoded_sha256"], item
+
+
+# ---- K3: GPU frames through the oracle / liblz4 ---------------------------------------------------
+FRAME_SIZES = [1, 4, 11, 12, 13, 14, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 255, 256, 1000, 4095, 4096,
+               10000, 65535, 65536, 65537, 100000, 262144, 1 << 20]
+
+
+@pytest.mark.parametrize("n", FRAME_SIZES)
+def test_gpu_frames_decode_through_oracle(ctx, orc, n):
+    for name, data in dg.corpus(n).items():
+        for sh, T in ((0, 1), (1, 4), (2, 8), (1, 2)):
+            fr = np.frombuffer(ctx.compress(data, 1, 5, sh, T), dtype=np.uint8)
+            rc, want = orc.compress(data, orc.LZ4, 5, sh, T)
+            assert fr[:12].tobytes() == want[:12].tobytes(), (name, sh, T)      # identical header fields
+            h = rs.hdr(fr)
+            assert h["ncomp"] == fr.size
+            rc, back = orc.decompress(fr)                                       # reference Decompress semantics
+            assert rc == 0 and np.array_equal(back, data), (name, n, sh, T)
+            if not h["flags"] & 0x2 and orc.liblz4() is not None:               # independent format referee
+                filt = {0: lambda d, t: d, 1: orc.shuffle, 2: orc.bitshuffle}[sh](data, T)
+                ref = orc.liblz4_decompress(fr[16:], n)
+                assert ref is not None and np.array_equal(ref, filt), (name, n, sh, T)
+            assert ctx.decompress(fr.tobytes()) == data.tobytes()               # and back through K4
+
+
+def test_compressed_size_within_one_percent_of_oracle(ctx, orc):
+    """north_star: compressed size within 1% of the reference at the same level (vs the restated
+    pierrec compressor: parity unpinned).  On the configs' data, 256 KiB frames."""
+    n = 262144
+    cases = {
+        "C3 smooth f32 + Shuffle T=4": (dg.smooth_f32(n // 4, 1), 1, 4),
+        "C4 smooth f64 + BitShuffle T=8": (dg.smooth_f64(n // 8, 2), 2, 8),
+        "C5 low-entropy int16 + Shuffle T=2": (dg.lowent_i16(n // 2, 3), 1, 2),
+        "C1 ramp + Shuffle T=4": (dg.ramp(100000), 1, 4),
+        "f32 i*0.001 + Shuffle T=4": (dg.f32_ramp(n // 4, 0.001), 1, 4),
+        "text NoShuffle": (dg.text_like(n, 9), 0, 1),
+    }
+    report = {}
+    for name, (data, sh, T) in cases.items():
+        mine = len(ctx.compress(data, 1, 5, sh, T))
+        rc, ref = orc.compress(data, orc.LZ4, 5, sh, T)
+        report[name] = (mine, int(ref.size), mine / ref.size)
+    print("\ncompressed size gpu vs oracle:", json.dumps(report, indent=1))
+    for name, (mine, ref, ratio) in report.items():
+        assert mine <= ref * 1.01 + 16, (name, mine, ref)
+
+
+# ---- K4: oracle / liblz4 frames into the GPU decoder ------------------------------------------------
+@pytest.mark.parametrize("n", FRAME_SIZES)
+def test_gpu_decodes_reference_style_frames(ctx, orc, n):
+    for name, data in dg.corpus(n).items():
+        for sh, T in ((0, 1), (1, 4), (2, 8)):
+            for policy in (0, 1):
+                rc, fr = orc.compress(data, orc.LZ4, 5, sh, T, policy)
+                rc, want = orc.decompress(fr)                    # what the reference's Decompress yields
+                assert rc == 0
+                assert ctx.decompress(fr.tobytes()) == want.tobytes(), (name, n, sh, T, policy)
+        if orc.liblz4() is not None and n >= 1:                  # third-party payload, LZ4 and LZ4HC ids
+            filt = orc.shuffle(data, 4)
+            payload = orc.liblz4_compress(filt)
+            for codec in (1, 2):
+                fr = rs.make_header(codec=codec, flags=0x1, typesize=4, norig=n, ncomp=16 + payload.size) + payload.tobytes()
+                assert ctx.decompress(fr) == data.tobytes(), (name, n, codec)
+            assert ctx.decompress(fr + b"trailing-bytes-are-ignored") == data.tobytes()   # blosc.go:393
+
+
+def test_gpu_decoder_rejects_malformed(ctx, pkg):
+    bad = [b"\xff\xff\xff\xff", b"\x10", b"\x00\x00\x00", b"\x0f\x01\x00", b"\x10a\x05\x00", b"\x11a\x00\x00\x00",
+           b"\x1fa\x01\x00\xff", b"\x40abcd\x00"]
+    for s in bad:
+        with pytest.raises((pkg.ErrDecompressionFailed, pkg.ErrSizeMismatch)):
+            ctx.decompress(rs.make_header(norig=64, ncomp=16 + len(s)) + s)
+    ok = b"\x11a\x01\x00" + b"\x10b"
+    assert ctx.decompress(rs.make_header(norig=7, ncomp=16 + len(ok)) + ok) == b"aaaaaab"
+    with pytest.raises(pkg.ErrDecompressionFailed):               # would overrun NBytesOrig
+        ctx.decompress(rs.make_header(norig=6, ncomp=16 + len(ok)) + ok)
+    with pytest.raises(pkg.ErrSizeMismatch):                      # decodes short
+        ctx.decompress(rs.make_header(norig=8, ncomp=16 + len(ok)) + ok)
+    # overlapping matches of every small offset and odd lengths
+    for off in range(1, 40):
+        for ml in (4, 5, 19, 64, 70, 300, 1000):
+            lit = bytes(range(1, off + 1))
+            tok_ml = ml - 4
+            stream = bytearray()
+            stream.append((min(len(lit), 15) << 4) | min(tok_ml, 15))
+            if len(lit) >= 15:
+                stream += _ext(len(lit) - 15)
+            stream += lit + struct.pack("<H", off)
+            if tok_ml >= 15:
+                stream += _ext(tok_ml - 15)
+            stream += b"\x50TAIL!"
+            want = bytearray(lit)
+            for i in range(ml):
+                want.append(want[len(want) - off])
+            want += b"TAIL!"
+            fr = rs.make_header(norig=len(want), ncomp=16 + len(stream)) + bytes(stream)
+            assert ctx.decompress(fr) == bytes(want), (off, ml)
+
+
+def _ext(v):
+    out = bytearray()
+    while v >= 255:
+        out.append(255); v -= 255
+    out.append(v)
+    return bytes(out)
+
+
+def test_raw_lz4_block_plugin_seam(ctx, orc):
+    """CodecInterface seam (codec.go:15-38): raw block compress/decompress, cross-checked."""
+    for name, data in dg.corpus(50000).items():
+        blk = ctx.lz4_block_compress(data)
+        assert np.array_equal(orc.lz4_decompress(np.frombuffer(blk, dtype=np.uint8), data.size), data), name
+        assert ctx.lz4_block_decompress(orc.lz4_compress(data), data.size) == data.tobytes(), name
+    assert ctx.lz4_block_decompress(b"", 10) == b""                # pierrec: empty src -> 0 bytes, no error
+
+
+# ---- K5 + batches -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 1023, 1024, 1025, 4096, 100000, 1 << 20, (1 << 20) + 3])
+def test_offsets_scan(ctx, torch_mod, n):
+    torch = torch_mod
+    lens = np.random.default_rng(n).integers(0, 1 << 22, n, dtype=np.uint32)
+    d_len = torch.from_numpy(lens.view(np.int32)).cuda()
+    d_off = torch.zeros(n, dtype=torch.int64, device="cuda")
+    d_tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ctx.scan_offsets_dev(d_len, n, d_off, d_tot, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = np.concatenate([[0], np.cumsum(lens.astype(np.uint64))])
+    assert np.array_equal(d_off.cpu().numpy().view(np.uint64), want[:-1])
+    assert int(d_tot.item()) == int(want[-1])
+
+
+def test_ragged_batch_host_api(ctx, orc):
+    """C5-like: random (memcpy) and low-entropy int16 frames of mixed sizes, one call."""
+    sizes = [32768, 65536, 1000, 131072, 13, 262144, 524288, 1, 99999, 2 << 20]
+    frames = []
+    for i, s in enumerate(sizes):
+        frames.append(dg.random_bytes(s, i) if i % 2 == 0 else dg.lowent_i16((s + 1) // 2, i)[:s].copy())
+    src = np.concatenate(frames)
+    lens = np.array(sizes, dtype=np.uint32)
+    offs = np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.uint64)
+    dst, foff, flen, status, total = ctx.compress_batch(src, offs, lens, shuffle=1, typesize=2)
+    assert not status.any()
+    assert np.array_equal(foff, np.concatenate([[0], np.cumsum((flen.astype(np.uint64) + 15) // 16 * 16)[:-1]]))
+    assert total == int(foff[-1]) + (int(flen[-1]) + 15) // 16 * 16
+    for f, data in enumerate(frames):
+        fr = dst[int(foff[f]):int(foff[f]) + int(flen[f])]
+        rc, want = orc.compress(data, orc.LZ4, 5, 1, 2)
+        assert fr[:12].tobytes() == want[:12].tobytes()
+        assert bool(fr[2] & 2) == bool(want[2] & 2), f            # same memcpy decision on these inputs
+        rc, back = orc.decompress(fr)
+        assert rc == 0 and np.array_equal(back, data), f
+    out, out_len, st = ctx.decompress_batch(dst, foff, flen, offs, src.size)
+    assert not st.any() and np.array_equal(out_len, lens) and np.array_equal(out, src)
+    # per-frame status: break two frames, the others still decode
+    broken = dst.copy()
+    broken[int(foff[3])] = 9                                         # bad version
+    broken[int(foff[5]) + 16:int(foff[5]) + int(flen[5])] ^= 0xFF   # corrupt payload
+    out, out_len, st = ctx.decompress_batch(broken, foff, flen, offs, src.size)
+    assert st[3] == 3 and st[5] in (5, 8) and not st[[0, 1, 2, 4, 6, 7, 8, 9]].any()
+    for f in (0, 1, 2, 4, 6, 7, 8, 9):
+        assert np.array_equal(out[int(offs[f]):int(offs[f]) + sizes[f]], frames[f])
+
+
+def test_device_batch_roundtrip_c3_shape(ctx, orc, torch_mod):
+    """Device-resident batch API on config C3's shape (256 KiB float32 frames, Shuffle T=4)."""
+    torch = torch_mod
+    nf, fl = 256, 262144
+    host = dg.smooth_f32(nf * fl // 4, 5)
+    d_src = torch.from_numpy(host).cuda()
+    d_off = torch.arange(nf, dtype=torch.int64, device="cuda") * fl
+    d_len = torch.full((nf,), fl, dtype=torch.int32, device="cuda")
+    cap = nf * fl + 32 * nf + 64
+    d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_foff = torch.empty(nf, dtype=torch.int64, device="cuda")
+    d_flen = torch.empty(nf, dtype=torch.int32, device="cuda")
+    d_st = torch.empty(nf, dtype=torch.int32, device="cuda")
+    d_tot = torch.empty(1, dtype=torch.int64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    ctx.compress_batch_dev(d_src, d_off, d_len, nf, nf * fl, fl, 1, 4, d_dst, cap, d_foff, d_flen, d_st, d_tot, s)
+    torch.cuda.synchronize()
+    assert not d_st.any()
+    foff, flen = d_foff.cpu().numpy(), d_flen.cpu().numpy()
+    comp = d_dst.cpu().numpy()
+    for f in (0, 1, 17, nf - 1):
+        fr = comp[foff[f]:foff[f] + flen[f]]
+        rc, back = orc.decompress(fr)
+        assert rc == 0 and np.array_equal(back, host[f * fl:(f + 1) * fl])
+    d_orig = torch.empty(nf, dtype=torch.int32, device="cuda")
+    d_doff = torch.empty(nf, dtype=torch.int64, device="cuda")
+    d_dtot = torch.empty(1, dtype=torch.int64, device="cuda")
+    d_st2 = torch.empty(nf, dtype=torch.int32, device="cuda")
+    ctx.frame_info_batch_dev(d_dst, d_foff, d_flen, nf, d_orig, d_doff, d_dtot, d_st2, s)
+    torch.cuda.synchronize()
+    assert int(d_dtot.item()) == nf * fl and not d_st2.any() and torch.equal(d_doff, d_off)
+    d_out = torch.zeros(nf * fl, dtype=torch.uint8, device="cuda")
+    d_olen = torch.empty(nf, dtype=torch.int32, device="cuda")
+    ctx.decompress_batch_dev(d_dst, d_foff, d_flen, nf, 0, d_out, d_doff, d_orig, nf * fl, fl, d_olen, d_st2, s)
+    torch.cuda.synchronize()
+    assert not d_st2.any() and torch.equal(d_out, d_src)
