@@ -28,6 +28,7 @@ struct b2b_ctx {
     size_t arena_cap = 0;
     int opt_quirk = 0;
     int opt_filter_ctas_per_sm = 0;
+    int opt_hash_log = 0;              // 0: default (kHashLogDefault)
     uint64_t opt_stage_bytes = 256ull << 20;
     uint64_t launches = 0;
     std::string last_err;
@@ -126,6 +127,26 @@ int launch_filter(b2b_ctx *ctx, const uint8_t *src, uint8_t *dst, const uint64_t
     return B2B_OK;
 }
 
+int launch_encode(b2b_ctx *ctx, const EncodeArgs &e, cudaStream_t s) {
+    const int hl = ctx->opt_hash_log ? ctx->opt_hash_log : kHashLogDefault;
+    const unsigned grid = (e.nframes + kCodecWarps - 1) / kCodecWarps;
+    const size_t smem = (size_t)kCodecWarps * sizeof(uint16_t) << hl;
+    auto go = [&](auto kernel) -> int {
+        if (smem > 48 * 1024)
+            CU(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<grid, kCodecThreads, smem, s>>>(e);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        return B2B_OK;
+    };
+    switch (hl) {
+        case 11: return go(lz4_encode_kernel<11>);
+        case 13: return go(lz4_encode_kernel<13>);
+        case 14: return go(lz4_encode_kernel<14>);
+        default: return go(lz4_encode_kernel<12>);
+    }
+}
+
 FrameMeta uniform_meta(int mode, int64_t typesize) {
     FrameMeta m; m.mode = 0; m.typesize = 0;
     if ((mode == B2B_SHUFFLE || mode == B2B_BITSHUFFLE) && typesize > 1 &&
@@ -184,9 +205,8 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     e.in = in; e.src_off = d_src_off; e.src_len = d_src_len; e.nframes = nframes;
     e.comp = d_comp; e.comp_off = d_comp_off; e.comp_len = d_comp_len; e.frame_len = d_frame_len;
     e.flags = d_flags; e.status = d_status; e.shuffle_flag = shuffle_flag; e.keep_raw = 0;
-    lz4_encode_kernel<<<(nframes + kCodecWarps - 1) / kCodecWarps, kCodecThreads, 0, s>>>(e);
-    ctx->launches++;
-    CU(ctx, cudaGetLastError());
+    rc = launch_encode(ctx, e, s);
+    if (rc) return rc;
 
     rc = launch_scan(ctx, d_frame_len, nframes, d_frame_off, d_total_out, kScanAlign16, scan_b, s);
     if (rc) return rc;
@@ -333,6 +353,9 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
     switch (option) {
         case B2B_OPT_REF_MEMCPY_QUIRK: ctx->opt_quirk = value != 0; return B2B_OK;
         case B2B_OPT_FILTER_CTAS_PER_SM: ctx->opt_filter_ctas_per_sm = (int)std::max<int64_t>(0, value); return B2B_OK;
+        case B2B_OPT_HASH_LOG:
+            if (value != 0 && (value < 11 || value > 14)) return B2B_EINVAL;
+            ctx->opt_hash_log = (int)value; return B2B_OK;
         case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (256ull << 20); return B2B_OK;
         default: return B2B_EINVAL;
     }
@@ -664,9 +687,10 @@ int b2b_lz4_block_compress(b2b_ctx *ctx, const void *src, size_t n, void *dst, s
     e.in = d_in; e.src_off = d_off; e.src_len = d_u32; e.nframes = 1; e.comp = d_comp;
     e.comp_off = d_off + 1; e.comp_len = d_u32 + 1; e.frame_len = d_u32 + 2; e.flags = d_u32 + 3;
     e.status = d_u32 + 4; e.shuffle_flag = 0; e.keep_raw = 1;
-    lz4_encode_kernel<<<1, kCodecThreads, 0, s>>>(e);
-    ctx->launches++;
-    CU(ctx, cudaGetLastError());
+    {
+        int rc2 = launch_encode(ctx, e, s);
+        if (rc2) return rc2;
+    }
     uint32_t h_res[5] = {0, 0, 0, 0, 0};
     CU(ctx, cudaMemcpyAsync(h_res, d_u32, sizeof h_res, cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaStreamSynchronize(s));

@@ -12,8 +12,7 @@ namespace b2b {
 
 constexpr int kCodecWarps = 4;                      // frames (warps) per CTA
 constexpr int kCodecThreads = kCodecWarps * 32;
-constexpr int kHashLog = 12;                        // per-warp hash table: 2^12 x u16 = 8 KiB
-constexpr int kHashSize = 1 << kHashLog;
+constexpr int kHashLogDefault = 12;                 // per-warp hash table: 2^12 x u16 = 8 KiB
 
 // status codes (mirror include/b2b.h)
 enum : uint32_t {
@@ -217,17 +216,23 @@ __global__ void frame_info_kernel(const uint8_t *frames, const uint64_t *frame_o
 }
 
 // =========================================================================================
-// K3: warp-cooperative greedy LZ4 block compressor
+// K3: warp-cooperative LZ4 block compressor
 // =========================================================================================
 // 32 candidate positions per step (consecutive while matches are being found, spread out
-// with the reference compressor's adaptive skip once literals pile up), a per-warp 2^12 x
-// u16 hash table in shared memory, MATCH.ANY for repeats inside the step, backward and
-// forward extension done 32 lanes wide, cooperative literal copies.  The output is one
-// valid LZ4 block per frame (last 5 bytes literal, last match starts >= 12 bytes before the
-// end), so the reference decoder reads it.
-__device__ __forceinline__ uint32_t lz4_hash4(uint32_t seq) {
-    return (seq * 2654435761u) >> (32 - kHashLog);
+// with the reference compressor's adaptive skip once literals pile up), a per-warp
+// 2^HL x u16 hash table in shared memory, MATCH.ANY for repeats inside the step, a bounded
+// look at the next four starts (the hit lanes already hold their candidates, so a slightly
+// later but longer match costs nothing to find), backward and forward extension 32 lanes
+// wide, cooperative literal copies.  Limits follow the reference's compressor (pierrec
+// CompressBlock, called at codec.go:66): no match starts or is extended inside the last 14
+// bytes, so the memcpy decision for short frames is the reference's.  The output is one
+// valid LZ4 block per frame.
+template <int HL> __device__ __forceinline__ uint32_t lz4_hash4(uint32_t seq) {
+    return (seq * 2654435761u) >> (32 - HL);
 }
+
+constexpr uint32_t kLazyWindow = 4;   // later starts considered after the first hit
+constexpr uint32_t kLazyWords = 8;    // bounded look-ahead: 4 + 4 * 8 = 36 bytes
 
 // writes a length extension (value already reduced by 15) at out, returns bytes written
 __device__ __forceinline__ uint32_t warp_put_len_ext(uint8_t *out, uint32_t v, int lane) {
@@ -237,15 +242,16 @@ __device__ __forceinline__ uint32_t warp_put_len_ext(uint8_t *out, uint32_t v, i
     return full + 1;
 }
 
+template <int HL>
 __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ src, uint32_t n,
                                                     uint8_t *__restrict__ out, uint16_t *table,
                                                     int lane) {
     uint32_t op = 0, anchor = 0;
-    if (n >= 13) {
-        for (uint32_t i = lane; i < kHashSize; i += kWarp) table[i] = 0;
+    if (n > 14) {
+        for (uint32_t i = lane; i < (1u << HL); i += kWarp) table[i] = 0;
         __syncwarp();
-        const uint32_t mfl = n - 12;      // a match may start at p < mfl
-        const uint32_t mlimit = n - 5;    // and must end at or before mlimit
+        const uint32_t mfl = n - 14;      // a match may start at p < mfl (pierrec: sn = n - mfLimit)
+        const uint32_t mlimit = n - 14;   // and is extended only below mlimit
         uint32_t si = 0;
         while (si < mfl) {
             // adaptive skip of the reference compressor: about 3 probes per 4 + lits/128 bytes
@@ -256,14 +262,10 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
             const bool valid = p64 < mfl;
             const uint32_t p = valid ? (uint32_t)p64 : 0u;
             const uint32_t seq = valid ? load32u(src + p) : 0u;
-            const uint32_t h = lz4_hash4(seq);
+            const uint32_t h = lz4_hash4<HL>(seq);
             const uint32_t c16 = table[h];
             const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
             const uint32_t same = __match_any_sync(0xffffffffu, seq) & vmask;
-            __syncwarp();
-            // of the lanes holding the same 4 bytes only the last one records its position
-            if (valid && (same >> lane) == 1u) table[h] = (uint16_t)p;
-            __syncwarp();
             // nearest earlier lane of this step with the same 4 bytes, else the table entry
             const uint32_t lower = same & ((1u << lane) - 1u);
             int64_t cand = 0;
@@ -280,14 +282,39 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
                 ok = cand >= 0 && ((int64_t)p - cand) < 65536 && load32u(src + cand) == seq;
             }
             const uint32_t hit = __ballot_sync(0xffffffffu, ok);
+            int pick = hit ? __ffs(hit) - 1 : 31;
+            if (hit && stride == 1) {
+                // bounded comparison of the first hit with the hits at the next kLazyWindow starts
+                const uint32_t window = hit & (((2u << kLazyWindow) - 1u) << pick);
+                uint32_t score = 0;
+                if ((window >> lane) & 1u) {
+                    uint32_t len = 4;
+                    const uint8_t *a = src + p + 4, *b = src + (uint32_t)cand + 4;
+                    for (uint32_t k = 0; k < kLazyWords; k++) {
+                        if (p + len + 4 > mlimit) break;
+                        const uint32_t x = load32u(a + 4 * k) ^ load32u(b + 4 * k);
+                        if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                        len += 4;
+                    }
+                    // longer wins; a later start pays one byte per position; ties go to the earlier lane
+                    score = ((64u + len - (uint32_t)(lane - pick)) << 5) | (31u - (uint32_t)lane);
+                }
+                const uint32_t best = __reduce_max_sync(0xffffffffu, score);
+                pick = 31 - (int)(best & 31u);
+            }
+            __syncwarp();
+            // every probed position up to the chosen start is recorded (of lanes holding the
+            // same 4 bytes the last one wins, so the table keeps the nearest occurrence)
+            const uint32_t upto = same & ((2u << pick) - 1u);
+            if (valid && lane <= pick && (upto >> lane) == 1u) table[h] = (uint16_t)p;
+            __syncwarp();
             if (hit == 0) {
                 const uint64_t nx = (uint64_t)si + 32ull * stride;
                 si = nx < mfl ? (uint32_t)nx : mfl;
                 continue;
             }
-            const int first = __ffs(hit) - 1;
-            uint32_t mp = __shfl_sync(0xffffffffu, p, first);                     // match start
-            uint32_t mc = (uint32_t)__shfl_sync(0xffffffffu, (uint32_t)cand, first);  // its source
+            uint32_t mp = __shfl_sync(0xffffffffu, p, pick);                         // match start
+            uint32_t mc = (uint32_t)__shfl_sync(0xffffffffu, (uint32_t)cand, pick);  // its source
             const uint32_t offset = mp - mc;
             // forward extension from mp + 4, 128 bytes per step
             uint32_t mend = mp + 4;
@@ -332,6 +359,9 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
             op += 2;
             if (ml >= 15) op += warp_put_len_ext(out + op, ml - 15, lane);
             si = mend; anchor = mend;
+            // like the reference, remember the position two bytes before the end of the match
+            if (lane == 0 && mend - 2 < mfl) table[lz4_hash4<HL>(load32u(src + mend - 2))] = (uint16_t)(mend - 2);
+            __syncwarp();
         }
     }
     // last literals
@@ -359,8 +389,9 @@ struct EncodeArgs {
     uint32_t keep_raw;          // 1: raw-block API, never substitute the memcpy payload
 };
 
+template <int HL>
 __global__ void __launch_bounds__(kCodecThreads) lz4_encode_kernel(EncodeArgs a) {
-    __shared__ uint16_t tables[kCodecWarps][kHashSize];
+    extern __shared__ __align__(16) uint16_t tables[];   // kCodecWarps x 2^HL entries
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t f = blockIdx.x * kCodecWarps + warp;
     if (f >= a.nframes) return;
@@ -369,7 +400,8 @@ __global__ void __launch_bounds__(kCodecThreads) lz4_encode_kernel(EncodeArgs a)
     if (n == 0) st = kEInvalidData;                       // blosc.go:269-271
     else if (n > 0xFFFFFFFFu - 16u) st = kEDataTooLarge;  // header fields are u32
     else {
-        c = warp_lz4_encode(a.in + a.src_off[f], n, a.comp + a.comp_off[f], tables[warp], lane);
+        c = warp_lz4_encode<HL>(a.in + a.src_off[f], n, a.comp + a.comp_off[f],
+                                tables + ((size_t)warp << HL), lane);
         if (c >= n && !a.keep_raw) { c = n; flags |= 0x2u; }  // blosc.go:342-345: store uncompressed
         flen = 16 + c;
     }

@@ -101,7 +101,10 @@ enum {
     /* number of CTAs per SM for the persistent filter kernels (tuning; 0 = built-in default) */
     B2B_OPT_FILTER_CTAS_PER_SM = 2,
     /* host batch path: bytes of uncompressed data per pipeline stage (0 = default 256 MiB) */
-    B2B_OPT_HOST_STAGE_BYTES = 3
+    B2B_OPT_HOST_STAGE_BYTES = 3,
+    /* log2 of the LZ4 match-finder's shared-memory hash table, 11..14 (0 = default 12).  Larger
+     * tables find more matches (ratio) and cost occupancy (speed). */
+    B2B_OPT_HASH_LOG = 4
 };
 B2B_API int b2b_set_option(b2b_ctx *ctx, int option, int64_t value);
 /* pre-size the device scratch arena so that later calls do not allocate */
@@ -159,10 +162,10 @@ B2B_API int b2b_shuffle_dev(b2b_ctx *ctx, int mode, int inverse, int64_t typesiz
                             const void *d_src, void *d_dst, size_t n, void *stream);
 
 /* Compress nframes frames.  total_src_bytes / max_frame_len are host-known bounds used to
- * size scratch (sum and max of d_src_len).  Output is PACKED: frame f is written at
- * d_dst + d_frame_off[f] (exclusive scan of d_frame_len, built on the device by a
+ * size scratch: the extent max(d_src_off[f] + d_src_len[f]) and max(d_src_len[f]).
+ * Output is PACKED: frame f is written at d_dst + d_frame_off[f] (exclusive scan of d_frame_len, built on the device by a
  * single-pass decoupled-look-back scan), d_total_out[0] = total bytes.  dst_cap must be
- * >= total_src_bytes + 16*nframes.  d_status[f] is a B2B_* code. */
+ * >= total_src_bytes + 32*nframes (frames start on 16-byte boundaries).  d_status[f] is a B2B_* code. */
 B2B_API int b2b_compress_batch_dev(b2b_ctx *ctx, const void *d_src, const uint64_t *d_src_off,
                                    const uint32_t *d_src_len, uint32_t nframes,
                                    uint64_t total_src_bytes, uint32_t max_frame_len, int shuffle,

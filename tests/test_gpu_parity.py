@@ -78,8 +78,10 @@ def test_filters_bit_exact_grid(ctx, orc, T):
 
 
 @pytest.mark.parametrize("T", [2, 4, 8, 16])
-@pytest.mark.parametrize("n", [16384 * T, 16384 * T + 16 * T, 3 * 16384 * T - 16 * T, (1 << 22) + 64, (1 << 22) + 7])
-def test_filters_tile_boundaries(ctx, orc, T, n):
+@pytest.mark.parametrize("shape", ["tile", "tile+16", "3tiles-16", "4M+64", "4M+7"])
+def test_filters_tile_boundaries(ctx, orc, T, shape):
+    n = {"tile": 16384 * T, "tile+16": 16384 * T + 16 * T, "3tiles-16": 3 * 16384 * T - 16 * T,
+         "4M+64": (1 << 22) + 64, "4M+7": (1 << 22) + 7}[shape]
     src = dg.random_bytes(n, n % 1000 + T)
     assert np.array_equal(ctx.shuffle(src, T, 1), orc.shuffle(src, T))
     assert np.array_equal(ctx.shuffle(src, T, 1, True), orc.unshuffle(src, T))
@@ -178,7 +180,12 @@ def test_gpu_frames_decode_through_oracle(ctx, orc, n):
         for sh, T in ((0, 1), (1, 4), (2, 8), (1, 2)):
             fr = np.frombuffer(ctx.compress(data, 1, 5, sh, T), dtype=np.uint8)
             rc, want = orc.compress(data, orc.LZ4, 5, sh, T)
-            assert fr[:12].tobytes() == want[:12].tobytes(), (name, sh, T)      # identical header fields
+            # identical header fields; the memcpy bit depends on the compressor (c >= n) and may
+            # only differ when the reference's own LZ4 size is at the border
+            assert fr[:2].tobytes() == want[:2].tobytes() and fr[3:12].tobytes() == want[3:12].tobytes()
+            assert (fr[2] & 0x5) == (want[2] & 0x5), (name, sh, T)
+            if abs(int(rs.hdr(want)["ncomp"]) - 16 - n) > max(16, n // 64) or (want[2] & 2 and n < 13):
+                assert (fr[2] & 2) == (want[2] & 2), (name, n, sh, T)
             h = rs.hdr(fr)
             assert h["ncomp"] == fr.size
             rc, back = orc.decompress(fr)                                       # reference Decompress semantics
