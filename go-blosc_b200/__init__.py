@@ -36,7 +36,7 @@ MIN_HEADER_SIZE = 16
 (OK, EINVALID_DATA, EINVALID_HEADER, EINVALID_VERSION, EINVALID_CODEC, ESIZE_MISMATCH,
  EDATA_TOO_LARGE, ECOMPRESSION_FAILED, EDECOMPRESSION_FAILED, ECUDA, EUNSUPPORTED,
  EDST_TOO_SMALL, EINVAL) = range(13)
-OPT_REF_MEMCPY_QUIRK, OPT_FILTER_CTAS_PER_SM, OPT_HOST_STAGE_BYTES, OPT_HASH_LOG = 1, 2, 3, 4
+OPT_REF_MEMCPY_QUIRK, OPT_FILTER_CTAS_PER_SM, OPT_HOST_STAGE_BYTES, OPT_HASH_LOG, OPT_KERNEL_TIMING = 1, 2, 3, 4, 5
 
 
 class Codec(enum.IntEnum):   # blosc.go:55-64
@@ -187,6 +187,8 @@ ABI = [
     ("b2b_set_option", _int, [_vp, _int, _i64]),
     ("b2b_reserve", _int, [_vp, _u64, _u32]),
     ("b2b_launch_count", _u64, [_vp]),
+    ("b2b_kernel_stats", _int, [_vp, _int, C.POINTER(C.c_char_p), C.POINTER(_u64), C.POINTER(C.c_double)]),
+    ("b2b_kernel_stats_reset", _int, [_vp]),
     ("b2b_max_frame_size", _sz, [_sz]),
     ("b2b_parse_header", _int, [_vp, _sz, C.POINTER(_CHeader)]),
     ("b2b_header_bytes", None, [C.POINTER(_CHeader), C.POINTER(C.c_uint8 * 16)]),
@@ -312,6 +314,18 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().b2b_launch_count(self._h))
+
+    def kernel_stats(self) -> dict:
+        """{kernel name: (launches, total device ms)}; times need OPT_KERNEL_TIMING."""
+        out = {}
+        for k in range(6):
+            name, n, ms = C.c_char_p(), C.c_uint64(0), C.c_double(0)
+            if lib().b2b_kernel_stats(self._h, k, C.byref(name), C.byref(n), C.byref(ms)) == 0:
+                out[name.value.decode()] = (int(n.value), float(ms.value))
+        return out
+
+    def kernel_stats_reset(self):
+        lib().b2b_kernel_stats_reset(self._h)
 
     # -- host-pointer, one frame (compressBackend / decompressBackend) ------------------------
     def compress(self, data, codec=Codec.LZ4, level=5, shuffle=Shuffle.Shuffle1, typesize=4) -> bytes:

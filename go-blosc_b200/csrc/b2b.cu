@@ -19,13 +19,26 @@
 
 using namespace b2b;
 
+enum KernelId { K_FILTER = 0, K_ENCODE, K_DECODE, K_SCAN, K_PACK, K_INFO, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"filter_batch_kernel", "lz4_encode_kernel", "lz4_decode_kernel",
+                                                  "scan_offsets_kernel", "pack_frames_kernel", "frame_info_kernel"};
+
+struct TimedLaunch { int id; cudaEvent_t a, b; };
+
 struct b2b_ctx {
+    int opt_timing = 0;                 // record CUDA events around every kernel launch
+    std::vector<TimedLaunch> pending;   // not yet folded into the sums
+    std::vector<cudaEvent_t> event_pool;
+    double kernel_ms[K_COUNT] = {0, 0, 0, 0, 0, 0};
+    uint64_t kernel_launches[K_COUNT] = {0, 0, 0, 0, 0, 0};
     int device = 0;
     int sm_count = 148;
     std::mutex mu;
     cudaStream_t stream = nullptr;     // for the host-pointer entry points
     uint8_t *arena = nullptr;          // device scratch, grow-only
     size_t arena_cap = 0;
+    uint8_t *hbuf[3] = {nullptr, nullptr, nullptr};   // device staging of the host-pointer paths
+    size_t hcap[3] = {0, 0, 0};
     int opt_quirk = 0;
     int opt_filter_ctas_per_sm = 0;
     int opt_hash_log = 0;              // 0: default (kHashLogDefault)
@@ -46,6 +59,35 @@ namespace {
     } while (0)
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// Brackets one kernel launch with CUDA events on the launching stream when timing is on.
+struct LaunchTimer {
+    b2b_ctx *ctx; int id; cudaStream_t s; TimedLaunch t{};
+    bool on;
+    LaunchTimer(b2b_ctx *c, int kid, cudaStream_t st) : ctx(c), id(kid), s(st), on(c->opt_timing != 0) {
+        ctx->launches++;
+        ctx->kernel_launches[id]++;
+        if (!on) return;
+        auto get = [&]() { cudaEvent_t e; if (!ctx->event_pool.empty()) { e = ctx->event_pool.back(); ctx->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+        t.id = id; t.a = get(); t.b = get();
+        cudaEventRecord(t.a, s);
+    }
+    ~LaunchTimer() {
+        if (!on) return;
+        cudaEventRecord(t.b, s);
+        ctx->pending.push_back(t);
+    }
+};
+
+void fold_timings(b2b_ctx *ctx) {
+    for (auto &t : ctx->pending) {
+        float ms = 0;
+        if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess)
+            ctx->kernel_ms[t.id] += ms;
+        ctx->event_pool.push_back(t.a); ctx->event_pool.push_back(t.b);
+    }
+    ctx->pending.clear();
+}
 
 // bump allocator over the ctx arena
 struct Arena {
@@ -68,6 +110,20 @@ int ensure_arena(b2b_ctx *ctx, uint64_t bytes) {
     ctx->arena = nullptr; ctx->arena_cap = 0;
     CU(ctx, cudaMalloc(&ctx->arena, bytes));
     ctx->arena_cap = bytes;
+    return B2B_OK;
+}
+
+// grow-only device staging buffer i of the host-pointer entry points
+int ensure_hbuf(b2b_ctx *ctx, int i, uint64_t bytes, uint8_t **out) {
+    bytes = align_up(bytes + 256, 1 << 20);
+    if (bytes > ctx->hcap[i]) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->hbuf[i]) CU(ctx, cudaFree(ctx->hbuf[i]));
+        ctx->hbuf[i] = nullptr; ctx->hcap[i] = 0;
+        CU(ctx, cudaMalloc(&ctx->hbuf[i], bytes));
+        ctx->hcap[i] = bytes;
+    }
+    *out = ctx->hbuf[i];
     return B2B_OK;
 }
 
@@ -103,8 +159,7 @@ int launch_scan(b2b_ctx *ctx, const uint32_t *d_len, uint32_t n, uint64_t *d_off
     ScanWork w;
     w.tile_state = reinterpret_cast<uint64_t *>(work);
     w.ticket = reinterpret_cast<uint32_t *>(work + (uint64_t)tiles * 8);
-    scan_offsets_kernel<<<tiles, kScanThreads, 0, s>>>(d_len, n, d_off, d_total, w, op);
-    ctx->launches++;
+    { LaunchTimer lt(ctx, K_SCAN, s); scan_offsets_kernel<<<tiles, kScanThreads, 0, s>>>(d_len, n, d_off, d_total, w, op); }
     CU(ctx, cudaGetLastError());
     return B2B_OK;
 }
@@ -121,8 +176,7 @@ int launch_filter(b2b_ctx *ctx, const uint8_t *src, uint8_t *dst, const uint64_t
     a.meta = meta; a.uniform = uniform; a.status = status; a.inverse = inverse;
     a.copy_inactive = 1;
     const uint64_t grid = (uint64_t)nframes * a.ft.tiles_per_frame;
-    filter_batch_kernel<<<(unsigned)grid, kFilterThreads, 0, s>>>(a);
-    ctx->launches++;
+    { LaunchTimer lt(ctx, K_FILTER, s); filter_batch_kernel<<<(unsigned)grid, kFilterThreads, 0, s>>>(a); }
     CU(ctx, cudaGetLastError());
     return B2B_OK;
 }
@@ -134,8 +188,7 @@ int launch_encode(b2b_ctx *ctx, const EncodeArgs &e, cudaStream_t s) {
     auto go = [&](auto kernel) -> int {
         if (smem > 48 * 1024)
             CU(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<grid, kCodecThreads, smem, s>>>(e);
-        ctx->launches++;
+        { LaunchTimer lt(ctx, K_ENCODE, s); kernel<<<grid, kCodecThreads, smem, s>>>(e); }
         CU(ctx, cudaGetLastError());
         return B2B_OK;
     };
@@ -218,8 +271,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     p.status = d_status; p.frame_off = d_frame_off; p.dst = static_cast<uint8_t *>(d_dst);
     p.nframes = nframes; p.tiles_per_frame = tiles_for((uint64_t)max_len + 16, nframes, ctx);
     p.codec = B2B_LZ4; p.typesize_u8 = (uint32_t)(uint8_t)typesize;     // blosc.go:362
-    pack_frames_kernel<<<(unsigned)((uint64_t)nframes * p.tiles_per_frame), kFilterThreads, 0, s>>>(p);
-    ctx->launches++;
+    { LaunchTimer lt(ctx, K_PACK, s); pack_frames_kernel<<<(unsigned)((uint64_t)nframes * p.tiles_per_frame), kFilterThreads, 0, s>>>(p); }
     CU(ctx, cudaGetLastError());
     return B2B_OK;
 }
@@ -245,8 +297,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     a.frame_len = d_frame_len; a.nframes = nframes; a.typesize_override = typesize_override;
     a.dst = static_cast<uint8_t *>(d_dst); a.scratch = d_stage; a.dst_off = d_dst_off;
     a.dst_cap = d_dst_cap; a.out_len = d_out_len; a.status = d_status; a.meta = d_meta;
-    lz4_decode_kernel<<<(nframes + kCodecWarps - 1) / kCodecWarps, kCodecThreads, 0, s>>>(a);
-    ctx->launches++;
+    { LaunchTimer lt(ctx, K_DECODE, s); lz4_decode_kernel<<<(nframes + kCodecWarps - 1) / kCodecWarps, kCodecThreads, 0, s>>>(a); }
     CU(ctx, cudaGetLastError());
 
     // unshuffle the frames that asked for it: stage -> dst (frames with mode 0 were decoded
@@ -257,8 +308,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     fa.ft.tiles_per_frame = tiles_for(max_orig, nframes, ctx);
     fa.meta = d_meta; fa.uniform = FrameMeta{0, 0}; fa.status = d_status; fa.inverse = 1;
     fa.copy_inactive = 0;  // mode 0 frames are already in dst
-    filter_batch_kernel<<<(unsigned)((uint64_t)nframes * fa.ft.tiles_per_frame), kFilterThreads, 0, s>>>(fa);
-    ctx->launches++;
+    { LaunchTimer lt(ctx, K_FILTER, s); filter_batch_kernel<<<(unsigned)((uint64_t)nframes * fa.ft.tiles_per_frame), kFilterThreads, 0, s>>>(fa); }
     CU(ctx, cudaGetLastError());
     return B2B_OK;
 }
@@ -340,7 +390,10 @@ void b2b_destroy(b2b_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    fold_timings(ctx);
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->arena) cudaFree(ctx->arena);
+    for (int i = 0; i < 3; i++) if (ctx->hbuf[i]) cudaFree(ctx->hbuf[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -356,6 +409,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
         case B2B_OPT_HASH_LOG:
             if (value != 0 && (value < 11 || value > 14)) return B2B_EINVAL;
             ctx->opt_hash_log = (int)value; return B2B_OK;
+        case B2B_OPT_KERNEL_TIMING: ctx->opt_timing = value != 0; return B2B_OK;
         case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (256ull << 20); return B2B_OK;
         default: return B2B_EINVAL;
     }
@@ -371,6 +425,26 @@ int b2b_reserve(b2b_ctx *ctx, uint64_t total, uint32_t nframes) {
 }
 
 uint64_t b2b_launch_count(b2b_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int b2b_kernel_stats(b2b_ctx *ctx, int kernel, const char **name, uint64_t *launches, double *total_ms) {
+    if (!ctx || kernel < 0 || kernel >= K_COUNT) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    fold_timings(ctx);
+    if (name) *name = kKernelNames[kernel];
+    if (launches) *launches = ctx->kernel_launches[kernel];
+    if (total_ms) *total_ms = ctx->kernel_ms[kernel];
+    return B2B_OK;
+}
+
+int b2b_kernel_stats_reset(b2b_ctx *ctx) {
+    if (!ctx) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    fold_timings(ctx);
+    for (int k = 0; k < K_COUNT; k++) { ctx->kernel_ms[k] = 0; ctx->kernel_launches[k] = 0; }
+    return B2B_OK;
+}
 
 size_t b2b_max_frame_size(size_t n) { return n + B2B_HEADER_SIZE; }
 size_t b2b_lz4_bound(size_t n) { return n + n / 255 + 16; }
@@ -426,10 +500,9 @@ int b2b_frame_info_batch_dev(b2b_ctx *ctx, const void *d_frames, const uint64_t 
     if (!d_frames || !d_frame_off || !d_frame_len || !d_orig_len || !d_dst_off || !d_status) return B2B_EINVAL;
     int rc = ensure_arena(ctx, scan_scratch_bytes(nframes) + 4096);
     if (rc) return rc;
-    frame_info_kernel<<<(nframes + 255) / 256, 256, 0, s>>>(static_cast<const uint8_t *>(d_frames),
-                                                            d_frame_off, d_frame_len, nframes,
-                                                            d_orig_len, d_status);
-    ctx->launches++;
+    { LaunchTimer lt(ctx, K_INFO, s);
+      frame_info_kernel<<<(nframes + 255) / 256, 256, 0, s>>>(static_cast<const uint8_t *>(d_frames), d_frame_off,
+                                                              d_frame_len, nframes, d_orig_len, d_status); }
     CU(ctx, cudaGetLastError());
     return launch_scan(ctx, d_orig_len, nframes, d_dst_off, d_total, kScanAlign16, ctx->arena, s);
 }
@@ -469,14 +542,14 @@ int b2b_shuffle(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, const voi
     CU(ctx, cudaSetDevice(ctx->device));
     // stage buffers live outside the arena (shuffle_dev may use the arena for in-place)
     uint8_t *d_in = nullptr, *d_out = nullptr;
-    CU(ctx, cudaMalloc(&d_in, n + 64));
-    if (cudaMalloc(&d_out, n + 64) != cudaSuccess) { cudaFree(d_in); ctx->last_err = "cudaMalloc"; return B2B_ECUDA; }
-    int rc = B2B_OK;
+    int rc = ensure_hbuf(ctx, 0, n + 64, &d_in);
+    if (rc) return rc;
+    rc = ensure_hbuf(ctx, 1, n + 64, &d_out);
+    if (rc) return rc;
     cudaError_t e = cudaMemcpyAsync(d_in, src, n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) rc = shuffle_dev_locked(ctx, mode, inverse, typesize, d_in, d_out, n, ctx->stream);
     if (e == cudaSuccess && rc == B2B_OK) e = cudaMemcpyAsync(dst, d_out, n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_in); cudaFree(d_out);
     if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return B2B_ECUDA; }
     return rc;
 }
@@ -503,10 +576,11 @@ int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, c
     uint8_t *d_in = nullptr, *d_out = nullptr, *d_tab = nullptr;
     const uint64_t tab_bytes = align_up(8ull * nframes, 256) * 2 + align_up(4ull * nframes, 256) * 3 + 256;
     cudaStream_t s = ctx->stream;
-    int rc = B2B_OK;
-    cudaError_t e = cudaMalloc(&d_in, span + 64);
-    if (e == cudaSuccess) e = cudaMalloc(&d_out, out_cap);
-    if (e == cudaSuccess) e = cudaMalloc(&d_tab, tab_bytes);
+    int rc = ensure_hbuf(ctx, 0, span + 64, &d_in);
+    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 1, out_cap, &d_out);
+    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 2, tab_bytes, &d_tab);
+    if (rc) return rc;
+    cudaError_t e = cudaSuccess;
     uint64_t *d_src_off = nullptr, *d_frame_off = nullptr, *d_total = nullptr;
     uint32_t *d_src_len = nullptr, *d_frame_len = nullptr, *d_status = nullptr;
     uint64_t h_total = 0;
@@ -544,7 +618,6 @@ int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, c
             }
         }
     }
-    cudaFree(d_in); cudaFree(d_out); cudaFree(d_tab);
     if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return B2B_ECUDA; }
     return rc;
 }
@@ -584,10 +657,11 @@ int b2b_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame
     uint8_t *d_in = nullptr, *d_out = nullptr, *d_tab = nullptr;
     const uint64_t tab_bytes = align_up(8ull * nframes, 256) * 2 + align_up(4ull * nframes, 256) * 4;
     cudaStream_t s = ctx->stream;
-    int rc = B2B_OK;
-    cudaError_t e = cudaMalloc(&d_in, span + 64);
-    if (e == cudaSuccess) e = cudaMalloc(&d_out, dst_span + 64);
-    if (e == cudaSuccess) e = cudaMalloc(&d_tab, tab_bytes);
+    int rc = ensure_hbuf(ctx, 0, span + 64, &d_in);
+    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 1, dst_span + 64, &d_out);
+    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 2, tab_bytes, &d_tab);
+    if (rc) return rc;
+    cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) {
         uint8_t *t = d_tab;
         uint64_t *d_frame_off = (uint64_t *)t; t += align_up(8ull * nframes, 256);
@@ -612,7 +686,6 @@ int b2b_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame
             if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         }
     }
-    cudaFree(d_in); cudaFree(d_out); cudaFree(d_tab);
     if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return B2B_ECUDA; }
     return rc;
 }

@@ -231,8 +231,8 @@ template <int HL> __device__ __forceinline__ uint32_t lz4_hash4(uint32_t seq) {
     return (seq * 2654435761u) >> (32 - HL);
 }
 
-constexpr uint32_t kLazyWindow = 4;   // later starts considered after the first hit
-constexpr uint32_t kLazyWords = 8;    // bounded look-ahead: 4 + 4 * 8 = 36 bytes
+constexpr uint32_t kLazyWindow = 2;   // later starts considered after the first hit
+constexpr uint32_t kLazyWords = 4;    // bounded look-ahead: 4 + 4 * 4 = 20 bytes
 
 // writes a length extension (value already reduced by 15) at out, returns bytes written
 __device__ __forceinline__ uint32_t warp_put_len_ext(uint8_t *out, uint32_t v, int lane) {
@@ -290,11 +290,19 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
                 if ((window >> lane) & 1u) {
                     uint32_t len = 4;
                     const uint8_t *a = src + p + 4, *b = src + (uint32_t)cand + 4;
-                    for (uint32_t k = 0; k < kLazyWords; k++) {
-                        if (p + len + 4 > mlimit) break;
-                        const uint32_t x = load32u(a + 4 * k) ^ load32u(b + 4 * k);
-                        if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-                        len += 4;
+                    if (p + 4 + 4 * kLazyWords <= mlimit) {
+                        // all loads are issued before the first compare (one memory round trip)
+                        uint32_t x[kLazyWords];
+#pragma unroll
+                        for (uint32_t k = 0; k < kLazyWords; k++) x[k] = load32u(a + 4 * k) ^ load32u(b + 4 * k);
+                        bool open = true;
+#pragma unroll
+                        for (uint32_t k = 0; k < kLazyWords; k++) {
+                            if (open) {
+                                if (x[k]) { len += (uint32_t)(__ffs((int)x[k]) - 1) >> 3; open = false; }
+                                else len += 4;
+                            }
+                        }
                     }
                     // longer wins; a later start pays one byte per position; ties go to the earlier lane
                     score = ((64u + len - (uint32_t)(lane - pick)) << 5) | (31u - (uint32_t)lane);
@@ -337,7 +345,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
                 }
             }
             // backward extension over the pending literals
-            for (;;) {
+            while (mp > anchor) {
                 const uint32_t k = lane + 1;
                 const bool eq = (mp >= anchor + k) && (mc >= k) && src[mp - k] == src[mc - k];
                 const uint32_t neq = ~__ballot_sync(0xffffffffu, eq);
@@ -359,9 +367,6 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
             op += 2;
             if (ml >= 15) op += warp_put_len_ext(out + op, ml - 15, lane);
             si = mend; anchor = mend;
-            // like the reference, remember the position two bytes before the end of the match
-            if (lane == 0 && mend - 2 < mfl) table[lz4_hash4<HL>(load32u(src + mend - 2))] = (uint16_t)(mend - 2);
-            __syncwarp();
         }
     }
     // last literals
@@ -390,7 +395,7 @@ struct EncodeArgs {
 };
 
 template <int HL>
-__global__ void __launch_bounds__(kCodecThreads) lz4_encode_kernel(EncodeArgs a) {
+__global__ void __launch_bounds__(kCodecThreads, HL <= 11 ? 12 : (HL == 12 ? 7 : 3)) lz4_encode_kernel(EncodeArgs a) {
     extern __shared__ __align__(16) uint16_t tables[];   // kCodecWarps x 2^HL entries
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t f = blockIdx.x * kCodecWarps + warp;

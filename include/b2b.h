@@ -104,13 +104,20 @@ enum {
     B2B_OPT_HOST_STAGE_BYTES = 3,
     /* log2 of the LZ4 match-finder's shared-memory hash table, 11..14 (0 = default 12).  Larger
      * tables find more matches (ratio) and cost occupancy (speed). */
-    B2B_OPT_HASH_LOG = 4
+    B2B_OPT_HASH_LOG = 4,
+    /* 1: bracket every kernel launch with CUDA events on its stream (see b2b_kernel_stats) */
+    B2B_OPT_KERNEL_TIMING = 5
 };
 B2B_API int b2b_set_option(b2b_ctx *ctx, int option, int64_t value);
 /* pre-size the device scratch arena so that later calls do not allocate */
 B2B_API int b2b_reserve(b2b_ctx *ctx, uint64_t total_uncompressed_bytes, uint32_t nframes);
 /* number of kernel launches issued through this ctx since creation (bench's gpu_launches) */
 B2B_API uint64_t b2b_launch_count(b2b_ctx *ctx);
+/* per-kernel launch counts and (with B2B_OPT_KERNEL_TIMING) summed device time; kernel = 0..5:
+ * filter, lz4 encode, lz4 decode, offsets scan, pack, frame info.  Synchronises pending events. */
+B2B_API int b2b_kernel_stats(b2b_ctx *ctx, int kernel, const char **name, uint64_t *launches,
+                             double *total_ms);
+B2B_API int b2b_kernel_stats_reset(b2b_ctx *ctx);
 
 /* ---- sizes and headers (host only; GetInfo / GetDecompressedSize never touch the GPU) -- */
 B2B_API size_t b2b_max_frame_size(size_t n); /* 16 + n: the memcpy frame bounds every frame */

@@ -68,7 +68,7 @@ d_olen = torch.empty(nf, dtype=torch.int32, device="cuda")
 from tools.perf_probe_lib import gen_f32 as gen2
 src64 = gen2(size // 4, f64=True)
 for label, data, sh, T in (("C3 f32 Shuffle T=4", src, 1, 4), ("C4 f64 BitShuffle T=8", src64, 2, 8)):
-    for hl in (12, 13, 14):
+    for hl in (11, 12):
         ctx.set_option(pkg.OPT_HASH_LOG, hl)
         comp = lambda: ctx.compress_batch_dev(data, d_off, d_len, nf, size, fl, sh, T, d_c, cap, d_foff, d_flen, d_st, d_tot, s)
         best, med = timeit(comp, iters=3, warm=1)
