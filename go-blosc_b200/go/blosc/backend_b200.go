@@ -1,0 +1,211 @@
+//go:build b200
+
+// cgo bridge: the reference's backend seam (compressBackend / decompressBackend, reference
+// blosc.go:320-434; ShuffleBuffer / UnshuffleBuffer, shuffle.go:298-323) bound to include/b2b.h.
+package blosc
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../lib -lb2b -Wl,-rpath,${SRCDIR}/../../lib
+#include <stdlib.h>
+#include "b2b.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"runtime"
+	"sync"
+	"unsafe"
+)
+
+// A cgo call pins an OS thread for its duration and a b2b_ctx serialises its callers, so
+// concurrent goroutines draw contexts from a pool (one stream + scratch arena each).
+var ctxPool = sync.Pool{New: func() any {
+	var h *C.b2b_ctx
+	if rc := C.b2b_init(C.int(deviceIndex()), &h); rc != C.B2B_OK {
+		return fmt.Errorf("b2b_init: %s (no CPU fallback)", C.GoString(C.b2b_strerror(rc)))
+	}
+	c := &gpuCtx{h: h}
+	runtime.SetFinalizer(c, func(c *gpuCtx) { C.b2b_destroy(c.h) })
+	return c
+}}
+
+type gpuCtx struct{ h *C.b2b_ctx }
+
+func deviceIndex() int { return 0 } // one process per GPU: set CUDA_VISIBLE_DEVICES per rank
+
+func withCtx(f func(*gpuCtx) error) error {
+	switch c := ctxPool.Get().(type) {
+	case *gpuCtx:
+		defer ctxPool.Put(c)
+		return f(c)
+	case error:
+		return c
+	}
+	return fmt.Errorf("b2b: no context")
+}
+
+// statusErr maps a B2B_* status to the reference's sentinel, bare or wrapped as the
+// reference does (SURVEY 8(b) "Errors").
+func statusErr(rc C.int, detail string) error {
+	switch rc {
+	case C.B2B_OK:
+		return nil
+	case C.B2B_EINVALID_DATA:
+		return ErrInvalidData // bare (blosc.go:269-271, 385-390)
+	case C.B2B_EINVALID_HEADER:
+		return ErrInvalidHeader // bare (blosc.go:297-299)
+	case C.B2B_EINVALID_VERSION:
+		return fmt.Errorf("%w: %s", ErrInvalidVersion, detail)
+	case C.B2B_EINVALID_CODEC:
+		return fmt.Errorf("%w: %s", ErrInvalidCodec, detail)
+	case C.B2B_ESIZE_MISMATCH:
+		return fmt.Errorf("%w: %s", ErrSizeMismatch, detail)
+	case C.B2B_EDATA_TOO_LARGE:
+		return fmt.Errorf("%w: %s", ErrDataTooLarge, detail)
+	case C.B2B_ECOMPRESSION_FAILED:
+		return fmt.Errorf("%w: %s", ErrCompressionFailed, detail)
+	case C.B2B_EDECOMPRESSION_FAILED:
+		return fmt.Errorf("%w: %s", ErrDecompressionFailed, detail)
+	}
+	return fmt.Errorf("b2b: %s (%s)", C.GoString(C.b2b_strerror(rc)), detail)
+}
+
+func compressBackend(data []byte, opts Options) ([]byte, error) {
+	if opts.Codec != LZ4 { // codecs that stay on the reference's CPU implementations
+		return compressOnCPU(data, opts)
+	}
+	dst := make([]byte, int(C.b2b_max_frame_size(C.size_t(len(data))))+64)
+	var n C.size_t
+	err := withCtx(func(c *gpuCtx) error {
+		rc := C.b2b_compress(c.h, unsafe.Pointer(&data[0]), C.size_t(len(data)), C.int(opts.Codec), C.int(opts.Level),
+			C.int(opts.Shuffle), C.int64_t(opts.TypeSize), unsafe.Pointer(&dst[0]), C.size_t(len(dst)), &n)
+		return statusErr(rc, opts.Codec.String())
+	})
+	if err != nil {
+		return nil, err
+	}
+	return dst[:int(n):int(n)], nil
+}
+
+func decompressBackend(data []byte, typeSize int) ([]byte, error) {
+	h, err := ParseHeader(data)
+	if err != nil {
+		return nil, err
+	}
+	if !h.IsMemcpy() && h.VersionLZ != uint8(LZ4) && h.VersionLZ != uint8(LZ4HC) {
+		return decompressOnCPU(data, typeSize, h) // Snappy / ZLIB / ZSTD (or ErrInvalidCodec)
+	}
+	capacity := int(h.NBytesOrig)
+	if reach := 255*len(data) + 64; capacity > reach { // an LZ4 block cannot expand more than 255x
+		capacity = reach
+	}
+	dst := make([]byte, capacity+1)
+	var n C.size_t
+	err = withCtx(func(c *gpuCtx) error {
+		rc := C.b2b_decompress(c.h, unsafe.Pointer(&data[0]), C.size_t(len(data)), C.int64_t(typeSize),
+			unsafe.Pointer(&dst[0]), C.size_t(capacity), &n)
+		if rc == C.B2B_EDST_TOO_SMALL && capacity < int(h.NBytesOrig) {
+			rc = C.B2B_ESIZE_MISMATCH
+		}
+		return statusErr(rc, fmt.Sprintf("expected %d", h.NBytesOrig))
+	})
+	if err != nil {
+		return nil, err
+	}
+	return dst[:int(n):int(n)], nil
+}
+
+func filterInPlace(data []byte, typeSize int, mode Shuffle, inverse int) {
+	if len(data) == 0 || (mode != Shuffle1 && mode != BitShuffle) {
+		return // default arm of the reference's switch: untouched
+	}
+	_ = withCtx(func(c *gpuCtx) error {
+		p := unsafe.Pointer(&data[0])
+		C.b2b_shuffle(c.h, C.int(mode), C.int(inverse), C.int64_t(typeSize), p, p, C.size_t(len(data)))
+		return nil
+	})
+}
+
+// ShuffleBuffer / UnshuffleBuffer mirror reference shuffle.go:298-323 (in place).
+func ShuffleBuffer(data []byte, typeSize int, mode Shuffle)   { filterInPlace(data, typeSize, mode, 0) }
+func UnshuffleBuffer(data []byte, typeSize int, mode Shuffle) { filterInPlace(data, typeSize, mode, 1) }
+
+// GPULZ4Codec implements CodecInterface over the raw-block entry points, for callers that
+// want only the codec stage on the device: RegisterCodec(LZ4, GPULZ4Codec{}) (codec.go:36-38).
+type GPULZ4Codec struct{}
+
+func (GPULZ4Codec) Name() string { return "lz4" }
+
+func (GPULZ4Codec) Compress(data []byte, level int) ([]byte, error) {
+	if len(data) == 0 {
+		return []byte{0}, nil
+	}
+	dst := make([]byte, int(C.b2b_lz4_bound(C.size_t(len(data)))))
+	var n C.size_t
+	err := withCtx(func(c *gpuCtx) error {
+		return statusErr(C.b2b_lz4_block_compress(c.h, unsafe.Pointer(&data[0]), C.size_t(len(data)),
+			unsafe.Pointer(&dst[0]), C.size_t(len(dst)), &n), "lz4 compress")
+	})
+	if err != nil {
+		return nil, err
+	}
+	return dst[:int(n)], nil
+}
+
+func (GPULZ4Codec) Decompress(data []byte, expectedSize int) ([]byte, error) {
+	buf := make([]byte, expectedSize+1)
+	if len(data) == 0 {
+		return buf[:0], nil
+	}
+	var n C.size_t
+	err := withCtx(func(c *gpuCtx) error {
+		return statusErr(C.b2b_lz4_block_decompress(c.h, unsafe.Pointer(&data[0]), C.size_t(len(data)),
+			unsafe.Pointer(&buf[0]), C.size_t(expectedSize), &n), "lz4 decompress")
+	})
+	if err != nil {
+		return nil, err
+	}
+	return buf[:int(n)], nil
+}
+
+// CompressChunks / DecompressChunks: many independent frames per call (no reference
+// counterpart; SURVEY 8(f) rank 1).  Frames come back as sub-slices of one packed buffer.
+func CompressChunks(chunks [][]byte, shuffle Shuffle, typeSize int) ([][]byte, error) {
+	n := len(chunks)
+	if n == 0 {
+		return nil, nil
+	}
+	var total uint64
+	off := make([]C.uint64_t, n)
+	ln := make([]C.uint32_t, n)
+	for i, c := range chunks {
+		off[i], ln[i] = C.uint64_t(total), C.uint32_t(len(c))
+		total += uint64(len(c))
+	}
+	src := make([]byte, total)
+	for i, c := range chunks {
+		copy(src[off[i]:], c)
+	}
+	dst := make([]byte, total+uint64(32*n)+64)
+	foff := make([]C.uint64_t, n)
+	flen := make([]C.uint32_t, n)
+	st := make([]C.uint32_t, n)
+	var out C.uint64_t
+	err := withCtx(func(c *gpuCtx) error {
+		return statusErr(C.b2b_compress_batch(c.h, unsafe.Pointer(&src[0]), &off[0], &ln[0], C.uint32_t(n), C.int(shuffle),
+			C.int64_t(typeSize), unsafe.Pointer(&dst[0]), C.uint64_t(len(dst)), &foff[0], &flen[0], &st[0], &out), "batch")
+	})
+	if err != nil {
+		return nil, err
+	}
+	frames := make([][]byte, n)
+	for i := range frames {
+		if st[i] != 0 {
+			return nil, statusErr(C.int(st[i]), fmt.Sprintf("chunk %d", i))
+		}
+		frames[i] = dst[foff[i] : uint64(foff[i])+uint64(flen[i])]
+	}
+	return frames, nil
+}

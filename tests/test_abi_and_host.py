@@ -107,3 +107,29 @@ def test_host_kernel_check_builds_and_passes():
                           stderr=subprocess.DEVNULL)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
+
+
+def test_cpp_host_mirror_abi_only(pkg):
+    """C++ host mirror, host-only entry points (no device): header, strings, argument errors."""
+    exe = os.path.join(ROOT, "go-blosc_b200", "lib", "blosc_host_test")
+    out = subprocess.run([exe, "--abi"], capture_output=True, text=True)
+    assert out.returncode == 0 and "abi: ok" in out.stdout, out.stdout
+
+
+def test_go_package_mirrors_every_exported_identifier():
+    """the Go host package keeps the reference's exported surface."""
+    go = ""
+    d = os.path.join(ROOT, "go-blosc_b200", "go", "blosc")
+    for f in os.listdir(d):
+        go += open(os.path.join(d, f)).read()
+    for ident in ["func Compress(", "func CompressWithOptions(", "func Decompress(", "func DecompressWithSize(",
+                  "func GetInfo(", "func GetDecompressedSize(", "func ParseHeader(", "func DefaultOptions(",
+                  "func ShuffleBuffer(", "func UnshuffleBuffer(", "func RegisterCodec(", "func GetCodec(",
+                  "func ListCodecs(", "type CodecInterface interface", "type Codec uint8", "type Shuffle uint8",
+                  "type Options struct", "type Header struct", "FormatVersion", "HeaderSize", "MinHeaderSize",
+                  "ErrInvalidData", "ErrInvalidHeader", "ErrInvalidVersion", "ErrInvalidCodec", "ErrSizeMismatch",
+                  "ErrDataTooLarge", "ErrCompressionFailed", "ErrDecompressionFailed", "HasShuffle", "HasBitShuffle",
+                  "IsMemcpy", "ShuffleMode", "func (h *Header) Bytes("]:
+        assert ident in go, ident
+    for sym in re.findall(r"C\.(b2b_\w+)\(", go):
+        assert sym in open(os.path.join(ROOT, "include", "b2b.h")).read(), sym
