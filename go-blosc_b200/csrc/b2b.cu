@@ -14,14 +14,16 @@
 
 #include "common.cuh"
 #include "filter_kernels.cuh"
+#include "lz4_encode.cuh"
 #include "lz4_kernels.cuh"
 #include "scan.cuh"
 
 using namespace b2b;
 
-enum KernelId { K_FILTER = 0, K_ENCODE, K_DECODE, K_SCAN, K_PACK, K_INFO, K_COUNT };
+enum KernelId { K_FILTER = 0, K_ENCODE, K_DECODE, K_SCAN, K_PACK, K_INFO, K_FINALIZE, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"filter_batch_kernel", "lz4_encode_kernel", "lz4_decode_kernel",
-                                                  "scan_offsets_kernel", "pack_frames_kernel", "frame_info_kernel"};
+                                                  "scan_offsets_kernel", "pack_frames_kernel", "frame_info_kernel",
+                                                  "finalize_frames_kernel"};
 
 struct TimedLaunch { int id; cudaEvent_t a, b; };
 
@@ -29,8 +31,8 @@ struct b2b_ctx {
     int opt_timing = 0;                 // record CUDA events around every kernel launch
     std::vector<TimedLaunch> pending;   // not yet folded into the sums
     std::vector<cudaEvent_t> event_pool;
-    double kernel_ms[K_COUNT] = {0, 0, 0, 0, 0, 0};
-    uint64_t kernel_launches[K_COUNT] = {0, 0, 0, 0, 0, 0};
+    double kernel_ms[K_COUNT] = {};
+    uint64_t kernel_launches[K_COUNT] = {};
     int device = 0;
     int sm_count = 148;
     std::mutex mu;
@@ -183,20 +185,25 @@ int launch_filter(b2b_ctx *ctx, const uint8_t *src, uint8_t *dst, const uint64_t
 
 int launch_encode(b2b_ctx *ctx, const EncodeArgs &e, cudaStream_t s) {
     const int hl = ctx->opt_hash_log ? ctx->opt_hash_log : kHashLogDefault;
-    const unsigned grid = (e.nframes + kCodecWarps - 1) / kCodecWarps;
-    const size_t smem = (size_t)kCodecWarps * sizeof(uint16_t) << hl;
+    const uint64_t warps = (uint64_t)e.nframes * e.segs_grid;
+    const size_t smem = (size_t)kEncWarps * sizeof(uint32_t) << hl;
+    // persistent CTAs: as many as fit on the device (warps pull items from the ticket)
+    const uint64_t per_sm = hl <= 10 ? 12 : hl == 11 ? 7 : hl == 12 ? 3 : 1;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((warps + kEncWarps - 1) / kEncWarps,
+                                                                     (uint64_t)ctx->sm_count * per_sm));
+    CU(ctx, cudaMemsetAsync(e.ticket, 0, 8, s));
     auto go = [&](auto kernel) -> int {
         if (smem > 48 * 1024)
             CU(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        { LaunchTimer lt(ctx, K_ENCODE, s); kernel<<<grid, kCodecThreads, smem, s>>>(e); }
+        { LaunchTimer lt(ctx, K_ENCODE, s); kernel<<<grid, kEncThreads, smem, s>>>(e); }
         CU(ctx, cudaGetLastError());
         return B2B_OK;
     };
     switch (hl) {
-        case 11: return go(lz4_encode_kernel<11>);
+        case 10: return go(lz4_encode_kernel<10>);
+        case 12: return go(lz4_encode_kernel<12>);
         case 13: return go(lz4_encode_kernel<13>);
-        case 14: return go(lz4_encode_kernel<14>);
-        default: return go(lz4_encode_kernel<12>);
+        default: return go(lz4_encode_kernel<11>);
     }
 }
 
@@ -210,11 +217,21 @@ FrameMeta uniform_meta(int mode, int64_t typesize) {
 }
 
 // ---- device-pointer cores (ctx->mu held by the caller) ----------------------------------
+uint64_t comp_scratch_bytes(uint64_t total_src, uint32_t nframes) {
+    // every segment slot holds the LZ4 worst case of 64 KiB; a frame's last, partial segment
+    // still takes a whole slot when the frame has more than one
+    const uint64_t multi = std::min<uint64_t>(nframes, total_src / kSegBytes + 1);
+    return total_src / kSegBytes * kSegSlot + (uint64_t)kSegSlot + multi * kSegSlot + 64ull * nframes +
+           total_src / 255 + 4096;
+}
+
+// raw_block: b2b_lz4_block_compress -- no filter, no header, no memcpy substitution
 int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d_src_off,
                               const uint32_t *d_src_len, uint32_t nframes, uint64_t total_src,
                               uint32_t max_len, int shuffle, int64_t typesize, void *d_dst,
                               uint64_t dst_cap, uint64_t *d_frame_off, uint32_t *d_frame_len,
-                              uint32_t *d_status, uint64_t *d_total_out, cudaStream_t s) {
+                              uint32_t *d_status, uint64_t *d_total_out, cudaStream_t s,
+                              bool raw_block = false) {
     if (nframes == 0) {
         if (d_total_out) CU(ctx, cudaMemsetAsync(d_total_out, 0, 8, s));
         return B2B_OK;
@@ -222,27 +239,36 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     if (!d_src || !d_src_off || !d_src_len || !d_dst || !d_frame_off || !d_frame_len || !d_status)
         return B2B_EINVAL;
     if (((uintptr_t)d_dst & 15u) != 0) return B2B_EINVAL;
-    if (dst_cap < total_src + 16ull * nframes + 15ull * nframes) return B2B_EDST_TOO_SMALL;
+    if (!raw_block && dst_cap < total_src + 31ull * nframes) return B2B_EDST_TOO_SMALL;
     if (typesize <= 0) typesize = 1;                                   // blosc.go:274-276
-    const FrameMeta fm = uniform_meta(shuffle, typesize);
+    const FrameMeta fm = raw_block ? FrameMeta{0, 0} : uniform_meta(shuffle, typesize);
     const bool filtered = fm.mode != 0;
-    const uint32_t shuffle_flag = shuffle == B2B_SHUFFLE ? B2B_FLAG_SHUFFLE
+    const uint32_t shuffle_flag = raw_block ? 0 : shuffle == B2B_SHUFFLE ? B2B_FLAG_SHUFFLE
                                 : shuffle == B2B_BITSHUFFLE ? B2B_FLAG_BITSHUFFLE : 0;  // blosc.go:348-353
 
     // scratch layout
-    const uint64_t comp_bytes = total_src + total_src / 255 + 48ull * nframes + 256;
+    const uint64_t comp_bytes = comp_scratch_bytes(total_src, nframes);
+    const uint64_t max_segs_total = total_src / kSegBytes + nframes + 1;
     const uint64_t need = (filtered ? align_up(total_src + 64, 256) : 0) + align_up(comp_bytes, 256) +
-                          3 * align_up(8ull * nframes, 256) + 2 * scan_scratch_bytes(nframes) + 4096;
+                          align_up(16 * max_segs_total, 256) + align_up(8 * max_segs_total, 256) +
+                          8 * align_up(8ull * nframes, 256) + 3 * scan_scratch_bytes(nframes) + 8192;
     int rc = ensure_arena(ctx, need);
     if (rc) return rc;
     Arena ar(ctx);
     uint8_t *d_shuf = filtered ? ar.take<uint8_t>(total_src + 64) : nullptr;
     uint8_t *d_comp = ar.take<uint8_t>(comp_bytes);
+    SegMeta *d_meta = ar.take<SegMeta>(max_segs_total);
+    SegPlace *d_place = ar.take<SegPlace>(max_segs_total);
     uint64_t *d_comp_off = ar.take<uint64_t>(nframes);
+    uint64_t *d_seg_base = ar.take<uint64_t>(nframes);
     uint32_t *d_comp_len = ar.take<uint32_t>(nframes);
     uint32_t *d_flags = ar.take<uint32_t>(nframes);
+    uint32_t *d_final_ll = ar.take<uint32_t>(nframes);
+    uint32_t *d_final_off = ar.take<uint32_t>(nframes);
     uint8_t *scan_a = ar.take<uint8_t>(scan_scratch_bytes(nframes));
     uint8_t *scan_b = ar.take<uint8_t>(scan_scratch_bytes(nframes));
+    uint8_t *scan_c = ar.take<uint8_t>(scan_scratch_bytes(nframes));
+    unsigned long long *d_ticket = ar.take<unsigned long long>(4);
 
     const uint8_t *in = static_cast<const uint8_t *>(d_src);
     if (filtered) {
@@ -251,27 +277,44 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
         if (rc) return rc;
         in = d_shuf;
     }
-    rc = launch_scan(ctx, d_src_len, nframes, d_comp_off, nullptr, kScanLz4Slot, scan_a, s);
+    rc = launch_scan(ctx, d_src_len, nframes, d_comp_off, nullptr, kScanSegSlot, scan_a, s);
     if (rc) return rc;
+    rc = launch_scan(ctx, d_src_len, nframes, d_seg_base, nullptr, kScanSegCount, scan_b, s);
+    if (rc) return rc;
+
+    uint64_t segs_grid = std::max<uint64_t>(1, ((uint64_t)max_len + kSegBytes - 1) / kSegBytes);
+    segs_grid = std::min<uint64_t>(segs_grid, std::max<uint64_t>(1, (1ull << 30) / nframes));
 
     EncodeArgs e;
     e.in = in; e.src_off = d_src_off; e.src_len = d_src_len; e.nframes = nframes;
-    e.comp = d_comp; e.comp_off = d_comp_off; e.comp_len = d_comp_len; e.frame_len = d_frame_len;
-    e.flags = d_flags; e.status = d_status; e.shuffle_flag = shuffle_flag; e.keep_raw = 0;
+    e.segs_grid = (uint32_t)segs_grid; e.comp = d_comp; e.comp_off = d_comp_off;
+    e.seg_base = d_seg_base; e.meta = d_meta; e.ticket = d_ticket;
     rc = launch_encode(ctx, e, s);
     if (rc) return rc;
 
-    rc = launch_scan(ctx, d_frame_len, nframes, d_frame_off, d_total_out, kScanAlign16, scan_b, s);
+    FinalizeArgs fa;
+    fa.src_len = d_src_len; fa.seg_base = d_seg_base; fa.meta = d_meta; fa.place = d_place;
+    fa.nframes = nframes; fa.shuffle_flag = shuffle_flag; fa.keep_raw = raw_block ? 1 : 0;
+    fa.comp_len = d_comp_len; fa.frame_len = d_frame_len; fa.flags = d_flags;
+    fa.final_ll = d_final_ll; fa.final_off = d_final_off; fa.status = d_status;
+    { LaunchTimer lt(ctx, K_FINALIZE, s); finalize_frames_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(fa); }
+    CU(ctx, cudaGetLastError());
+
+    rc = launch_scan(ctx, d_frame_len, nframes, d_frame_off, d_total_out, kScanAlign16, scan_c, s);
     if (rc) return rc;
 
     PackArgs p;
-    p.comp = d_comp; p.comp_off = d_comp_off;
+    p.in = in;
     p.raw = ctx->opt_quirk ? static_cast<const uint8_t *>(d_src) : in;   // SURVEY F4 policy
-    p.src_off = d_src_off; p.src_len = d_src_len; p.comp_len = d_comp_len; p.flags = d_flags;
-    p.status = d_status; p.frame_off = d_frame_off; p.dst = static_cast<uint8_t *>(d_dst);
-    p.nframes = nframes; p.tiles_per_frame = tiles_for((uint64_t)max_len + 16, nframes, ctx);
+    p.src_off = d_src_off; p.src_len = d_src_len; p.comp = d_comp; p.comp_off = d_comp_off;
+    p.seg_base = d_seg_base; p.meta = d_meta; p.place = d_place; p.comp_len = d_comp_len;
+    p.flags = d_flags; p.final_ll = d_final_ll; p.final_off = d_final_off; p.status = d_status;
+    p.frame_off = d_frame_off; p.dst = static_cast<uint8_t *>(d_dst);
+    p.nframes = nframes; p.segs_grid = (uint32_t)segs_grid;
     p.codec = B2B_LZ4; p.typesize_u8 = (uint32_t)(uint8_t)typesize;     // blosc.go:362
-    { LaunchTimer lt(ctx, K_PACK, s); pack_frames_kernel<<<(unsigned)((uint64_t)nframes * p.tiles_per_frame), kFilterThreads, 0, s>>>(p); }
+    p.header = raw_block ? 0 : 1;
+    { LaunchTimer lt(ctx, K_PACK, s);
+      pack_frames_kernel<<<(unsigned)((uint64_t)nframes * segs_grid), kFilterThreads, 0, s>>>(p); }
     CU(ctx, cudaGetLastError());
     return B2B_OK;
 }
@@ -407,7 +450,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
         case B2B_OPT_REF_MEMCPY_QUIRK: ctx->opt_quirk = value != 0; return B2B_OK;
         case B2B_OPT_FILTER_CTAS_PER_SM: ctx->opt_filter_ctas_per_sm = (int)std::max<int64_t>(0, value); return B2B_OK;
         case B2B_OPT_HASH_LOG:
-            if (value != 0 && (value < 11 || value > 14)) return B2B_EINVAL;
+            if (value != 0 && (value < 10 || value > 13)) return B2B_EINVAL;
             ctx->opt_hash_log = (int)value; return B2B_OK;
         case B2B_OPT_KERNEL_TIMING: ctx->opt_timing = value != 0; return B2B_OK;
         case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (256ull << 20); return B2B_OK;
@@ -419,8 +462,9 @@ int b2b_reserve(b2b_ctx *ctx, uint64_t total, uint32_t nframes) {
     if (!ctx) return B2B_EINVAL;
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
-    const uint64_t need = 2 * align_up(total + 64, 256) + total / 255 + 64ull * nframes +
-                          8 * align_up(8ull * nframes, 256) + 2 * scan_scratch_bytes(nframes) + (1 << 20);
+    const uint64_t need = align_up(total + 64, 256) + comp_scratch_bytes(total, nframes) +
+                          24 * (total / kSegBytes + nframes + 1) + 8 * align_up(8ull * nframes, 256) +
+                          3 * scan_scratch_bytes(nframes) + (1 << 20);
     return ensure_arena(ctx, need);
 }
 
@@ -742,34 +786,29 @@ int b2b_lz4_block_compress(b2b_ctx *ctx, const void *src, size_t n, void *dst, s
     }
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
-    const uint64_t slot = align_up(b2b_lz4_bound(n), 16);
-    int rc = ensure_arena(ctx, align_up(n + 64, 256) + slot + 4096);
+    const uint64_t out_cap = align_up(b2b_lz4_bound(n) + 64, 256);
+    uint8_t *d_in = nullptr, *d_out = nullptr, *d_tab = nullptr;
+    int rc = ensure_hbuf(ctx, 0, n + 64, &d_in);
+    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 1, out_cap, &d_out);
+    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 2, 4096, &d_tab);
     if (rc) return rc;
-    Arena ar(ctx);
-    uint8_t *d_in = ar.take<uint8_t>(n + 64);
-    uint8_t *d_comp = ar.take<uint8_t>(slot);
-    uint64_t *d_off = ar.take<uint64_t>(2);
-    uint32_t *d_u32 = ar.take<uint32_t>(8);
     cudaStream_t s = ctx->stream;
-    const uint64_t h_off[2] = {0, 0}; const uint32_t h_len = (uint32_t)n;
+    uint64_t *d_off = reinterpret_cast<uint64_t *>(d_tab);            // [0] src_off, [1] frame_off, [2] total
+    uint32_t *d_u32 = reinterpret_cast<uint32_t *>(d_tab + 256);      // [0] src_len, [1] frame_len, [2] status
+    const uint64_t h_off[3] = {0, 0, 0};
+    const uint32_t h_u32[3] = {(uint32_t)n, 0, 0};
     CU(ctx, cudaMemcpyAsync(d_in, src, n, cudaMemcpyHostToDevice, s));
-    CU(ctx, cudaMemcpyAsync(d_off, h_off, 16, cudaMemcpyHostToDevice, s));
-    CU(ctx, cudaMemcpyAsync(d_u32, &h_len, 4, cudaMemcpyHostToDevice, s));
-    // raw block: run the encoder warp directly, keep its true length (no memcpy substitution)
-    EncodeArgs e;
-    e.in = d_in; e.src_off = d_off; e.src_len = d_u32; e.nframes = 1; e.comp = d_comp;
-    e.comp_off = d_off + 1; e.comp_len = d_u32 + 1; e.frame_len = d_u32 + 2; e.flags = d_u32 + 3;
-    e.status = d_u32 + 4; e.shuffle_flag = 0; e.keep_raw = 1;
-    {
-        int rc2 = launch_encode(ctx, e, s);
-        if (rc2) return rc2;
-    }
-    uint32_t h_res[5] = {0, 0, 0, 0, 0};
+    CU(ctx, cudaMemcpyAsync(d_off, h_off, sizeof h_off, cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemcpyAsync(d_u32, h_u32, sizeof h_u32, cudaMemcpyHostToDevice, s));
+    rc = compress_batch_dev_locked(ctx, d_in, d_off, d_u32, 1, n, (uint32_t)n, B2B_NOSHUFFLE, 1, d_out, out_cap,
+                                   d_off + 1, d_u32 + 1, d_u32 + 2, d_off + 2, s, /*raw_block=*/true);
+    if (rc) return rc;
+    uint32_t h_res[3] = {0, 0, 0};
     CU(ctx, cudaMemcpyAsync(h_res, d_u32, sizeof h_res, cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaStreamSynchronize(s));
-    if (h_res[4]) return (int)h_res[4];
-    const uint32_t c = h_res[1];
-    CU(ctx, cudaMemcpyAsync(dst, d_comp, c, cudaMemcpyDeviceToHost, s));
+    if (h_res[2]) return (int)h_res[2];
+    const uint32_t c = h_res[1] - 16;   // frame_len counts a header that the raw API does not write
+    CU(ctx, cudaMemcpyAsync(dst, d_out, c, cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaStreamSynchronize(s));
     *out_len = c;
     return B2B_OK;
@@ -789,8 +828,7 @@ int b2b_lz4_block_decompress(b2b_ctx *ctx, const void *src, size_t n, void *dst,
     int rc = b2b_decompress_batch(ctx, fr.data(), &foff, &flen, 1, 0, dst, expected, &doff, &got, &st);
     if (rc) return rc;
     // codec.go:77-84 returns buf[:n]: a short decode is not an error at this level
-    if (st == B2B_ESIZE_MISMATCH) return B2B_ESIZE_MISMATCH;
-    if (st) return (int)st;
+    if (st && st != B2B_ESIZE_MISMATCH) return (int)st;
     *out_len = got;
     return B2B_OK;
 }

@@ -1,0 +1,398 @@
+// lz4_encode.cuh -- K3: LZ4 block compression of a batch of frames, segment-parallel.
+//
+// Replaces lz4Codec.Compress (codec.go:63-75 -> pierrec/lz4 CompressBlock) and the frame
+// assembly of compressBackend (blosc.go:336-373).  The reference can only decode ONE LZ4
+// block per frame, so a frame is still one block on the wire, but it is produced in
+// parallel:
+//
+//   encode   one warp per 64 KiB SEGMENT of a frame.  A segment only references itself (the
+//            LZ4 window is 64 KiB anyway), so segments are independent, positions fit the 16
+//            bits of a hash-table entry exactly, and the reference compressor's adaptive skip
+//            restarts at every segment (after a byte shuffle: at every byte plane).
+//            The warp writes the segment's sequences in final wire format into a scratch
+//            slot, EXCEPT the token / literal run of its first sequence and its trailing
+//            literals, which depend on the neighbouring segments.
+//   finalize one thread per frame walks the segment summaries: trailing literals of segment
+//            k are carried into the first sequence of the next segment that has a match
+//            (they are contiguous in the input), which fixes every segment's place in the
+//            block, the block size c and the memcpy decision (c >= n, blosc.go:342-345).
+//   pack     (after the offsets scan, K5) one CTA per segment writes the merged first token,
+//            its literals and the segment body at the frame's packed position; memcpy frames
+//            copy the raw bytes instead.  Segment 0 writes the 16-byte header.
+//
+// Match finder per warp: 32 candidate positions per step (consecutive, or spread with the
+// reference's skip schedule once literals pile up), a 2^HL-entry shared-memory hash table whose
+// 32-bit entries hold a 17-bit position and 15 check bits of the hash (a candidate is only
+// fetched from global memory when the check bits agree), MATCH.ANY for repeats inside the
+// step, a bounded look at the next two starts, 32-lane-wide backward / forward extension.
+// The last kWarmBytes of the previous segment are entered into the table first, so runs and
+// periodic patterns continue across a segment boundary instead of being re-emitted.
+// Warps take (frame, segment) items from an atomic ticket: planes of very different
+// compressibility would otherwise leave most warps of a CTA idle.
+#pragma once
+#include "common.cuh"
+
+namespace b2b {
+
+constexpr uint32_t kSegBytes = 65536;
+constexpr uint32_t kSegSlot = 65840;   // align16(65536 + 65536/255 + 32): worst case of one segment
+constexpr int kEncWarps = 4;           // segments (warps) per CTA
+constexpr int kEncThreads = kEncWarps * 32;
+constexpr int kHashLogDefault = 10;    // 2^10 x u32 = 4 KiB per warp: 48 resident warps per SM
+constexpr uint32_t kWarmBytes = 512;   // tail of the previous segment pre-loaded into the hash table
+constexpr uint32_t kLazyWindow = 2;    // later starts considered after the first hit
+constexpr uint32_t kLazyWords = 4;     // bounded look-ahead: 4 + 4 * 4 = 20 bytes
+
+struct SegMeta {
+    uint32_t first_ll;   // literals before the first match (whole segment if there is none)
+    uint32_t body_len;   // bytes in the scratch slot
+    uint32_t trail_ll;   // literals after the last match
+    uint32_t info;       // bit 8: has a match; bits 0..3: match-length nibble of the first token
+};
+struct SegPlace {
+    uint32_t out_off;    // payload offset of this segment's (merged) first token
+    uint32_t lit_total;  // literals of that token: carried ones + first_ll
+};
+
+__host__ __device__ __forceinline__ uint32_t seg_count(uint32_t n) { return (n + kSegBytes - 1) / kSegBytes; }
+// scratch bytes of one frame's slots: exact LZ4 bound for single-segment frames
+__host__ __device__ __forceinline__ uint64_t frame_slot_bytes(uint32_t n) {
+    const uint32_t s = seg_count(n);
+    if (s > 1) return (uint64_t)s * kSegSlot;
+    return ((uint64_t)n + n / 255u + 32ull + 15ull) & ~15ull;
+}
+__host__ __device__ __forceinline__ uint32_t len_ext_bytes(uint32_t v) { return v >= 15 ? (v - 15) / 255u + 1u : 0u; }
+
+__device__ __forceinline__ uint32_t enc_load32u(const uint8_t *p) {
+    const uint32_t r = (uint32_t)((uintptr_t)p & 3u);
+    const uint32_t *q = reinterpret_cast<const uint32_t *>((uintptr_t)p - r);
+    const uint32_t lo = q[0];
+    if (r == 0) return lo;
+    return __funnelshift_r(lo, q[1], 8u * r);
+}
+
+// writes a length extension (value already reduced by 15) at out, returns bytes written
+__device__ __forceinline__ uint32_t warp_put_len_ext(uint8_t *out, uint32_t v, int lane) {
+    const uint32_t full = v / 255u, last = v - full * 255u;
+    for (uint32_t i = lane; i < full; i += kWarp) out[i] = 255;
+    if (lane == 0) out[full] = (uint8_t)last;
+    return full + 1;
+}
+
+// One segment.  org: first byte of the warm-up window (W bytes before the segment, 0 for the
+// first one), L the segment length, tail: bytes of the frame after it.  Positions below are
+// relative to org.  Limits follow the reference compressor relative to the END OF THE FRAME:
+// no match starts or is extended inside the frame's last 14 bytes (pierrec mfLimit), which
+// also keeps the reference's memcpy decision for short frames.
+template <int HL>
+__device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict__ org, uint32_t W,
+                                                       uint32_t L, uint64_t tail,
+                                                       uint8_t *__restrict__ body, uint32_t *table,
+                                                       int lane) {
+    SegMeta m;
+    m.first_ll = L; m.body_len = 0; m.trail_ll = L; m.info = 0;
+    const int64_t fl = (int64_t)L + (int64_t)tail - 14;          // frame limit in segment coordinates
+    uint32_t mfl = L >= 4 ? L - 3 : 0;                           // a match of 4 bytes must fit the segment
+    if (fl < (int64_t)mfl) mfl = fl > 0 ? (uint32_t)fl : 0u;
+    uint32_t mlimit = L;
+    if (fl < (int64_t)L) mlimit = fl > 0 ? (uint32_t)fl : 0u;
+    if (mfl == 0) return m;
+    mfl += W; mlimit += W;
+
+    for (uint32_t i = lane; i < (1u << HL); i += kWarp) table[i] = 0;
+    __syncwarp();
+    // warm-up: enter the tail of the previous segment (ascending, so the nearest position wins)
+    for (uint32_t q0 = 0; q0 < W; q0 += kWarp) {
+        const uint32_t q = q0 + lane;
+        if (q + 3 < W) {
+            const uint32_t hv = enc_load32u(org + q) * 2654435761u;
+            table[hv >> (32 - HL)] = (((hv >> (17 - HL)) & 0x7FFFu) << 17) | q;
+        }
+        __syncwarp();
+    }
+    uint32_t op = 0, anchor = W, si = W;
+    bool have_first = false;
+    while (si < mfl) {
+        // adaptive skip of the reference compressor: about 3 probes per 4 + lits/128 bytes
+        const uint32_t lits = si - anchor;
+        const uint32_t stride = lits < 256 ? 1u : (4u + (lits >> 7)) / 3u;
+        const uint32_t p = si + (uint32_t)lane * stride;
+        const bool valid = p < mfl;
+        const uint32_t seq = valid ? enc_load32u(org + p) : 0u;
+        const uint32_t hv = seq * 2654435761u;
+        const uint32_t h = hv >> (32 - HL);
+        const uint32_t chk = (hv >> (17 - HL)) & 0x7FFFu;
+        const uint32_t ent = table[h];
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        const uint32_t same = __match_any_sync(0xffffffffu, seq) & vmask;
+        // nearest earlier lane of this step with the same 4 bytes, else the table entry
+        const uint32_t lower = same & ((1u << lane) - 1u);
+        uint32_t cand = 0;
+        bool ok = false;
+        if (valid && lower) {
+            const uint32_t src_lane = 31u - (uint32_t)__clz((int)lower);
+            cand = p - (uint32_t)(lane - src_lane) * stride;
+            ok = true;
+        } else if (valid && (ent >> 17) == chk) {
+            cand = ent & 0x1FFFFu;
+            ok = cand < p && p - cand < 65536u && enc_load32u(org + cand) == seq;
+        }
+        const uint32_t hit = __ballot_sync(0xffffffffu, ok);
+        int pick = hit ? __ffs(hit) - 1 : 31;
+        if (hit && stride == 1) {
+            // bounded comparison of the first hit with the hits at the next kLazyWindow starts
+            const uint32_t window = hit & (((2u << kLazyWindow) - 1u) << pick);
+            uint32_t score = 0;
+            if ((window >> lane) & 1u) {
+                uint32_t len = 4;
+                if (p + 4 + 4 * kLazyWords <= mlimit) {
+                    uint32_t x[kLazyWords];
+#pragma unroll
+                    for (uint32_t k = 0; k < kLazyWords; k++)
+                        x[k] = enc_load32u(org + p + 4 + 4 * k) ^ enc_load32u(org + cand + 4 + 4 * k);
+                    bool open = true;
+#pragma unroll
+                    for (uint32_t k = 0; k < kLazyWords; k++) {
+                        if (open) {
+                            if (x[k]) { len += (uint32_t)(__ffs((int)x[k]) - 1) >> 3; open = false; }
+                            else len += 4;
+                        }
+                    }
+                }
+                // longer wins; a later start pays one byte per position; ties go to the earlier lane
+                score = ((64u + len - (uint32_t)(lane - pick)) << 5) | (31u - (uint32_t)lane);
+            }
+            pick = 31 - (int)(__reduce_max_sync(0xffffffffu, score) & 31u);
+        }
+        __syncwarp();
+        // every probed position up to the chosen start is recorded (of lanes holding the same 4
+        // bytes the last one wins, so the table keeps the nearest occurrence)
+        const uint32_t upto = same & ((2u << pick) - 1u);
+        if (valid && lane <= pick && (upto >> lane) == 1u) table[h] = (chk << 17) | p;
+        __syncwarp();
+        if (hit == 0) {
+            si += 32u * stride;
+            continue;
+        }
+        uint32_t mp = __shfl_sync(0xffffffffu, p, pick);      // match start
+        uint32_t mc = __shfl_sync(0xffffffffu, cand, pick);   // its source
+        const uint32_t offset = mp - mc;
+        // forward extension from mp + 4, 128 bytes per step
+        uint32_t mend = mp + 4;
+        {
+            uint32_t cpos = mc + 4;
+            for (;;) {
+                const uint32_t a = mend + 4u * lane;
+                uint32_t x = 0xFFFFFFFFu;
+                if (a < mlimit) {
+                    x = enc_load32u(org + a) ^ enc_load32u(org + cpos + 4u * lane);
+                    const uint32_t avail = mlimit - a;
+                    if (avail < 4) x |= 0xFFFFFFFFu << (8u * avail);
+                }
+                const uint32_t diff = __ballot_sync(0xffffffffu, x != 0);
+                if (diff == 0) { mend += 128; cpos += 128; continue; }
+                const int fl2 = __ffs(diff) - 1;
+                const uint32_t xf = __shfl_sync(0xffffffffu, x, fl2);
+                mend += 4u * fl2 + ((uint32_t)(__ffs((int)xf) - 1) >> 3);
+                break;
+            }
+        }
+        // backward extension over the pending literals (never into the previous segment)
+        while (mp > anchor) {
+            const uint32_t k = lane + 1;
+            const bool eq = (mp >= anchor + k) && (mc >= k) && org[mp - k] == org[mc - k];
+            const uint32_t neq = ~__ballot_sync(0xffffffffu, eq);
+            const uint32_t back = neq ? (uint32_t)(__ffs((int)neq) - 1) : 32u;
+            mp -= back; mc -= back;
+            if (back < 32) break;
+        }
+        const uint32_t ll = mp - anchor, ml = mend - mp - 4;
+        if (!have_first) {
+            // token and literals of the first sequence are written by the pack pass
+            have_first = true;
+            m.first_ll = ll;
+            m.info = 0x100u | (ml < 15 ? ml : 15u);
+        } else {
+            const uint32_t tok_pos = op++;
+            if (ll >= 15) op += warp_put_len_ext(body + op, ll - 15, lane);
+            warp_copy(body + op, org + anchor, ll, lane);
+            op += ll;
+            if (lane == 0) body[tok_pos] = (uint8_t)(((ll < 15 ? ll : 15u) << 4) | (ml < 15 ? ml : 15u));
+        }
+        if (lane == 0) { body[op] = (uint8_t)offset; body[op + 1] = (uint8_t)(offset >> 8); }
+        op += 2;
+        if (ml >= 15) op += warp_put_len_ext(body + op, ml - 15, lane);
+        si = mend; anchor = mend;
+    }
+    m.body_len = op;
+    m.trail_ll = W + L - anchor;
+    return m;
+}
+
+struct EncodeArgs {
+    const uint8_t *in;          // (shuffled) input, frame f at src_off[f]
+    const uint64_t *src_off;
+    const uint32_t *src_len;
+    uint32_t nframes;
+    uint32_t segs_grid;         // items per frame in the ticket space; an item strides over segments
+    uint8_t *comp;              // scratch: segment s of frame f at comp_off[f] + s * kSegSlot
+    const uint64_t *comp_off;
+    const uint64_t *seg_base;   // index of frame f's first segment in meta / place
+    SegMeta *meta;
+    unsigned long long *ticket; // zero before launch
+};
+
+template <int HL>
+__global__ void __launch_bounds__(kEncThreads, HL <= 10 ? 12 : (HL == 11 ? 7 : (HL == 12 ? 3 : 1)))
+lz4_encode_kernel(EncodeArgs a) {
+    extern __shared__ __align__(16) uint32_t enc_tables[];   // kEncWarps x 2^HL entries
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t items = (uint64_t)a.nframes * a.segs_grid;
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(a.ticket, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= items) break;
+        const uint32_t f = (uint32_t)(item / a.segs_grid), s0 = (uint32_t)(item % a.segs_grid);
+        const uint32_t n = a.src_len[f];
+        const uint32_t nseg = seg_count(n);
+        const uint8_t *frame = a.in + a.src_off[f];
+        for (uint32_t s = s0; s < nseg; s += a.segs_grid) {
+            const uint32_t B = s * kSegBytes;
+            const uint32_t L = n - B < kSegBytes ? n - B : kSegBytes;
+            const uint32_t W = B < kWarmBytes ? B : kWarmBytes;
+            const SegMeta m = warp_encode_segment<HL>(frame + B - W, W, L, (uint64_t)n - B - L,
+                                                      a.comp + a.comp_off[f] + (uint64_t)s * kSegSlot,
+                                                      enc_tables + ((size_t)warp << HL), lane);
+            if (lane == 0) a.meta[a.seg_base[f] + s] = m;
+            __syncwarp();
+        }
+    }
+}
+
+// ---- finalize: one thread per frame ------------------------------------------------------
+struct FinalizeArgs {
+    const uint32_t *src_len;
+    const uint64_t *seg_base;
+    const SegMeta *meta;
+    SegPlace *place;
+    uint32_t nframes;
+    uint32_t shuffle_flag;      // B2B_FLAG_SHUFFLE / B2B_FLAG_BITSHUFFLE / 0 (set even when T<=1)
+    uint32_t keep_raw;          // raw-block API: never substitute the memcpy payload
+    uint32_t *comp_len;         // out: payload bytes stored (c, or n for memcpy)
+    uint32_t *frame_len;        // out: 16 + payload (0 when status != 0)
+    uint32_t *flags;            // out: header flags
+    uint32_t *final_ll;         // out: literals of the closing token
+    uint32_t *final_off;        // out: payload offset of the closing token
+    uint32_t *status;
+};
+
+__global__ void finalize_frames_kernel(FinalizeArgs a) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.nframes) return;
+    const uint32_t n = a.src_len[f];
+    uint32_t st = 0, flags = a.shuffle_flag, c = 0, flen = 0;
+    if (n == 0) st = 1;                                   // ErrInvalidData, blosc.go:269-271
+    else if (n > 0xFFFFFFFFu - 16u) st = 6;               // header fields are u32
+    else {
+        const uint32_t nseg = seg_count(n);
+        const uint64_t base = a.seg_base[f];
+        uint64_t out = 0, carry = 0;
+        for (uint32_t s = 0; s < nseg; s++) {
+            const SegMeta m = a.meta[base + s];
+            SegPlace pl; pl.out_off = 0; pl.lit_total = 0;
+            if (m.info & 0x100u) {
+                const uint64_t lt = carry + m.first_ll;
+                pl.out_off = (uint32_t)(out > 0xFFFFFFFFull ? 0xFFFFFFFFull : out);
+                pl.lit_total = (uint32_t)lt;
+                out += 1ull + len_ext_bytes((uint32_t)lt) + lt + m.body_len;
+                carry = m.trail_ll;
+            } else {
+                carry += m.trail_ll;                      // no match: the whole segment is carried
+            }
+            a.place[base + s] = pl;
+        }
+        a.final_ll[f] = (uint32_t)carry;
+        a.final_off[f] = (uint32_t)(out > 0xFFFFFFFFull ? 0xFFFFFFFFull : out);
+        out += 1ull + len_ext_bytes((uint32_t)carry) + carry;
+        if (out >= n && !a.keep_raw) { c = n; flags |= 0x2u; }   // blosc.go:342-345: store uncompressed
+        else c = (uint32_t)out;
+        flen = 16 + c;
+    }
+    a.comp_len[f] = c; a.frame_len[f] = flen; a.flags[f] = flags; a.status[f] = st;
+}
+
+// ---- pack: one CTA per segment -------------------------------------------------------------
+struct PackArgs {
+    const uint8_t *in;          // what the LZ4 block was made from (shuffled bytes)
+    const uint8_t *raw;         // what a memcpy frame stores (shuffled bytes, or the caller's
+                                //   original bytes under B2B_OPT_REF_MEMCPY_QUIRK)
+    const uint64_t *src_off;
+    const uint32_t *src_len;
+    const uint8_t *comp;
+    const uint64_t *comp_off;
+    const uint64_t *seg_base;
+    const SegMeta *meta;
+    const SegPlace *place;
+    const uint32_t *comp_len, *flags, *final_ll, *final_off, *status;
+    const uint64_t *frame_off;  // packed offsets (16-byte aligned)
+    uint8_t *dst;
+    uint32_t nframes, segs_grid, codec, typesize_u8;
+    uint32_t header;            // 1: write the 16-byte frame header (0 for the raw-block API)
+};
+
+// token with literal length lt and match nibble, followed by the length extension; returns bytes
+__device__ __forceinline__ uint32_t cta_put_token(uint8_t *dst, uint32_t lt, uint32_t nib) {
+    if (threadIdx.x == 0) dst[0] = (uint8_t)(((lt < 15 ? lt : 15u) << 4) | nib);
+    if (lt < 15) return 1;
+    const uint32_t v = lt - 15, full = v / 255u;
+    for (uint32_t i = threadIdx.x; i < full; i += blockDim.x) dst[1 + i] = 255;
+    if (threadIdx.x == 0) dst[1 + full] = (uint8_t)(v - full * 255u);
+    return 2 + full;
+}
+
+__global__ void __launch_bounds__(kFilterThreads) pack_frames_kernel(PackArgs a) {
+    const uint64_t item = blockIdx.x;
+    const uint32_t f = (uint32_t)(item / a.segs_grid), s0 = (uint32_t)(item % a.segs_grid);
+    if (f >= a.nframes || a.status[f] != 0) return;
+    const uint32_t n = a.src_len[f], c = a.comp_len[f], flags = a.flags[f];
+    const uint32_t nseg = seg_count(n);
+    uint8_t *out = a.dst + a.frame_off[f];
+    if (a.header) {
+        if (s0 == 0 && threadIdx.x == 0) {
+            // blosc.go:358-366: [2, codec, flags, uint8(T), n, n, 16 + c]
+            uint4 h;
+            h.x = 2u | (a.codec << 8) | (flags << 16) | (a.typesize_u8 << 24);
+            h.y = n; h.z = n; h.w = 16u + c;
+            *reinterpret_cast<uint4 *>(out) = h;
+        }
+        out += 16;
+    }
+    const uint64_t base = a.seg_base[f];
+    for (uint32_t s = s0; s < nseg; s += a.segs_grid) {
+        const uint32_t B = s * kSegBytes;
+        const uint32_t L = n - B < kSegBytes ? n - B : kSegBytes;
+        if (flags & 0x2u) {                                   // memcpy frame
+            cta_copy(out + B, a.raw + a.src_off[f] + B, L);
+            continue;
+        }
+        const uint8_t *frame = a.in + a.src_off[f];
+        const SegMeta m = a.meta[base + s];
+        if (m.info & 0x100u) {
+            const SegPlace pl = a.place[base + s];
+            uint8_t *d = out + pl.out_off;
+            const uint32_t hdr = cta_put_token(d, pl.lit_total, m.info & 15u);
+            // carried + leading literals are one contiguous input range ending at the match start
+            cta_copy(d + hdr, frame + ((uint64_t)B + m.first_ll - pl.lit_total), pl.lit_total);
+            cta_copy(d + hdr + pl.lit_total, a.comp + a.comp_off[f] + (uint64_t)s * kSegSlot, m.body_len);
+        }
+        if (s == nseg - 1) {                                  // closing token: the last literals
+            const uint32_t lf = a.final_ll[f];
+            uint8_t *d = out + a.final_off[f];
+            const uint32_t hdr = cta_put_token(d, lf, 0);
+            cta_copy(d + hdr, frame + (n - lf), lf);
+        }
+    }
+}
+
+}  // namespace b2b

@@ -7,6 +7,7 @@
 // until it meets an inclusive prefix.  Descriptor = 2 flag bits | 62-bit value.
 #pragma once
 #include "common.cuh"
+#include "lz4_encode.cuh"
 
 namespace b2b {
 
@@ -19,12 +20,14 @@ constexpr uint64_t kScanValMask = (1ull << 62) - 1;
 enum ScanOp : int {
     kScanIdentity = 0,   // x
     kScanAlign16 = 1,    // (x + 15) & ~15     packed frames start on 16-byte boundaries
-    kScanLz4Slot = 2     // align16(x + x/255 + 16) scratch slot of one LZ4 block
+    kScanSegSlot = 2,    // scratch bytes of the frame's segment slots (lz4_encode.cuh)
+    kScanSegCount = 3    // number of 64 KiB segments of the frame
 };
 
 __device__ __forceinline__ uint64_t scan_apply(int op, uint32_t x) {
     if (op == kScanAlign16) return ((uint64_t)x + 15ull) & ~15ull;
-    if (op == kScanLz4Slot) return ((uint64_t)x + x / 255u + 16ull + 15ull) & ~15ull;
+    if (op == kScanSegSlot) return frame_slot_bytes(x);
+    if (op == kScanSegCount) return seg_count(x);
     return x;
 }
 

@@ -35,7 +35,7 @@ def gen_f32(n_elems, device="cuda"):
     return x.to(torch.float32).view(torch.uint8)
 
 
-size = int(os.environ.get("PROBE_BYTES", 1 << 30))
+size = int(os.environ.get("PROBE_BYTES", 4 << 30))
 src = gen_f32(size // 4)
 dst = torch.empty_like(src)
 print(f"device {torch.cuda.get_device_name(0)}, buffer {size >> 20} MiB")
@@ -68,7 +68,7 @@ d_olen = torch.empty(nf, dtype=torch.int32, device="cuda")
 from tools.perf_probe_lib import gen_f32 as gen2
 src64 = gen2(size // 4, f64=True)
 for label, data, sh, T in (("C3 f32 Shuffle T=4", src, 1, 4), ("C4 f64 BitShuffle T=8", src64, 2, 8)):
-    for hl in (11, 12):
+    for hl in (10, 11):
         ctx.set_option(pkg.OPT_HASH_LOG, hl)
         comp = lambda: ctx.compress_batch_dev(data, d_off, d_len, nf, size, fl, sh, T, d_c, cap, d_foff, d_flen, d_st, d_tot, s)
         best, med = timeit(comp, iters=3, warm=1)
