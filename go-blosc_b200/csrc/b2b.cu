@@ -39,8 +39,12 @@ struct b2b_ctx {
     cudaStream_t stream = nullptr;     // for the host-pointer entry points
     uint8_t *arena = nullptr;          // device scratch, grow-only
     size_t arena_cap = 0;
-    uint8_t *hbuf[3] = {nullptr, nullptr, nullptr};   // device staging of the host-pointer paths
-    size_t hcap[3] = {0, 0, 0};
+    // device staging of the host-pointer paths: {in, out, tables} x 2 pipeline slots
+    uint8_t *hbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t hcap[6] = {0, 0, 0, 0, 0, 0};
+    cudaStream_t s_in = nullptr, s_out = nullptr;     // H2D / D2H streams of the host batch pipeline
+    cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
     int opt_quirk = 0;
     int opt_filter_ctas_per_sm = 0;
     int opt_hash_log = 0;              // 0: default (kHashLogDefault)
@@ -119,7 +123,7 @@ int ensure_arena(b2b_ctx *ctx, uint64_t bytes) {
 int ensure_hbuf(b2b_ctx *ctx, int i, uint64_t bytes, uint8_t **out) {
     bytes = align_up(bytes + 256, 1 << 20);
     if (bytes > ctx->hcap[i]) {
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        CU(ctx, cudaDeviceSynchronize());
         if (ctx->hbuf[i]) CU(ctx, cudaFree(ctx->hbuf[i]));
         ctx->hbuf[i] = nullptr; ctx->hcap[i] = 0;
         CU(ctx, cudaMalloc(&ctx->hbuf[i], bytes));
@@ -422,9 +426,15 @@ int b2b_init(int device, b2b_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return B2B_ECUDA; }
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        delete ctx; return B2B_ECUDA;
-    }
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++)
+        ok = cudaEventCreateWithFlags(&ctx->ev_in_ready[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_in_free[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_out_free[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { b2b_destroy(ctx); return B2B_ECUDA; }
     *out = ctx;
     return B2B_OK;
 }
@@ -436,7 +446,15 @@ void b2b_destroy(b2b_ctx *ctx) {
     fold_timings(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->arena) cudaFree(ctx->arena);
-    for (int i = 0; i < 3; i++) if (ctx->hbuf[i]) cudaFree(ctx->hbuf[i]);
+    for (int i = 0; i < 6; i++) if (ctx->hbuf[i]) cudaFree(ctx->hbuf[i]);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_in_ready[i]) cudaEventDestroy(ctx->ev_in_ready[i]);
+        if (ctx->ev_in_free[i]) cudaEventDestroy(ctx->ev_in_free[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+        if (ctx->ev_out_free[i]) cudaEventDestroy(ctx->ev_out_free[i]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -598,6 +616,31 @@ int b2b_shuffle(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, const voi
     return rc;
 }
 
+// Host batches run as a 2-slot pipeline over chunks of frames: H2D of chunk k+1 (stream s_in)
+// overlaps the kernels of chunk k (ctx->stream) and the D2H of chunk k-1 (stream s_out).  The
+// kernels of successive chunks share the scratch arena, which is safe because they are
+// ordered on one stream.  Pinned caller buffers are DMA'd directly; pageable ones make the
+// copies synchronous (still correct).
+struct HostChunk { uint32_t f0, f1; uint64_t lo, hi; uint32_t max_len; };
+
+static std::vector<HostChunk> split_chunks(const uint64_t *off, const uint32_t *len, uint32_t nframes,
+                                           uint64_t stage_bytes) {
+    std::vector<HostChunk> out;
+    uint32_t f = 0;
+    while (f < nframes) {
+        HostChunk c{f, f, ~0ull, 0, 0};
+        uint64_t bytes = 0;
+        while (c.f1 < nframes && (c.f1 == c.f0 || bytes + len[c.f1] <= stage_bytes)) {
+            c.lo = std::min(c.lo, off[c.f1]); c.hi = std::max(c.hi, off[c.f1] + len[c.f1]);
+            c.max_len = std::max(c.max_len, len[c.f1]);
+            bytes += len[c.f1]; c.f1++;
+        }
+        out.push_back(c);
+        f = c.f1;
+    }
+    return out;
+}
+
 int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, const uint32_t *src_len,
                        uint32_t nframes, int shuffle, int64_t typesize, void *dst, uint64_t dst_cap,
                        uint64_t *frame_off, uint32_t *frame_len, uint32_t *status, uint64_t *total_out) {
@@ -606,63 +649,87 @@ int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, c
     if (!src || !src_off || !src_len || !dst || !frame_off || !frame_len || !status) return B2B_EINVAL;
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
-    // extent of the source region that the frames cover, and host-known bounds
-    uint64_t lo = ~0ull, hi = 0, total = 0; uint32_t max_len = 0;
-    for (uint32_t f = 0; f < nframes; f++) {
-        lo = std::min(lo, src_off[f]); hi = std::max(hi, src_off[f] + src_len[f]);
-        total += src_len[f]; max_len = std::max(max_len, src_len[f]);
-    }
-    const uint64_t span = hi - lo;
+    const uint8_t *hsrc = static_cast<const uint8_t *>(src);
+    uint8_t *hdst = static_cast<uint8_t *>(dst);
+    const std::vector<HostChunk> chunks = split_chunks(src_off, src_len, nframes, ctx->opt_stage_bytes);
     std::vector<uint64_t> rel(nframes);
-    for (uint32_t f = 0; f < nframes; f++) rel[f] = src_off[f] - lo;
-    // for the filter scratch the frames are addressed by rel offsets inside [0, span)
-    const uint64_t out_cap = span + 31ull * nframes + 64;
-    uint8_t *d_in = nullptr, *d_out = nullptr, *d_tab = nullptr;
-    const uint64_t tab_bytes = align_up(8ull * nframes, 256) * 2 + align_up(4ull * nframes, 256) * 3 + 256;
-    cudaStream_t s = ctx->stream;
-    int rc = ensure_hbuf(ctx, 0, span + 64, &d_in);
-    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 1, out_cap, &d_out);
-    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 2, tab_bytes, &d_tab);
-    if (rc) return rc;
+    struct Pending { bool live = false; uint32_t f0 = 0, n = 0; int slot = 0; uint64_t h_total = 0; };
+    Pending prev;
+    uint64_t running = 0;
+    int rc = B2B_OK;
     cudaError_t e = cudaSuccess;
-    uint64_t *d_src_off = nullptr, *d_frame_off = nullptr, *d_total = nullptr;
-    uint32_t *d_src_len = nullptr, *d_frame_len = nullptr, *d_status = nullptr;
-    uint64_t h_total = 0;
-    if (e == cudaSuccess) {
-        uint8_t *t = d_tab;
-        d_src_off = (uint64_t *)t; t += align_up(8ull * nframes, 256);
-        d_frame_off = (uint64_t *)t; t += align_up(8ull * nframes, 256);
-        d_src_len = (uint32_t *)t; t += align_up(4ull * nframes, 256);
-        d_frame_len = (uint32_t *)t; t += align_up(4ull * nframes, 256);
-        d_status = (uint32_t *)t; t += align_up(4ull * nframes, 256);
-        d_total = (uint64_t *)t;
-        e = cudaMemcpyAsync(d_in, static_cast<const uint8_t *>(src) + lo, span, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_src_off, rel.data(), 8ull * nframes, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_src_len, src_len, 4ull * nframes, cudaMemcpyHostToDevice, s);
+    uint8_t *d_in[2], *d_out[2], *d_tab[2];
+    uint64_t tab_sz[2] = {0, 0};
+
+    // drain: read back the tables of the previous chunk, then its packed bytes
+    auto drain = [&](Pending &p) -> int {
+        if (!p.live) return B2B_OK;
+        p.live = false;
+        const uint64_t a8 = align_up(8ull * p.n, 256), a4 = align_up(4ull * p.n, 256);
+        uint8_t *t = d_tab[p.slot];
+        const uint64_t *d_frame_off = (const uint64_t *)(t + a8);
+        const uint32_t *d_frame_len = (const uint32_t *)(t + 2 * a8 + a4);
+        const uint32_t *d_status = (const uint32_t *)(t + 2 * a8 + 2 * a4);
+        const uint64_t *d_total = (const uint64_t *)(t + 2 * a8 + 3 * a4);
+        cudaStream_t so = ctx->s_out;
+        CU(ctx, cudaStreamWaitEvent(so, ctx->ev_done[p.slot], 0));
+        CU(ctx, cudaMemcpyAsync(frame_off + p.f0, d_frame_off, 8ull * p.n, cudaMemcpyDeviceToHost, so));
+        CU(ctx, cudaMemcpyAsync(frame_len + p.f0, d_frame_len, 4ull * p.n, cudaMemcpyDeviceToHost, so));
+        CU(ctx, cudaMemcpyAsync(status + p.f0, d_status, 4ull * p.n, cudaMemcpyDeviceToHost, so));
+        CU(ctx, cudaMemcpyAsync(&p.h_total, d_total, 8, cudaMemcpyDeviceToHost, so));
+        CU(ctx, cudaStreamSynchronize(so));
+        if (running + p.h_total > dst_cap) return B2B_EDST_TOO_SMALL;
+        CU(ctx, cudaMemcpyAsync(hdst + running, d_out[p.slot], p.h_total, cudaMemcpyDeviceToHost, so));
+        CU(ctx, cudaEventRecord(ctx->ev_out_free[p.slot], so));
+        for (uint32_t i = 0; i < p.n; i++) frame_off[p.f0 + i] += running;
+        running += p.h_total;
+        return B2B_OK;
+    };
+
+    for (size_t k = 0; k < chunks.size() && rc == B2B_OK; k++) {
+        const HostChunk &c = chunks[k];
+        const int slot = (int)(k & 1);
+        const uint32_t n = c.f1 - c.f0;
+        const uint64_t span = c.hi - c.lo, out_cap = span + 31ull * n + 64;
+        const uint64_t a8 = align_up(8ull * n, 256), a4 = align_up(4ull * n, 256);
+        tab_sz[slot] = 2 * a8 + 3 * a4 + 256;
+        rc = ensure_hbuf(ctx, 3 * slot + 0, span + 64, &d_in[slot]);
+        if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 1, out_cap, &d_out[slot]);
+        if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 2, tab_sz[slot], &d_tab[slot]);
+        if (rc) break;
+        uint8_t *t = d_tab[slot];
+        uint64_t *d_src_off = (uint64_t *)t, *d_frame_off = (uint64_t *)(t + a8);
+        uint32_t *d_src_len = (uint32_t *)(t + 2 * a8), *d_frame_len = (uint32_t *)(t + 2 * a8 + a4);
+        uint32_t *d_status = (uint32_t *)(t + 2 * a8 + 2 * a4);
+        uint64_t *d_total = (uint64_t *)(t + 2 * a8 + 3 * a4);
+        for (uint32_t f = c.f0; f < c.f1; f++) rel[f] = src_off[f] - c.lo;
+        // H2D of this chunk (after the kernels that last read this slot's input are done)
+        if (k >= 2) e = cudaStreamWaitEvent(ctx->s_in, ctx->ev_in_free[slot], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in[slot], hsrc + c.lo, span, cudaMemcpyHostToDevice, ctx->s_in);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_src_off, rel.data() + c.f0, 8ull * n, cudaMemcpyHostToDevice, ctx->s_in);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_src_len, src_len + c.f0, 4ull * n, cudaMemcpyHostToDevice, ctx->s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_ready[slot], ctx->s_in);
+        // kernels
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_in_ready[slot], 0);
+        if (e == cudaSuccess && k >= 2) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_out_free[slot], 0);
+        if (e != cudaSuccess) break;
+        rc = compress_batch_dev_locked(ctx, d_in[slot], d_src_off, d_src_len, n, span, c.max_len, shuffle, typesize,
+                                       d_out[slot], out_cap, d_frame_off, d_frame_len, d_status, d_total, ctx->stream);
+        if (rc) break;
+        e = cudaEventRecord(ctx->ev_done[slot], ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_free[slot], ctx->stream);
+        if (e != cudaSuccess) break;
+        // while this chunk computes, ship the previous one
+        rc = drain(prev);
+        prev.live = true; prev.f0 = c.f0; prev.n = n; prev.slot = slot;
     }
-    if (e == cudaSuccess) {
-        // the shuffle scratch is addressed with the same offsets as the source: size it by span
-        rc = compress_batch_dev_locked(ctx, d_in, d_src_off, d_src_len, nframes, span, max_len, shuffle,
-                                       typesize, d_out, out_cap, d_frame_off, d_frame_len, d_status,
-                                       d_total, s);
-        (void)total;
-    }
-    if (e == cudaSuccess && rc == B2B_OK) {
-        e = cudaMemcpyAsync(frame_off, d_frame_off, 8ull * nframes, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(frame_len, d_frame_len, 4ull * nframes, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, 4ull * nframes, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_total, d_total, 8, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e == cudaSuccess) {
-            if (h_total > dst_cap) rc = B2B_EDST_TOO_SMALL;
-            else {
-                e = cudaMemcpyAsync(dst, d_out, h_total, cudaMemcpyDeviceToHost, s);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-                if (total_out) *total_out = h_total;
-            }
-        }
-    }
+    if (rc == B2B_OK && e == cudaSuccess) rc = drain(prev);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->s_out);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e4 = cudaStreamSynchronize(ctx->s_in);
+    if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : (e3 != cudaSuccess ? e3 : e4);
     if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return B2B_ECUDA; }
+    if (rc == B2B_OK && total_out) *total_out = running;
     return rc;
 }
 
@@ -677,59 +744,73 @@ int b2b_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
     const uint8_t *hf = static_cast<const uint8_t *>(frames);
-    uint64_t lo = ~0ull, hi = 0; uint32_t max_orig = 0;
-    std::vector<uint64_t> rel(nframes);
+    uint8_t *hdst = static_cast<uint8_t *>(dst);
+    // capacity of slot f: what the header announces, clipped to the caller's buffer and to what an
+    // LZ4 block of that size can possibly produce (never allocate more than 255x the input)
     std::vector<uint32_t> cap(nframes);
-    for (uint32_t f = 0; f < nframes; f++) { lo = std::min(lo, frame_off[f]); hi = std::max(hi, frame_off[f] + frame_len[f]); }
-    const uint64_t span = hi - lo;
     for (uint32_t f = 0; f < nframes; f++) {
-        rel[f] = frame_off[f] - lo;
-        // capacity of slot f: what the header announces, clipped to the caller's buffer
         uint32_t norig = 0;
         if (frame_len[f] >= 16) {
             const uint8_t *p = hf + frame_off[f];
             norig = (uint32_t)p[4] | ((uint32_t)p[5] << 8) | ((uint32_t)p[6] << 16) | ((uint32_t)p[7] << 24);
         }
-        uint64_t room = dst_off[f] <= dst_cap ? dst_cap - dst_off[f] : 0;
-        // an LZ4 block cannot expand by more than 255x: never allocate beyond that
+        const uint64_t room = dst_off[f] <= dst_cap ? dst_cap - dst_off[f] : 0;
         const uint64_t reach = 255ull * frame_len[f] + 64;
         cap[f] = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(norig, room), reach);
-        max_orig = std::max(max_orig, cap[f]);
     }
-    uint64_t dst_span = 0;
-    for (uint32_t f = 0; f < nframes; f++) dst_span = std::max(dst_span, dst_off[f] + cap[f]);
-    uint8_t *d_in = nullptr, *d_out = nullptr, *d_tab = nullptr;
-    const uint64_t tab_bytes = align_up(8ull * nframes, 256) * 2 + align_up(4ull * nframes, 256) * 4;
-    cudaStream_t s = ctx->stream;
-    int rc = ensure_hbuf(ctx, 0, span + 64, &d_in);
-    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 1, dst_span + 64, &d_out);
-    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 2, tab_bytes, &d_tab);
-    if (rc) return rc;
+    // chunks by OUTPUT bytes (the larger side)
+    const std::vector<HostChunk> chunks = split_chunks(dst_off, cap.data(), nframes, ctx->opt_stage_bytes);
+    std::vector<uint64_t> rel_in(nframes), rel_out(nframes);
+    int rc = B2B_OK;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) {
-        uint8_t *t = d_tab;
-        uint64_t *d_frame_off = (uint64_t *)t; t += align_up(8ull * nframes, 256);
-        uint64_t *d_dst_off = (uint64_t *)t; t += align_up(8ull * nframes, 256);
-        uint32_t *d_frame_len = (uint32_t *)t; t += align_up(4ull * nframes, 256);
-        uint32_t *d_cap = (uint32_t *)t; t += align_up(4ull * nframes, 256);
-        uint32_t *d_out_len = (uint32_t *)t; t += align_up(4ull * nframes, 256);
-        uint32_t *d_status = (uint32_t *)t;
-        e = cudaMemcpyAsync(d_in, hf + lo, span, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_frame_off, rel.data(), 8ull * nframes, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dst_off, dst_off, 8ull * nframes, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_frame_len, frame_len, 4ull * nframes, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_cap, cap.data(), 4ull * nframes, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess)
-            rc = decompress_batch_dev_locked(ctx, d_in, d_frame_off, d_frame_len, nframes, typesize_override,
-                                             d_out, d_dst_off, d_cap, dst_span, max_orig, d_out_len,
-                                             d_status, s);
-        if (e == cudaSuccess && rc == B2B_OK) {
-            e = cudaMemcpyAsync(out_len, d_out_len, 4ull * nframes, cudaMemcpyDeviceToHost, s);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, 4ull * nframes, cudaMemcpyDeviceToHost, s);
-            if (e == cudaSuccess && dst_span) e = cudaMemcpyAsync(dst, d_out, dst_span, cudaMemcpyDeviceToHost, s);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    uint8_t *d_in[2], *d_out[2], *d_tab[2];
+    for (size_t k = 0; k < chunks.size() && rc == B2B_OK; k++) {
+        const HostChunk &c = chunks[k];
+        const int slot = (int)(k & 1);
+        const uint32_t n = c.f1 - c.f0;
+        uint64_t in_lo = ~0ull, in_hi = 0; uint32_t max_cap = 0;
+        for (uint32_t f = c.f0; f < c.f1; f++) {
+            in_lo = std::min(in_lo, frame_off[f]); in_hi = std::max(in_hi, frame_off[f] + frame_len[f]);
+            max_cap = std::max(max_cap, cap[f]);
         }
+        const uint64_t in_span = in_hi - in_lo, out_span = c.hi - c.lo;
+        for (uint32_t f = c.f0; f < c.f1; f++) { rel_in[f] = frame_off[f] - in_lo; rel_out[f] = dst_off[f] - c.lo; }
+        const uint64_t a8 = align_up(8ull * n, 256), a4 = align_up(4ull * n, 256);
+        rc = ensure_hbuf(ctx, 3 * slot + 0, in_span + 64, &d_in[slot]);
+        if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 1, out_span + 64, &d_out[slot]);
+        if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 2, 2 * a8 + 4 * a4 + 256, &d_tab[slot]);
+        if (rc) break;
+        uint8_t *t = d_tab[slot];
+        uint64_t *d_frame_off = (uint64_t *)t, *d_dst_off = (uint64_t *)(t + a8);
+        uint32_t *d_frame_len = (uint32_t *)(t + 2 * a8), *d_cap = (uint32_t *)(t + 2 * a8 + a4);
+        uint32_t *d_out_len = (uint32_t *)(t + 2 * a8 + 2 * a4), *d_status = (uint32_t *)(t + 2 * a8 + 3 * a4);
+        if (k >= 2) e = cudaStreamWaitEvent(ctx->s_in, ctx->ev_in_free[slot], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in[slot], hf + in_lo, in_span, cudaMemcpyHostToDevice, ctx->s_in);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_frame_off, rel_in.data() + c.f0, 8ull * n, cudaMemcpyHostToDevice, ctx->s_in);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dst_off, rel_out.data() + c.f0, 8ull * n, cudaMemcpyHostToDevice, ctx->s_in);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_frame_len, frame_len + c.f0, 4ull * n, cudaMemcpyHostToDevice, ctx->s_in);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_cap, cap.data() + c.f0, 4ull * n, cudaMemcpyHostToDevice, ctx->s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_ready[slot], ctx->s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_in_ready[slot], 0);
+        if (e == cudaSuccess && k >= 2) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_out_free[slot], 0);
+        if (e != cudaSuccess) break;
+        rc = decompress_batch_dev_locked(ctx, d_in[slot], d_frame_off, d_frame_len, n, typesize_override, d_out[slot],
+                                         d_dst_off, d_cap, out_span, max_cap, d_out_len, d_status, ctx->stream);
+        if (rc) break;
+        e = cudaEventRecord(ctx->ev_done[slot], ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_free[slot], ctx->stream);
+        // D2H of this chunk on the output stream (overlaps the next chunk's H2D and kernels)
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[slot], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_len + c.f0, d_out_len, 4ull * n, cudaMemcpyDeviceToHost, ctx->s_out);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(status + c.f0, d_status, 4ull * n, cudaMemcpyDeviceToHost, ctx->s_out);
+        if (e == cudaSuccess && out_span) e = cudaMemcpyAsync(hdst + c.lo, d_out[slot], out_span, cudaMemcpyDeviceToHost, ctx->s_out);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_out_free[slot], ctx->s_out);
+        if (e != cudaSuccess) break;
     }
+    cudaError_t e2 = cudaStreamSynchronize(ctx->s_out);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e4 = cudaStreamSynchronize(ctx->s_in);
+    if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : (e3 != cudaSuccess ? e3 : e4);
     if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return B2B_ECUDA; }
     return rc;
 }

@@ -40,7 +40,7 @@ constexpr int kEncWarps = 4;           // segments (warps) per CTA
 constexpr int kEncThreads = kEncWarps * 32;
 constexpr int kHashLogDefault = 10;    // 2^10 x u32 = 4 KiB per warp: 48 resident warps per SM
 constexpr uint32_t kWarmBytes = 512;   // tail of the previous segment pre-loaded into the hash table
-constexpr uint32_t kLazyWindow = 2;    // later starts considered after the first hit
+constexpr uint32_t kLazyWindow = 0;    // later starts considered after the first hit (0: plain greedy)
 constexpr uint32_t kLazyWords = 4;     // bounded look-ahead: 4 + 4 * 4 = 20 bytes
 
 struct SegMeta {
@@ -63,12 +63,13 @@ __host__ __device__ __forceinline__ uint64_t frame_slot_bytes(uint32_t n) {
 }
 __host__ __device__ __forceinline__ uint32_t len_ext_bytes(uint32_t v) { return v >= 15 ? (v - 15) / 255u + 1u : 0u; }
 
+// Unaligned 32-bit load as two aligned words and a funnel shift (no branch).  Callers only use
+// it at least 8 bytes before the end of the frame (all match limits are >= 14 bytes short of
+// it), so the second word is always inside the buffer.
 __device__ __forceinline__ uint32_t enc_load32u(const uint8_t *p) {
     const uint32_t r = (uint32_t)((uintptr_t)p & 3u);
     const uint32_t *q = reinterpret_cast<const uint32_t *>((uintptr_t)p - r);
-    const uint32_t lo = q[0];
-    if (r == 0) return lo;
-    return __funnelshift_r(lo, q[1], 8u * r);
+    return __funnelshift_r(q[0], q[1], 8u * r);
 }
 
 // writes a length extension (value already reduced by 15) at out, returns bytes written
@@ -139,7 +140,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
         }
         const uint32_t hit = __ballot_sync(0xffffffffu, ok);
         int pick = hit ? __ffs(hit) - 1 : 31;
-        if (hit && stride == 1) {
+        if (kLazyWindow > 0 && hit && stride == 1) {
             // bounded comparison of the first hit with the hits at the next kLazyWindow starts
             const uint32_t window = hit & (((2u << kLazyWindow) - 1u) << pick);
             uint32_t score = 0;

@@ -13,7 +13,7 @@
 
 #include "../oracle/blosc_oracle.h"
 
-static int INSERT_AFTER = 0, LAZY = 0, WAYS = 1, LAZYCAP = 1 << 30, SEG = 0; static int HASHLOG = 12, HASHBYTES = 4, SKIPLOG = 7, SKIPDIV = 3, INSERT_END = 0, PREFER_TABLE = 0;
+static int INSERT_AFTER = 0, LAZY = 0, WAYS = 1, LAZYCAP = 1 << 30, SEG = 0, FIXD = 0; static int HASHLOG = 12, HASHBYTES = 4, SKIPLOG = 7, SKIPDIV = 3, INSERT_END = 0, PREFER_TABLE = 0;
 
 static inline uint32_t ld32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline uint64_t ld64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
@@ -53,6 +53,7 @@ size_t model_encode(const uint8_t *src, uint32_t n, uint8_t *out, long *nseq) {
                 if (srcl >= 0) { uint64_t dist = (uint64_t)(l - srcl) * stride; cand = (int64_t)p[l] - (int64_t)dist; ok = dist < 65536; }
                 if (PREFER_TABLE && tab_ok) { cand = ctab; ok = 1; }
                 if (!ok && tab_ok) { cand = ctab; ok = 1; }
+                if (!ok && FIXD > 0 && p[l] >= (uint32_t)FIXD && ld32(src + p[l] - FIXD) == seq[l]) { cand = (int64_t)p[l] - FIXD; ok = 1; }
                 if (ok) {
                     if (first < 0) first_hit = l;
                     uint32_t e = p[l] + 4, cc = (uint32_t)cand + 4;
@@ -151,6 +152,7 @@ int main(int argc, char **argv) {
         if (!strcmp(argv[i], "ways")) WAYS = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "lazycap")) LAZYCAP = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "seg")) SEG = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "fixd")) FIXD = atoi(argv[i + 1]);
     }
     const uint32_t n = 262144;
     uint8_t *raw = malloc(n), *sh = malloc(n), *o1 = malloc(n * 2), *o2 = malloc(n * 2), *back = malloc(n);
