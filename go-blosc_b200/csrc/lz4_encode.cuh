@@ -213,15 +213,27 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             have_first = true;
             m.first_ll = ll;
             m.info = 0x100u | (ml < 15 ? ml : 15u);
+            if (lane < 2) body[op + lane] = (uint8_t)(offset >> (8 * lane));
+            op += 2;
+        } else if (ll <= 28) {
+            // short literal run: token, literals and offset leave in ONE predicated byte store
+            uint32_t v = ((ll < 15 ? ll : 15u) << 4) | (ml < 15 ? ml : 15u);
+            const uint32_t ext = ll >= 15 ? 1u : 0u;                 // 15..28 literals: one extension byte
+            if ((uint32_t)lane == 1 && ext) v = ll - 15;
+            if ((uint32_t)lane > ext && (uint32_t)lane <= ext + ll) v = org[anchor + lane - 1 - ext];
+            if ((uint32_t)lane == ext + ll + 1) v = offset;
+            if ((uint32_t)lane == ext + ll + 2) v = offset >> 8;
+            if ((uint32_t)lane < ext + ll + 3) body[op + lane] = (uint8_t)v;
+            op += ext + ll + 3;
         } else {
             const uint32_t tok_pos = op++;
-            if (ll >= 15) op += warp_put_len_ext(body + op, ll - 15, lane);
+            op += warp_put_len_ext(body + op, ll - 15, lane);
             warp_copy(body + op, org + anchor, ll, lane);
             op += ll;
-            if (lane == 0) body[tok_pos] = (uint8_t)(((ll < 15 ? ll : 15u) << 4) | (ml < 15 ? ml : 15u));
+            if (lane == 0) body[tok_pos] = (uint8_t)(0xF0u | (ml < 15 ? ml : 15u));
+            if (lane < 2) body[op + lane] = (uint8_t)(offset >> (8 * lane));
+            op += 2;
         }
-        if (lane == 0) { body[op] = (uint8_t)offset; body[op + 1] = (uint8_t)(offset >> 8); }
-        op += 2;
         if (ml >= 15) op += warp_put_len_ext(body + op, ml - 15, lane);
         si = mend; anchor = mend;
     }

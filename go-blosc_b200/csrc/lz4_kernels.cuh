@@ -95,13 +95,43 @@ __device__ __forceinline__ int64_t warp_lz4_decode(const uint8_t *__restrict__ s
     for (;;) {
         if (ip >= clen) return -1;
         const uint32_t tok = src[ip++];
-        uint64_t ll = tok >> 4;
+        const uint32_t lln = tok >> 4, mln = tok & 15u;
+        // ---- fast path: a short sequence (no length extensions), one predicated byte per lane.
+        // The literal load and the match load are issued together when the match source lies
+        // entirely before this sequence's output (offset >= literals + match length).
+        if (lln < 15 && mln < 15 && ip + lln + 2 <= clen) {
+            const uint32_t ll = lln, ml = mln + 4;
+            const uint32_t off = (uint32_t)src[ip + ll] | ((uint32_t)src[ip + ll + 1] << 8);
+            if (ll + ml > cap - op) return -2;
+            if (off == 0 || off > op + ll) return -1;
+            uint8_t *d = dst + op;
+            __syncwarp();   // every earlier store of this warp is ordered before the loads below
+            if (off >= ll + ml) {
+                uint32_t lit = 0, mv = 0;
+                if ((uint32_t)lane < ll) lit = src[ip + lane];
+                if ((uint32_t)lane < ml) mv = d[(int)(ll + lane) - (int)off];
+                if ((uint32_t)lane < ll) d[lane] = (uint8_t)lit;
+                if ((uint32_t)lane < ml) d[ll + lane] = (uint8_t)mv;
+            } else {
+                if ((uint32_t)lane < ll) d[lane] = src[ip + lane];
+                __syncwarp();
+                if ((uint32_t)lane < ml) {
+                    uint32_t k = lane;
+                    if (off < ml) k = lane - off * (uint32_t)__float2int_rz(__int2float_rn(lane) / __int2float_rn((int)off));
+                    d[ll + lane] = d[(int)(ll + k) - (int)off];
+                }
+            }
+            ip += ll + 2; op += ll + ml;
+            continue;
+        }
+        // ---- general path
+        uint64_t ll = lln;
         if (ll == 15 && !warp_read_len_ext(src, clen, ip, ll, lane)) return -1;
         if (ll > (uint64_t)(clen - ip)) return -1;
         if (ll > (uint64_t)(cap - op)) return -2;
         if (ll) warp_copy(dst + op, src + ip, (uint32_t)ll, lane);
         ip += (uint32_t)ll; op += (uint32_t)ll;
-        uint64_t ml = tok & 15u;
+        uint64_t ml = mln;
         if (ip == clen) { if (ml != 0) return -1; break; }
         if (clen - ip < 2) return -1;
         const uint32_t off = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8);
