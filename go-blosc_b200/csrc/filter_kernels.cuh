@@ -334,7 +334,7 @@ __device__ __forceinline__ void run_bitshuffle_fast(const uint8_t *s, uint8_t *d
     }
 }
 
-__global__ void __launch_bounds__(kFilterThreads) filter_batch_kernel(FilterArgs a) {
+__global__ void __launch_bounds__(kFilterThreads, 6) filter_batch_kernel(FilterArgs a) {
     __shared__ __align__(16) uint8_t smem[kTileBytes];
     const uint32_t tpf = a.ft.tiles_per_frame;
     const uint32_t f = blockIdx.x / tpf, tile0 = blockIdx.x % tpf;
