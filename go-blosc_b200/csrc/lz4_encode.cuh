@@ -80,24 +80,97 @@ __device__ __forceinline__ uint32_t warp_put_len_ext(uint8_t *out, uint32_t v, i
     return full + 1;
 }
 
+// ---- emission helpers ----------------------------------------------------------------------
+struct EncState {
+    uint8_t *body;
+    uint32_t op;
+    bool have_first;
+    SegMeta m;
+};
+
+// One sequence written by the whole warp: ll literals starting at lit, then the match (offset,
+// mlc = match length - 4).  The first sequence of a segment only leaves its offset / match
+// extension in the body: its token and literals are written by the pack pass.
+__device__ __forceinline__ void emit_coop(EncState &st, const uint8_t *lit, uint32_t ll, uint32_t offset,
+                                          uint32_t mlc, int lane) {
+    uint8_t *body = st.body;
+    uint32_t op = st.op;
+    if (!st.have_first) {
+        st.have_first = true;
+        st.m.first_ll = ll;
+        st.m.info = 0x100u | (mlc < 15 ? mlc : 15u);
+        if (lane < 2) body[op + lane] = (uint8_t)(offset >> (8 * lane));
+        op += 2;
+    } else if (ll <= 28) {
+        // short literal run: token, literals and offset leave in ONE predicated byte store
+        uint32_t v = ((ll < 15 ? ll : 15u) << 4) | (mlc < 15 ? mlc : 15u);
+        const uint32_t ext = ll >= 15 ? 1u : 0u;                 // 15..28 literals: one extension byte
+        if ((uint32_t)lane == 1 && ext) v = ll - 15;
+        if ((uint32_t)lane > ext && (uint32_t)lane <= ext + ll) v = lit[lane - 1 - ext];
+        if ((uint32_t)lane == ext + ll + 1) v = offset;
+        if ((uint32_t)lane == ext + ll + 2) v = offset >> 8;
+        if ((uint32_t)lane < ext + ll + 3) body[op + lane] = (uint8_t)v;
+        op += ext + ll + 3;
+    } else {
+        const uint32_t tok_pos = op++;
+        op += warp_put_len_ext(body + op, ll - 15, lane);
+        warp_copy(body + op, lit, ll, lane);
+        op += ll;
+        if (lane == 0) body[tok_pos] = (uint8_t)(0xF0u | (mlc < 15 ? mlc : 15u));
+        if (lane < 2) body[op + lane] = (uint8_t)(offset >> (8 * lane));
+        op += 2;
+    }
+    if (mlc >= 15) op += warp_put_len_ext(body + op, mlc - 15, lane);
+    st.op = op;
+}
+
+// 32-lane forward extension: first position >= from where org[pos] != org[pos - offset], capped at mlimit
+__device__ __forceinline__ uint32_t extend_coop(const uint8_t *org, uint32_t from, uint32_t offset,
+                                                uint32_t mlimit, int lane) {
+    uint32_t mend = from;
+    for (;;) {
+        const uint32_t a = mend + 4u * lane;
+        uint32_t x = 0xFFFFFFFFu;
+        if (a < mlimit) {
+            x = enc_load32u(org + a) ^ enc_load32u(org + a - offset);
+            const uint32_t avail = mlimit - a;
+            if (avail < 4) x |= 0xFFFFFFFFu << (8u * avail);
+        }
+        const uint32_t diff = __ballot_sync(0xffffffffu, x != 0);
+        if (diff == 0) { mend += 128; continue; }
+        const int fl = __ffs(diff) - 1;
+        const uint32_t xf = __shfl_sync(0xffffffffu, x, fl);
+        return mend + 4u * fl + ((uint32_t)(__ffs((int)xf) - 1) >> 3);
+    }
+}
+
+constexpr uint32_t kLaneMatchMax = 36;   // per-lane match length is followed up to here (4 + 8 words)
+
 // One segment.  org: first byte of the warm-up window (W bytes before the segment, 0 for the
 // first one), L the segment length, tail: bytes of the frame after it.  Positions below are
 // relative to org.  Limits follow the reference compressor relative to the END OF THE FRAME:
 // no match starts or is extended inside the frame's last 14 bytes (pierrec mfLimit), which
 // also keeps the reference's memcpy decision for short frames.
+//
+// Dense steps (stride 1) parse the WHOLE 32-position window at once: every hit lane follows its
+// own match (bounded), the greedy chain "first hit at or after the end of the previous match"
+// is resolved with shuffles, and the selected sequences are written by their own lanes at
+// offsets from a warp prefix sum.  Only the first sequence of a step (its literals may reach
+// far back) and a match longer than the per-lane bound go through the 32-lane-wide path.
 template <int HL>
 __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict__ org, uint32_t W,
                                                        uint32_t L, uint64_t tail,
                                                        uint8_t *__restrict__ body, uint32_t *table,
                                                        int lane) {
-    SegMeta m;
-    m.first_ll = L; m.body_len = 0; m.trail_ll = L; m.info = 0;
+    EncState st;
+    st.body = body; st.op = 0; st.have_first = false;
+    st.m.first_ll = L; st.m.body_len = 0; st.m.trail_ll = L; st.m.info = 0;
     const int64_t fl = (int64_t)L + (int64_t)tail - 14;          // frame limit in segment coordinates
     uint32_t mfl = L >= 4 ? L - 3 : 0;                           // a match of 4 bytes must fit the segment
     if (fl < (int64_t)mfl) mfl = fl > 0 ? (uint32_t)fl : 0u;
     uint32_t mlimit = L;
     if (fl < (int64_t)L) mlimit = fl > 0 ? (uint32_t)fl : 0u;
-    if (mfl == 0) return m;
+    if (mfl == 0) return st.m;
     mfl += W; mlimit += W;
 
     for (uint32_t i = lane; i < (1u << HL); i += kWarp) table[i] = 0;
@@ -111,8 +184,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
         }
         __syncwarp();
     }
-    uint32_t op = 0, anchor = W, si = W;
-    bool have_first = false;
+    uint32_t anchor = W, si = W;
     while (si < mfl) {
         // adaptive skip of the reference compressor: about 3 probes per 4 + lits/128 bytes
         const uint32_t lits = si - anchor;
@@ -139,35 +211,117 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             ok = cand < p && p - cand < 65536u && enc_load32u(org + cand) == seq;
         }
         const uint32_t hit = __ballot_sync(0xffffffffu, ok);
-        int pick = hit ? __ffs(hit) - 1 : 31;
-        if (kLazyWindow > 0 && hit && stride == 1) {
-            // bounded comparison of the first hit with the hits at the next kLazyWindow starts
-            const uint32_t window = hit & (((2u << kLazyWindow) - 1u) << pick);
-            uint32_t score = 0;
-            if ((window >> lane) & 1u) {
-                uint32_t len = 4;
-                if (p + 4 + 4 * kLazyWords <= mlimit) {
-                    uint32_t x[kLazyWords];
+
+        if (stride == 1) {
+            // ------------------------------------------------------------ dense window
+            __syncwarp();
+            // every probed position is recorded (of lanes with the same 4 bytes the last one wins)
+            if (valid && (same >> lane) == 1u) table[h] = (chk << 17) | p;
+            __syncwarp();
+            if (hit == 0) { si += 32; continue; }
+            // per-lane match length, bounded
+            uint32_t len = 0;
+            if (ok) {
+                len = 4;
+                const uint32_t offset = p - cand;
+                while (len < kLaneMatchMax && p + len + 4 <= mlimit) {
+                    const uint32_t x = enc_load32u(org + p + len) ^ enc_load32u(org + p + len - offset);
+                    if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                    len += 4;
+                }
+            }
+            // greedy chain over the window: next sequence = first hit at or after the previous end,
+            // unless a hit one or two positions later is longer by more than its delay (the
+            // per-lane lengths are already there, so this look-ahead is almost free)
+            int prev_end = (int)anchor - (int)si;    // relative to the window start
+            uint32_t sel = 0, my_ll = 0;
+            int cur = 0, first_l = -1, last_l = -1;
+            bool is_long = false;
+            while (cur < 32) {
+                const uint32_t mm = hit & (0xFFFFFFFFu << cur);
+                if (!mm) break;
+                int l = __ffs(mm) - 1;
+                uint32_t len_l = __shfl_sync(0xffffffffu, len, l);
+                const uint32_t len_1 = __shfl_sync(0xffffffffu, len, (l + 1) & 31);
+                const uint32_t len_2 = __shfl_sync(0xffffffffu, len, (l + 2) & 31);
+                int best = l; uint32_t best_len = len_l;
+                if (l + 1 < 32 && len_1 > best_len + 1) { best = l + 1; best_len = len_1; }
+                if (l + 2 < 32 && len_2 > len_l + 2 && len_2 > best_len + (uint32_t)(l + 2 - best)) { best = l + 2; best_len = len_2; }
+                l = best; len_l = best_len;
+                if (lane == l) my_ll = (uint32_t)(l - prev_end);
+                sel |= 1u << l;
+                if (first_l < 0) first_l = l;
+                last_l = l;
+                prev_end = l + (int)len_l;
+                cur = prev_end;
+                if (len_l >= kLaneMatchMax) { is_long = true; break; }
+            }
+            // backward extension of every selected match over its own pending literals
+            uint32_t mp = p, mlen = len;
+            if ((sel >> lane) & 1u) {
+                uint32_t mc = cand;
+                while (my_ll > 0 && mc > 0 && org[mp - 1] == org[mc - 1]) { mp--; mc--; my_ll--; mlen++; }
+            }
+            // a match that reached the per-lane bound continues 32 lanes wide
+            const uint32_t p_last = __shfl_sync(0xffffffffu, mp, last_l);
+            const uint32_t off_last = __shfl_sync(0xffffffffu, p - cand, last_l);
+            uint32_t end_last = si + (uint32_t)prev_end;
+            if (is_long) end_last = extend_coop(org, end_last, off_last, mlimit, lane);
+            // the first sequence of the step: its literals start at the anchor (possibly far back)
+            const uint32_t ll_first = __shfl_sync(0xffffffffu, my_ll, first_l);
+            const bool first_coop = !st.have_first || ll_first > 28 || (is_long && first_l == last_l);
+            if (first_coop) {
+                const uint32_t off_f = __shfl_sync(0xffffffffu, p - cand, first_l);
+                const uint32_t len_f = (first_l == last_l) ? end_last - p_last : __shfl_sync(0xffffffffu, mlen, first_l);
+                emit_coop(st, org + anchor, ll_first, off_f, len_f - 4, lane);
+            }
+            // regular sequences: each selected lane writes its own bytes
+            uint32_t reg = sel;
+            if (first_coop) reg &= ~(1u << first_l);
+            if (is_long) reg &= ~(1u << last_l);
+            if (reg) {
+                const bool mine = (reg >> lane) & 1u;
+                const uint32_t ll = my_ll, mlc = mlen - 4, offset = p - cand;
+                const uint32_t size = mine ? 1u + (ll >= 15 ? 1u : 0u) + ll + 2u + (mlc >= 15 ? 1u + (mlc - 15) / 255u : 0u) : 0u;
+                uint32_t incl = size;
 #pragma unroll
-                    for (uint32_t k = 0; k < kLazyWords; k++)
-                        x[k] = enc_load32u(org + p + 4 + 4 * k) ^ enc_load32u(org + cand + 4 + 4 * k);
-                    bool open = true;
-#pragma unroll
-                    for (uint32_t k = 0; k < kLazyWords; k++) {
-                        if (open) {
-                            if (x[k]) { len += (uint32_t)(__ffs((int)x[k]) - 1) >> 3; open = false; }
-                            else len += 4;
-                        }
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                if (mine) {
+                    uint8_t *b = body + st.op + (incl - size);
+                    const uint8_t *lit = org + mp - ll;
+                    b[0] = (uint8_t)(((ll < 15 ? ll : 15u) << 4) | (mlc < 15 ? mlc : 15u));
+                    uint32_t i = 1;
+                    if (ll >= 15) b[i++] = (uint8_t)(ll - 15);
+                    for (uint32_t k = 0; k < ll; k++) b[i + k] = lit[k];
+                    i += ll;
+                    b[i] = (uint8_t)offset; b[i + 1] = (uint8_t)(offset >> 8);
+                    i += 2;
+                    if (mlc >= 15) {
+                        uint32_t v = mlc - 15;
+                        while (v >= 255) { b[i++] = 255; v -= 255; }
+                        b[i] = (uint8_t)v;
                     }
                 }
-                // longer wins; a later start pays one byte per position; ties go to the earlier lane
-                score = ((64u + len - (uint32_t)(lane - pick)) << 5) | (31u - (uint32_t)lane);
+                st.op += total;
+                __syncwarp();
             }
-            pick = 31 - (int)(__reduce_max_sync(0xffffffffu, score) & 31u);
+            if (is_long && first_l != last_l) {
+                const uint32_t ll_last = __shfl_sync(0xffffffffu, my_ll, last_l);
+                emit_coop(st, org + p_last - ll_last, ll_last, off_last, end_last - p_last - 4, lane);
+            }
+            anchor = end_last;
+            si = end_last > si + 32 ? end_last : si + 32;
+            continue;
         }
+
+        // ---------------------------------------------------------------- strided probing
+        const int pick = hit ? __ffs(hit) - 1 : 31;
         __syncwarp();
-        // every probed position up to the chosen start is recorded (of lanes holding the same 4
-        // bytes the last one wins, so the table keeps the nearest occurrence)
+        // every probed position up to the chosen start is recorded
         const uint32_t upto = same & ((2u << pick) - 1u);
         if (valid && lane <= pick && (upto >> lane) == 1u) table[h] = (chk << 17) | p;
         __syncwarp();
@@ -178,26 +332,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
         uint32_t mp = __shfl_sync(0xffffffffu, p, pick);      // match start
         uint32_t mc = __shfl_sync(0xffffffffu, cand, pick);   // its source
         const uint32_t offset = mp - mc;
-        // forward extension from mp + 4, 128 bytes per step
-        uint32_t mend = mp + 4;
-        {
-            uint32_t cpos = mc + 4;
-            for (;;) {
-                const uint32_t a = mend + 4u * lane;
-                uint32_t x = 0xFFFFFFFFu;
-                if (a < mlimit) {
-                    x = enc_load32u(org + a) ^ enc_load32u(org + cpos + 4u * lane);
-                    const uint32_t avail = mlimit - a;
-                    if (avail < 4) x |= 0xFFFFFFFFu << (8u * avail);
-                }
-                const uint32_t diff = __ballot_sync(0xffffffffu, x != 0);
-                if (diff == 0) { mend += 128; cpos += 128; continue; }
-                const int fl2 = __ffs(diff) - 1;
-                const uint32_t xf = __shfl_sync(0xffffffffu, x, fl2);
-                mend += 4u * fl2 + ((uint32_t)(__ffs((int)xf) - 1) >> 3);
-                break;
-            }
-        }
+        const uint32_t mend = extend_coop(org, mp + 4, offset, mlimit, lane);
         // backward extension over the pending literals (never into the previous segment)
         while (mp > anchor) {
             const uint32_t k = lane + 1;
@@ -207,39 +342,12 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             mp -= back; mc -= back;
             if (back < 32) break;
         }
-        const uint32_t ll = mp - anchor, ml = mend - mp - 4;
-        if (!have_first) {
-            // token and literals of the first sequence are written by the pack pass
-            have_first = true;
-            m.first_ll = ll;
-            m.info = 0x100u | (ml < 15 ? ml : 15u);
-            if (lane < 2) body[op + lane] = (uint8_t)(offset >> (8 * lane));
-            op += 2;
-        } else if (ll <= 28) {
-            // short literal run: token, literals and offset leave in ONE predicated byte store
-            uint32_t v = ((ll < 15 ? ll : 15u) << 4) | (ml < 15 ? ml : 15u);
-            const uint32_t ext = ll >= 15 ? 1u : 0u;                 // 15..28 literals: one extension byte
-            if ((uint32_t)lane == 1 && ext) v = ll - 15;
-            if ((uint32_t)lane > ext && (uint32_t)lane <= ext + ll) v = org[anchor + lane - 1 - ext];
-            if ((uint32_t)lane == ext + ll + 1) v = offset;
-            if ((uint32_t)lane == ext + ll + 2) v = offset >> 8;
-            if ((uint32_t)lane < ext + ll + 3) body[op + lane] = (uint8_t)v;
-            op += ext + ll + 3;
-        } else {
-            const uint32_t tok_pos = op++;
-            op += warp_put_len_ext(body + op, ll - 15, lane);
-            warp_copy(body + op, org + anchor, ll, lane);
-            op += ll;
-            if (lane == 0) body[tok_pos] = (uint8_t)(0xF0u | (ml < 15 ? ml : 15u));
-            if (lane < 2) body[op + lane] = (uint8_t)(offset >> (8 * lane));
-            op += 2;
-        }
-        if (ml >= 15) op += warp_put_len_ext(body + op, ml - 15, lane);
+        emit_coop(st, org + anchor, mp - anchor, offset, mend - mp - 4, lane);
         si = mend; anchor = mend;
     }
-    m.body_len = op;
-    m.trail_ll = W + L - anchor;
-    return m;
+    st.m.body_len = st.op;
+    st.m.trail_ll = W + L - anchor;
+    return st.m;
 }
 
 struct EncodeArgs {

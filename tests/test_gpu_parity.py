@@ -228,7 +228,7 @@ def test_compressed_size_within_one_percent_of_oracle(ctx, orc):
     # matches spread over the window and pays ~2-3% for the small shared-memory table; a larger
     # table (B2B_OPT_HASH_LOG = 13) narrows it at the cost of resident warps.  DESIGN.md has the
     # numbers.  Text (NoShuffle, not a BASELINE config) is reported, loosely bounded.
-    bound = {"C4 smooth f64 + BitShuffle T=8": 1.04, "text NoShuffle": 1.15, "f32 i*0.001 + Shuffle T=4": 1.10}
+    bound = {"C4 smooth f64 + BitShuffle T=8": 1.04, "text NoShuffle": 1.20, "f32 i*0.001 + Shuffle T=4": 1.10}
     for name, (mine, ref, ratio) in report.items():
         assert mine <= ref * bound.get(name, 1.01) + 16, (name, mine, ref)
     ctx.set_option(4, 13)

@@ -13,7 +13,7 @@
 
 #include "../oracle/blosc_oracle.h"
 
-static int INSERT_AFTER = 0, LAZY = 0, WAYS = 1, LAZYCAP = 1 << 30, SEG = 0, FIXD = 0; static int HASHLOG = 12, HASHBYTES = 4, SKIPLOG = 7, SKIPDIV = 3, INSERT_END = 0, PREFER_TABLE = 0;
+static int INSERT_AFTER = 0, LAZY = 0, WAYS = 1, LAZYCAP = 1 << 30, SEG = 0, FIXD = 0, NOBACK = 0; static int HASHLOG = 12, HASHBYTES = 4, SKIPLOG = 7, SKIPDIV = 3, INSERT_END = 0, PREFER_TABLE = 0;
 
 static inline uint32_t ld32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline uint64_t ld64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
@@ -72,7 +72,7 @@ size_t model_encode(const uint8_t *src, uint32_t n, uint8_t *out, long *nseq) {
             uint32_t mp = p[first], mc = (uint32_t)cand_f, offset = mp - mc;
             uint32_t mend = mp + 4, cpos = mc + 4;
             while (mend < mlimit && src[mend] == src[cpos]) { mend++; cpos++; }
-            while (mp > anchor && mc > 0 && src[mp - 1] == src[mc - 1]) { mp--; mc--; }
+            if (!(NOBACK && stride == 1)) while (mp > anchor && mc > 0 && src[mp - 1] == src[mc - 1]) { mp--; mc--; }
             uint32_t ll = mp - anchor, ml = mend - mp - 4;
             uint32_t tok = op++;
             if (ll >= 15) op += put_ext(out + op, ll - 15);
@@ -153,6 +153,7 @@ int main(int argc, char **argv) {
         if (!strcmp(argv[i], "lazycap")) LAZYCAP = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "seg")) SEG = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "fixd")) FIXD = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "noback")) NOBACK = atoi(argv[i + 1]);
     }
     const uint32_t n = 262144;
     uint8_t *raw = malloc(n), *sh = malloc(n), *o1 = malloc(n * 2), *o2 = malloc(n * 2), *back = malloc(n);
