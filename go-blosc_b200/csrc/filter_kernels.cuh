@@ -317,6 +317,133 @@ __device__ __forceinline__ void run_shuffle_fast(const uint8_t *s, uint8_t *d, u
     }
 }
 
+// ---- K2, coalesced form: every lane moves ONE 16-byte vector in and out --------------------
+// A group of 8 elements (8*T bytes) spans L = T/2 consecutive lanes.  Lane r of a group holds
+// 8/L whole elements after the load and must end up with output vector r = the 8x8 bit
+// matrices of byte positions 2r and 2r+1, which need two bytes of EVERY element of the group:
+// an all-to-all inside the group by __shfl_xor (L-1 rounds of 16/L bytes).  The partner order
+// r^s is undone with a block-xor permutation (PRMT / register swaps).  Bit unshuffle is the
+// mirror image.  All global accesses are 512 contiguous bytes per warp instruction.
+__device__ __forceinline__ uint32_t sel4(uint32_t i, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const uint32_t lo = (i & 1u) ? b : a, hi = (i & 1u) ? d : c;
+    return (i & 2u) ? hi : lo;
+}
+
+// permute the L blocks of an 8-byte value: out[block b] = in[block b ^ r]
+template <int L> __device__ __forceinline__ void xor_blocks(uint32_t &lo, uint32_t &hi, uint32_t r) {
+    if constexpr (L == 8) {   // 1-byte blocks
+        if (r & 1u) { lo = prmt(lo, lo, 0x2301); hi = prmt(hi, hi, 0x2301); }
+        if (r & 2u) { lo = prmt(lo, lo, 0x1032); hi = prmt(hi, hi, 0x1032); }
+        if (r & 4u) { const uint32_t t = lo; lo = hi; hi = t; }
+    } else if constexpr (L == 4) {   // 2-byte blocks
+        if (r & 1u) { lo = prmt(lo, lo, 0x1032); hi = prmt(hi, hi, 0x1032); }
+        if (r & 2u) { const uint32_t t = lo; lo = hi; hi = t; }
+    } else {   // L == 2: 4-byte blocks
+        if (r & 1u) { const uint32_t t = lo; lo = hi; hi = t; }
+    }
+}
+
+template <int T> __device__ __forceinline__ uint4 bitshuffle_vec(uint4 v, int lane) {
+    constexpr int L = T / 2;
+    const uint32_t r = (uint32_t)lane & (L - 1);
+    const uint32_t FULL = 0xffffffffu;
+    uint32_t xlo_a, xhi_a, xlo_b, xhi_b;   // X'_{2r} and X'_{2r+1}: blocks in partner order s
+    if constexpr (T == 4) {
+        // 4 elements per lane, 2 u16 units each; column u = unit u of the 4 elements (8 bytes)
+        const uint32_t c0a = prmt(v.x, v.y, 0x5410), c0b = prmt(v.z, v.w, 0x5410);
+        const uint32_t c1a = prmt(v.x, v.y, 0x7632), c1b = prmt(v.z, v.w, 0x7632);
+        const uint32_t sa = r ? c0a : c1a, sb = r ? c0b : c1b;            // column of the partner
+        const uint32_t ra = __shfl_xor_sync(FULL, sa, 1), rb = __shfl_xor_sync(FULL, sb, 1);
+        const uint32_t oa = r ? c1a : c0a, ob = r ? c1b : c0b;            // own column r
+        // block s=0: own elements, block s=1: the partner's; low bytes -> j=2r, high -> j=2r+1
+        xlo_a = prmt(oa, ob, 0x6420); xhi_a = prmt(ra, rb, 0x6420);
+        xlo_b = prmt(oa, ob, 0x7531); xhi_b = prmt(ra, rb, 0x7531);
+    } else if constexpr (T == 8) {
+        // 2 elements per lane (x,y) (z,w), 4 units each; column u = (e0.unit u, e1.unit u)
+        const uint32_t c0 = prmt(v.x, v.z, 0x5410), c1 = prmt(v.x, v.z, 0x7632);
+        const uint32_t c2 = prmt(v.y, v.w, 0x5410), c3 = prmt(v.y, v.w, 0x7632);
+        uint32_t R[4];
+        R[0] = sel4(r, c0, c1, c2, c3);
+#pragma unroll
+        for (int s = 1; s < 4; s++) R[s] = __shfl_xor_sync(FULL, sel4(r ^ s, c0, c1, c2, c3), s);
+        xlo_a = prmt(R[0], R[1], 0x6420); xhi_a = prmt(R[2], R[3], 0x6420);
+        xlo_b = prmt(R[0], R[1], 0x7531); xhi_b = prmt(R[2], R[3], 0x7531);
+    } else {   // T == 16: one element per lane, 8 units
+        uint32_t R[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            const uint32_t i = r ^ (uint32_t)s;
+            const uint32_t w = sel4(i >> 1, v.x, v.y, v.z, v.w);
+            const uint32_t u = (i & 1u) ? (w >> 16) : (w & 0xFFFFu);
+            R[s] = s ? __shfl_xor_sync(FULL, u, s) : u;
+        }
+        const uint32_t t01 = prmt(R[0], R[1], 0x5140), t23 = prmt(R[2], R[3], 0x5140);
+        const uint32_t t45 = prmt(R[4], R[5], 0x5140), t67 = prmt(R[6], R[7], 0x5140);
+        xlo_a = prmt(t01, t23, 0x5410); xhi_a = prmt(t45, t67, 0x5410);
+        xlo_b = prmt(t01, t23, 0x7632); xhi_b = prmt(t45, t67, 0x7632);
+    }
+    xor_blocks<L>(xlo_a, xhi_a, r);
+    xor_blocks<L>(xlo_b, xhi_b, r);
+    bit_transpose8(xlo_a, xhi_a);
+    bit_transpose8(xlo_b, xhi_b);
+    return make_uint4(xlo_a, xhi_a, xlo_b, xhi_b);
+}
+
+template <int T> __device__ __forceinline__ uint4 bitunshuffle_vec(uint4 v, int lane) {
+    constexpr int L = T / 2;
+    const uint32_t r = (uint32_t)lane & (L - 1);
+    const uint32_t FULL = 0xffffffffu;
+    uint32_t alo = v.x, ahi = v.y, blo = v.z, bhi = v.w;   // Y_{2r}, Y_{2r+1}
+    bit_transpose8(alo, ahi);                              // X_{2r}: byte m = element m, byte 2r
+    bit_transpose8(blo, bhi);                              // X_{2r+1}
+    xor_blocks<L>(alo, ahi, r);                            // block s now belongs to lane r^s
+    xor_blocks<L>(blo, bhi, r);
+    if constexpr (T == 4) {
+        // block = 4 elements; packet for a lane = its 4 elements' unit r: (a.byte, b.byte) x 4
+        const uint32_t p0a = prmt(alo, blo, 0x5140), p0b = prmt(alo, blo, 0x7362);   // own block
+        const uint32_t p1a = prmt(ahi, bhi, 0x5140), p1b = prmt(ahi, bhi, 0x7362);   // partner's
+        const uint32_t qa = __shfl_xor_sync(FULL, p1a, 1), qb = __shfl_xor_sync(FULL, p1b, 1);
+        // own elements e=0..3: unit r from p0, unit r^1 from q
+        const uint32_t u0a = r ? qa : p0a, u0b = r ? qb : p0b;   // unit 0 of elements (0,1) (2,3)
+        const uint32_t u1a = r ? p0a : qa, u1b = r ? p0b : qb;   // unit 1
+        return make_uint4(prmt(u0a, u1a, 0x5410), prmt(u0a, u1a, 0x7632), prmt(u0b, u1b, 0x5410),
+                          prmt(u0b, u1b, 0x7632));
+    } else if constexpr (T == 8) {
+        // block = 2 elements; packet s = (a.b0, b.b0, a.b1, b.b1) of block s = unit r of 2 elements
+        uint32_t P[4];
+        P[0] = prmt(alo, blo, 0x5140); P[1] = prmt(alo, blo, 0x7362);
+        P[2] = prmt(ahi, bhi, 0x5140); P[3] = prmt(ahi, bhi, 0x7362);
+        uint32_t U[4];   // U[s] = unit (r^s) of my two elements
+        U[0] = P[0];
+#pragma unroll
+        for (int s = 1; s < 4; s++) U[s] = __shfl_xor_sync(FULL, P[s], s);
+        // unit u of my elements = U[u ^ r]
+        const uint32_t u0 = sel4(r, U[0], U[1], U[2], U[3]), u1 = sel4(r ^ 1u, U[0], U[1], U[2], U[3]);
+        const uint32_t u2 = sel4(r ^ 2u, U[0], U[1], U[2], U[3]), u3 = sel4(r ^ 3u, U[0], U[1], U[2], U[3]);
+        // element 0 = low halves of u0..u3, element 1 = high halves
+        return make_uint4(prmt(u0, u1, 0x5410), prmt(u2, u3, 0x5410), prmt(u0, u1, 0x7632),
+                          prmt(u2, u3, 0x7632));
+    } else {   // T == 16: block = 1 element; packet s = (a.byte s, b.byte s)
+        uint32_t U[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            const uint32_t aw = s < 4 ? alo : ahi, bw = s < 4 ? blo : bhi;
+            const uint32_t pk = ((aw >> (8 * (s & 3))) & 0xFFu) | (((bw >> (8 * (s & 3))) & 0xFFu) << 8);
+            U[s] = s ? __shfl_xor_sync(FULL, pk, s) : pk;
+        }
+        // unit u of my element = U[u ^ r]; word k = (unit 2k, unit 2k+1)
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t i0 = (uint32_t)(2 * k) ^ r, i1 = (uint32_t)(2 * k + 1) ^ r;
+            const uint32_t e0 = (i0 & 4u) ? sel4(i0 & 3u, U[4], U[5], U[6], U[7]) : sel4(i0 & 3u, U[0], U[1], U[2], U[3]);
+            const uint32_t e1 = (i1 & 4u) ? sel4(i1 & 3u, U[4], U[5], U[6], U[7]) : sel4(i1 & 3u, U[0], U[1], U[2], U[3]);
+            w[k] = (e0 & 0xFFFFu) | (e1 << 16);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 template <int T>
 __device__ __forceinline__ void run_bitshuffle_fast(const uint8_t *s, uint8_t *d, uint64_t G,
                                                     uint32_t tile0, uint32_t tstride,
@@ -326,10 +453,31 @@ __device__ __forceinline__ void run_bitshuffle_fast(const uint8_t *s, uint8_t *d
     for (uint64_t t = tile0; t < ntiles; t += tstride) {
         const uint64_t g0 = t * GPT;
         const uint32_t vg = (uint32_t)(G - g0 < GPT ? G - g0 : GPT);
-        for (uint32_t g = threadIdx.x; g < vg; g += kFilterThreads) {
-            const uint64_t b = (g0 + g) * 8 * T;
-            if (!inverse) bitshuffle_group<T>(s + b, d + b);
-            else bitunshuffle_group<T>(s + b, d + b);
+        if constexpr (T == 2) {
+            for (uint32_t g = threadIdx.x; g < vg; g += kFilterThreads) {
+                const uint64_t b = (g0 + g) * 8 * T;
+                if (!inverse) bitshuffle_group<T>(s + b, d + b);
+                else bitunshuffle_group<T>(s + b, d + b);
+            }
+        } else {
+            // one 16-byte vector per lane and pass; groups never straddle a warp (8*T <= 128 bytes)
+            const uint32_t vbytes = vg * 8 * T;
+            const uint8_t *ts = s + g0 * 8 * T;
+            uint8_t *td = d + g0 * 8 * T;
+            const int lane = threadIdx.x & 31;
+            constexpr int NV = kTileBytes / 16 / kFilterThreads;
+            uint4 v[NV];
+#pragma unroll
+            for (int it = 0; it < NV; it++) {
+                const uint32_t b = 16u * (it * kFilterThreads + threadIdx.x);
+                v[it] = b < vbytes ? ldg128_stream(ts + b) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int it = 0; it < NV; it++) {
+                const uint32_t b = 16u * (it * kFilterThreads + threadIdx.x);
+                const uint4 o = inverse ? bitunshuffle_vec<T>(v[it], lane) : bitshuffle_vec<T>(v[it], lane);
+                if (b < vbytes) stg128_stream(td + b, o);
+            }
         }
     }
 }
