@@ -121,25 +121,33 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
             stg128(dst + 16ull * (i + 2 * kWarp), c); stg128(dst + 16ull * (i + 3 * kWarp), d);
         }
         for (; i < nvec; i += kWarp) stg128(dst + 16ull * i, ldg128(src + 16ull * i));
-    } else if ((sh & 3u) == 0) {
-        nvec = n >> 4;
-        for (uint32_t i = lane; i < nvec; i += kWarp) {
-            const uint32_t *s = reinterpret_cast<const uint32_t *>(src + 16ull * i);
-            uint4 v = make_uint4(s[0], s[1], s[2], s[3]);
-            stg128(dst + 16ull * i, v);
-        }
     } else {
-        // the 5th aligned word reaches up to 3 bytes past the 16 copied: keep it in range
-        nvec = (n - 3) >> 4;
-        const uint32_t r = 8u * (sh & 3u);
-        for (uint32_t i = lane; i < nvec; i += kWarp) {
-            const uint32_t *s =
-                reinterpret_cast<const uint32_t *>((uintptr_t)(src + 16ull * i) & ~(uintptr_t)3);
-            uint32_t w0 = s[0], w1 = s[1], w2 = s[2], w3 = s[3], w4 = s[4];
-            uint4 v = make_uint4(__funnelshift_r(w0, w1, r), __funnelshift_r(w1, w2, r),
-                                 __funnelshift_r(w2, w3, r), __funnelshift_r(w3, w4, r));
-            stg128(dst + 16ull * i, v);
+        // byte-misaligned source: two aligned 16-byte loads per output vector (the second one is
+        // the next lane's first: an L1 hit) and a funnel shift.  The last vectors are left to the
+        // byte tail so that the second load never leaves [src, src + n).
+        nvec = n >= 32 ? (n - 16) >> 4 : 0;
+        const uint8_t *al = src - sh;                      // 16-byte aligned
+        const uint32_t ws = sh >> 2, bs = 8u * (sh & 3u);
+        auto realign = [&](const uint4 &a, const uint4 &b) -> uint4 {
+            uint32_t w0, w1, w2, w3, w4;
+            switch (ws) {
+                case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+                case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+                case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+                default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
+            }
+            return make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs),
+                              __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
+        };
+        uint32_t i = lane;
+        for (; i + kWarp < nvec; i += 2 * kWarp) {
+            const uint4 a0 = ldg128(al + 16ull * i), b0 = ldg128(al + 16ull * i + 16);
+            const uint4 a1 = ldg128(al + 16ull * (i + kWarp)), b1 = ldg128(al + 16ull * (i + kWarp) + 16);
+            stg128(dst + 16ull * i, realign(a0, b0));
+            stg128(dst + 16ull * (i + kWarp), realign(a1, b1));
         }
+        for (; i < nvec; i += kWarp)
+            stg128(dst + 16ull * i, realign(ldg128(al + 16ull * i), ldg128(al + 16ull * i + 16)));
     }
     for (uint32_t i = (nvec << 4) + lane; i < n; i += kWarp) dst[i] = src[i];
 }
