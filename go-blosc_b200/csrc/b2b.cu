@@ -48,6 +48,7 @@ struct b2b_ctx {
     int opt_quirk = 0;
     int opt_filter_ctas_per_sm = 0;
     int opt_hash_log = 0;              // 0: default (kHashLogDefault)
+    uint32_t opt_tune[4] = {0, 0, 0, 0};   // encoder experiment knobs (0: built-in default)
     uint64_t opt_stage_bytes = 256ull << 20;
     uint64_t launches = 0;
     std::string last_err;
@@ -192,7 +193,7 @@ int launch_encode(b2b_ctx *ctx, const EncodeArgs &e, cudaStream_t s) {
     const uint64_t warps = (uint64_t)e.nframes * e.segs_grid;
     const size_t smem = (size_t)kEncWarps * sizeof(uint32_t) << hl;
     // persistent CTAs: as many as fit on the device (warps pull items from the ticket)
-    const uint64_t per_sm = hl <= 10 ? 12 : hl == 11 ? 7 : hl == 12 ? 3 : 1;
+    const uint64_t per_sm = hl <= 10 ? 8 : hl == 11 ? 5 : hl == 12 ? 2 : 1;   // __launch_bounds__ of the kernel
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((warps + kEncWarps - 1) / kEncWarps,
                                                                      (uint64_t)ctx->sm_count * per_sm));
     CU(ctx, cudaMemsetAsync(e.ticket, 0, 8, s));
@@ -293,6 +294,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     e.in = in; e.src_off = d_src_off; e.src_len = d_src_len; e.nframes = nframes;
     e.segs_grid = (uint32_t)segs_grid; e.comp = d_comp; e.comp_off = d_comp_off;
     e.seg_base = d_seg_base; e.meta = d_meta; e.ticket = d_ticket;
+    for (int i = 0; i < 4; i++) e.tune[i] = ctx->opt_tune[i];
     rc = launch_encode(ctx, e, s);
     if (rc) return rc;
 
@@ -471,6 +473,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
             if (value != 0 && (value < 10 || value > 13)) return B2B_EINVAL;
             ctx->opt_hash_log = (int)value; return B2B_OK;
         case B2B_OPT_KERNEL_TIMING: ctx->opt_timing = value != 0; return B2B_OK;
+        case 100: case 101: case 102: case 103: ctx->opt_tune[option - 100] = (uint32_t)value; return B2B_OK;
         case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (256ull << 20); return B2B_OK;
         default: return B2B_EINVAL;
     }

@@ -144,7 +144,28 @@ __device__ __forceinline__ uint32_t extend_coop(const uint8_t *org, uint32_t fro
     }
 }
 
-constexpr uint32_t kLaneMatchMax = 36;   // per-lane match length is followed up to here (4 + 8 words)
+// ---- dense parse: every lane owns a strip of the input -------------------------------------
+// In compressible regions one step covers 32 strips of kStrip bytes.  Each lane walks ITS strip
+// like a scalar LZ4 compressor (probe / insert at every position, follow a hit, jump behind it);
+// the hash table is shared, so lanes find each other's positions.  The loop is a two-state machine
+// (probing | following a match, 4 bytes per turn) so that lanes in different phases still share
+// most instructions.  A lane follows its own match at most kStripCap bytes beyond its strip; what
+// is still matching there ("open") is finished 32 lanes wide.  Afterwards matches that overlap a
+// match of an earlier strip are dropped or trimmed (prefix maximum of the match ends over the
+// lanes), literal runs are measured from the previous surviving match, a prefix sum of the encoded
+// sizes places every lane's sequences, and each lane writes its own bytes.
+// kStrip is deliberately not a divisor of the power-of-two periods typed arrays have after a
+// shuffle: with period P, the nearest earlier occurrence of a position lies in a lower lane's
+// strip at an EARLIER turn (P mod kStrip turns before), so it is already in the table.
+constexpr uint32_t kStrip = 61;
+constexpr uint32_t kStripCap = 61;       // own match followed this far past the strip end
+constexpr uint32_t kListMax = 16;        // matches (>= 4 bytes, disjoint) that can start in one strip
+constexpr uint32_t kLaneLitEmit = 32;    // literal runs up to here are written by the owning lane
+
+struct LaneLists {
+    uint32_t a[kListMax][32];            // start (17 bits) | length << 17 (the last match of a lane keeps its end in a register)
+    uint16_t off[kListMax][32];
+};
 
 // One segment.  org: first byte of the warm-up window (W bytes before the segment, 0 for the
 // first one), L the segment length, tail: bytes of the frame after it.  Positions below are
@@ -161,7 +182,8 @@ template <int HL>
 __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict__ org, uint32_t W,
                                                        uint32_t L, uint64_t tail,
                                                        uint8_t *__restrict__ body, uint32_t *table,
-                                                       int lane) {
+                                                       LaneLists *lists, int lane, uint32_t dense_lits,
+                                                       uint32_t strip, uint32_t strip_cap) {
     EncState st;
     st.body = body; st.op = 0; st.have_first = false;
     st.m.first_ll = L; st.m.body_len = 0; st.m.trail_ll = L; st.m.info = 0;
@@ -185,10 +207,262 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
         __syncwarp();
     }
     uint32_t anchor = W, si = W;
+    uint32_t rep = 0;                                            // this lane's last match offset
     while (si < mfl) {
         // adaptive skip of the reference compressor: about 3 probes per 4 + lits/128 bytes
         const uint32_t lits = si - anchor;
-        const uint32_t stride = lits < 256 ? 1u : (4u + (lits >> 7)) / 3u;
+        const uint32_t stride = lits < dense_lits ? 1u : (4u + (lits >> 7)) / 3u;
+        if (stride == 1) {
+            // ------------------------------------------------------------ dense step: strips
+            uint32_t pos = si + (uint32_t)lane * strip;
+            if (pos > mfl) pos = mfl;
+            const uint32_t send = pos + strip < mfl ? pos + strip : mfl;
+            const uint32_t cap = send + strip_cap < mlimit ? send + strip_cap : mlimit;
+            uint32_t cnt = 0, e = 0, moff = 0, mst = 0, my_last = 0;
+            bool ext = false, my_open = false;
+            while (__any_sync(0xffffffffu, ext || pos < send)) {
+                if (!ext) {
+                    if (pos < send) {
+                        // ---- four consecutive positions per turn: one 12-byte window, four probes in flight
+                        const uintptr_t pa = (uintptr_t)(org + pos);
+                        const uint32_t r8 = 8u * (uint32_t)(pa & 3u);
+                        const uint32_t *q = reinterpret_cast<const uint32_t *>(pa & ~(uintptr_t)3);
+                        const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+                        const uint32_t v0 = __funnelshift_r(w0, w1, r8), v1 = __funnelshift_r(w1, w2, r8);
+                        uint32_t seq[4], ent[4], chk[4];
+                        seq[0] = v0; seq[1] = __funnelshift_r(v0, v1, 8);
+                        seq[2] = __funnelshift_r(v0, v1, 16); seq[3] = __funnelshift_r(v0, v1, 24);
+                        const uint32_t nv = send - pos < 4u ? send - pos : 4u;
+                        uint32_t hh[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t hv = seq[k] * 2654435761u;
+                            hh[k] = hv >> (32 - HL); chk[k] = (hv >> (17 - HL)) & 0x7FFFu;
+                            ent[k] = table[hh[k]];
+                        }
+                        // the lane's previous offset is tried as well (constant strides, periodic data)
+                        uint32_t rs[4] = {0, 0, 0, 0};
+                        const bool rep_ok = rep != 0 && rep <= pos;
+                        if (rep_ok) {
+                            const uintptr_t ra = (uintptr_t)(org + pos - rep);
+                            const uint32_t rr8 = 8u * (uint32_t)(ra & 3u);
+                            const uint32_t *rq = reinterpret_cast<const uint32_t *>(ra & ~(uintptr_t)3);
+                            const uint32_t x0 = rq[0], x1 = rq[1], x2 = rq[2];
+                            const uint32_t y0 = __funnelshift_r(x0, x1, rr8), y1 = __funnelshift_r(x1, x2, rr8);
+                            rs[0] = y0; rs[1] = __funnelshift_r(y0, y1, 8);
+                            rs[2] = __funnelshift_r(y0, y1, 16); rs[3] = __funnelshift_r(y0, y1, 24);
+                        }
+                        // first position with a candidate.  A table entry whose check bits agree is taken
+                        // unverified: the first turn of the extension compares the bytes anyway.
+                        int pick = -1;
+                        uint32_t pc = 0;
+                        bool sure = false;
+#pragma unroll
+                        for (int k = 3; k >= 0; k--) {
+                            const uint32_t c = ent[k] & 0x1FFFFu, p = pos + k;
+                            if ((uint32_t)k < nv) {
+                                if (rep_ok && rs[k] == seq[k]) { pick = k; pc = p - rep; sure = true; }
+                                if ((ent[k] >> 17) == chk[k] && c < p && p - c < 65536u) { pick = k; pc = c; sure = false; }
+                            }
+                        }
+                        if (pick < 0) {
+                            // repeats inside the group (runs, periods 1..3): nearest earlier position
+                            if (nv > 3 && (seq[3] == seq[0])) { pick = 3; pc = pos; }
+                            if (nv > 3 && (seq[3] == seq[1])) { pick = 3; pc = pos + 1; }
+                            if (nv > 3 && (seq[3] == seq[2])) { pick = 3; pc = pos + 2; }
+                            if (nv > 2 && (seq[2] == seq[0])) { pick = 2; pc = pos; }
+                            if (nv > 2 && (seq[2] == seq[1])) { pick = 2; pc = pos + 1; }
+                            if (nv > 1 && (seq[1] == seq[0])) { pick = 1; pc = pos; }
+                            sure = true;
+                        }
+                        // positions up to the chosen one are recorded (like the scalar compressor, which
+                        // does not enter the positions it jumps over)
+                        const uint32_t upto = pick < 0 ? nv : (uint32_t)pick + 1u;
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if ((uint32_t)k < upto) table[hh[k]] = (chk[k] << 17) | (pos + k);
+                        if (pick >= 0) { ext = true; mst = pos + pick; moff = mst - pc; e = sure ? mst + 4 : mst; }
+                        else pos += nv;
+                    }
+                } else {
+                    bool done = true, cancel = false;
+                    if (e + 8 <= cap) {
+                        const uintptr_t ea = (uintptr_t)(org + e), ca = (uintptr_t)(org + e - moff);
+                        const uint32_t er8 = 8u * (uint32_t)(ea & 3u), cr8 = 8u * (uint32_t)(ca & 3u);
+                        const uint32_t *eq = reinterpret_cast<const uint32_t *>(ea & ~(uintptr_t)3);
+                        const uint32_t *cq = reinterpret_cast<const uint32_t *>(ca & ~(uintptr_t)3);
+                        const uint32_t e0 = eq[0], e1 = eq[1], e2 = eq[2], c0 = cq[0], c1 = cq[1], c2 = cq[2];
+                        const uint32_t x0 = __funnelshift_r(e0, e1, er8) ^ __funnelshift_r(c0, c1, cr8);
+                        const uint32_t x1 = __funnelshift_r(e1, e2, er8) ^ __funnelshift_r(c1, c2, cr8);
+                        if (x0) { cancel = e == mst; e += (uint32_t)(__ffs((int)x0) - 1) >> 3; }
+                        else if (x1) e += 4u + ((uint32_t)(__ffs((int)x1) - 1) >> 3);
+                        else { e += 8; done = false; }
+                    } else {
+                        if (e == mst) {
+                            if (enc_load32u(org + e) == enc_load32u(org + e - moff)) e += 4; else cancel = true;
+                        }
+                        if (!cancel) while (e < cap && org[e] == org[e - moff]) e++;
+                    }
+                    if (cancel) { ext = false; pos = mst + 1; done = false; }
+                    if (done) {
+                        my_open = e >= cap && cap < mlimit;
+                        lists->a[cnt][lane] = mst | ((e - mst) << 17);
+                        lists->off[cnt][lane] = (uint16_t)moff;
+                        cnt++;
+                        pos = e; rep = moff; my_last = e; ext = false;
+                    }
+                }
+            }
+            const uint32_t region_end = si + 32u * strip < mfl ? si + 32u * strip : mfl;
+            const uint32_t any_match = __ballot_sync(0xffffffffu, cnt != 0);
+            if (any_match == 0) { si = region_end; continue; }
+            // ---- open matches are finished 32 lanes wide, in stream order; one that an earlier
+            // finished match already covers is left alone (it is dropped below)
+            {
+                uint32_t opens = __ballot_sync(0xffffffffu, my_open);
+                uint32_t erun = 0;
+                while (opens) {
+                    const int j = __ffs(opens) - 1;
+                    const uint32_t ce = __shfl_sync(0xffffffffu, my_last, j);
+                    const uint32_t oj = __shfl_sync(0xffffffffu, moff, j);
+                    if (ce > erun) {
+                        erun = extend_coop(org, ce, oj, mlimit, lane);
+                        if (lane == j) my_last = erun;
+                    }
+                    opens &= opens - 1;
+                    opens &= __ballot_sync(0xffffffffu, my_last > erun);
+                }
+            }
+            // ---- drop / trim against the matches of earlier strips
+            uint32_t ein;                                      // everything before ein is taken
+            {
+                uint32_t incl = my_last;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d && t > incl) incl = t;
+                }
+                ein = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0 || ein < anchor) ein = anchor;
+            }
+            uint32_t kf = 0, f_ms = 0;                         // first surviving match, its (trimmed) start
+            while (kf < cnt) {
+                const uint32_t a = lists->a[kf][lane];
+                const uint32_t ms = a & 0x1FFFFu;
+                const uint32_t me = kf + 1 == cnt ? my_last : ms + (a >> 17);
+                if (me > ein && (ms >= ein || me - ein >= 4)) { f_ms = ms > ein ? ms : ein; break; }
+                kf++;
+            }
+            const bool kept = kf < cnt;
+            uint32_t prev;                                     // end of the previous surviving match
+            uint32_t last_kept_end;
+            {
+                uint32_t incl = kept ? my_last : 0u;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d && t > incl) incl = t;
+                }
+                prev = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0 || prev < anchor) prev = anchor;
+                last_kept_end = __shfl_sync(0xffffffffu, incl, 31);
+            }
+            const uint32_t keptm = __ballot_sync(0xffffffffu, kept);
+            if (keptm == 0) { si = region_end; continue; }
+            // the first sequence of the segment leaves only its offset / match extension in the body
+            const bool seg_first = !st.have_first && lane == __ffs(keptm) - 1;
+            // ---- backward extension over the pending literals (down to the previous surviving match,
+            // possibly in another strip) and the encoded size of this lane's sequences
+            uint32_t size = 0;
+            {
+                uint32_t pe = prev;
+                for (uint32_t k = kf; k < cnt; k++) {
+                    const uint32_t a = lists->a[k][lane];
+                    uint32_t ms = k == kf ? f_ms : (a & 0x1FFFFu);
+                    const uint32_t me = k + 1 == cnt ? my_last : (a & 0x1FFFFu) + (a >> 17);
+                    uint32_t mc = ms - lists->off[k][lane];
+                    while (ms > pe && mc > 0 && org[ms - 1] == org[mc - 1]) { ms--; mc--; }
+                    const uint32_t len = me - ms;
+                    lists->a[k][lane] = ms | ((len < 0x7FFFu ? len : 0x7FFFu) << 17);
+                    const uint32_t ll = ms - pe, mlc = len - 4;
+                    if (seg_first && k == kf) size += 2u + len_ext_bytes(mlc);
+                    else size += 1u + len_ext_bytes(ll) + ll + 2u + len_ext_bytes(mlc);
+                    pe = me;
+                }
+            }
+            uint32_t incl = size;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            // ---- every lane writes its own sequences; long literal runs are left to the warp
+            uint32_t g_dst0 = 0, g_src0 = 0, g_len0 = 0, g_dst1 = 0, g_src1 = 0, g_len1 = 0;
+            {
+                uint8_t *b = body + st.op + (incl - size);
+                uint32_t pe = prev, ng = 0;
+                for (uint32_t k = kf; k < cnt; k++) {
+                    const uint32_t a = lists->a[k][lane];
+                    const uint32_t ms = a & 0x1FFFFu;
+                    const uint32_t me = k + 1 == cnt ? my_last : ms + (a >> 17);
+                    const uint32_t offset = lists->off[k][lane];
+                    const uint32_t ll = ms - pe, mlc = me - ms - 4;
+                    if (seg_first && k == kf) {
+                        st.m.first_ll = ll;
+                        st.m.info = 0x100u | (mlc < 15 ? mlc : 15u);
+                    } else {
+                        *b++ = (uint8_t)(((ll < 15 ? ll : 15u) << 4) | (mlc < 15 ? mlc : 15u));
+                        if (ll >= 15) {
+                            uint32_t v = ll - 15;
+                            while (v >= 255) { *b++ = 255; v -= 255; }
+                            *b++ = (uint8_t)v;
+                        }
+                        if (ll <= kLaneLitEmit) {
+                            const uint8_t *lit = org + pe;
+                            for (uint32_t i = 0; i < ll; i++) b[i] = lit[i];
+                        } else {
+                            if (ng == 0) { g_dst0 = (uint32_t)(b - body); g_src0 = pe; g_len0 = ll; }
+                            else { g_dst1 = (uint32_t)(b - body); g_src1 = pe; g_len1 = ll; }
+                            ng++;
+                        }
+                        b += ll;
+                    }
+                    b[0] = (uint8_t)offset; b[1] = (uint8_t)(offset >> 8);
+                    b += 2;
+                    if (mlc >= 15) {
+                        uint32_t v = mlc - 15;
+                        while (v >= 255) { *b++ = 255; v -= 255; }
+                        *b++ = (uint8_t)v;
+                    }
+                    pe = me;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const uint32_t gd_r = r ? g_dst1 : g_dst0, gs_r = r ? g_src1 : g_src0, gl_r = r ? g_len1 : g_len0;
+                uint32_t gaps = __ballot_sync(0xffffffffu, gl_r != 0);
+                while (gaps) {
+                    const int j = __ffs(gaps) - 1;
+                    gaps &= gaps - 1;
+                    const uint32_t gd = __shfl_sync(0xffffffffu, gd_r, j), gs = __shfl_sync(0xffffffffu, gs_r, j);
+                    const uint32_t gl = __shfl_sync(0xffffffffu, gl_r, j);
+                    warp_copy(body + gd, org + gs, gl, lane);
+                }
+            }
+            if (!st.have_first) {
+                // the lane that wrote the first sequence of the segment publishes its summary
+                const int fl0 = __ffs(keptm) - 1;
+                st.m.first_ll = __shfl_sync(0xffffffffu, st.m.first_ll, fl0);
+                st.m.info = __shfl_sync(0xffffffffu, st.m.info, fl0);
+                st.have_first = true;
+            }
+            st.op += total;
+            anchor = last_kept_end;
+            si = region_end > anchor ? region_end : anchor;
+            __syncwarp();
+            continue;
+        }
         const uint32_t p = si + (uint32_t)lane * stride;
         const bool valid = p < mfl;
         const uint32_t seq = valid ? enc_load32u(org + p) : 0u;
@@ -211,112 +485,6 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             ok = cand < p && p - cand < 65536u && enc_load32u(org + cand) == seq;
         }
         const uint32_t hit = __ballot_sync(0xffffffffu, ok);
-
-        if (stride == 1) {
-            // ------------------------------------------------------------ dense window
-            __syncwarp();
-            // every probed position is recorded (of lanes with the same 4 bytes the last one wins)
-            if (valid && (same >> lane) == 1u) table[h] = (chk << 17) | p;
-            __syncwarp();
-            if (hit == 0) { si += 32; continue; }
-            // per-lane match length, bounded
-            uint32_t len = 0;
-            if (ok) {
-                len = 4;
-                const uint32_t offset = p - cand;
-                while (len < kLaneMatchMax && p + len + 4 <= mlimit) {
-                    const uint32_t x = enc_load32u(org + p + len) ^ enc_load32u(org + p + len - offset);
-                    if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-                    len += 4;
-                }
-            }
-            // greedy chain over the window: next sequence = first hit at or after the previous end,
-            // unless a hit one or two positions later is longer by more than its delay (the
-            // per-lane lengths are already there, so this look-ahead is almost free)
-            int prev_end = (int)anchor - (int)si;    // relative to the window start
-            uint32_t sel = 0, my_ll = 0;
-            int cur = 0, first_l = -1, last_l = -1;
-            bool is_long = false;
-            while (cur < 32) {
-                const uint32_t mm = hit & (0xFFFFFFFFu << cur);
-                if (!mm) break;
-                int l = __ffs(mm) - 1;
-                uint32_t len_l = __shfl_sync(0xffffffffu, len, l);
-                const uint32_t len_1 = __shfl_sync(0xffffffffu, len, (l + 1) & 31);
-                const uint32_t len_2 = __shfl_sync(0xffffffffu, len, (l + 2) & 31);
-                int best = l; uint32_t best_len = len_l;
-                if (l + 1 < 32 && len_1 > best_len + 1) { best = l + 1; best_len = len_1; }
-                if (l + 2 < 32 && len_2 > len_l + 2 && len_2 > best_len + (uint32_t)(l + 2 - best)) { best = l + 2; best_len = len_2; }
-                l = best; len_l = best_len;
-                if (lane == l) my_ll = (uint32_t)(l - prev_end);
-                sel |= 1u << l;
-                if (first_l < 0) first_l = l;
-                last_l = l;
-                prev_end = l + (int)len_l;
-                cur = prev_end;
-                if (len_l >= kLaneMatchMax) { is_long = true; break; }
-            }
-            // backward extension of every selected match over its own pending literals
-            uint32_t mp = p, mlen = len;
-            if ((sel >> lane) & 1u) {
-                uint32_t mc = cand;
-                while (my_ll > 0 && mc > 0 && org[mp - 1] == org[mc - 1]) { mp--; mc--; my_ll--; mlen++; }
-            }
-            // a match that reached the per-lane bound continues 32 lanes wide
-            const uint32_t p_last = __shfl_sync(0xffffffffu, mp, last_l);
-            const uint32_t off_last = __shfl_sync(0xffffffffu, p - cand, last_l);
-            uint32_t end_last = si + (uint32_t)prev_end;
-            if (is_long) end_last = extend_coop(org, end_last, off_last, mlimit, lane);
-            // the first sequence of the step: its literals start at the anchor (possibly far back)
-            const uint32_t ll_first = __shfl_sync(0xffffffffu, my_ll, first_l);
-            const bool first_coop = !st.have_first || ll_first > 28 || (is_long && first_l == last_l);
-            if (first_coop) {
-                const uint32_t off_f = __shfl_sync(0xffffffffu, p - cand, first_l);
-                const uint32_t len_f = (first_l == last_l) ? end_last - p_last : __shfl_sync(0xffffffffu, mlen, first_l);
-                emit_coop(st, org + anchor, ll_first, off_f, len_f - 4, lane);
-            }
-            // regular sequences: each selected lane writes its own bytes
-            uint32_t reg = sel;
-            if (first_coop) reg &= ~(1u << first_l);
-            if (is_long) reg &= ~(1u << last_l);
-            if (reg) {
-                const bool mine = (reg >> lane) & 1u;
-                const uint32_t ll = my_ll, mlc = mlen - 4, offset = p - cand;
-                const uint32_t size = mine ? 1u + (ll >= 15 ? 1u : 0u) + ll + 2u + (mlc >= 15 ? 1u + (mlc - 15) / 255u : 0u) : 0u;
-                uint32_t incl = size;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                if (mine) {
-                    uint8_t *b = body + st.op + (incl - size);
-                    const uint8_t *lit = org + mp - ll;
-                    b[0] = (uint8_t)(((ll < 15 ? ll : 15u) << 4) | (mlc < 15 ? mlc : 15u));
-                    uint32_t i = 1;
-                    if (ll >= 15) b[i++] = (uint8_t)(ll - 15);
-                    for (uint32_t k = 0; k < ll; k++) b[i + k] = lit[k];
-                    i += ll;
-                    b[i] = (uint8_t)offset; b[i + 1] = (uint8_t)(offset >> 8);
-                    i += 2;
-                    if (mlc >= 15) {
-                        uint32_t v = mlc - 15;
-                        while (v >= 255) { b[i++] = 255; v -= 255; }
-                        b[i] = (uint8_t)v;
-                    }
-                }
-                st.op += total;
-                __syncwarp();
-            }
-            if (is_long && first_l != last_l) {
-                const uint32_t ll_last = __shfl_sync(0xffffffffu, my_ll, last_l);
-                emit_coop(st, org + p_last - ll_last, ll_last, off_last, end_last - p_last - 4, lane);
-            }
-            anchor = end_last;
-            si = end_last > si + 32 ? end_last : si + 32;
-            continue;
-        }
 
         // ---------------------------------------------------------------- strided probing
         const int pick = hit ? __ffs(hit) - 1 : 31;
@@ -343,7 +511,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             if (back < 32) break;
         }
         emit_coop(st, org + anchor, mp - anchor, offset, mend - mp - 4, lane);
-        si = mend; anchor = mend;
+        si = mend; anchor = mend; rep = offset;
     }
     st.m.body_len = st.op;
     st.m.trail_ll = W + L - anchor;
@@ -361,12 +529,14 @@ struct EncodeArgs {
     const uint64_t *seg_base;   // index of frame f's first segment in meta / place
     SegMeta *meta;
     unsigned long long *ticket; // zero before launch
+    uint32_t tune[4];           // experiment knobs (0: default)
 };
 
 template <int HL>
-__global__ void __launch_bounds__(kEncThreads, HL <= 10 ? 12 : (HL == 11 ? 7 : (HL == 12 ? 3 : 1)))
+__global__ void __launch_bounds__(kEncThreads, HL <= 10 ? 8 : (HL == 11 ? 5 : (HL == 12 ? 2 : 1)))
 lz4_encode_kernel(EncodeArgs a) {
     extern __shared__ __align__(16) uint32_t enc_tables[];   // kEncWarps x 2^HL entries
+    __shared__ LaneLists enc_lists[kEncWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t items = (uint64_t)a.nframes * a.segs_grid;
     for (;;) {
@@ -384,7 +554,9 @@ lz4_encode_kernel(EncodeArgs a) {
             const uint32_t W = B < kWarmBytes ? B : kWarmBytes;
             const SegMeta m = warp_encode_segment<HL>(frame + B - W, W, L, (uint64_t)n - B - L,
                                                       a.comp + a.comp_off[f] + (uint64_t)s * kSegSlot,
-                                                      enc_tables + ((size_t)warp << HL), lane);
+                                                      enc_tables + ((size_t)warp << HL), &enc_lists[warp], lane,
+                                                      a.tune[0] ? a.tune[0] : 256u, a.tune[1] ? a.tune[1] : kStrip,
+                                                      a.tune[2] ? a.tune[2] : kStripCap);
             if (lane == 0) a.meta[a.seg_base[f] + s] = m;
             __syncwarp();
         }

@@ -84,66 +84,197 @@ __device__ __forceinline__ void warp_match_copy(uint8_t *dst, uint32_t off, uint
     }
 }
 
-// Returns the number of bytes produced, -1 for a malformed stream, -2 if it would overrun cap.
-// Strictness follows the oracle: zero offsets, offsets beyond the output so far, reads past
-// the stream, writes past cap and a final token with a non-zero match nibble are errors;
-// an empty stream decodes to 0 bytes (pierrec UncompressBlock, used at codec.go:79).
-__device__ __forceinline__ int64_t warp_lz4_decode(const uint8_t *__restrict__ src, uint32_t clen,
-                                                   uint8_t *dst, uint32_t cap, int lane) {
-    if (clen == 0) return 0;
-    uint32_t ip = 0, op = 0;
-    for (;;) {
-        if (ip >= clen) return -1;
-        const uint32_t tok = src[ip++];
-        const uint32_t lln = tok >> 4, mln = tok & 15u;
-        // ---- fast path: a short sequence (no length extensions), one predicated byte per lane.
-        // The literal load and the match load are issued together when the match source lies
-        // entirely before this sequence's output (offset >= literals + match length).
-        if (lln < 15 && mln < 15 && ip + lln + 2 <= clen) {
-            const uint32_t ll = lln, ml = mln + 4;
-            const uint32_t off = (uint32_t)src[ip + ll] | ((uint32_t)src[ip + ll + 1] << 8);
-            if (ll + ml > cap - op) return -2;
-            if (off == 0 || off > op + ll) return -1;
-            uint8_t *d = dst + op;
-            __syncwarp();   // every earlier store of this warp is ordered before the loads below
-            if (off >= ll + ml) {
-                uint32_t lit = 0, mv = 0;
-                if ((uint32_t)lane < ll) lit = src[ip + lane];
-                if ((uint32_t)lane < ml) mv = d[(int)(ll + lane) - (int)off];
-                if ((uint32_t)lane < ll) d[lane] = (uint8_t)lit;
-                if ((uint32_t)lane < ml) d[ll + lane] = (uint8_t)mv;
-            } else {
-                if ((uint32_t)lane < ll) d[lane] = src[ip + lane];
-                __syncwarp();
-                if ((uint32_t)lane < ml) {
-                    uint32_t k = lane;
-                    if (off < ml) k = lane - off * (uint32_t)__float2int_rz(__int2float_rn(lane) / __int2float_rn((int)off));
-                    d[ll + lane] = d[(int)(ll + k) - (int)off];
-                }
-            }
-            ip += ll + 2; op += ll + ml;
-            continue;
+// ---- batched decode -----------------------------------------------------------------------
+// A "regular" token carries at most one length-extension byte per field (literals <= 269,
+// match <= 273).  The decoder parses such tokens 32 stream positions at a time: every lane
+// decodes the token that WOULD start at its byte, the real chain of token starts is then walked
+// with one shuffle per token, and the sequences found are appended to a per-warp table in shared
+// memory.  A full table (up to 32 sequences, one per lane) is then copied out at once:
+//   literals  every lane copies the first kLaneLit bytes of its own run, longer runs are finished
+//             32 lanes wide;
+//   matches   lanes whose source lies before the batch (or inside their own literals) copy their
+//             own match, byte by byte, all at the same time; matches that read what another match
+//             of the same batch writes, and long ones, follow in stream order, 32 lanes wide.
+// Tokens with longer extensions, the closing token and anything malformed go through the
+// sequence-at-a-time path below (warp_decode_one), which also reports every error.
+constexpr uint32_t kLaneLit = 16;     // literal bytes a lane copies by itself
+constexpr uint32_t kLaneMatch = 24;   // longest match a lane copies by itself
+constexpr uint32_t kBatchFill = 21;   // a window adds at most 11 tokens: parse while count <= 21
+
+struct SeqTable {
+    uint32_t a[32];   // offset | literals << 16
+    uint32_t b[32];   // (literal position - batch start in the stream) | match length << 16
+};
+
+// Copies out the `count` sequences of the table.  0: ok, -1 malformed, -2 would overrun cap.
+__device__ __forceinline__ int warp_flush_batch(const uint8_t *__restrict__ src, uint32_t batch_ip,
+                                                uint8_t *dst, uint32_t &op, uint32_t cap, uint32_t count,
+                                                const SeqTable *tab, int lane) {
+    __syncwarp();
+    const bool act = (uint32_t)lane < count;
+    uint32_t a = 0, b = 0;
+    if (act) { a = tab->a[lane]; b = tab->b[lane]; }
+    const uint32_t off = a & 0xFFFFu, ll = a >> 16, ml = b >> 16, lrel = b & 0xFFFFu;
+    const uint32_t tot = ll + ml;
+    uint32_t incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - tot;
+    const bool ovf = act && incl > cap - op;
+    const bool bad = act && (off == 0 || off > op + excl + ll);
+    const uint32_t fail = __ballot_sync(0xffffffffu, ovf || bad);
+    if (fail) {
+        const uint32_t ob = __ballot_sync(0xffffffffu, ovf);
+        return ((ob >> (__ffs(fail) - 1)) & 1u) ? -2 : -1;
+    }
+    // ---- literals (the source is the compressed stream: no ordering between lanes)
+    uint8_t *d = dst + op + excl;
+    const uint8_t *s = src + batch_ip + lrel;
+    const uint32_t pl = ll < kLaneLit ? ll : kLaneLit;
+    const uint32_t maxpl = __reduce_max_sync(0xffffffffu, pl);
+    for (uint32_t i0 = 0; i0 < maxpl; i0 += 4) {
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (i0 + k < pl) v[k] = s[i0 + k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (i0 + k < pl) d[i0 + k] = (uint8_t)v[k];
+    }
+    uint32_t tails = __ballot_sync(0xffffffffu, ll > kLaneLit);
+    while (tails) {
+        const int j = __ffs(tails) - 1;
+        tails &= tails - 1;
+        const uint32_t dj = __shfl_sync(0xffffffffu, excl, j), sj = __shfl_sync(0xffffffffu, lrel, j);
+        const uint32_t lj = __shfl_sync(0xffffffffu, ll, j);
+        warp_copy(dst + op + dj + kLaneLit, src + batch_ip + sj + kLaneLit, lj - kLaneLit, lane);
+    }
+    __syncwarp();
+    // ---- matches
+    const uint32_t mpos = op + excl + ll;                 // where this lane's match starts
+    const uint32_t first_match = op + __shfl_sync(0xffffffffu, ll, 0);
+    const uint32_t s_end = mpos - off + (ml < off ? ml : off);
+    const bool indep = act && ml <= kLaneMatch && (s_end <= first_match || off <= ll);
+    const uint32_t pm = indep ? ml : 0u;
+    const uint32_t maxpm = __reduce_max_sync(0xffffffffu, pm);
+    {
+        uint8_t *m0 = dst + mpos;
+        const uint8_t *ms = m0 - off;                     // all reads stay inside [ms, m0)
+        uint32_t k = 0;
+        for (uint32_t i0 = 0; i0 < maxpm; i0 += 4) {
+            uint32_t v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (i0 + q < pm) { v[q] = ms[k]; k = (k + 1 == off) ? 0u : k + 1; }
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (i0 + q < pm) m0[i0 + q] = (uint8_t)v[q];
         }
-        // ---- general path
-        uint64_t ll = lln;
-        if (ll == 15 && !warp_read_len_ext(src, clen, ip, ll, lane)) return -1;
-        if (ll > (uint64_t)(clen - ip)) return -1;
-        if (ll > (uint64_t)(cap - op)) return -2;
-        if (ll) warp_copy(dst + op, src + ip, (uint32_t)ll, lane);
-        ip += (uint32_t)ll; op += (uint32_t)ll;
-        uint64_t ml = mln;
-        if (ip == clen) { if (ml != 0) return -1; break; }
-        if (clen - ip < 2) return -1;
-        const uint32_t off = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8);
-        ip += 2;
-        if (off == 0 || off > op) return -1;
-        if (ml == 15 && !warp_read_len_ext(src, clen, ip, ml, lane)) return -1;
-        ml += 4;
-        if (ml > (uint64_t)(cap - op)) return -2;
-        __syncwarp();  // literals and earlier matches are visible to every lane
-        warp_match_copy(dst + op, off, (uint32_t)ml, lane);
-        op += (uint32_t)ml;
+    }
+    uint32_t rest = __ballot_sync(0xffffffffu, act && !indep);
+    while (rest) {
+        const int j = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const uint32_t pj = __shfl_sync(0xffffffffu, mpos, j), oj = __shfl_sync(0xffffffffu, off, j);
+        const uint32_t mj = __shfl_sync(0xffffffffu, ml, j);
         __syncwarp();
+        warp_match_copy(dst + pj, oj, mj, lane);
+    }
+    op += total;
+    return 0;
+}
+
+// One sequence, 32 lanes wide.  1: sequence done, 0: that was the closing token (stream ends),
+// -1 malformed, -2 would overrun cap.  Strictness follows the oracle: zero offsets, offsets
+// beyond the output so far, reads past the stream, writes past cap and a final token with a
+// non-zero match nibble are errors (pierrec UncompressBlock, used at codec.go:79).
+__device__ __forceinline__ int warp_decode_one(const uint8_t *__restrict__ src, uint32_t clen, uint8_t *dst,
+                                               uint32_t cap, uint32_t &ip, uint32_t &op, int lane) {
+    if (ip >= clen) return -1;
+    const uint32_t tok = src[ip++];
+    uint64_t ll = tok >> 4;
+    if (ll == 15 && !warp_read_len_ext(src, clen, ip, ll, lane)) return -1;
+    if (ll > (uint64_t)(clen - ip)) return -1;
+    if (ll > (uint64_t)(cap - op)) return -2;
+    if (ll) warp_copy(dst + op, src + ip, (uint32_t)ll, lane);
+    ip += (uint32_t)ll; op += (uint32_t)ll;
+    uint64_t ml = tok & 15u;
+    if (ip == clen) return ml != 0 ? -1 : 0;
+    if (clen - ip < 2) return -1;
+    const uint32_t off = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8);
+    ip += 2;
+    if (off == 0 || off > op) return -1;
+    if (ml == 15 && !warp_read_len_ext(src, clen, ip, ml, lane)) return -1;
+    ml += 4;
+    if (ml > (uint64_t)(cap - op)) return -2;
+    __syncwarp();  // literals and earlier matches are visible to every lane
+    warp_match_copy(dst + op, off, (uint32_t)ml, lane);
+    op += (uint32_t)ml;
+    __syncwarp();
+    return 1;
+}
+
+// Returns the number of bytes produced, -1 for a malformed stream, -2 if it would overrun cap.
+// An empty stream decodes to 0 bytes.
+__device__ __forceinline__ int64_t warp_lz4_decode(const uint8_t *__restrict__ src, uint32_t clen,
+                                                   uint8_t *dst, uint32_t cap, SeqTable *tab, int lane) {
+    if (clen == 0) return 0;
+    uint32_t ip = 0, op = 0, count = 0, batch_ip = 0;
+    const uint32_t last = clen - 1;
+    for (;;) {
+        // ---- every lane decodes the token that would start at its byte of the window
+        const uint32_t p = ip + lane;
+        uint32_t nxt = 0xFFFFu, ta = 0, tb = 0;
+        {
+            const uint32_t t = src[p < last ? p : last];
+            const uint32_t e1 = src[p + 1 < last ? p + 1 : last];
+            const bool x1 = (t >> 4) == 15u;
+            const uint32_t ll = (t >> 4) + (x1 ? e1 : 0u);
+            const uint32_t lit = p + 1 + (x1 ? 1u : 0u);
+            const uint64_t oq = (uint64_t)lit + ll;           // offset bytes at oq, oq + 1
+            const uint32_t o0 = oq < last ? (uint32_t)oq : last, o1 = oq + 1 < last ? (uint32_t)oq + 1 : last;
+            const uint32_t o2 = oq + 2 < last ? (uint32_t)oq + 2 : last;
+            const uint32_t off = (uint32_t)src[o0] | ((uint32_t)src[o1] << 8);
+            const uint32_t e2 = src[o2];
+            const bool x2 = (t & 15u) == 15u;
+            const uint32_t ml = (t & 15u) + 4u + (x2 ? e2 : 0u);
+            const bool regular = p < clen && !(x1 && (p + 1 >= clen || e1 == 255u)) && oq + 2 <= clen &&
+                                 !(x2 && (oq + 2 >= clen || e2 == 255u));
+            if (regular) {
+                nxt = (uint32_t)oq + 2u + (x2 ? 1u : 0u) - ip;
+                ta = off | (ll << 16);
+                tb = (lit - batch_ip) | (ml << 16);
+            }
+        }
+        // ---- walk the chain of real token starts inside the window
+        uint32_t starts = 0, cur = 0;
+        bool other = false;
+        while (cur < 32) {
+            const uint32_t x = __shfl_sync(0xffffffffu, nxt, cur);
+            if (x == 0xFFFFu) { other = true; break; }
+            starts |= 1u << cur;
+            cur = x;
+        }
+        if ((starts >> lane) & 1u) {
+            const uint32_t slot = count + __popc(starts & ((1u << lane) - 1u));
+            tab->a[slot] = ta; tab->b[slot] = tb;
+        }
+        count += __popc(starts);
+        ip += cur;
+        if (other || count > kBatchFill) {
+            if (count) {
+                const int r = warp_flush_batch(src, batch_ip, dst, op, cap, count, tab, lane);
+                if (r < 0) return r;
+                count = 0;
+                __syncwarp();
+            }
+            if (other) {
+                const int r = warp_decode_one(src, clen, dst, cap, ip, op, lane);
+                if (r < 0) return r;
+                if (r == 0) break;
+            }
+            batch_ip = ip;
+        }
     }
     return (int64_t)op;
 }
@@ -181,6 +312,7 @@ __device__ __forceinline__ uint32_t check_header(const uint8_t *fr, uint32_t fle
 }
 
 __global__ void __launch_bounds__(kCodecThreads) lz4_decode_kernel(DecodeArgs a) {
+    __shared__ SeqTable seq_tables[kCodecWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t f = blockIdx.x * kCodecWarps + warp;
     if (f >= a.nframes) return;
@@ -214,7 +346,7 @@ __global__ void __launch_bounds__(kCodecThreads) lz4_decode_kernel(DecodeArgs a)
                 else { warp_copy(out, fr + 16, plen, lane); produced = plen; }
             } else {
                 const uint32_t dcap = cap < norig ? cap : norig;
-                const int64_t got = warp_lz4_decode(fr + 16, plen, out, dcap, lane);
+                const int64_t got = warp_lz4_decode(fr + 16, plen, out, dcap, &seq_tables[warp], lane);
                 if (got == -1) st = kEDecompressionFailed;            // blosc.go:410-413
                 else if (got == -2) st = dcap == norig ? kEDecompressionFailed : kEDstTooSmall;
                 else if ((uint64_t)got != norig) { st = kESizeMismatch; produced = (uint32_t)got; }  // blosc.go:429-431
