@@ -37,19 +37,30 @@ struct b2b_ctx {
     int sm_count = 148;
     std::mutex mu;
     cudaStream_t stream = nullptr;     // for the host-pointer entry points
-    uint8_t *arena = nullptr;          // device scratch, grow-only
+    uint8_t *arena = nullptr;          // device scratch in use, grow-only (= arenas[cur_arena])
     size_t arena_cap = 0;
-    // device staging of the host-pointer paths: {in, out, tables} x 2 pipeline slots
-    uint8_t *hbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t hcap[6] = {0, 0, 0, 0, 0, 0};
-    cudaStream_t s_in = nullptr, s_out = nullptr;     // H2D / D2H streams of the host batch pipeline
-    cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
-    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
+    // arena 0 serves the device-pointer entry points; 1..kSlots the chunks of the host pipeline, whose
+    // kernels run on one stream per slot so that small chunks overlap on the device
+    uint8_t *arenas[5] = {};
+    size_t arena_caps[5] = {};
+    int cur_arena = 0;
+    cudaStream_t s_k[4] = {};
+    // device staging of the host-pointer paths: {in, out, tables} x kSlots pipeline slots, and one
+    // pinned host table block per slot (offsets / lengths / status travel through it, so that no
+    // copy of the pipeline ever touches pageable memory and blocks the host)
+    static constexpr int kSlots = 4;
+    uint8_t *hbuf[3 * kSlots] = {};
+    size_t hcap[3 * kSlots] = {};
+    uint8_t *ptab[kSlots] = {};
+    size_t ptab_cap[kSlots] = {};
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_tab = nullptr;   // H2D / D2H / table streams
+    cudaEvent_t ev_in_ready[kSlots] = {}, ev_in_free[kSlots] = {};
+    cudaEvent_t ev_done[kSlots] = {}, ev_out_free[kSlots] = {}, ev_tab[kSlots] = {};
     int opt_quirk = 0;
     int opt_filter_ctas_per_sm = 0;
     int opt_hash_log = 0;              // 0: default (kHashLogDefault)
     uint32_t opt_tune[4] = {0, 0, 0, 0};   // encoder experiment knobs (0: built-in default)
-    uint64_t opt_stage_bytes = 256ull << 20;
+    uint64_t opt_stage_bytes = 128ull << 20;
     uint64_t launches = 0;
     std::string last_err;
 };
@@ -115,9 +126,17 @@ int ensure_arena(b2b_ctx *ctx, uint64_t bytes) {
     CU(ctx, cudaDeviceSynchronize());
     if (ctx->arena) CU(ctx, cudaFree(ctx->arena));
     ctx->arena = nullptr; ctx->arena_cap = 0;
+    ctx->arenas[ctx->cur_arena] = nullptr; ctx->arena_caps[ctx->cur_arena] = 0;
     CU(ctx, cudaMalloc(&ctx->arena, bytes));
     ctx->arena_cap = bytes;
+    ctx->arenas[ctx->cur_arena] = ctx->arena; ctx->arena_caps[ctx->cur_arena] = bytes;
     return B2B_OK;
+}
+
+void select_arena(b2b_ctx *ctx, int i) {
+    ctx->arenas[ctx->cur_arena] = ctx->arena; ctx->arena_caps[ctx->cur_arena] = ctx->arena_cap;
+    ctx->cur_arena = i;
+    ctx->arena = ctx->arenas[i]; ctx->arena_cap = ctx->arena_caps[i];
 }
 
 // grow-only device staging buffer i of the host-pointer entry points
@@ -131,6 +150,20 @@ int ensure_hbuf(b2b_ctx *ctx, int i, uint64_t bytes, uint8_t **out) {
         ctx->hcap[i] = bytes;
     }
     *out = ctx->hbuf[i];
+    return B2B_OK;
+}
+
+// grow-only pinned host table block of pipeline slot i
+int ensure_ptab(b2b_ctx *ctx, int i, uint64_t bytes, uint8_t **out) {
+    bytes = align_up(bytes + 256, 1 << 16);
+    if (bytes > ctx->ptab_cap[i]) {
+        CU(ctx, cudaDeviceSynchronize());
+        if (ctx->ptab[i]) CU(ctx, cudaFreeHost(ctx->ptab[i]));
+        ctx->ptab[i] = nullptr; ctx->ptab_cap[i] = 0;
+        CU(ctx, cudaHostAlloc((void **)&ctx->ptab[i], bytes, cudaHostAllocDefault));
+        ctx->ptab_cap[i] = bytes;
+    }
+    *out = ctx->ptab[i];
     return B2B_OK;
 }
 
@@ -430,12 +463,15 @@ int b2b_init(int device, b2b_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; i++)
-        ok = cudaEventCreateWithFlags(&ctx->ev_in_ready[i], cudaEventDisableTiming) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_tab, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < b2b_ctx::kSlots && ok; i++)
+        ok = cudaStreamCreateWithFlags(&ctx->s_k[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_in_ready[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_in_free[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ev_out_free[i], cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&ctx->ev_out_free[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_tab[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { b2b_destroy(ctx); return B2B_ECUDA; }
     *out = ctx;
     return B2B_OK;
@@ -447,11 +483,16 @@ void b2b_destroy(b2b_ctx *ctx) {
     cudaDeviceSynchronize();
     fold_timings(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    if (ctx->arena) cudaFree(ctx->arena);
-    for (int i = 0; i < 6; i++) if (ctx->hbuf[i]) cudaFree(ctx->hbuf[i]);
+    select_arena(ctx, 0);
+    for (int i = 0; i < 5; i++) if (ctx->arenas[i]) cudaFree(ctx->arenas[i]);
+    for (int i = 0; i < 4; i++) if (ctx->s_k[i]) cudaStreamDestroy(ctx->s_k[i]);
+    for (int i = 0; i < 3 * b2b_ctx::kSlots; i++) if (ctx->hbuf[i]) cudaFree(ctx->hbuf[i]);
+    for (int i = 0; i < b2b_ctx::kSlots; i++) if (ctx->ptab[i]) cudaFreeHost(ctx->ptab[i]);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
-    for (int i = 0; i < 2; i++) {
+    if (ctx->s_tab) cudaStreamDestroy(ctx->s_tab);
+    for (int i = 0; i < b2b_ctx::kSlots; i++) {
+        if (ctx->ev_tab[i]) cudaEventDestroy(ctx->ev_tab[i]);
         if (ctx->ev_in_ready[i]) cudaEventDestroy(ctx->ev_in_ready[i]);
         if (ctx->ev_in_free[i]) cudaEventDestroy(ctx->ev_in_free[i]);
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
@@ -474,7 +515,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
             ctx->opt_hash_log = (int)value; return B2B_OK;
         case B2B_OPT_KERNEL_TIMING: ctx->opt_timing = value != 0; return B2B_OK;
         case 100: case 101: case 102: case 103: ctx->opt_tune[option - 100] = (uint32_t)value; return B2B_OK;
-        case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (256ull << 20); return B2B_OK;
+        case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (128ull << 20); return B2B_OK;
         default: return B2B_EINVAL;
     }
 }
@@ -619,11 +660,17 @@ int b2b_shuffle(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, const voi
     return rc;
 }
 
-// Host batches run as a 2-slot pipeline over chunks of frames: H2D of chunk k+1 (stream s_in)
-// overlaps the kernels of chunk k (ctx->stream) and the D2H of chunk k-1 (stream s_out).  The
-// kernels of successive chunks share the scratch arena, which is safe because they are
-// ordered on one stream.  Pinned caller buffers are DMA'd directly; pageable ones make the
-// copies synchronous (still correct).
+// Host batches run as a kSlots-deep pipeline over chunks of frames (B2B_OPT_HOST_STAGE_BYTES each):
+//   s_in    H2D of the chunk's bytes and of its tables (from the slot's pinned table block)
+//   s_k[i]  the kernels of the chunk in slot i, with the slot's own scratch arena: a chunk is far
+//           too small to fill the device (one warp works a 64 KiB segment / one frame serially for
+//           about a millisecond), so the chunks in flight have to overlap on the device as well
+//   s_tab   D2H of the chunk's result tables into the pinned block
+//   s_out   D2H of the chunk's bytes
+// The host only ever waits for a chunk's TABLES (one chunk behind the one it just launched), never
+// for a bulk copy, so H2D of chunk k+1, the kernels of chunk k and D2H of chunk k-1 overlap and
+// both PCIe directions stay busy.  Pinned caller buffers are DMA'd directly; pageable ones make
+// the bulk copies synchronous (still correct).
 struct HostChunk { uint32_t f0, f1; uint64_t lo, hi; uint32_t max_len; };
 
 static std::vector<HostChunk> split_chunks(const uint64_t *off, const uint32_t *len, uint32_t nframes,
@@ -644,6 +691,16 @@ static std::vector<HostChunk> split_chunks(const uint64_t *off, const uint32_t *
     return out;
 }
 
+static int sync_pipeline(b2b_ctx *ctx, cudaError_t e, int rc) {
+    const cudaError_t e1 = cudaStreamSynchronize(ctx->s_out), e2 = cudaStreamSynchronize(ctx->s_tab);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < b2b_ctx::kSlots; i++) { const cudaError_t ek = cudaStreamSynchronize(ctx->s_k[i]); if (e3 == cudaSuccess) e3 = ek; }
+    const cudaError_t e4 = cudaStreamSynchronize(ctx->s_in);
+    if (e == cudaSuccess) e = e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3 != cudaSuccess ? e3 : e4;
+    if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return B2B_ECUDA; }
+    return rc;
+}
+
 int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, const uint32_t *src_len,
                        uint32_t nframes, int shuffle, int64_t typesize, void *dst, uint64_t dst_cap,
                        uint64_t *frame_off, uint32_t *frame_len, uint32_t *status, uint64_t *total_out) {
@@ -652,86 +709,94 @@ int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, c
     if (!src || !src_off || !src_len || !dst || !frame_off || !frame_len || !status) return B2B_EINVAL;
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
+    constexpr int S = b2b_ctx::kSlots;
     const uint8_t *hsrc = static_cast<const uint8_t *>(src);
     uint8_t *hdst = static_cast<uint8_t *>(dst);
     const std::vector<HostChunk> chunks = split_chunks(src_off, src_len, nframes, ctx->opt_stage_bytes);
-    std::vector<uint64_t> rel(nframes);
-    struct Pending { bool live = false; uint32_t f0 = 0, n = 0; int slot = 0; uint64_t h_total = 0; };
-    Pending prev;
     uint64_t running = 0;
     int rc = B2B_OK;
     cudaError_t e = cudaSuccess;
-    uint8_t *d_in[2], *d_out[2], *d_tab[2];
-    uint64_t tab_sz[2] = {0, 0};
+    uint8_t *d_out[S] = {};
+    // table block of a chunk of n frames (same layout on the device and in the pinned block):
+    //   [src_off u64 n][frame_off u64 n][src_len u32 n][frame_len u32 n][status u32 n][total u64]
+    auto layout = [](uint32_t n, uint64_t &a8, uint64_t &a4) { a8 = align_up(8ull * n, 256); a4 = align_up(4ull * n, 256); };
 
-    // drain: read back the tables of the previous chunk, then its packed bytes
-    auto drain = [&](Pending &p) -> int {
-        if (!p.live) return B2B_OK;
-        p.live = false;
-        const uint64_t a8 = align_up(8ull * p.n, 256), a4 = align_up(4ull * p.n, 256);
-        uint8_t *t = d_tab[p.slot];
-        const uint64_t *d_frame_off = (const uint64_t *)(t + a8);
-        const uint32_t *d_frame_len = (const uint32_t *)(t + 2 * a8 + a4);
-        const uint32_t *d_status = (const uint32_t *)(t + 2 * a8 + 2 * a4);
-        const uint64_t *d_total = (const uint64_t *)(t + 2 * a8 + 3 * a4);
-        cudaStream_t so = ctx->s_out;
-        CU(ctx, cudaStreamWaitEvent(so, ctx->ev_done[p.slot], 0));
-        CU(ctx, cudaMemcpyAsync(frame_off + p.f0, d_frame_off, 8ull * p.n, cudaMemcpyDeviceToHost, so));
-        CU(ctx, cudaMemcpyAsync(frame_len + p.f0, d_frame_len, 4ull * p.n, cudaMemcpyDeviceToHost, so));
-        CU(ctx, cudaMemcpyAsync(status + p.f0, d_status, 4ull * p.n, cudaMemcpyDeviceToHost, so));
-        CU(ctx, cudaMemcpyAsync(&p.h_total, d_total, 8, cudaMemcpyDeviceToHost, so));
-        CU(ctx, cudaStreamSynchronize(so));
-        if (running + p.h_total > dst_cap) return B2B_EDST_TOO_SMALL;
-        CU(ctx, cudaMemcpyAsync(hdst + running, d_out[p.slot], p.h_total, cudaMemcpyDeviceToHost, so));
-        CU(ctx, cudaEventRecord(ctx->ev_out_free[p.slot], so));
-        for (uint32_t i = 0; i < p.n; i++) frame_off[p.f0 + i] += running;
-        running += p.h_total;
+    // retire: the chunk's tables are on the host -> ship its packed bytes, publish its tables
+    auto retire = [&](size_t k) -> int {
+        const HostChunk &c = chunks[k];
+        const int slot = (int)(k % S);
+        const uint32_t n = c.f1 - c.f0;
+        uint64_t a8, a4; layout(n, a8, a4);
+        CU(ctx, cudaEventSynchronize(ctx->ev_tab[slot]));
+        const uint8_t *t = ctx->ptab[slot];
+        const uint64_t *h_frame_off = (const uint64_t *)(t + a8);
+        const uint32_t *h_frame_len = (const uint32_t *)(t + 2 * a8 + a4);
+        const uint32_t *h_status = (const uint32_t *)(t + 2 * a8 + 2 * a4);
+        const uint64_t h_total = *(const uint64_t *)(t + 2 * a8 + 3 * a4);
+        if (running + h_total > dst_cap) return B2B_EDST_TOO_SMALL;
+        if (h_total) CU(ctx, cudaMemcpyAsync(hdst + running, d_out[slot], h_total, cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(ctx, cudaEventRecord(ctx->ev_out_free[slot], ctx->s_out));
+        for (uint32_t i = 0; i < n; i++) frame_off[c.f0 + i] = h_frame_off[i] + running;
+        memcpy(frame_len + c.f0, h_frame_len, 4ull * n);
+        memcpy(status + c.f0, h_status, 4ull * n);
+        running += h_total;
         return B2B_OK;
     };
 
+    size_t launched = 0, retired = 0;
     for (size_t k = 0; k < chunks.size() && rc == B2B_OK; k++) {
         const HostChunk &c = chunks[k];
-        const int slot = (int)(k & 1);
+        const int slot = (int)(k % S);
         const uint32_t n = c.f1 - c.f0;
         const uint64_t span = c.hi - c.lo, out_cap = span + 31ull * n + 64;
-        const uint64_t a8 = align_up(8ull * n, 256), a4 = align_up(4ull * n, 256);
-        tab_sz[slot] = 2 * a8 + 3 * a4 + 256;
-        rc = ensure_hbuf(ctx, 3 * slot + 0, span + 64, &d_in[slot]);
+        uint64_t a8, a4; layout(n, a8, a4);
+        const uint64_t tab_bytes = 2 * a8 + 3 * a4 + 256;
+        uint8_t *d_in = nullptr, *d_tab = nullptr, *h_tab = nullptr;
+        // a slot is reused kSlots chunks later: that chunk must have been retired (its tables read)
+        while (retired + S <= k && rc == B2B_OK) rc = retire(retired++);
+        if (rc) break;
+        rc = ensure_hbuf(ctx, 3 * slot + 0, span + 64, &d_in);
         if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 1, out_cap, &d_out[slot]);
-        if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 2, tab_sz[slot], &d_tab[slot]);
+        if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 2, tab_bytes, &d_tab);
+        if (rc == B2B_OK) rc = ensure_ptab(ctx, slot, tab_bytes, &h_tab);
         if (rc) break;
-        uint8_t *t = d_tab[slot];
-        uint64_t *d_src_off = (uint64_t *)t, *d_frame_off = (uint64_t *)(t + a8);
-        uint32_t *d_src_len = (uint32_t *)(t + 2 * a8), *d_frame_len = (uint32_t *)(t + 2 * a8 + a4);
-        uint32_t *d_status = (uint32_t *)(t + 2 * a8 + 2 * a4);
-        uint64_t *d_total = (uint64_t *)(t + 2 * a8 + 3 * a4);
-        for (uint32_t f = c.f0; f < c.f1; f++) rel[f] = src_off[f] - c.lo;
-        // H2D of this chunk (after the kernels that last read this slot's input are done)
-        if (k >= 2) e = cudaStreamWaitEvent(ctx->s_in, ctx->ev_in_free[slot], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in[slot], hsrc + c.lo, span, cudaMemcpyHostToDevice, ctx->s_in);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_src_off, rel.data() + c.f0, 8ull * n, cudaMemcpyHostToDevice, ctx->s_in);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_src_len, src_len + c.f0, 4ull * n, cudaMemcpyHostToDevice, ctx->s_in);
+        uint64_t *d_src_off = (uint64_t *)d_tab, *d_frame_off = (uint64_t *)(d_tab + a8);
+        uint32_t *d_src_len = (uint32_t *)(d_tab + 2 * a8), *d_frame_len = (uint32_t *)(d_tab + 2 * a8 + a4);
+        uint32_t *d_status = (uint32_t *)(d_tab + 2 * a8 + 2 * a4);
+        uint64_t *d_total = (uint64_t *)(d_tab + 2 * a8 + 3 * a4);
+        uint64_t *h_src_off = (uint64_t *)h_tab;
+        uint32_t *h_src_len = (uint32_t *)(h_tab + 2 * a8);
+        for (uint32_t i = 0; i < n; i++) h_src_off[i] = src_off[c.f0 + i] - c.lo;
+        memcpy(h_src_len, src_len + c.f0, 4ull * n);
+        // H2D (the kernels that last read this slot's input must be done)
+        if (k >= (size_t)S) e = cudaStreamWaitEvent(ctx->s_in, ctx->ev_in_free[slot], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, hsrc + c.lo, span, cudaMemcpyHostToDevice, ctx->s_in);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_src_off, h_src_off, 8ull * n, cudaMemcpyHostToDevice, ctx->s_in);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_src_len, h_src_len, 4ull * n, cudaMemcpyHostToDevice, ctx->s_in);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_ready[slot], ctx->s_in);
-        // kernels
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_in_ready[slot], 0);
-        if (e == cudaSuccess && k >= 2) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_out_free[slot], 0);
+        // kernels (the D2H that last read this slot's output must be done)
+        cudaStream_t sk = ctx->s_k[slot];
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(sk, ctx->ev_in_ready[slot], 0);
+        if (e == cudaSuccess && k >= (size_t)S) e = cudaStreamWaitEvent(sk, ctx->ev_out_free[slot], 0);
         if (e != cudaSuccess) break;
-        rc = compress_batch_dev_locked(ctx, d_in[slot], d_src_off, d_src_len, n, span, c.max_len, shuffle, typesize,
-                                       d_out[slot], out_cap, d_frame_off, d_frame_len, d_status, d_total, ctx->stream);
+        select_arena(ctx, 1 + slot);
+        rc = compress_batch_dev_locked(ctx, d_in, d_src_off, d_src_len, n, span, c.max_len, shuffle, typesize,
+                                       d_out[slot], out_cap, d_frame_off, d_frame_len, d_status, d_total, sk);
+        select_arena(ctx, 0);
         if (rc) break;
-        e = cudaEventRecord(ctx->ev_done[slot], ctx->stream);
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_free[slot], ctx->stream);
+        e = cudaEventRecord(ctx->ev_done[slot], sk);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_free[slot], sk);
+        // result tables -> pinned block
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_tab, ctx->ev_done[slot], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_tab + a8, d_tab + a8, a8 + 3 * a4 + 8 - 0, cudaMemcpyDeviceToHost, ctx->s_tab);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_tab[slot], ctx->s_tab);
         if (e != cudaSuccess) break;
-        // while this chunk computes, ship the previous one
-        rc = drain(prev);
-        prev.live = true; prev.f0 = c.f0; prev.n = n; prev.slot = slot;
+        launched = k + 1;
+        // while this chunk is in flight, ship the one before it
+        while (retired + 1 < launched && rc == B2B_OK) rc = retire(retired++);
     }
-    if (rc == B2B_OK && e == cudaSuccess) rc = drain(prev);
-    cudaError_t e2 = cudaStreamSynchronize(ctx->s_out);
-    cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
-    cudaError_t e4 = cudaStreamSynchronize(ctx->s_in);
-    if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : (e3 != cudaSuccess ? e3 : e4);
-    if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return B2B_ECUDA; }
+    while (rc == B2B_OK && e == cudaSuccess && retired < launched) rc = retire(retired++);
+    rc = sync_pipeline(ctx, e, rc);
     if (rc == B2B_OK && total_out) *total_out = running;
     return rc;
 }
@@ -746,6 +811,7 @@ int b2b_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame
     if (!dst && dst_cap) return B2B_EINVAL;
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
+    constexpr int S = b2b_ctx::kSlots;
     const uint8_t *hf = static_cast<const uint8_t *>(frames);
     uint8_t *hdst = static_cast<uint8_t *>(dst);
     // capacity of slot f: what the header announces, clipped to the caller's buffer and to what an
@@ -763,59 +829,78 @@ int b2b_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame
     }
     // chunks by OUTPUT bytes (the larger side)
     const std::vector<HostChunk> chunks = split_chunks(dst_off, cap.data(), nframes, ctx->opt_stage_bytes);
-    std::vector<uint64_t> rel_in(nframes), rel_out(nframes);
     int rc = B2B_OK;
     cudaError_t e = cudaSuccess;
-    uint8_t *d_in[2], *d_out[2], *d_tab[2];
+    // table block: [frame_off u64 n][dst_off u64 n][frame_len u32 n][cap u32 n][out_len u32 n][status u32 n]
+    auto retire = [&](size_t k) -> int {
+        const HostChunk &c = chunks[k];
+        const int slot = (int)(k % S);
+        const uint32_t n = c.f1 - c.f0;
+        const uint64_t a8 = align_up(8ull * n, 256), a4 = align_up(4ull * n, 256);
+        CU(ctx, cudaEventSynchronize(ctx->ev_tab[slot]));
+        const uint8_t *t = ctx->ptab[slot];
+        memcpy(out_len + c.f0, t + 2 * a8 + 2 * a4, 4ull * n);
+        memcpy(status + c.f0, t + 2 * a8 + 3 * a4, 4ull * n);
+        return B2B_OK;
+    };
+    size_t launched = 0, retired = 0;
     for (size_t k = 0; k < chunks.size() && rc == B2B_OK; k++) {
         const HostChunk &c = chunks[k];
-        const int slot = (int)(k & 1);
+        const int slot = (int)(k % S);
         const uint32_t n = c.f1 - c.f0;
+        while (retired + S <= k && rc == B2B_OK) rc = retire(retired++);
+        if (rc) break;
         uint64_t in_lo = ~0ull, in_hi = 0; uint32_t max_cap = 0;
         for (uint32_t f = c.f0; f < c.f1; f++) {
             in_lo = std::min(in_lo, frame_off[f]); in_hi = std::max(in_hi, frame_off[f] + frame_len[f]);
             max_cap = std::max(max_cap, cap[f]);
         }
         const uint64_t in_span = in_hi - in_lo, out_span = c.hi - c.lo;
-        for (uint32_t f = c.f0; f < c.f1; f++) { rel_in[f] = frame_off[f] - in_lo; rel_out[f] = dst_off[f] - c.lo; }
         const uint64_t a8 = align_up(8ull * n, 256), a4 = align_up(4ull * n, 256);
-        rc = ensure_hbuf(ctx, 3 * slot + 0, in_span + 64, &d_in[slot]);
-        if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 1, out_span + 64, &d_out[slot]);
-        if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 2, 2 * a8 + 4 * a4 + 256, &d_tab[slot]);
+        const uint64_t tab_bytes = 2 * a8 + 4 * a4 + 256;
+        uint8_t *d_in = nullptr, *d_out = nullptr, *d_tab = nullptr, *h_tab = nullptr;
+        rc = ensure_hbuf(ctx, 3 * slot + 0, in_span + 64, &d_in);
+        if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 1, out_span + 64, &d_out);
+        if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 2, tab_bytes, &d_tab);
+        if (rc == B2B_OK) rc = ensure_ptab(ctx, slot, tab_bytes, &h_tab);
         if (rc) break;
-        uint8_t *t = d_tab[slot];
-        uint64_t *d_frame_off = (uint64_t *)t, *d_dst_off = (uint64_t *)(t + a8);
-        uint32_t *d_frame_len = (uint32_t *)(t + 2 * a8), *d_cap = (uint32_t *)(t + 2 * a8 + a4);
-        uint32_t *d_out_len = (uint32_t *)(t + 2 * a8 + 2 * a4), *d_status = (uint32_t *)(t + 2 * a8 + 3 * a4);
-        if (k >= 2) e = cudaStreamWaitEvent(ctx->s_in, ctx->ev_in_free[slot], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in[slot], hf + in_lo, in_span, cudaMemcpyHostToDevice, ctx->s_in);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_frame_off, rel_in.data() + c.f0, 8ull * n, cudaMemcpyHostToDevice, ctx->s_in);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dst_off, rel_out.data() + c.f0, 8ull * n, cudaMemcpyHostToDevice, ctx->s_in);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_frame_len, frame_len + c.f0, 4ull * n, cudaMemcpyHostToDevice, ctx->s_in);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_cap, cap.data() + c.f0, 4ull * n, cudaMemcpyHostToDevice, ctx->s_in);
+        uint64_t *d_frame_off = (uint64_t *)d_tab, *d_dst_off = (uint64_t *)(d_tab + a8);
+        uint32_t *d_frame_len = (uint32_t *)(d_tab + 2 * a8), *d_cap = (uint32_t *)(d_tab + 2 * a8 + a4);
+        uint32_t *d_out_len = (uint32_t *)(d_tab + 2 * a8 + 2 * a4), *d_status = (uint32_t *)(d_tab + 2 * a8 + 3 * a4);
+        uint64_t *h_frame_off = (uint64_t *)h_tab, *h_dst_off = (uint64_t *)(h_tab + a8);
+        for (uint32_t i = 0; i < n; i++) {
+            h_frame_off[i] = frame_off[c.f0 + i] - in_lo;
+            h_dst_off[i] = dst_off[c.f0 + i] - c.lo;
+        }
+        memcpy(h_tab + 2 * a8, frame_len + c.f0, 4ull * n);
+        memcpy(h_tab + 2 * a8 + a4, cap.data() + c.f0, 4ull * n);
+        if (k >= (size_t)S) e = cudaStreamWaitEvent(ctx->s_in, ctx->ev_in_free[slot], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, hf + in_lo, in_span, cudaMemcpyHostToDevice, ctx->s_in);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab, h_tab, 2 * a8 + 2 * a4, cudaMemcpyHostToDevice, ctx->s_in);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_ready[slot], ctx->s_in);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_in_ready[slot], 0);
-        if (e == cudaSuccess && k >= 2) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_out_free[slot], 0);
+        cudaStream_t sk = ctx->s_k[slot];
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(sk, ctx->ev_in_ready[slot], 0);
+        if (e == cudaSuccess && k >= (size_t)S) e = cudaStreamWaitEvent(sk, ctx->ev_out_free[slot], 0);
         if (e != cudaSuccess) break;
-        rc = decompress_batch_dev_locked(ctx, d_in[slot], d_frame_off, d_frame_len, n, typesize_override, d_out[slot],
-                                         d_dst_off, d_cap, out_span, max_cap, d_out_len, d_status, ctx->stream);
+        select_arena(ctx, 1 + slot);
+        rc = decompress_batch_dev_locked(ctx, d_in, d_frame_off, d_frame_len, n, typesize_override, d_out,
+                                         d_dst_off, d_cap, out_span, max_cap, d_out_len, d_status, sk);
+        select_arena(ctx, 0);
         if (rc) break;
-        e = cudaEventRecord(ctx->ev_done[slot], ctx->stream);
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_free[slot], ctx->stream);
-        // D2H of this chunk on the output stream (overlaps the next chunk's H2D and kernels)
+        e = cudaEventRecord(ctx->ev_done[slot], sk);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_free[slot], sk);
+        // bytes out on s_out, result tables on s_tab
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[slot], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out_len + c.f0, d_out_len, 4ull * n, cudaMemcpyDeviceToHost, ctx->s_out);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(status + c.f0, d_status, 4ull * n, cudaMemcpyDeviceToHost, ctx->s_out);
-        if (e == cudaSuccess && out_span) e = cudaMemcpyAsync(hdst + c.lo, d_out[slot], out_span, cudaMemcpyDeviceToHost, ctx->s_out);
+        if (e == cudaSuccess && out_span) e = cudaMemcpyAsync(hdst + c.lo, d_out, out_span, cudaMemcpyDeviceToHost, ctx->s_out);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_out_free[slot], ctx->s_out);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_tab, ctx->ev_done[slot], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_tab + 2 * a8 + 2 * a4, d_tab + 2 * a8 + 2 * a4, 2 * a4, cudaMemcpyDeviceToHost, ctx->s_tab);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_tab[slot], ctx->s_tab);
         if (e != cudaSuccess) break;
+        launched = k + 1;
     }
-    cudaError_t e2 = cudaStreamSynchronize(ctx->s_out);
-    cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
-    cudaError_t e4 = cudaStreamSynchronize(ctx->s_in);
-    if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : (e3 != cudaSuccess ? e3 : e4);
-    if (e != cudaSuccess) { ctx->last_err = cudaGetErrorString(e); return B2B_ECUDA; }
-    return rc;
+    while (rc == B2B_OK && e == cudaSuccess && retired < launched) rc = retire(retired++);
+    return sync_pipeline(ctx, e, rc);
 }
 
 int b2b_compress(b2b_ctx *ctx, const void *src, size_t n, int codec, int level, int shuffle,

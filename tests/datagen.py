@@ -73,3 +73,45 @@ def corpus(n):
         "period7_noise": (np.tile(np.arange(7, dtype=np.uint8), n // 7 + 1)[:n]
                           ^ (random_bytes(n, 5) > 250).astype(np.uint8)),
     }
+
+
+def strip_adversarial(n, seed=0):
+    """Inputs aimed at the strip-parallel encoder (61-byte strips, 32 per step, 64 KiB segments)
+    and the batched decoder (32-position token windows, <= 32 sequences per batch): periods equal
+    to / around the strip and the step, matches that span strips, steps and segments, runs broken
+    by single bytes, sequences with exactly one extension byte, dense 4-byte matches."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for period in (1, 2, 3, 4, 5, 60, 61, 62, 64, 122, 183, 244, 1951, 1952, 1953, 4096):
+        base = rng.integers(0, 256, period, dtype=np.uint8)
+        out[f"period{period}"] = np.tile(base, n // period + 1)[:n].copy()
+    # runs of random length (1..400) of random bytes: overlapping matches of every length class
+    runs = []
+    total = 0
+    while total < n:
+        k = int(rng.integers(1, 401)); runs.append(np.full(k, rng.integers(0, 256), dtype=np.uint8)); total += k
+    out["runs"] = np.concatenate(runs)[:n].copy()
+    # noise with a copy of an earlier chunk every ~200 bytes (matches 4..300 long at far offsets)
+    a = rng.integers(0, 256, n, dtype=np.uint8)
+    pos = 300
+    while pos + 310 < n:
+        ln = int(rng.integers(4, 300)); src = int(rng.integers(0, pos - ln)) if pos > ln else 0
+        if pos - src < 65535:
+            a[pos:pos + ln] = a[src:src + ln]
+        pos += ln + int(rng.integers(1, 200))
+    out["copies"] = a
+    # literal runs of 15..40 bytes between 4..8-byte matches (one-extension-byte tokens)
+    b = rng.integers(0, 256, n, dtype=np.uint8)
+    pos = 64
+    while pos + 64 < n:
+        ln = int(rng.integers(4, 9)); b[pos:pos + ln] = b[pos - 50:pos - 50 + ln]; pos += ln + int(rng.integers(15, 41))
+    out["lit_ext"] = b
+    # two-symbol text: dense short matches, long dependency chains inside a decode batch
+    out["binary_text"] = rng.integers(0, 2, n, dtype=np.uint8) * 7 + 65
+    # a long match that starts in one strip / segment and ends far in a later one
+    c = rng.integers(0, 256, n, dtype=np.uint8)
+    if n > 3000:
+        half = n // 2
+        c[half:half + half // 2] = c[10:10 + half // 2] if half - 10 < 65535 else c[half - 65000:half - 65000 + half // 2]
+    out["long_copy"] = c
+    return out

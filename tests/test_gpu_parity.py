@@ -205,6 +205,28 @@ def test_gpu_frames_decode_through_oracle(ctx, orc, n):
             assert ctx.decompress(fr.tobytes()) == data.tobytes()               # and back through K4
 
 
+@pytest.mark.parametrize("n", [61, 122, 1951, 1952, 1953, 3904, 65535, 65536, 65537, 65536 + 1952, 131072 + 61, 300000])
+def test_strip_encoder_and_batched_decoder_adversarial(ctx, orc, n):
+    """Round trips aimed at the strip / step / segment boundaries of K3 and the batch logic of K4:
+    GPU frame -> oracle decoder, liblz4 referee and GPU decoder; oracle frame -> GPU decoder."""
+    for name, data in dg.strip_adversarial(n, seed=n).items():
+        for sh, T in ((0, 1), (1, 4)):
+            fr = np.frombuffer(ctx.compress(data, 1, 5, sh, T), dtype=np.uint8)
+            rc, back = orc.decompress(fr)
+            assert rc == 0 and np.array_equal(back, data), (name, n, sh, T)
+            if not rs.hdr(fr)["flags"] & 0x2 and orc.liblz4() is not None:
+                filt = orc.shuffle(data, T) if sh else data
+                ref = orc.liblz4_decompress(fr[16:], n)
+                assert ref is not None and np.array_equal(ref, filt), (name, n, sh, T)
+            assert ctx.decompress(fr.tobytes()) == data.tobytes(), (name, n, sh, T)
+            rc, ofr = orc.compress(data, orc.LZ4, 5, sh, T)
+            assert ctx.decompress(ofr.tobytes()) == data.tobytes(), (name, n, sh, T)
+            if orc.liblz4() is not None:
+                payload = orc.liblz4_compress(orc.shuffle(data, T) if sh else data)
+                hfr = rs.make_header(codec=1, flags=0x1 if sh else 0, typesize=T, norig=n, ncomp=16 + payload.size) + payload.tobytes()
+                assert ctx.decompress(hfr) == data.tobytes(), (name, n, sh, T)
+
+
 def test_compressed_size_within_one_percent_of_oracle(ctx, orc):
     """north_star: compressed size within 1% of the reference at the same level (vs the restated
     pierrec compressor: parity unpinned).  On the configs' data, 256 KiB frames."""
