@@ -420,7 +420,12 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                         }
                         if (ll <= kLaneLitEmit) {
                             const uint8_t *lit = org + pe;
-                            for (uint32_t i = 0; i < ll; i++) b[i] = lit[i];
+                            uint32_t i = 0;
+                            for (; i + 4 <= ll; i += 4) {
+                                const uint8_t v0 = lit[i], v1 = lit[i + 1], v2 = lit[i + 2], v3 = lit[i + 3];
+                                b[i] = v0; b[i + 1] = v1; b[i + 2] = v2; b[i + 3] = v3;
+                            }
+                            for (; i < ll; i++) b[i] = lit[i];
                         } else {
                             if (ng == 0) { g_dst0 = (uint32_t)(b - body); g_src0 = pe; g_len0 = ll; }
                             else { g_dst1 = (uint32_t)(b - body); g_src1 = pe; g_len1 = ll; }

@@ -220,28 +220,40 @@ __device__ __forceinline__ int64_t warp_lz4_decode(const uint8_t *__restrict__ s
                                                    uint8_t *dst, uint32_t cap, SeqTable *tab, int lane) {
     if (clen == 0) return 0;
     uint32_t ip = 0, op = 0, count = 0, batch_ip = 0;
-    const uint32_t last = clen - 1;
+    // A window's speculative reads reach at most 305 bytes past its start (31 + token + two
+    // extension bytes + 269 literals + offset).  The last stretch of the stream, where that could
+    // leave it, is decoded a sequence at a time (which also holds all end-of-stream rules).
+    constexpr uint32_t kWindowReach = 306;
     for (;;) {
+        if (clen - ip < kWindowReach) {
+            if (count) {
+                const int r = warp_flush_batch(src, batch_ip, dst, op, cap, count, tab, lane);
+                if (r < 0) return r;
+                count = 0;
+                __syncwarp();
+            }
+            const int r = warp_decode_one(src, clen, dst, cap, ip, op, lane);
+            if (r < 0) return r;
+            if (r == 0) break;
+            batch_ip = ip;
+            continue;
+        }
         // ---- every lane decodes the token that would start at its byte of the window
         const uint32_t p = ip + lane;
         uint32_t nxt = 0xFFFFu, ta = 0, tb = 0;
         {
-            const uint32_t t = src[p < last ? p : last];
-            const uint32_t e1 = src[p + 1 < last ? p + 1 : last];
+            const uint32_t t = src[p], e1 = src[p + 1];
             const bool x1 = (t >> 4) == 15u;
             const uint32_t ll = (t >> 4) + (x1 ? e1 : 0u);
             const uint32_t lit = p + 1 + (x1 ? 1u : 0u);
-            const uint64_t oq = (uint64_t)lit + ll;           // offset bytes at oq, oq + 1
-            const uint32_t o0 = oq < last ? (uint32_t)oq : last, o1 = oq + 1 < last ? (uint32_t)oq + 1 : last;
-            const uint32_t o2 = oq + 2 < last ? (uint32_t)oq + 2 : last;
-            const uint32_t off = (uint32_t)src[o0] | ((uint32_t)src[o1] << 8);
-            const uint32_t e2 = src[o2];
+            const uint32_t oq = lit + ll;                     // offset bytes at oq, oq + 1
+            const uint32_t off = (uint32_t)src[oq] | ((uint32_t)src[oq + 1] << 8);
+            const uint32_t e2 = src[oq + 2];
             const bool x2 = (t & 15u) == 15u;
             const uint32_t ml = (t & 15u) + 4u + (x2 ? e2 : 0u);
-            const bool regular = p < clen && !(x1 && (p + 1 >= clen || e1 == 255u)) && oq + 2 <= clen &&
-                                 !(x2 && (oq + 2 >= clen || e2 == 255u));
+            const bool regular = !(x1 && e1 == 255u) && !(x2 && e2 == 255u);
             if (regular) {
-                nxt = (uint32_t)oq + 2u + (x2 ? 1u : 0u) - ip;
+                nxt = oq + 2u + (x2 ? 1u : 0u) - ip;
                 ta = off | (ll << 16);
                 tb = (lit - batch_ip) | (ml << 16);
             }
@@ -311,7 +323,7 @@ __device__ __forceinline__ uint32_t check_header(const uint8_t *fr, uint32_t fle
     return kOk;
 }
 
-__global__ void __launch_bounds__(kCodecThreads) lz4_decode_kernel(DecodeArgs a) {
+__global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_kernel(DecodeArgs a) {
     __shared__ SeqTable seq_tables[kCodecWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t f = blockIdx.x * kCodecWarps + warp;
