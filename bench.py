@@ -43,6 +43,21 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def committed_traffic(kernel, bytes_per_gpu):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed
+    ncu --set full capture, if that capture was taken at this launch size (else None)."""
+    p = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        if int(t["bytes_per_gpu"]) != int(bytes_per_gpu):
+            return None
+        k = t["kernels"][kernel]
+        return k["dram_read"] + k["dram_write"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def workload_name(total_bytes, nframes):
     return (f"C3: float32 smooth field, {total_bytes / 2**30:g} GiB per GPU = {nframes} frames x 256 KiB, "
             f"LZ4 level 5 + Shuffle1 typesize 4, compress then decompress")
@@ -308,12 +323,19 @@ def run_gpu(args):
             if n:
                 kernels[name] = {"launches": n, "avg_ms": ms / n, "share_of_step": ms / t_total}
         kernels["filter_batch_kernel"]["achieved_gbs_algorithmic"] = 2 * total / (fil_ms / fil_n / 1e3) / 1e9
+        kernels["filter_batch_kernel"]["frac_of_peak"] = kernels["filter_batch_kernel"]["achieved_gbs_algorithmic"] / peak
         kernels["lz4_decode_kernel"]["achieved_gbs_algorithmic"] = (comp_total + total) / (dec_ms / dec_n / 1e3) / 1e9
+        kernels["lz4_decode_kernel"]["frac_of_peak"] = kernels["lz4_decode_kernel"]["achieved_gbs_algorithmic"] / peak
+        for kname in ("filter_batch_kernel", "lz4_decode_kernel", "pack_frames_kernel"):
+            kernels[kname]["traffic"] = committed_traffic(kname, total)
+        traffic = args.traffic_bytes if args.traffic_bytes is not None else committed_traffic("lz4_encode_kernel", total)
         roofline = {"kernel": "lz4_encode_kernel", "bound": "hbm", "achieved": algo_c / (enc_avg / 1e3) / 1e9, "peak": peak,
-                    "unit": "GB/s", "frac": algo_c / (enc_avg / 1e3) / 1e9 / peak, "traffic": args.traffic_bytes,
+                    "unit": "GB/s", "frac": algo_c / (enc_avg / 1e3) / 1e9 / peak, "traffic": traffic,
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": algo_c,
-                    "note": "latency/issue-bound kernel (serial LZ4 parse per frame); see DESIGN.md and profiles/"}
+                    "traffic_source": "profiles/r01b_traffic.json (ncu --set full at this launch size)" if traffic else None,
+                    "note": "dominant kernel of the step; it is issue/latency-bound (per-lane LZ4 match search over a "
+                            "shared-memory hash table), not HBM-bound: DESIGN.md section 4 and profiles/r01b_ncu_summary.md"}
         # e2e through the host-pointer C ABI with pinned host buffers
         e2e = run_e2e(torch, pkg, ctx, args, dev, src, nf, total, world)
         # CPU baseline (oracle port), bounded sample
