@@ -220,6 +220,10 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             const uint32_t cap = send + strip_cap < mlimit ? send + strip_cap : mlimit;
             uint32_t cnt = 0, e = 0, moff = 0, mst = 0, my_last = 0;
             bool ext = false, my_open = false;
+            {   // the next step's strips: bring their lines into L2 while this step is parsed
+                const uint32_t a = si + 32u * strip + 64u * (uint32_t)lane;
+                if (a < mlimit) asm volatile("prefetch.global.L2 [%0];" ::"l"(org + a));
+            }
             while (__any_sync(0xffffffffu, ext || pos < send)) {
                 if (!ext) {
                     if (pos < send) {
@@ -560,7 +564,8 @@ lz4_encode_kernel(EncodeArgs a) {
             const SegMeta m = warp_encode_segment<HL>(frame + B - W, W, L, (uint64_t)n - B - L,
                                                       a.comp + a.comp_off[f] + (uint64_t)s * kSegSlot,
                                                       enc_tables + ((size_t)warp << HL), &enc_lists[warp], lane,
-                                                      a.tune[0] ? a.tune[0] : 256u, a.tune[1] ? a.tune[1] : kStrip,
+                                                      a.tune[0] ? a.tune[0] : 256u,
+                                                      a.tune[1] ? (a.tune[1] < 4u * kListMax ? a.tune[1] : 4u * kListMax) : kStrip,
                                                       a.tune[2] ? a.tune[2] : kStripCap);
             if (lane == 0) a.meta[a.seg_base[f] + s] = m;
             __syncwarp();
