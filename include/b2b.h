@@ -100,7 +100,7 @@ enum {
     B2B_OPT_REF_MEMCPY_QUIRK = 1,
     /* number of CTAs per SM for the persistent filter kernels (tuning; 0 = built-in default) */
     B2B_OPT_FILTER_CTAS_PER_SM = 2,
-    /* host batch path: bytes of uncompressed data per pipeline stage (0 = default 256 MiB) */
+    /* host batch path: bytes of uncompressed data per pipeline chunk (0 = default 128 MiB; 4 chunks in flight) */
     B2B_OPT_HOST_STAGE_BYTES = 3,
     /* log2 of the LZ4 match-finder's shared-memory hash table, 11..14 (0 = default 12).  Larger
      * tables find more matches (ratio) and cost occupancy (speed). */
