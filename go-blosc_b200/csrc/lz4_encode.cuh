@@ -72,6 +72,34 @@ __device__ __forceinline__ uint32_t enc_load32u(const uint8_t *p) {
     return __funnelshift_r(q[0], q[1], 8u * r);
 }
 
+// The input of a segment seen as aligned 32-bit words: w = org rounded down to 4 bytes, sh = what was
+// rounded off.  Byte position p of the segment is byte (p + sh) of w; all index arithmetic is 32-bit
+// and the loads stay in the global address space (LDG with a scaled index).
+struct WordView {
+    const uint32_t *w;
+    uint32_t sh;
+};
+__device__ __forceinline__ WordView word_view(const uint8_t *org) {
+    WordView v;
+    v.sh = (uint32_t)((uintptr_t)org & 3u);
+    v.w = reinterpret_cast<const uint32_t *>(org - v.sh);
+    return v;
+}
+// unaligned 32-bit load at byte position p (same safety rule as enc_load32u)
+__device__ __forceinline__ uint32_t wv_load32(const WordView &v, uint32_t p) {
+    const uint32_t a = p + v.sh;
+    const uint32_t *q = v.w + (a >> 2);
+    return __funnelshift_r(q[0], q[1], a << 3);
+}
+// 8 bytes at position p as two words (three aligned loads)
+__device__ __forceinline__ void wv_load64(const WordView &v, uint32_t p, uint32_t &lo, uint32_t &hi) {
+    const uint32_t a = p + v.sh;
+    const uint32_t *q = v.w + (a >> 2);
+    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+    lo = __funnelshift_r(w0, w1, a << 3);
+    hi = __funnelshift_r(w1, w2, a << 3);
+}
+
 // writes a length extension (value already reduced by 15) at out, returns bytes written
 __device__ __forceinline__ uint32_t warp_put_len_ext(uint8_t *out, uint32_t v, int lane) {
     const uint32_t full = v / 255u, last = v - full * 255u;
@@ -125,14 +153,14 @@ __device__ __forceinline__ void emit_coop(EncState &st, const uint8_t *lit, uint
 }
 
 // 32-lane forward extension: first position >= from where org[pos] != org[pos - offset], capped at mlimit
-__device__ __forceinline__ uint32_t extend_coop(const uint8_t *org, uint32_t from, uint32_t offset,
+__device__ __forceinline__ uint32_t extend_coop(const WordView &in, uint32_t from, uint32_t offset,
                                                 uint32_t mlimit, int lane) {
     uint32_t mend = from;
     for (;;) {
         const uint32_t a = mend + 4u * lane;
         uint32_t x = 0xFFFFFFFFu;
         if (a < mlimit) {
-            x = enc_load32u(org + a) ^ enc_load32u(org + a - offset);
+            x = wv_load32(in, a) ^ wv_load32(in, a - offset);
             const uint32_t avail = mlimit - a;
             if (avail < 4) x |= 0xFFFFFFFFu << (8u * avail);
         }
@@ -195,13 +223,14 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
     if (mfl == 0) return st.m;
     mfl += W; mlimit += W;
 
+    const WordView in = word_view(org);
     for (uint32_t i = lane; i < (1u << HL); i += kWarp) table[i] = 0;
     __syncwarp();
     // warm-up: enter the tail of the previous segment (ascending, so the nearest position wins)
     for (uint32_t q0 = 0; q0 < W; q0 += kWarp) {
         const uint32_t q = q0 + lane;
         if (q + 3 < W) {
-            const uint32_t hv = enc_load32u(org + q) * 2654435761u;
+            const uint32_t hv = wv_load32(in, q) * 2654435761u;
             table[hv >> (32 - HL)] = (((hv >> (17 - HL)) & 0x7FFFu) << 17) | q;
         }
         __syncwarp();
@@ -228,11 +257,8 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                 if (!ext) {
                     if (pos < send) {
                         // ---- four consecutive positions per turn: one 12-byte window, four probes in flight
-                        const uintptr_t pa = (uintptr_t)(org + pos);
-                        const uint32_t r8 = 8u * (uint32_t)(pa & 3u);
-                        const uint32_t *q = reinterpret_cast<const uint32_t *>(pa & ~(uintptr_t)3);
-                        const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
-                        const uint32_t v0 = __funnelshift_r(w0, w1, r8), v1 = __funnelshift_r(w1, w2, r8);
+                        uint32_t v0, v1;
+                        wv_load64(in, pos, v0, v1);
                         uint32_t seq[4], ent[4], chk[4];
                         seq[0] = v0; seq[1] = __funnelshift_r(v0, v1, 8);
                         seq[2] = __funnelshift_r(v0, v1, 16); seq[3] = __funnelshift_r(v0, v1, 24);
@@ -248,11 +274,8 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                         uint32_t rs[4] = {0, 0, 0, 0};
                         const bool rep_ok = rep != 0 && rep <= pos;
                         if (rep_ok) {
-                            const uintptr_t ra = (uintptr_t)(org + pos - rep);
-                            const uint32_t rr8 = 8u * (uint32_t)(ra & 3u);
-                            const uint32_t *rq = reinterpret_cast<const uint32_t *>(ra & ~(uintptr_t)3);
-                            const uint32_t x0 = rq[0], x1 = rq[1], x2 = rq[2];
-                            const uint32_t y0 = __funnelshift_r(x0, x1, rr8), y1 = __funnelshift_r(x1, x2, rr8);
+                            uint32_t y0, y1;
+                            wv_load64(in, pos - rep, y0, y1);
                             rs[0] = y0; rs[1] = __funnelshift_r(y0, y1, 8);
                             rs[2] = __funnelshift_r(y0, y1, 16); rs[3] = __funnelshift_r(y0, y1, 24);
                         }
@@ -263,10 +286,11 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                         bool sure = false;
 #pragma unroll
                         for (int k = 3; k >= 0; k--) {
-                            const uint32_t c = ent[k] & 0x1FFFFu, p = pos + k;
+                            // c is the candidate position if the check bits agree, else >= 2^17 (> any position)
+                            const uint32_t c = ent[k] ^ (chk[k] << 17), p = pos + k;
                             if ((uint32_t)k < nv) {
                                 if (rep_ok && rs[k] == seq[k]) { pick = k; pc = p - rep; sure = true; }
-                                if ((ent[k] >> 17) == chk[k] && c < p && p - c < 65536u) { pick = k; pc = c; sure = false; }
+                                if (p - c - 1u < 65535u) { pick = k; pc = c; sure = false; }     // c < p, p - c <= 65535
                             }
                         }
                         if (pick < 0) {
@@ -291,19 +315,16 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                 } else {
                     bool done = true, cancel = false;
                     if (e + 8 <= cap) {
-                        const uintptr_t ea = (uintptr_t)(org + e), ca = (uintptr_t)(org + e - moff);
-                        const uint32_t er8 = 8u * (uint32_t)(ea & 3u), cr8 = 8u * (uint32_t)(ca & 3u);
-                        const uint32_t *eq = reinterpret_cast<const uint32_t *>(ea & ~(uintptr_t)3);
-                        const uint32_t *cq = reinterpret_cast<const uint32_t *>(ca & ~(uintptr_t)3);
-                        const uint32_t e0 = eq[0], e1 = eq[1], e2 = eq[2], c0 = cq[0], c1 = cq[1], c2 = cq[2];
-                        const uint32_t x0 = __funnelshift_r(e0, e1, er8) ^ __funnelshift_r(c0, c1, cr8);
-                        const uint32_t x1 = __funnelshift_r(e1, e2, er8) ^ __funnelshift_r(c1, c2, cr8);
+                        uint32_t a0, a1, b0, b1;
+                        wv_load64(in, e, a0, a1);
+                        wv_load64(in, e - moff, b0, b1);
+                        const uint32_t x0 = a0 ^ b0, x1 = a1 ^ b1;
                         if (x0) { cancel = e == mst; e += (uint32_t)(__ffs((int)x0) - 1) >> 3; }
                         else if (x1) e += 4u + ((uint32_t)(__ffs((int)x1) - 1) >> 3);
                         else { e += 8; done = false; }
                     } else {
                         if (e == mst) {
-                            if (enc_load32u(org + e) == enc_load32u(org + e - moff)) e += 4; else cancel = true;
+                            if (wv_load32(in, e) == wv_load32(in, e - moff)) e += 4; else cancel = true;
                         }
                         if (!cancel) while (e < cap && org[e] == org[e - moff]) e++;
                     }
@@ -330,7 +351,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                     const uint32_t ce = __shfl_sync(0xffffffffu, my_last, j);
                     const uint32_t oj = __shfl_sync(0xffffffffu, moff, j);
                     if (ce > erun) {
-                        erun = extend_coop(org, ce, oj, mlimit, lane);
+                        erun = extend_coop(in, ce, oj, mlimit, lane);
                         if (lane == j) my_last = erun;
                     }
                     opens &= opens - 1;
@@ -474,7 +495,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
         }
         const uint32_t p = si + (uint32_t)lane * stride;
         const bool valid = p < mfl;
-        const uint32_t seq = valid ? enc_load32u(org + p) : 0u;
+        const uint32_t seq = valid ? wv_load32(in, p) : 0u;
         const uint32_t hv = seq * 2654435761u;
         const uint32_t h = hv >> (32 - HL);
         const uint32_t chk = (hv >> (17 - HL)) & 0x7FFFu;
@@ -491,7 +512,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             ok = true;
         } else if (valid && (ent >> 17) == chk) {
             cand = ent & 0x1FFFFu;
-            ok = cand < p && p - cand < 65536u && enc_load32u(org + cand) == seq;
+            ok = cand < p && p - cand < 65536u && wv_load32(in, cand) == seq;
         }
         const uint32_t hit = __ballot_sync(0xffffffffu, ok);
 
@@ -509,7 +530,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
         uint32_t mp = __shfl_sync(0xffffffffu, p, pick);      // match start
         uint32_t mc = __shfl_sync(0xffffffffu, cand, pick);   // its source
         const uint32_t offset = mp - mc;
-        const uint32_t mend = extend_coop(org, mp + 4, offset, mlimit, lane);
+        const uint32_t mend = extend_coop(in, mp + 4, offset, mlimit, lane);
         // backward extension over the pending literals (never into the previous segment)
         while (mp > anchor) {
             const uint32_t k = lane + 1;
