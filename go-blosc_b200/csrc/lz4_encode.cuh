@@ -280,7 +280,8 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                             rs[2] = __funnelshift_r(y0, y1, 16); rs[3] = __funnelshift_r(y0, y1, 24);
                         }
                         // first position with a candidate.  A table entry whose check bits agree is taken
-                        // unverified: the first turn of the extension compares the bytes anyway.
+                        // unverified: the first turn of the extension compares the bytes anyway.  At the same
+                        // position the lane's previous offset wins over the table (fewer, longer sequences).
                         int pick = -1;
                         uint32_t pc = 0;
                         bool sure = false;
@@ -289,8 +290,8 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                             // c is the candidate position if the check bits agree, else >= 2^17 (> any position)
                             const uint32_t c = ent[k] ^ (chk[k] << 17), p = pos + k;
                             if ((uint32_t)k < nv) {
-                                if (rep_ok && rs[k] == seq[k]) { pick = k; pc = p - rep; sure = true; }
                                 if (p - c - 1u < 65535u) { pick = k; pc = c; sure = false; }     // c < p, p - c <= 65535
+                                if (rep_ok && rs[k] == seq[k]) { pick = k; pc = p - rep; sure = true; }   // preferred: known good
                             }
                         }
                         if (pick < 0) {

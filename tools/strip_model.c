@@ -27,7 +27,7 @@ static uint32_t hashf(const uint8_t *p) {
 static size_t put_ext(uint8_t *o, size_t v) { size_t k = 0; while (v >= 255) { o[k++] = 255; v -= 255; } o[k++] = (uint8_t)v; return k; }
 
 
-static int STRIP = 64, CAPX = 2, SM = 0, NOTRIMBACK = 0, BACKX = 0, REP = 0, GROUP = 4, WAYS2 = 0, UPTO = 0, INGRP = 0, MINM = 4;
+static int STRIP = 64, CAPX = 2, SM = 0, NOTRIMBACK = 0, BACKX = 0, REP = 0, GROUP = 4, WAYS2 = 0, UPTO = 0, INGRP = 0, MINM = 4, PHASED = 0, RECMAX = 16, HALVES = 1, SKIPCONT = 0, NOSHIFT = 0, REPFIRST = 0;
 static double COST_A = 0, COST_B = 0; static long NSTEPS = 0, NOPEN = 0, NDROP = 0, NTRIM = 0;
 typedef struct { uint32_t ms, me, off; int open; } mt_t;
 
@@ -44,6 +44,52 @@ size_t model_encode(const uint8_t *src, uint32_t n, uint8_t *out, long *nseq) {
             for (int l = 0; l < 32; l++) { uint64_t a = (uint64_t)si + (uint64_t)l * STRIP; pos[l] = a < mfl ? (uint32_t)a : mfl; uint64_t e = a + STRIP; send[l] = e < mfl ? (uint32_t)e : mfl; { uint32_t lo = si > anchor ? si : anchor; lanch[l] = pos[l] > lo + BACKX ? pos[l] - BACKX : lo; if (lanch[l] > pos[l]) lanch[l] = pos[l]; } cnt[l] = 0; }
             uint32_t region_end = send[31];
             int lane_iters[32] = {0}; double costA = 0; static uint32_t rep[32];
+            if (PHASED) {
+                static uint32_t rpos[32][64], rcand[32][64]; int rn[32];
+                int lastk[32]; uint32_t lastoff[32]; for (int l = 0; l < 32; l++) { lastk[l] = -2; lastoff[l] = 0; }
+                uint32_t pe_l[32]; for (int l = 0; l < 32; l++) pe_l[l] = lanch[l];
+                int nturns = (STRIP + 3) / 4; int HT = HALVES > 1 ? (nturns + HALVES - 1) / HALVES : nturns;
+                for (int t0 = 0; t0 < nturns; t0 += HT) {
+                for (int l = 0; l < 32; l++) rn[l] = 0;
+                for (uint32_t t = t0; t < (uint32_t)(t0 + HT) && t < (uint32_t)nturns; t++) {
+                    static uint32_t e4[32][4], h4[32][4], s4[32][4], c4[32][4]; int nv[32];
+                    for (int l = 0; l < 32; l++) { uint32_t p0 = pos[l] + 4 * t; nv[l] = 0; if (p0 >= send[l]) continue; nv[l] = send[l] - p0 < 4 ? (int)(send[l] - p0) : 4;
+                        for (int k = 0; k < nv[l]; k++) { s4[l][k] = ld32(src + p0 + k); uint32_t hv = s4[l][k] * 2654435761u; h4[l][k] = hv >> (32 - HASHLOG); c4[l][k] = (hv >> (17 - HASHLOG)) & 0x7FFF; e4[l][k] = table[h4[l][k]]; } }
+                    if (!SKIPCONT) for (int l = 0; l < 32; l++) for (int k = 0; k < nv[l]; k++) table[h4[l][k]] = (c4[l][k] << 17) | (pos[l] + 4 * t + k);
+                    static int doins[32][4];
+                    for (int l = 0; l < 32; l++) for (int k = 0; k < nv[l]; k++) {
+                        doins[l][k] = 1;
+                        uint32_t p = pos[l] + 4 * t + k; uint32_t e_ = e4[l][k]; uint32_t c = e_ & 0x1FFFF;
+                        int ok = (e_ >> 17) == c4[l][k] && c < p && p - c < 65536;
+                        uint32_t cand = c;
+                        if (!ok && REP && rep[l] && p >= rep[l] && ld32(src + p - rep[l]) == s4[l][k]) { ok = 1; cand = p - rep[l]; }
+                        if (!ok && INGRP) for (int j = k - 1; j >= 0; j--) if (s4[l][j] == s4[l][k]) { ok = 1; cand = p - (k - j); break; }
+                        if (!ok) continue;
+                        int idx = (int)(4 * t + k);
+                        if (idx == lastk[l] + 1 && p - cand == lastoff[l]) { lastk[l] = idx; doins[l][k] = 0; continue; }
+                        lastk[l] = idx; lastoff[l] = p - cand;
+                        if (rn[l] < RECMAX) { rpos[l][rn[l]] = p; rcand[l][rn[l]] = cand; rn[l]++; }
+                    }
+                    if (SKIPCONT) for (int l = 0; l < 32; l++) for (int k = 0; k < nv[l]; k++) if (doins[l][k] || SKIPCONT == 2) table[h4[l][k]] = (c4[l][k] << 17) | (pos[l] + 4 * t + k);
+                }
+                for (int l = 0; l < 32; l++) { uint32_t pe = pe_l[l];
+                    for (int r = 0; r < rn[l]; r++) {
+                        uint32_t p = rpos[l][r], cand = rcand[l][r];
+                        if (p < pe) { if (NOSHIFT) continue; uint32_t d = pe - p; p += d; cand += d; if (p >= send[l]) continue; }
+                        if (p + 4 > n || ld32(src + p) != ld32(src + cand)) continue;
+                        uint32_t cap = send[l] + CAPX * STRIP; if (cap > mlimit) cap = mlimit;
+                        uint32_t e = p + 4, cc = cand + 4;
+                        while (e < cap && src[e] == src[cc]) { e++; cc++; }
+                        int open = (e >= cap && cap < mlimit);
+                        uint32_t ms = p, mc = cand;
+                        while (ms > pe && mc > 0 && src[ms - 1] == src[mc - 1]) { ms--; mc--; }
+                        rep[l] = ms - mc;
+                        mt_t m = { ms, e, ms - mc, open }; if (cnt[l] < 127) lists[l][cnt[l]++] = m; pe = e;
+                    }
+                    pe_l[l] = pe;
+                }
+                }
+            } else
             for (;;) {
                 int any = 0; static uint32_t ent[32][4][2], hh[32][4], sq[32][4], ck[32][4]; int act[32], nv[32];
                 const uint32_t HM = (1u << HASHLOG) - 1; (void)HM;
@@ -59,6 +105,7 @@ size_t model_encode(const uint8_t *src, uint32_t n, uint8_t *out, long *nseq) {
                     int pick = -1; uint32_t cand = 0;
                     for (int k = 0; k < nv[l] && pick < 0; k++) {
                         uint32_t p = pos[l] + k;
+                        if (REPFIRST && REP && rep[l] && p >= rep[l] && ld32(src + p - rep[l]) == sq[l][k]) { pick = k; cand = p - rep[l]; break; }
                         for (int w = 0; w < (WAYS2 ? 2 : 1) && pick < 0; w++) {
                             uint32_t e_ = ent[l][k][w]; uint32_t chk = WAYS2 ? (((ck[l][k] << 1) | (hh[l][k] & 1u)) & 0x7FFF) : ck[l][k];
                             uint32_t c = e_ & 0x1FFFF; int ok = (e_ >> 17) == chk && c < p && p - c < 65536 && ld32(src + c) == sq[l][k];
@@ -189,6 +236,12 @@ int main(int argc, char **argv) {
         if (!strcmp(argv[i], "ways2")) WAYS2 = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "upto")) UPTO = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "minm")) MINM = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "phased")) PHASED = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "recmax")) RECMAX = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "halves")) HALVES = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "skipcont")) SKIPCONT = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "noshift")) NOSHIFT = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "repfirst")) REPFIRST = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "ingrp")) INGRP = atoi(argv[i + 1]);
     }
     const uint32_t n = 262144;
