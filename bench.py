@@ -95,27 +95,36 @@ class ClockSampler:
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.samples, self.stop = index, [], False
+        self.index, self.samples, self.stop, self.proc = index, [], False, None
         self.thread = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
+        # one streaming nvidia-smi (a sample every 50 ms) instead of one process per sample
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [p.strip() for p in line.strip().split(",")]
                 if len(parts) >= 7:
                     self.samples.append(parts)
-            except Exception:
-                pass
-            time.sleep(0.15)
+                if self.stop:
+                    break
+        except Exception:
+            pass
 
     def __enter__(self):
         self.thread.start()
+        time.sleep(0.3)          # let the first samples arrive before the timed region starts
         return self
 
     def __exit__(self, *a):
         self.stop = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
         self.thread.join(timeout=6)
 
     def summary(self):

@@ -208,6 +208,11 @@ ABI = [
     ("b2b_decompress_batch_dev", _int, [_vp, _vp, _vp, _vp, _u32, _i64, _vp, _vp, _vp, _u64, _u32,
                                         _vp, _vp, _vp]),
     ("b2b_scan_offsets_dev", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
+    ("b2b_index_segments", _u32, [_u32]),
+    ("b2b_compress_batch_dev_indexed", _int, [_vp, _vp, _vp, _vp, _u32, _u64, _u32, _int, _i64, _vp, _u64,
+                                              _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
+    ("b2b_decompress_batch_dev_indexed", _int, [_vp, _vp, _vp, _vp, _u32, _i64, _vp, _vp, _vp, _u64, _u32,
+                                                _vp, _vp, _vp, _u32, _vp]),
 ]
 
 _lib = None
@@ -459,6 +464,36 @@ class Context:
                                             _dev_ptr(d_dst), _dev_ptr(d_dst_off), _dev_ptr(d_dst_cap),
                                             total_dst_bytes, max_orig_len, _dev_ptr(d_out_len),
                                             _dev_ptr(d_status), C.c_void_p(stream))
+        if rc:
+            _raise(rc, self._h)
+
+    # ---- side-car decode index (b2b.h): standard frames, independent 64 KiB segments, an index of
+    # sequence boundaries outside the frames; decode with one warp per index entry
+    @staticmethod
+    def index_segments(max_frame_len: int) -> int:
+        return int(lib().b2b_index_segments(int(max_frame_len)))
+
+    def compress_batch_dev_indexed(self, d_src, d_src_off, d_src_len, nframes, total_src_bytes, max_frame_len,
+                                   shuffle, typesize, d_dst, dst_cap, d_frame_off, d_frame_len, d_status,
+                                   d_total_out, d_index, segs_per_frame, stream=0):
+        rc = lib().b2b_compress_batch_dev_indexed(self._h, _dev_ptr(d_src), _dev_ptr(d_src_off),
+                                                  _dev_ptr(d_src_len), nframes, total_src_bytes, max_frame_len,
+                                                  int(shuffle), int(typesize), _dev_ptr(d_dst), dst_cap,
+                                                  _dev_ptr(d_frame_off), _dev_ptr(d_frame_len),
+                                                  _dev_ptr(d_status), _dev_ptr(d_total_out), _dev_ptr(d_index),
+                                                  int(segs_per_frame), C.c_void_p(stream))
+        if rc:
+            _raise(rc, self._h)
+
+    def decompress_batch_dev_indexed(self, d_frames, d_frame_off, d_frame_len, nframes, typesize_override, d_dst,
+                                     d_dst_off, d_dst_cap, total_dst_bytes, max_orig_len, d_out_len, d_status,
+                                     d_index, segs_per_frame, stream=0):
+        rc = lib().b2b_decompress_batch_dev_indexed(self._h, _dev_ptr(d_frames), _dev_ptr(d_frame_off),
+                                                    _dev_ptr(d_frame_len), nframes, int(typesize_override),
+                                                    _dev_ptr(d_dst), _dev_ptr(d_dst_off), _dev_ptr(d_dst_cap),
+                                                    total_dst_bytes, max_orig_len, _dev_ptr(d_out_len),
+                                                    _dev_ptr(d_status), _dev_ptr(d_index), int(segs_per_frame),
+                                                    C.c_void_p(stream))
         if rc:
             _raise(rc, self._h)
 

@@ -269,7 +269,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
                               uint32_t max_len, int shuffle, int64_t typesize, void *d_dst,
                               uint64_t dst_cap, uint64_t *d_frame_off, uint32_t *d_frame_len,
                               uint32_t *d_status, uint64_t *d_total_out, cudaStream_t s,
-                              bool raw_block = false) {
+                              bool raw_block = false, uint64_t *d_index = nullptr, uint32_t segs_per_frame = 0) {
     if (nframes == 0) {
         if (d_total_out) CU(ctx, cudaMemsetAsync(d_total_out, 0, 8, s));
         return B2B_OK;
@@ -328,6 +328,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     e.segs_grid = (uint32_t)segs_grid; e.comp = d_comp; e.comp_off = d_comp_off;
     e.seg_base = d_seg_base; e.meta = d_meta; e.ticket = d_ticket;
     for (int i = 0; i < 4; i++) e.tune[i] = ctx->opt_tune[i];
+    e.independent = d_index ? 1u : 0u;
     rc = launch_encode(ctx, e, s);
     if (rc) return rc;
 
@@ -336,6 +337,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     fa.nframes = nframes; fa.shuffle_flag = shuffle_flag; fa.keep_raw = raw_block ? 1 : 0;
     fa.comp_len = d_comp_len; fa.frame_len = d_frame_len; fa.flags = d_flags;
     fa.final_ll = d_final_ll; fa.final_off = d_final_off; fa.status = d_status;
+    fa.index = d_index; fa.segs_per_frame = segs_per_frame;
     { LaunchTimer lt(ctx, K_FINALIZE, s); finalize_frames_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(fa); }
     CU(ctx, cudaGetLastError());
 
@@ -362,7 +364,8 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
                                 const uint32_t *d_frame_len, uint32_t nframes,
                                 int64_t typesize_override, void *d_dst, const uint64_t *d_dst_off,
                                 const uint32_t *d_dst_cap, uint64_t total_dst, uint32_t max_orig,
-                                uint32_t *d_out_len, uint32_t *d_status, cudaStream_t s) {
+                                uint32_t *d_out_len, uint32_t *d_status, cudaStream_t s,
+                                const uint64_t *d_index = nullptr, uint32_t segs_per_frame = 0) {
     if (nframes == 0) return B2B_OK;
     if (!d_frames || !d_frame_off || !d_frame_len || !d_dst || !d_dst_off || !d_dst_cap ||
         !d_out_len || !d_status)
@@ -379,7 +382,21 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     a.frame_len = d_frame_len; a.nframes = nframes; a.typesize_override = typesize_override;
     a.dst = static_cast<uint8_t *>(d_dst); a.scratch = d_stage; a.dst_off = d_dst_off;
     a.dst_cap = d_dst_cap; a.out_len = d_out_len; a.status = d_status; a.meta = d_meta;
-    { LaunchTimer lt(ctx, K_DECODE, s); lz4_decode_kernel<<<(nframes + kCodecWarps - 1) / kCodecWarps, kCodecThreads, 0, s>>>(a); }
+    if (d_index && segs_per_frame) {
+        // one warp per (frame, segment): sub-streams between the index entries decode independently
+        IndexedDecodeArgs ia; ia.d = a; ia.index = d_index; ia.segs_per_frame = segs_per_frame;
+        const uint64_t items = (uint64_t)nframes * segs_per_frame;
+        if (items > (1ull << 31)) return B2B_EINVAL;
+        CU(ctx, cudaMemsetAsync(d_status, 0, 4ull * nframes, s));
+        { LaunchTimer lt(ctx, K_DECODE, s);
+          lz4_decode_indexed_kernel<<<(unsigned)((items + kCodecWarps - 1) / kCodecWarps), kCodecThreads, 0, s>>>(ia); }
+        CU(ctx, cudaGetLastError());
+        index_finish_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(a);
+        ctx->launches++;
+    } else {
+        LaunchTimer lt(ctx, K_DECODE, s);
+        lz4_decode_kernel<<<(nframes + kCodecWarps - 1) / kCodecWarps, kCodecThreads, 0, s>>>(a);
+    }
     CU(ctx, cudaGetLastError());
 
     // unshuffle the frames that asked for it: stage -> dst (frames with mode 0 were decoded
@@ -594,6 +611,39 @@ int b2b_compress_batch_dev(b2b_ctx *ctx, const void *d_src, const uint64_t *d_sr
                                      max_frame_len, shuffle, typesize, d_dst, dst_cap, d_frame_off,
                                      d_frame_len, d_status, d_total_out, (cudaStream_t)stream);
 }
+
+int b2b_compress_batch_dev_indexed(b2b_ctx *ctx, const void *d_src, const uint64_t *d_src_off,
+                                   const uint32_t *d_src_len, uint32_t nframes, uint64_t total_src_bytes,
+                                   uint32_t max_frame_len, int shuffle, int64_t typesize, void *d_dst,
+                                   uint64_t dst_cap, uint64_t *d_frame_off, uint32_t *d_frame_len,
+                                   uint32_t *d_status, uint64_t *d_total_out, uint64_t *d_index,
+                                   uint32_t segs_per_frame, void *stream) {
+    if (!ctx || !d_index) return B2B_EINVAL;
+    if (segs_per_frame < b2b_index_segments(max_frame_len)) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    return compress_batch_dev_locked(ctx, d_src, d_src_off, d_src_len, nframes, total_src_bytes,
+                                     max_frame_len, shuffle, typesize, d_dst, dst_cap, d_frame_off,
+                                     d_frame_len, d_status, d_total_out, (cudaStream_t)stream, false,
+                                     d_index, segs_per_frame);
+}
+
+int b2b_decompress_batch_dev_indexed(b2b_ctx *ctx, const void *d_frames, const uint64_t *d_frame_off,
+                                     const uint32_t *d_frame_len, uint32_t nframes, int64_t typesize_override,
+                                     void *d_dst, const uint64_t *d_dst_off, const uint32_t *d_dst_cap,
+                                     uint64_t total_dst_bytes, uint32_t max_orig_len, uint32_t *d_out_len,
+                                     uint32_t *d_status, const uint64_t *d_index, uint32_t segs_per_frame,
+                                     void *stream) {
+    if (!ctx || !d_index || segs_per_frame == 0) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    return decompress_batch_dev_locked(ctx, d_frames, d_frame_off, d_frame_len, nframes,
+                                       typesize_override, d_dst, d_dst_off, d_dst_cap,
+                                       total_dst_bytes, max_orig_len, d_out_len, d_status,
+                                       (cudaStream_t)stream, d_index, segs_per_frame);
+}
+
+uint32_t b2b_index_segments(uint32_t max_frame_len) { return max_frame_len ? (max_frame_len + kSegBytes - 1) / kSegBytes : 1; }
 
 int b2b_frame_info_batch_dev(b2b_ctx *ctx, const void *d_frames, const uint64_t *d_frame_off,
                              const uint32_t *d_frame_len, uint32_t nframes, uint32_t *d_orig_len,

@@ -561,6 +561,7 @@ struct EncodeArgs {
     SegMeta *meta;
     unsigned long long *ticket; // zero before launch
     uint32_t tune[4];           // experiment knobs (0: default)
+    uint32_t independent;       // 1: no warm-up window, segments never reference each other (decode index)
 };
 
 template <int HL>
@@ -582,7 +583,7 @@ lz4_encode_kernel(EncodeArgs a) {
         for (uint32_t s = s0; s < nseg; s += a.segs_grid) {
             const uint32_t B = s * kSegBytes;
             const uint32_t L = n - B < kSegBytes ? n - B : kSegBytes;
-            const uint32_t W = B < kWarmBytes ? B : kWarmBytes;
+            const uint32_t W = a.independent ? 0u : (B < kWarmBytes ? B : kWarmBytes);
             const SegMeta m = warp_encode_segment<HL>(frame + B - W, W, L, (uint64_t)n - B - L,
                                                       a.comp + a.comp_off[f] + (uint64_t)s * kSegSlot,
                                                       enc_tables + ((size_t)warp << HL), &enc_lists[warp], lane,
@@ -610,6 +611,10 @@ struct FinalizeArgs {
     uint32_t *final_ll;         // out: literals of the closing token
     uint32_t *final_off;        // out: payload offset of the closing token
     uint32_t *status;
+    // side-car decode index (optional): entry (f, s) = payload offset of the token that opens segment
+    // s's sequences | output position of that token's first literal << 32; ~0 if the segment has none
+    uint64_t *index;
+    uint32_t segs_per_frame;
 };
 
 __global__ void finalize_frames_kernel(FinalizeArgs a) {
@@ -617,19 +622,26 @@ __global__ void finalize_frames_kernel(FinalizeArgs a) {
     if (f >= a.nframes) return;
     const uint32_t n = a.src_len[f];
     uint32_t st = 0, flags = a.shuffle_flag, c = 0, flen = 0;
+    if (a.index && (n == 0 || n > 0xFFFFFFFFu - 16u))
+        for (uint32_t s = 0; s < a.segs_per_frame; s++) a.index[(uint64_t)f * a.segs_per_frame + s] = ~0ull;
     if (n == 0) st = 1;                                   // ErrInvalidData, blosc.go:269-271
     else if (n > 0xFFFFFFFFu - 16u) st = 6;               // header fields are u32
     else {
         const uint32_t nseg = seg_count(n);
         const uint64_t base = a.seg_base[f];
         uint64_t out = 0, carry = 0;
+        if (a.index) for (uint32_t s = nseg; s < a.segs_per_frame; s++) a.index[(uint64_t)f * a.segs_per_frame + s] = ~0ull;
         for (uint32_t s = 0; s < nseg; s++) {
             const SegMeta m = a.meta[base + s];
             SegPlace pl; pl.out_off = 0; pl.lit_total = 0;
+            if (a.index && s < a.segs_per_frame) a.index[(uint64_t)f * a.segs_per_frame + s] = ~0ull;
             if (m.info & 0x100u) {
                 const uint64_t lt = carry + m.first_ll;
                 pl.out_off = (uint32_t)(out > 0xFFFFFFFFull ? 0xFFFFFFFFull : out);
                 pl.lit_total = (uint32_t)lt;
+                if (a.index && s < a.segs_per_frame)
+                    a.index[(uint64_t)f * a.segs_per_frame + s] =
+                        (uint64_t)pl.out_off | (((uint64_t)s * kSegBytes + m.first_ll - lt) << 32);
                 out += 1ull + len_ext_bytes((uint32_t)lt) + lt + m.body_len;
                 carry = m.trail_ll;
             } else {

@@ -189,8 +189,11 @@ __device__ __forceinline__ int warp_flush_batch(const uint8_t *__restrict__ src,
 // beyond the output so far, reads past the stream, writes past cap and a final token with a
 // non-zero match nibble are errors (pierrec UncompressBlock, used at codec.go:79).
 __device__ __forceinline__ int warp_decode_one(const uint8_t *__restrict__ src, uint32_t clen, uint8_t *dst,
-                                               uint32_t cap, uint32_t &ip, uint32_t &op, int lane) {
-    if (ip >= clen) return -1;
+                                               uint32_t cap, uint32_t &ip, uint32_t &op, int lane,
+                                               bool open_end = false) {
+    // open_end: this is a sub-stream cut out of a block at a sequence boundary (decode index): it
+    // ends after a complete sequence instead of with a literal-only token
+    if (ip >= clen) return (open_end && ip == clen) ? 0 : -1;
     const uint32_t tok = src[ip++];
     uint64_t ll = tok >> 4;
     if (ll == 15 && !warp_read_len_ext(src, clen, ip, ll, lane)) return -1;
@@ -217,7 +220,8 @@ __device__ __forceinline__ int warp_decode_one(const uint8_t *__restrict__ src, 
 // Returns the number of bytes produced, -1 for a malformed stream, -2 if it would overrun cap.
 // An empty stream decodes to 0 bytes.
 __device__ __forceinline__ int64_t warp_lz4_decode(const uint8_t *__restrict__ src, uint32_t clen,
-                                                   uint8_t *dst, uint32_t cap, SeqTable *tab, int lane) {
+                                                   uint8_t *dst, uint32_t cap, SeqTable *tab, int lane,
+                                                   bool open_end = false) {
     if (clen == 0) return 0;
     uint32_t ip = 0, op = 0, count = 0, batch_ip = 0;
     // A window's speculative reads reach at most 305 bytes past its start (31 + token + two
@@ -232,7 +236,7 @@ __device__ __forceinline__ int64_t warp_lz4_decode(const uint8_t *__restrict__ s
                 count = 0;
                 __syncwarp();
             }
-            const int r = warp_decode_one(src, clen, dst, cap, ip, op, lane);
+            const int r = warp_decode_one(src, clen, dst, cap, ip, op, lane, open_end);
             if (r < 0) return r;
             if (r == 0) break;
             batch_ip = ip;
@@ -281,7 +285,7 @@ __device__ __forceinline__ int64_t warp_lz4_decode(const uint8_t *__restrict__ s
                 __syncwarp();
             }
             if (other) {
-                const int r = warp_decode_one(src, clen, dst, cap, ip, op, lane);
+                const int r = warp_decode_one(src, clen, dst, cap, ip, op, lane, open_end);
                 if (r < 0) return r;
                 if (r == 0) break;
             }
@@ -372,6 +376,85 @@ __global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_kernel(DecodeArgs
         a.out_len[f] = produced;
         a.meta[f] = m;
     }
+}
+
+// ---- decode with a side-car index ------------------------------------------
+// Frames that K3 produced with independent segments come with an index of sequence boundaries: one
+// (payload offset, output position) pair per 64 KiB segment.  One warp decodes one sub-stream; the
+// frame itself is an ordinary single LZ4 block (the reference decodes it without the index).
+// status[] must be zero before the launch; index_finish_kernel turns it into out_len / meta.
+struct IndexedDecodeArgs {
+    DecodeArgs d;
+    const uint64_t *index;      // segs_per_frame entries per frame, ~0 = no entry
+    uint32_t segs_per_frame;
+};
+
+__global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_indexed_kernel(IndexedDecodeArgs ia) {
+    __shared__ SeqTable seq_tables[kCodecWarps];
+    const DecodeArgs &a = ia.d;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t item = (uint64_t)blockIdx.x * kCodecWarps + warp;
+    const uint32_t f = (uint32_t)(item / ia.segs_per_frame), sg = (uint32_t)(item % ia.segs_per_frame);
+    if (f >= a.nframes) return;
+    const uint8_t *fr = a.frames + a.frame_off[f];
+    const uint32_t flen = a.frame_len[f];
+    uint32_t flags = 0, codec = 0, tsz = 0, norig = 0, ncomp = 0;
+    uint32_t st = check_header(fr, flen, flags, codec, tsz, norig, ncomp);
+    const bool is_memcpy = (flags & 0x2u) != 0;
+    if (st == kOk && !is_memcpy) {
+        if (codec < 1 || codec > 5) st = kEInvalidCodec;
+        else if (codec != 1 && codec != 2) st = kEUnsupported;
+    }
+    if (st == kOk && a.dst_cap[f] < norig) st = kEDstTooSmall;
+    if (st != kOk) { if (sg == 0 && lane == 0) atomicMax(a.status + f, st); return; }
+    const uint32_t plen = ncomp - 16;
+    const uint64_t T = a.typesize_override > 0 ? (uint64_t)a.typesize_override : (uint64_t)tsz;
+    const uint32_t mode = (flags & 0x4u) ? 2u : ((flags & 0x1u) ? 1u : 0u);
+    const bool active = mode != 0 && T > 1 && (uint64_t)norig >= T;
+    uint8_t *out = (active ? a.scratch : a.dst) + a.dst_off[f];
+    if (is_memcpy) {                                            // 64 KiB slices of the raw copy
+        if (plen != norig) { if (sg == 0 && lane == 0) atomicMax(a.status + f, (uint32_t)kESizeMismatch); return; }
+        for (uint64_t b = (uint64_t)sg * 65536u; b < norig; b += (uint64_t)ia.segs_per_frame * 65536u) {
+            const uint32_t n = norig - b < 65536u ? (uint32_t)(norig - b) : 65536u;
+            warp_copy(out + b, fr + 16 + b, n, lane);
+        }
+        return;
+    }
+    const uint64_t *idx = ia.index + (uint64_t)f * ia.segs_per_frame;
+    uint64_t e0 = idx[sg];
+    if (e0 == ~0ull) { if (sg != 0) return; e0 = 0; }          // the stream itself starts at (0, 0)
+    uint64_t e1 = ~0ull;
+    for (uint32_t k = sg + 1; k < ia.segs_per_frame && e1 == ~0ull; k++) e1 = idx[k];
+    const uint32_t ip0 = (uint32_t)e0, op0 = (uint32_t)(e0 >> 32);
+    const bool last = e1 == ~0ull;
+    const uint32_t ip1 = last ? plen : (uint32_t)e1, op1 = last ? norig : (uint32_t)(e1 >> 32);
+    if (ip0 > ip1 || ip1 > plen || op0 > op1 || op1 > norig) {  // a corrupt index must not become a wild copy
+        if (lane == 0) atomicMax(a.status + f, (uint32_t)kEDecompressionFailed);
+        return;
+    }
+    if (ip0 == ip1 && op0 == op1) return;
+    const int64_t got = warp_lz4_decode(fr + 16 + ip0, ip1 - ip0, out + op0, op1 - op0, &seq_tables[warp], lane, !last);
+    if (got < 0) { if (lane == 0) atomicMax(a.status + f, (uint32_t)kEDecompressionFailed); }
+    else if ((uint64_t)got != op1 - op0) { if (lane == 0) atomicMax(a.status + f, (uint32_t)kESizeMismatch); }
+}
+
+// out_len / meta of the indexed decode, from the accumulated status and the header
+__global__ void index_finish_kernel(DecodeArgs a) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.nframes) return;
+    uint32_t flags = 0, codec = 0, tsz = 0, norig = 0, ncomp = 0;
+    const uint32_t hs = check_header(a.frames + a.frame_off[f], a.frame_len[f], flags, codec, tsz, norig, ncomp);
+    const uint32_t st = a.status[f];
+    FrameMeta m; m.mode = 0; m.typesize = 0;
+    uint32_t produced = 0;
+    if (st == kOk && hs == kOk) {
+        const uint64_t T = a.typesize_override > 0 ? (uint64_t)a.typesize_override : (uint64_t)tsz;
+        const uint32_t mode = (flags & 0x4u) ? 2u : ((flags & 0x1u) ? 1u : 0u);
+        if (mode != 0 && T > 1 && (uint64_t)norig >= T) { m.mode = mode; m.typesize = (uint32_t)T; }
+        produced = norig;
+    }
+    a.out_len[f] = produced;
+    a.meta[f] = m;
 }
 
 // header-only pass for b2b_frame_info_batch_dev

@@ -197,6 +197,34 @@ B2B_API int b2b_decompress_batch_dev(b2b_ctx *ctx, const void *d_frames,
                                      uint64_t total_dst_bytes, uint32_t max_orig_len,
                                      uint32_t *d_out_len, uint32_t *d_status, void *stream);
 
+/* ---- side-car decode index (no reference counterpart) ------------------
+ * The reference's wire format has ONE LZ4 block per frame (blosc.go:393), so a frame decodes on one
+ * warp however large it is.  b2b_compress_batch_dev_indexed produces the same standard frames
+ * (every decoder, the reference's included, reads them) but compresses each 64 KiB segment
+ * without reference to the others and also returns, outside the frames, an index of sequence
+ * boundaries: d_index[f * segs_per_frame + s] = payload offset of the token that opens segment s
+ * | output position of its first literal << 32, or ~0 when segment s opens no sequence.
+ * segs_per_frame >= b2b_index_segments(max_frame_len).  b2b_decompress_batch_dev_indexed decodes
+ * such frames with one warp per index entry (d_dst_cap[f] must be >= NBytesOrig); results are
+ * identical to b2b_decompress_batch_dev.  The index is advisory: frames travel without it. */
+B2B_API uint32_t b2b_index_segments(uint32_t max_frame_len);
+B2B_API int b2b_compress_batch_dev_indexed(b2b_ctx *ctx, const void *d_src, const uint64_t *d_src_off,
+                                           const uint32_t *d_src_len, uint32_t nframes,
+                                           uint64_t total_src_bytes, uint32_t max_frame_len,
+                                           int shuffle, int64_t typesize, void *d_dst,
+                                           uint64_t dst_cap, uint64_t *d_frame_off,
+                                           uint32_t *d_frame_len, uint32_t *d_status,
+                                           uint64_t *d_total_out, uint64_t *d_index,
+                                           uint32_t segs_per_frame, void *stream);
+B2B_API int b2b_decompress_batch_dev_indexed(b2b_ctx *ctx, const void *d_frames,
+                                             const uint64_t *d_frame_off, const uint32_t *d_frame_len,
+                                             uint32_t nframes, int64_t typesize_override, void *d_dst,
+                                             const uint64_t *d_dst_off, const uint32_t *d_dst_cap,
+                                             uint64_t total_dst_bytes, uint32_t max_orig_len,
+                                             uint32_t *d_out_len, uint32_t *d_status,
+                                             const uint64_t *d_index, uint32_t segs_per_frame,
+                                             void *stream);
+
 /* K5 on its own: d_off = exclusive scan of d_len (u32 -> u64), d_total[0] = sum. */
 B2B_API int b2b_scan_offsets_dev(b2b_ctx *ctx, const uint32_t *d_len, uint32_t n, uint64_t *d_off,
                                  uint64_t *d_total, void *stream);

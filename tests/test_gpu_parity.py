@@ -426,3 +426,67 @@ def test_device_batch_roundtrip_c3_shape(ctx, orc, torch_mod):
     ctx.decompress_batch_dev(d_dst, d_foff, d_flen, nf, 0, d_out, d_doff, d_orig, nf * fl, fl, d_olen, d_st2, s)
     torch.cuda.synchronize()
     assert not d_st2.any() and torch.equal(d_out, d_src)
+
+
+# ---- side-car decode index -----------------------------------------------------
+@pytest.mark.parametrize("shuffle,T", [(0, 1), (1, 4), (2, 8)])
+def test_indexed_frames_are_standard_and_decode_in_parallel(ctx, orc, torch_mod, shuffle, T):
+    """Frames from b2b_compress_batch_dev_indexed are ordinary go-blosc frames (the oracle = reference
+    Decompress reads them, so does the plain GPU decoder); with the index they decode with one warp per
+    64 KiB segment to the same bytes.  Ragged sizes from 1 B to 2 MiB, compressible / random / mixed."""
+    torch = torch_mod
+    rng = np.random.default_rng(11)
+    sizes = [1, 13, 4096, 65535, 65536, 65537, 131072, 200000, 262144, 1 << 20, (2 << 20) + 5, 300000, 70000]
+    parts = []
+    for k, n in enumerate(sizes):
+        kind = k % 4
+        if kind == 0: d = dg.smooth_f32((n + 3) // 4, k)[:n]
+        elif kind == 1: d = dg.lowent_i16((n + 1) // 2, k)[:n]
+        elif kind == 2: d = dg.random_bytes(n, k)
+        else: d = dg.strip_adversarial(n, k)["copies"]
+        parts.append(np.ascontiguousarray(d))
+    lens = np.array(sizes, dtype=np.uint32)
+    offs = np.concatenate([[0], np.cumsum((lens[:-1].astype(np.uint64) + 15) // 16 * 16)]).astype(np.uint64)
+    total = int(offs[-1] + lens[-1])
+    host = np.zeros(total, dtype=np.uint8)
+    for o, d in zip(offs, parts):
+        host[int(o):int(o) + d.size] = d
+    nf, mx = len(sizes), int(lens.max())
+    spf = ctx.index_segments(mx)
+    assert spf == (mx + 65535) // 65536
+    d_src = torch.from_numpy(host).cuda()
+    d_off = torch.from_numpy(offs.astype(np.int64)).cuda(); d_len = torch.from_numpy(lens.astype(np.int32)).cuda()
+    cap = total + 32 * nf + 64
+    d_c = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    d_foff = torch.empty(nf, dtype=torch.int64, device="cuda"); d_flen = torch.empty(nf, dtype=torch.int32, device="cuda")
+    d_st = torch.empty(nf, dtype=torch.int32, device="cuda"); d_tot = torch.empty(1, dtype=torch.int64, device="cuda")
+    d_idx = torch.empty(nf * spf, dtype=torch.int64, device="cuda")
+    ctx.compress_batch_dev_indexed(d_src, d_off, d_len, nf, total, mx, shuffle, T, d_c, cap, d_foff, d_flen, d_st, d_tot, d_idx, spf)
+    torch.cuda.synchronize()
+    assert not bool(d_st.any())
+    foff, flen = d_foff.cpu().numpy(), d_flen.cpu().numpy()
+    comp = d_c.cpu().numpy()
+    for f in range(nf):                                   # standard frames: reference semantics decode them
+        fr = comp[int(foff[f]):int(foff[f]) + int(flen[f])]
+        rc, back = orc.decompress(fr)
+        assert rc == 0 and np.array_equal(back, parts[f]), (f, sizes[f])
+    for indexed in (True, False):                         # and both GPU decoders give the same bytes
+        d_out = torch.zeros(total, dtype=torch.uint8, device="cuda")
+        d_olen = torch.empty(nf, dtype=torch.int32, device="cuda"); d_st2 = torch.empty(nf, dtype=torch.int32, device="cuda")
+        if indexed:
+            ctx.decompress_batch_dev_indexed(d_c, d_foff, d_flen, nf, 0, d_out, d_off, d_len, total, mx, d_olen, d_st2, d_idx, spf)
+        else:
+            ctx.decompress_batch_dev(d_c, d_foff, d_flen, nf, 0, d_out, d_off, d_len, total, mx, d_olen, d_st2)
+        torch.cuda.synchronize()
+        assert not bool(d_st2.any()), (indexed, d_st2.cpu().numpy())
+        assert np.array_equal(d_olen.cpu().numpy().astype(np.uint32), lens)
+        out = d_out.cpu().numpy()
+        for f in range(nf):
+            assert np.array_equal(out[int(offs[f]):int(offs[f]) + sizes[f]], parts[f]), (indexed, f, sizes[f])
+    # a corrupt index is reported, never followed out of bounds
+    bad = d_idx.clone(); bad[spf * 9 + 1] = (5 << 32) | 0x7FFFFFF0
+    d_out = torch.zeros(total, dtype=torch.uint8, device="cuda")
+    ctx.decompress_batch_dev_indexed(d_c, d_foff, d_flen, nf, 0, d_out, d_off, d_len, total, mx, d_olen, d_st2, bad, spf)
+    torch.cuda.synchronize()
+    st = d_st2.cpu().numpy()
+    assert st[9] != 0 and not st[:9].any() and not st[10:].any()

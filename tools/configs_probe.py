@@ -70,3 +70,17 @@ flags = torch.stack([d_c[int(o) + 2] for o in d_foff[:14].cpu()]).cpu().numpy()
 print(f"C5 mixed (T=2 Shuffle1, {nf} frames of 32 KiB..2 MiB, {acc >> 20} MiB, random/low-entropy alternating): ratio {int(d_tot.item()) / acc:.4f}, "
       f"compress {acc / min(tc) / 1e6:.1f} GB/s, decompress {acc / min(td) / 1e6:.1f} GB/s, exact={torch.equal(d_out, src)}, "
       f"status ok={not bool(d_st.any())}, memcpy flag of the first 14 frames={[int(x) >> 1 & 1 for x in flags]}")
+
+# ---- the same C5 batch with the side-car decode index (independent 64 KiB segments, one warp per segment)
+spf = ctx.index_segments(mx)
+d_idx = torch.empty(nf * spf, dtype=torch.int64, device="cuda")
+compi = lambda: ctx.compress_batch_dev_indexed(src, d_off, d_len, nf, acc, mx, 1, 2, d_c, cap, d_foff, d_flen, d_st, d_tot, d_idx, spf, s)
+deci = lambda: ctx.decompress_batch_dev_indexed(d_c, d_foff, d_flen, nf, 0, d_out, d_off, d_len, acc, mx, d_olen, d_st, d_idx, spf, s)
+compi(); d_out.zero_(); deci(); torch.cuda.synchronize()
+tc, td = [], []
+for _ in range(3):
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record(); compi(); e[1].record(); deci(); e[2].record(); torch.cuda.synchronize()
+    tc.append(e[0].elapsed_time(e[1])); td.append(e[1].elapsed_time(e[2]))
+print(f"C5 mixed with decode index ({spf} entries per frame): ratio {int(d_tot.item()) / acc:.4f}, compress {acc / min(tc) / 1e6:.1f} GB/s, "
+      f"decompress {acc / min(td) / 1e6:.1f} GB/s, exact={torch.equal(d_out, src)}, status ok={not bool(d_st.any())}")

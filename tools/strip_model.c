@@ -27,7 +27,7 @@ static uint32_t hashf(const uint8_t *p) {
 static size_t put_ext(uint8_t *o, size_t v) { size_t k = 0; while (v >= 255) { o[k++] = 255; v -= 255; } o[k++] = (uint8_t)v; return k; }
 
 
-static int STRIP = 64, CAPX = 2, SM = 0, NOTRIMBACK = 0, BACKX = 0, REP = 0, GROUP = 4, WAYS2 = 0, UPTO = 0, INGRP = 0, MINM = 4, PHASED = 0, RECMAX = 16, HALVES = 1, SKIPCONT = 0, NOSHIFT = 0, REPFIRST = 0;
+static int STRIP = 64, CAPX = 2, SM = 0, NOTRIMBACK = 0, BACKX = 0, REP = 0, GROUP = 4, WAYS2 = 0, UPTO = 0, INGRP = 0, MINM = 4, PHASED = 0, RECMAX = 16, HALVES = 1, SKIPCONT = 0, NOSHIFT = 0, REPFIRST = 0, LCMP = 16, SHORTRULE = 0, SHORTLEN = 6, SHORTLL = 15, REPWIN = 0;
 static double COST_A = 0, COST_B = 0; static long NSTEPS = 0, NOPEN = 0, NDROP = 0, NTRIM = 0;
 typedef struct { uint32_t ms, me, off; int open; } mt_t;
 
@@ -105,13 +105,22 @@ size_t model_encode(const uint8_t *src, uint32_t n, uint8_t *out, long *nseq) {
                     int pick = -1; uint32_t cand = 0;
                     for (int k = 0; k < nv[l] && pick < 0; k++) {
                         uint32_t p = pos[l] + k;
-                        if (REPFIRST && REP && rep[l] && p >= rep[l] && ld32(src + p - rep[l]) == sq[l][k]) { pick = k; cand = p - rep[l]; break; }
+                        if (REPFIRST == 1 && REP && rep[l] && p >= rep[l] && (REPWIN == 0 || pos[l] - lanch[l] < (uint32_t)REPWIN) && ld32(src + p - rep[l]) == sq[l][k]) { pick = k; cand = p - rep[l]; break; }
+                        if (REPFIRST == 2) { /* longest of table / rep / fixed offsets, compared over LCMP bytes */
+                            uint32_t best = 0, bc = 0; uint32_t cs[4]; int nc = 0;
+                            uint32_t e_ = ent[l][k][0]; uint32_t c = e_ & 0x1FFFF;
+                            if ((e_ >> 17) == ck[l][k] && c < p && p - c < 65536 && ld32(src + c) == sq[l][k]) cs[nc++] = c;
+                            if (REP && rep[l] && p >= rep[l] && ld32(src + p - rep[l]) == sq[l][k]) cs[nc++] = p - rep[l];
+                            for (int q = 0; q < nc; q++) { uint32_t len = 4; while (len < (uint32_t)LCMP && p + len < mlimit && src[p + len] == src[cs[q] + len]) len++; if (len > best) { best = len; bc = cs[q]; } }
+                            if (nc) { pick = k; cand = bc; break; }
+                            continue;
+                        }
                         for (int w = 0; w < (WAYS2 ? 2 : 1) && pick < 0; w++) {
                             uint32_t e_ = ent[l][k][w]; uint32_t chk = WAYS2 ? (((ck[l][k] << 1) | (hh[l][k] & 1u)) & 0x7FFF) : ck[l][k];
                             uint32_t c = e_ & 0x1FFFF; int ok = (e_ >> 17) == chk && c < p && p - c < 65536 && ld32(src + c) == sq[l][k];
                             if (ok) { pick = k; cand = c; }
                         }
-                        if (pick < 0 && REP && rep[l] && p >= rep[l] && ld32(src + p - rep[l]) == sq[l][k]) { pick = k; cand = p - rep[l]; }
+                        if (pick < 0 && REP && rep[l] && p >= rep[l] && (REPWIN == 0 || pos[l] - lanch[l] < (uint32_t)REPWIN) && ld32(src + p - rep[l]) == sq[l][k]) { pick = k; cand = p - rep[l]; }
                     }
                     if (pick < 0 && INGRP) { /* repeats inside the group: nearest earlier position of the group with the same 4 bytes */
                         for (int k = 1; k < nv[l] && pick < 0; k++) for (int j = k - 1; j >= 0; j--) if (sq[l][j] == sq[l][k]) { pick = k; cand = pos[l] + j; break; } }
@@ -145,6 +154,7 @@ size_t model_encode(const uint8_t *src, uint32_t n, uint8_t *out, long *nseq) {
                     uint32_t e = m.me, cc = m.me - m.off; while (e < mlimit && src[e] == src[cc]) { e++; cc++; } m.me = e; NOPEN++; }
                 if (m.me <= E) { NDROP++; continue; }
                 if (m.ms < E) { NTRIM++; m.ms = E; if (m.me - m.ms < 4) { NDROP++; continue; } }
+                if (SHORTRULE && (int)(m.me - m.ms) < SHORTLEN && m.ms - anchor >= (uint32_t)SHORTLL) { NDROP++; continue; }
                 /* emit */
                 uint32_t ll = m.ms - anchor, ml = m.me - m.ms - 4;
                 uint32_t tok = op++;
@@ -242,6 +252,11 @@ int main(int argc, char **argv) {
         if (!strcmp(argv[i], "skipcont")) SKIPCONT = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "noshift")) NOSHIFT = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "repfirst")) REPFIRST = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "lcmp")) LCMP = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "shortrule")) SHORTRULE = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "repwin")) REPWIN = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "shortlen")) SHORTLEN = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "shortll")) SHORTLL = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "ingrp")) INGRP = atoi(argv[i + 1]);
     }
     const uint32_t n = 262144;
