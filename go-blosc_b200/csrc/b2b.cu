@@ -370,12 +370,13 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     if (!d_frames || !d_frame_off || !d_frame_len || !d_dst || !d_dst_off || !d_dst_cap ||
         !d_out_len || !d_status)
         return B2B_EINVAL;
-    const uint64_t need = align_up(total_dst + 64, 256) + align_up(8ull * nframes, 256) + 4096;
+    const uint64_t need = align_up(total_dst + 64, 256) + align_up(8ull * nframes, 256) + 8192;
     int rc = ensure_arena(ctx, need);
     if (rc) return rc;
     Arena ar(ctx);
     uint8_t *d_stage = ar.take<uint8_t>(total_dst + 64);
     FrameMeta *d_meta = ar.take<FrameMeta>(nframes);
+    unsigned long long *d_ticket = ar.take<unsigned long long>(4);
 
     DecodeArgs a;
     a.frames = static_cast<const uint8_t *>(d_frames); a.frame_off = d_frame_off;
@@ -384,12 +385,14 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     a.dst_cap = d_dst_cap; a.out_len = d_out_len; a.status = d_status; a.meta = d_meta;
     if (d_index && segs_per_frame) {
         // one warp per (frame, segment): sub-streams between the index entries decode independently
-        IndexedDecodeArgs ia; ia.d = a; ia.index = d_index; ia.segs_per_frame = segs_per_frame;
+        IndexedDecodeArgs ia; ia.d = a; ia.index = d_index; ia.segs_per_frame = segs_per_frame; ia.ticket = d_ticket;
         const uint64_t items = (uint64_t)nframes * segs_per_frame;
-        if (items > (1ull << 31)) return B2B_EINVAL;
         CU(ctx, cudaMemsetAsync(d_status, 0, 4ull * nframes, s));
+        CU(ctx, cudaMemsetAsync(d_ticket, 0, 8, s));
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((items + kCodecWarps - 1) / kCodecWarps,
+                                                                         (uint64_t)ctx->sm_count * 8));
         { LaunchTimer lt(ctx, K_DECODE, s);
-          lz4_decode_indexed_kernel<<<(unsigned)((items + kCodecWarps - 1) / kCodecWarps), kCodecThreads, 0, s>>>(ia); }
+          lz4_decode_indexed_kernel<<<grid, kCodecThreads, 0, s>>>(ia); }
         CU(ctx, cudaGetLastError());
         index_finish_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(a);
         ctx->launches++;

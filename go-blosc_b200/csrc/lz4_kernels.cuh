@@ -387,15 +387,15 @@ struct IndexedDecodeArgs {
     DecodeArgs d;
     const uint64_t *index;      // segs_per_frame entries per frame, ~0 = no entry
     uint32_t segs_per_frame;
+    unsigned long long *ticket; // zero before launch: warps pull (frame, segment) items from it
 };
 
-__global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_indexed_kernel(IndexedDecodeArgs ia) {
-    __shared__ SeqTable seq_tables[kCodecWarps];
+// One (frame, segment) item.  Most items are empty (segments that open no sequence, e.g. the
+// incompressible planes of a shuffled frame), which is why the warps of the persistent kernel below
+// pull items from a ticket instead of owning one each: a CTA slot is never held by idle warps.
+__device__ __forceinline__ void warp_decode_index_item(const IndexedDecodeArgs &ia, uint32_t f, uint32_t sg,
+                                                       SeqTable *tab, int lane) {
     const DecodeArgs &a = ia.d;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t item = (uint64_t)blockIdx.x * kCodecWarps + warp;
-    const uint32_t f = (uint32_t)(item / ia.segs_per_frame), sg = (uint32_t)(item % ia.segs_per_frame);
-    if (f >= a.nframes) return;
     const uint8_t *fr = a.frames + a.frame_off[f];
     const uint32_t flen = a.frame_len[f];
     uint32_t flags = 0, codec = 0, tsz = 0, norig = 0, ncomp = 0;
@@ -433,9 +433,24 @@ __global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_indexed_kernel(In
         return;
     }
     if (ip0 == ip1 && op0 == op1) return;
-    const int64_t got = warp_lz4_decode(fr + 16 + ip0, ip1 - ip0, out + op0, op1 - op0, &seq_tables[warp], lane, !last);
+    const int64_t got = warp_lz4_decode(fr + 16 + ip0, ip1 - ip0, out + op0, op1 - op0, tab, lane, !last);
     if (got < 0) { if (lane == 0) atomicMax(a.status + f, (uint32_t)kEDecompressionFailed); }
     else if ((uint64_t)got != op1 - op0) { if (lane == 0) atomicMax(a.status + f, (uint32_t)kESizeMismatch); }
+}
+
+__global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_indexed_kernel(IndexedDecodeArgs ia) {
+    __shared__ SeqTable seq_tables[kCodecWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t items = (uint64_t)ia.d.nframes * ia.segs_per_frame;
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(ia.ticket, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= items) break;
+        warp_decode_index_item(ia, (uint32_t)(item / ia.segs_per_frame), (uint32_t)(item % ia.segs_per_frame),
+                               &seq_tables[warp], lane);
+        __syncwarp();
+    }
 }
 
 // out_len / meta of the indexed decode, from the accumulated status and the header

@@ -77,8 +77,15 @@ for key, hl, tune in [(k, h, t) for k in which for h in hashlogs for t in tunes]
     label = f"{label} hl={hl} tune={tune}"
     data = gen()
     d_out = torch.empty_like(data)
-    comp = lambda: ctx.compress_batch_dev(data, d_off, d_len, nf, size, fl, sh, T, d_c, cap, d_foff, d_flen, d_st, d_tot, s)
-    dec = lambda: ctx.decompress_batch_dev(d_c, d_foff, d_flen, nf, 0, d_out, d_off, d_len, size, fl, d_olen, d_st, s)
+    if os.environ.get("PROBE_INDEXED"):
+        spf = ctx.index_segments(fl)
+        d_idx = torch.empty(nf * spf, dtype=torch.int64, device="cuda")
+        label += " indexed"
+        comp = lambda: ctx.compress_batch_dev_indexed(data, d_off, d_len, nf, size, fl, sh, T, d_c, cap, d_foff, d_flen, d_st, d_tot, d_idx, spf, s)
+        dec = lambda: ctx.decompress_batch_dev_indexed(d_c, d_foff, d_flen, nf, 0, d_out, d_off, d_len, size, fl, d_olen, d_st, d_idx, spf, s)
+    else:
+        comp = lambda: ctx.compress_batch_dev(data, d_off, d_len, nf, size, fl, sh, T, d_c, cap, d_foff, d_flen, d_st, d_tot, s)
+        dec = lambda: ctx.decompress_batch_dev(d_c, d_foff, d_flen, nf, 0, d_out, d_off, d_len, size, fl, d_olen, d_st, s)
     comp(); dec(); torch.cuda.synchronize()
     ctx.kernel_stats_reset()
     tc, td = [], []
