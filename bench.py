@@ -201,7 +201,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -377,7 +377,7 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     ctx.close()
     return 0 if ok else 1
 

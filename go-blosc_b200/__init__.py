@@ -26,7 +26,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb2b.so")
+LIB_PATH = os.environ.get("B2B_LIB_PATH") or os.path.join(_HERE, "lib", "libb2b.so")   # override: A/B builds of the same ABI
 VERSION = "1.0.0"          # blosc.go:49
 FORMAT_VERSION = 2         # blosc.go:50
 HEADER_SIZE = 16           # blosc.go:118-121

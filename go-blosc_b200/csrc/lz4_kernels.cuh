@@ -97,8 +97,14 @@ __device__ __forceinline__ void warp_match_copy(uint8_t *dst, uint32_t off, uint
 //             of the same batch writes, and long ones, follow in stream order, 32 lanes wide.
 // Tokens with longer extensions, the closing token and anything malformed go through the
 // sequence-at-a-time path below (warp_decode_one), which also reports every error.
-constexpr uint32_t kLaneLit = 16;     // literal bytes a lane copies by itself
-constexpr uint32_t kLaneMatch = 24;   // longest match a lane copies by itself
+#ifndef B2B_LANE_LIT
+#define B2B_LANE_LIT 16
+#endif
+#ifndef B2B_LANE_MATCH
+#define B2B_LANE_MATCH 24
+#endif
+constexpr uint32_t kLaneLit = B2B_LANE_LIT;       // literal bytes a lane copies by itself
+constexpr uint32_t kLaneMatch = B2B_LANE_MATCH;   // longest match a lane copies by itself
 constexpr uint32_t kBatchFill = 21;   // a window adds at most 11 tokens: parse while count <= 21
 
 struct SeqTable {
