@@ -482,8 +482,103 @@ __device__ __forceinline__ void run_bitshuffle_fast(const uint8_t *s, uint8_t *d
     }
 }
 
+// ---- K2, T = 8 and 16: shared-memory staged ------------------------------------------------------
+// A group is 8 elements x T bytes.  The lane all-to-all above needs T/2 - 1 shuffles per 16 bytes
+// and, for T = 16, runs out of registers; here the tile is staged in shared memory with the group
+// rows padded (128 -> 144 bytes, 64 -> 72 bytes), one thread takes (group g, byte positions
+// 4q..4q+3): 8 LDS.32, one per element (word index 36g + 4m + q resp. 18g + 2m + q: the 32 lanes of
+// a warp hit 32 different banks), two 4x4 byte transposes, four 8x8 bit transposes, and 32
+// contiguous output bytes.  Unshuffle is the mirror image (32 contiguous input bytes per thread,
+// STS.32 into the padded rows, coalesced rows out).
+template <int T> struct BitSmemCfg {
+    static constexpr uint32_t kRow = 8 * T;                          // bytes of one group
+    static constexpr uint32_t kPad = T == 16 ? 16 : 8;               // row padding
+    static constexpr uint32_t kStride = kRow + kPad;
+    static constexpr uint32_t kGroups = kTileBytes / kRow;           // groups per tile
+    static constexpr uint32_t kQ = T / 4;                            // threads per group
+};
+constexpr uint32_t kFilterSmemBytes = BitSmemCfg<16>::kGroups * BitSmemCfg<16>::kStride;   // 18 432 >= both layouts
+static_assert(BitSmemCfg<8>::kGroups * BitSmemCfg<8>::kStride <= kFilterSmemBytes, "smem");
+
+// tile byte b (16-byte chunk) <-> its place in the padded rows
+template <int T> __device__ __forceinline__ uint32_t bit_smem_pos(uint32_t b) {
+    using C = BitSmemCfg<T>;
+    return (b / C::kRow) * C::kStride + (b % C::kRow);
+}
+
+template <int T>
+__device__ __forceinline__ void run_bitshuffle_smem(const uint8_t *s, uint8_t *d, uint64_t G, uint32_t tile0,
+                                                    uint32_t tstride, bool inverse, uint8_t *smem) {
+    using C = BitSmemCfg<T>;
+    const uint64_t ntiles = (G + C::kGroups - 1) / C::kGroups;
+    for (uint64_t t = tile0; t < ntiles; t += tstride) {
+        const uint64_t g0 = t * C::kGroups;
+        const uint32_t vg = (uint32_t)(G - g0 < C::kGroups ? G - g0 : C::kGroups);
+        const uint32_t vbytes = vg * C::kRow;
+        const uint8_t *ts = s + g0 * C::kRow;
+        uint8_t *td = d + g0 * C::kRow;
+        if (!inverse) {
+#pragma unroll
+            for (int it = 0; it < kTileBytes / 16 / kFilterThreads; it++) {
+                const uint32_t b = 16u * (it * kFilterThreads + threadIdx.x);
+                if (b < vbytes) {
+                    const uint4 v = ldg128_stream(ts + b);
+                    uint8_t *p = smem + bit_smem_pos<T>(b);                 // 16-byte aligned for T = 16, 8 for T = 8
+                    if constexpr (T == 16) *reinterpret_cast<uint4 *>(p) = v;
+                    else { *reinterpret_cast<uint2 *>(p) = make_uint2(v.x, v.y); *reinterpret_cast<uint2 *>(p + 8) = make_uint2(v.z, v.w); }
+                }
+            }
+            __syncthreads();
+            for (uint32_t item = threadIdx.x; item < vg * C::kQ; item += kFilterThreads) {
+                const uint32_t g = item / C::kQ, q = item % C::kQ;
+                const uint8_t *row = smem + g * C::kStride + 4u * q;
+                uint32_t w[8];
+#pragma unroll
+                for (int m = 0; m < 8; m++) w[m] = *reinterpret_cast<const uint32_t *>(row + T * m);
+                uint32_t lo[4], hi[4];
+                transpose4x4(w[0], w[1], w[2], w[3], lo[0], lo[1], lo[2], lo[3]);   // byte m of lo[k] = element m, byte 4q+k
+                transpose4x4(w[4], w[5], w[6], w[7], hi[0], hi[1], hi[2], hi[3]);
+#pragma unroll
+                for (int k = 0; k < 4; k++) bit_transpose8(lo[k], hi[k]);
+                uint8_t *o = td + g * C::kRow + 32u * q;                                // dst[8gT + 8j ..], j = 4q..4q+3
+                stg128_stream(o, make_uint4(lo[0], hi[0], lo[1], hi[1]));
+                stg128_stream(o + 16, make_uint4(lo[2], hi[2], lo[3], hi[3]));
+            }
+            __syncthreads();
+        } else {
+            for (uint32_t item = threadIdx.x; item < vg * C::kQ; item += kFilterThreads) {
+                const uint32_t g = item / C::kQ, q = item % C::kQ;
+                const uint8_t *in = ts + g * C::kRow + 32u * q;
+                const uint4 a = ldg128_stream(in), b = ldg128_stream(in + 16);
+                uint32_t lo[4] = {a.x, a.z, b.x, b.z}, hi[4] = {a.y, a.w, b.y, b.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) bit_transpose8(lo[k], hi[k]);             // byte m = element m, byte 4q+k
+                uint32_t w[8];
+                transpose4x4(lo[0], lo[1], lo[2], lo[3], w[0], w[1], w[2], w[3]);     // w[m] = element m, bytes 4q..4q+3
+                transpose4x4(hi[0], hi[1], hi[2], hi[3], w[4], w[5], w[6], w[7]);
+                uint8_t *row = smem + g * C::kStride + 4u * q;
+#pragma unroll
+                for (int m = 0; m < 8; m++) *reinterpret_cast<uint32_t *>(row + T * m) = w[m];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < kTileBytes / 16 / kFilterThreads; it++) {
+                const uint32_t b = 16u * (it * kFilterThreads + threadIdx.x);
+                if (b < vbytes) {
+                    const uint8_t *p = smem + bit_smem_pos<T>(b);
+                    uint4 v;
+                    if constexpr (T == 16) v = *reinterpret_cast<const uint4 *>(p);
+                    else { const uint2 x = *reinterpret_cast<const uint2 *>(p), y = *reinterpret_cast<const uint2 *>(p + 8); v = make_uint4(x.x, x.y, y.x, y.y); }
+                    stg128_stream(td + b, v);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kFilterThreads, 6) filter_batch_kernel(FilterArgs a) {
-    __shared__ __align__(16) uint8_t smem[kTileBytes];
+    __shared__ __align__(16) uint8_t smem[kFilterSmemBytes];
     const uint32_t tpf = a.ft.tiles_per_frame;
     const uint32_t f = blockIdx.x / tpf, tile0 = blockIdx.x % tpf;
     if (f >= a.ft.nframes) return;
@@ -527,10 +622,10 @@ __global__ void __launch_bounds__(kFilterThreads, 6) filter_batch_kernel(FilterA
     } else {
         const uint64_t G = E / 8;
         covered = G * 8 * T;
-        if (aligned && T == 8) run_bitshuffle_fast<8>(s, d, G, tile0, tpf, inverse);
+        if (aligned && T == 8) run_bitshuffle_smem<8>(s, d, G, tile0, tpf, inverse, smem);
         else if (aligned && T == 4) run_bitshuffle_fast<4>(s, d, G, tile0, tpf, inverse);
         else if (aligned && T == 2) run_bitshuffle_fast<2>(s, d, G, tile0, tpf, inverse);
-        else if (aligned && T == 16) run_bitshuffle_fast<16>(s, d, G, tile0, tpf, inverse);
+        else if (aligned && T == 16) run_bitshuffle_smem<16>(s, d, G, tile0, tpf, inverse, smem);
         else {
             // items (g, j): 8 bytes each; a tile is kTileBytes / 8 items
             const uint64_t items = G * T, ipt = kTileBytes / 8;
