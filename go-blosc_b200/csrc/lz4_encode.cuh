@@ -5,30 +5,30 @@
 // block per frame, so a frame is still one block on the wire, but it is produced in
 // parallel:
 //
-//   encode   one warp per 64 KiB SEGMENT of a frame.  A segment only references itself (the
-//            LZ4 window is 64 KiB anyway), so segments are independent, positions fit the 16
-//            bits of a hash-table entry exactly, and the reference compressor's adaptive skip
-//            restarts at every segment (after a byte shuffle: at every byte plane).
-//            The warp writes the segment's sequences in final wire format into a scratch
-//            slot, EXCEPT the token / literal run of its first sequence and its trailing
+//   encode   one warp per 64 KiB SEGMENT of a frame (warps take (frame, segment) items from an
+//            atomic ticket: byte planes of very different compressibility would otherwise leave
+//            most warps of a CTA idle).  A segment references only itself and the last kWarmBytes
+//            of its predecessor (entered into the hash table first, so runs and periodic patterns
+//            continue across the boundary), so positions fit a table entry and the reference
+//            compressor's adaptive skip restarts at every segment (after a byte shuffle: at every
+//            byte plane).  The warp writes the segment's sequences in final wire format into a
+//            scratch slot, EXCEPT the token / literal run of its first sequence and its trailing
 //            literals, which depend on the neighbouring segments.
 //   finalize one thread per frame walks the segment summaries: trailing literals of segment
 //            k are carried into the first sequence of the next segment that has a match
 //            (they are contiguous in the input), which fixes every segment's place in the
-//            block, the block size c and the memcpy decision (c >= n, blosc.go:342-345).
+//            block, the block size c and the memcpy decision (c >= n, blosc.go:342-345).  It
+//            also writes the optional side-car decode index (one entry per segment).
 //   pack     (after the offsets scan, K5) one CTA per segment writes the merged first token,
 //            its literals and the segment body at the frame's packed position; memcpy frames
 //            copy the raw bytes instead.  Segment 0 writes the 16-byte header.
 //
-// Match finder per warp: 32 candidate positions per step (consecutive, or spread with the
-// reference's skip schedule once literals pile up), a 2^HL-entry shared-memory hash table whose
-// 32-bit entries hold a 17-bit position and 15 check bits of the hash (a candidate is only
-// fetched from global memory when the check bits agree), MATCH.ANY for repeats inside the
-// step, a bounded look at the next two starts, 32-lane-wide backward / forward extension.
-// The last kWarmBytes of the previous segment are entered into the table first, so runs and
-// periodic patterns continue across a segment boundary instead of being re-emitted.
-// Warps take (frame, segment) items from an atomic ticket: planes of very different
-// compressibility would otherwise leave most warps of a CTA idle.
+// Match finder: a 2^HL-entry shared-memory hash table per warp whose 32-bit entries hold a
+// 17-bit position and 15 check bits of the multiplicative 4-byte hash (a candidate is only
+// fetched from global memory when the check bits agree).  Compressible regions are parsed by
+// STRIPS (one 61-byte strip per lane, see "dense parse" below); incompressible regions by the
+// reference's skip schedule (32 probes per step at a growing stride, MATCH.ANY for repeats
+// inside the step, first hit wins, 32-lane-wide backward / forward extension).
 #pragma once
 #include "common.cuh"
 
@@ -38,10 +38,8 @@ constexpr uint32_t kSegBytes = 65536;
 constexpr uint32_t kSegSlot = 65840;   // align16(65536 + 65536/255 + 32): worst case of one segment
 constexpr int kEncWarps = 4;           // segments (warps) per CTA
 constexpr int kEncThreads = kEncWarps * 32;
-constexpr int kHashLogDefault = 10;    // 2^10 x u32 = 4 KiB per warp: 48 resident warps per SM
+constexpr int kHashLogDefault = 10;    // 2^10 x u32 = 4 KiB (+ 3 KiB of match lists) per warp: 32 resident warps per SM
 constexpr uint32_t kWarmBytes = 512;   // tail of the previous segment pre-loaded into the hash table
-constexpr uint32_t kLazyWindow = 0;    // later starts considered after the first hit (0: plain greedy)
-constexpr uint32_t kLazyWords = 4;     // bounded look-ahead: 4 + 4 * 4 = 20 bytes
 
 struct SegMeta {
     uint32_t first_ll;   // literals before the first match (whole segment if there is none)
