@@ -226,7 +226,7 @@ int launch_encode(b2b_ctx *ctx, const EncodeArgs &e, cudaStream_t s) {
     const uint64_t warps = (uint64_t)e.nframes * e.segs_grid;
     const size_t smem = (size_t)kEncWarps * sizeof(uint32_t) << hl;
     // persistent CTAs: as many as fit on the device (warps pull items from the ticket)
-    const uint64_t per_sm = hl <= 10 ? 8 : hl == 11 ? 5 : hl == 12 ? 2 : 1;   // __launch_bounds__ of the kernel
+    const uint64_t per_sm = hl <= 10 ? 7 : hl == 11 ? 5 : hl == 12 ? 2 : 1;   // __launch_bounds__ of the kernel
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((warps + kEncWarps - 1) / kEncWarps,
                                                                      (uint64_t)ctx->sm_count * per_sm));
     CU(ctx, cudaMemsetAsync(e.ticket, 0, 8, s));

@@ -98,6 +98,18 @@ __device__ __forceinline__ void wv_load64(const WordView &v, uint32_t p, uint32_
     hi = __funnelshift_r(w1, w2, a << 3);
 }
 
+// the same in two halves, so that the loads can be issued one turn before their use
+__device__ __forceinline__ void wv_issue64(const WordView &v, uint32_t p, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
+    const uint32_t *q = v.w + ((p + v.sh) >> 2);
+    w0 = q[0]; w1 = q[1]; w2 = q[2];
+}
+__device__ __forceinline__ void wv_finish64(const WordView &v, uint32_t p, uint32_t w0, uint32_t w1, uint32_t w2,
+                                            uint32_t &lo, uint32_t &hi) {
+    const uint32_t a = (p + v.sh) << 3;
+    lo = __funnelshift_r(w0, w1, a);
+    hi = __funnelshift_r(w1, w2, a);
+}
+
 // writes a length extension (value already reduced by 15) at out, returns bytes written
 __device__ __forceinline__ uint32_t warp_put_len_ext(uint8_t *out, uint32_t v, int lane) {
     const uint32_t full = v / 255u, last = v - full * 255u;
@@ -185,7 +197,9 @@ __device__ __forceinline__ uint32_t extend_coop(const WordView &in, uint32_t fro
 // strip at an EARLIER turn (P mod kStrip turns before), so it is already in the table.
 constexpr uint32_t kStrip = 61;
 constexpr uint32_t kStripCap = 61;       // own match followed this far past the strip end
-constexpr uint32_t kListMax = 16;        // matches (>= 4 bytes, disjoint) that can start in one strip
+constexpr uint32_t kListMax = 14;        // matches a lane records per strip (a 15th would need 61 bytes of
+                                         // back-to-back 4-byte matches; the lane then stops probing).  14 rather
+                                         // than 16 keeps a CTA at 26.5 KiB of shared memory: 8 CTAs per SM, not 7
 constexpr uint32_t kLaneLitEmit = 32;    // literal runs up to here are written by the owning lane
 
 struct LaneLists {
@@ -247,6 +261,10 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             const uint32_t cap = send + strip_cap < mlimit ? send + strip_cap : mlimit;
             uint32_t cnt = 0, e = 0, moff = 0, mst = 0, my_last = 0;
             bool ext = false, my_open = false;
+            // the 8 + 8 bytes the next extension turn compares, loaded a turn ahead (the candidate is
+            // typically kilobytes back: an L2 round trip that would otherwise open every turn).  Doing
+            // the same for the probe window and the previous-offset window was measured and did not pay.
+            uint32_t xa0 = 0, xa1 = 0, xa2 = 0, xb0 = 0, xb1 = 0, xb2 = 0;
             {   // the next step's strips: bring their lines into L2 while this step is parsed
                 const uint32_t a = si + 32u * strip + 64u * (uint32_t)lane;
                 if (a < mlimit) asm volatile("prefetch.global.L2 [%0];" ::"l"(org + a));
@@ -308,19 +326,24 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
 #pragma unroll
                         for (int k = 0; k < 4; k++)
                             if ((uint32_t)k < upto) table[hh[k]] = (chk[k] << 17) | (pos + k);
-                        if (pick >= 0) { ext = true; mst = pos + pick; moff = mst - pc; e = sure ? mst + 4 : mst; }
-                        else pos += nv;
+                        if (pick >= 0) {
+                            ext = true; mst = pos + pick; moff = mst - pc; e = sure ? mst + 4 : mst;
+                            if (e + 8 <= cap) { wv_issue64(in, e, xa0, xa1, xa2); wv_issue64(in, e - moff, xb0, xb1, xb2); }
+                        } else pos += nv;
                     }
                 } else {
                     bool done = true, cancel = false;
                     if (e + 8 <= cap) {
                         uint32_t a0, a1, b0, b1;
-                        wv_load64(in, e, a0, a1);
-                        wv_load64(in, e - moff, b0, b1);
+                        wv_finish64(in, e, xa0, xa1, xa2, a0, a1);
+                        wv_finish64(in, e - moff, xb0, xb1, xb2, b0, b1);
                         const uint32_t x0 = a0 ^ b0, x1 = a1 ^ b1;
                         if (x0) { cancel = e == mst; e += (uint32_t)(__ffs((int)x0) - 1) >> 3; }
                         else if (x1) e += 4u + ((uint32_t)(__ffs((int)x1) - 1) >> 3);
-                        else { e += 8; done = false; }
+                        else {
+                            e += 8; done = false;
+                            if (e + 8 <= cap) { wv_issue64(in, e, xa0, xa1, xa2); wv_issue64(in, e - moff, xb0, xb1, xb2); }
+                        }
                     } else {
                         if (e == mst) {
                             if (wv_load32(in, e) == wv_load32(in, e - moff)) e += 4; else cancel = true;
@@ -333,7 +356,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                         lists->a[cnt][lane] = mst | ((e - mst) << 17);
                         lists->off[cnt][lane] = (uint16_t)moff;
                         cnt++;
-                        pos = e; rep = moff; my_last = e; ext = false;
+                        pos = cnt < kListMax ? e : send; rep = moff; my_last = e; ext = false;
                     }
                 }
             }
@@ -563,7 +586,7 @@ struct EncodeArgs {
 };
 
 template <int HL>
-__global__ void __launch_bounds__(kEncThreads, HL <= 10 ? 8 : (HL == 11 ? 5 : (HL == 12 ? 2 : 1)))
+__global__ void __launch_bounds__(kEncThreads, HL <= 10 ? 7 : (HL == 11 ? 5 : (HL == 12 ? 2 : 1)))
 lz4_encode_kernel(EncodeArgs a) {
     extern __shared__ __align__(16) uint32_t enc_tables[];   // kEncWarps x 2^HL entries
     __shared__ LaneLists enc_lists[kEncWarps];
@@ -574,7 +597,10 @@ lz4_encode_kernel(EncodeArgs a) {
         if (lane == 0) item = atomicAdd(a.ticket, 1ull);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= items) break;
-        const uint32_t f = (uint32_t)(item / a.segs_grid), s0 = (uint32_t)(item % a.segs_grid);
+        // segment-major ticket order: segment k of every frame before segment k+1 of any.  After a byte
+        // shuffle segment k is byte plane k, so segments of equal cost sit together and the launch ends
+        // on whatever the last plane costs instead of on one late, expensive segment
+        const uint32_t f = (uint32_t)(item % a.nframes), s0 = (uint32_t)(item / a.nframes);
         const uint32_t n = a.src_len[f];
         const uint32_t nseg = seg_count(n);
         const uint8_t *frame = a.in + a.src_off[f];
@@ -586,7 +612,7 @@ lz4_encode_kernel(EncodeArgs a) {
                                                       a.comp + a.comp_off[f] + (uint64_t)s * kSegSlot,
                                                       enc_tables + ((size_t)warp << HL), &enc_lists[warp], lane,
                                                       a.tune[0] ? a.tune[0] : 256u,
-                                                      a.tune[1] ? (a.tune[1] < 4u * kListMax ? a.tune[1] : 4u * kListMax) : kStrip,
+                                                      a.tune[1] ? (a.tune[1] < 64u ? a.tune[1] : 64u) : kStrip,
                                                       a.tune[2] ? a.tune[2] : kStripCap);
             if (lane == 0) a.meta[a.seg_base[f] + s] = m;
             __syncwarp();
