@@ -286,18 +286,14 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                             hh[k] = hv >> (32 - HL); chk[k] = (hv >> (17 - HL)) & 0x7FFFu;
                             ent[k] = table[hh[k]];
                         }
-                        // the lane's previous offset is tried as well (constant strides, periodic data)
-                        uint32_t rs[4] = {0, 0, 0, 0};
+                        // the lane's previous offset is tried as well (constant strides, periodic data).  Its
+                        // window is typically kilobytes back (an L2 hit): the loads go out here and are only
+                        // looked at after the table candidates and the inserts
+                        uint32_t r0 = 0, r1 = 0, r2 = 0;
                         const bool rep_ok = rep != 0 && rep <= pos;
-                        if (rep_ok) {
-                            uint32_t y0, y1;
-                            wv_load64(in, pos - rep, y0, y1);
-                            rs[0] = y0; rs[1] = __funnelshift_r(y0, y1, 8);
-                            rs[2] = __funnelshift_r(y0, y1, 16); rs[3] = __funnelshift_r(y0, y1, 24);
-                        }
-                        // first position with a candidate.  A table entry whose check bits agree is taken
-                        // unverified: the first turn of the extension compares the bytes anyway.  At the same
-                        // position the lane's previous offset wins over the table (fewer, longer sequences).
+                        if (rep_ok) wv_issue64(in, pos - rep, r0, r1, r2);
+                        // first position with a table candidate.  An entry whose check bits agree is taken
+                        // unverified: the first turn of the extension compares the bytes anyway.
                         int pick = -1;
                         uint32_t pc = 0;
                         bool sure = false;
@@ -305,10 +301,24 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                         for (int k = 3; k >= 0; k--) {
                             // c is the candidate position if the check bits agree, else >= 2^17 (> any position)
                             const uint32_t c = ent[k] ^ (chk[k] << 17), p = pos + k;
-                            if ((uint32_t)k < nv) {
-                                if (p - c - 1u < 65535u) { pick = k; pc = c; sure = false; }     // c < p, p - c <= 65535
-                                if (rep_ok && rs[k] == seq[k]) { pick = k; pc = p - rep; sure = true; }   // preferred: known good
-                            }
+                            if ((uint32_t)k < nv && p - c - 1u < 65535u) { pick = k; pc = c; }   // c < p, p - c <= 65535
+                        }
+                        // positions up to the chosen one are recorded (like the scalar compressor, which
+                        // does not enter the positions it jumps over)
+                        const uint32_t upto = pick < 0 ? nv : (uint32_t)pick + 1u;
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if ((uint32_t)k < upto) table[hh[k]] = (chk[k] << 17) | (pos + k);
+                        // the previous offset wins at the same or an earlier position (fewer, longer sequences)
+                        if (rep_ok) {
+                            uint32_t y0, y1;
+                            wv_finish64(in, pos - rep, r0, r1, r2, y0, y1);
+                            const uint32_t lim = pick < 0 ? nv : (uint32_t)pick + 1u;
+                            if (lim > 3 && __funnelshift_r(y0, y1, 24) == seq[3]) { pick = 3; sure = true; }
+                            if (lim > 2 && __funnelshift_r(y0, y1, 16) == seq[2]) { pick = 2; sure = true; }
+                            if (lim > 1 && __funnelshift_r(y0, y1, 8) == seq[1]) { pick = 1; sure = true; }
+                            if (y0 == seq[0]) { pick = 0; sure = true; }
+                            if (sure) pc = pos + (uint32_t)pick - rep;
                         }
                         if (pick < 0) {
                             // repeats inside the group (runs, periods 1..3): nearest earlier position
@@ -320,12 +330,6 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                             if (nv > 1 && (seq[1] == seq[0])) { pick = 1; pc = pos; }
                             sure = true;
                         }
-                        // positions up to the chosen one are recorded (like the scalar compressor, which
-                        // does not enter the positions it jumps over)
-                        const uint32_t upto = pick < 0 ? nv : (uint32_t)pick + 1u;
-#pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if ((uint32_t)k < upto) table[hh[k]] = (chk[k] << 17) | (pos + k);
                         if (pick >= 0) {
                             ext = true; mst = pos + pick; moff = mst - pc; e = sure ? mst + 4 : mst;
                             if (e + 8 <= cap) { wv_issue64(in, e, xa0, xa1, xa2); wv_issue64(in, e - moff, xb0, xb1, xb2); }
