@@ -316,6 +316,52 @@ def test_gpu_decoder_rejects_malformed(ctx, pkg):
             assert ctx.decompress(fr) == bytes(want), (off, ml)
 
 
+@pytest.mark.parametrize("kind", ["smooth_f32", "lowent_i16", "text", "copies"])
+def test_gpu_decoder_fuzz_mutated_frames_match_oracle(ctx, orc, kind):
+    """Fuzz contract of the reference (fuzz_test.go: no panic, an error or the right bytes): valid
+    frames with random bytes flipped / truncated / length fields changed go through the GPU batch decoder
+    and through the oracle; every frame must get the oracle's status and, when it decodes, the oracle's
+    bytes.  The whole batch of mutants is one launch, so a wild access in any of them would be seen."""
+    rng = np.random.default_rng({"smooth_f32": 1, "lowent_i16": 2, "text": 3, "copies": 4}[kind])
+    frames, caps = [], []
+    for n in (700, 5000, 70000):
+        data = dg.corpus(n)[kind] if kind != "copies" else dg.strip_adversarial(n, 5)["copies"]
+        sh, T = (1, 4) if kind in ("smooth_f32",) else (1, 2) if kind == "lowent_i16" else (0, 1)
+        base = np.frombuffer(ctx.compress(data, 1, 5, sh, T), dtype=np.uint8)
+        if base[2] & 2:                       # memcpy frames have no LZ4 stream to break
+            continue
+        for _ in range(40):
+            m = base.copy()
+            what = int(rng.integers(0, 5))
+            if what == 0:                     # flip 1..4 payload bytes
+                for _ in range(int(rng.integers(1, 5))):
+                    m[int(rng.integers(16, m.size))] ^= np.uint8(rng.integers(1, 256))
+            elif what == 1:                   # overwrite a short payload run with 0xFF (length extensions)
+                p0 = int(rng.integers(16, m.size)); m[p0:p0 + int(rng.integers(1, 6))] = 255
+            elif what == 2:                   # truncate the stream (NBytesComp follows)
+                cut = int(rng.integers(17, m.size)); m = m[:cut].copy(); m[12:16] = np.frombuffer(struct.pack("<I", cut), dtype=np.uint8)
+            elif what == 3:                   # NBytesOrig off by a little
+                no = int(rs.hdr(m)["norig"]) + int(rng.integers(-3, 4)); m[4:8] = np.frombuffer(struct.pack("<I", max(no, 1)), dtype=np.uint8)
+            else:                             # zero an offset-looking pair somewhere
+                p0 = int(rng.integers(16, m.size - 1)); m[p0] = 0; m[p0 + 1] = 0
+            frames.append(m); caps.append(int(rs.hdr(m)["norig"]))
+    if not frames:
+        pytest.skip("only memcpy frames for this kind")
+    want = [orc.decompress(f) for f in frames]
+    flen = np.array([f.size for f in frames], dtype=np.uint32)
+    foff = np.concatenate([[0], np.cumsum((flen[:-1].astype(np.uint64) + 15) // 16 * 16)]).astype(np.uint64)
+    blob = np.zeros(int(foff[-1] + flen[-1]) + 64, dtype=np.uint8)
+    for o, f in zip(foff, frames):
+        blob[int(o):int(o) + f.size] = f
+    cap = np.array(caps, dtype=np.uint64)
+    doff = np.concatenate([[0], np.cumsum((cap[:-1] + 15) // 16 * 16)]).astype(np.uint64)
+    out, olen, st = ctx.decompress_batch(blob, foff, flen, doff, int(doff[-1] + cap[-1]) + 64)
+    for k, (rc, ref) in enumerate(want):
+        assert int(st[k]) == rc, (kind, k, int(st[k]), rc)
+        if rc == 0:
+            assert int(olen[k]) == ref.size and np.array_equal(out[int(doff[k]):int(doff[k]) + ref.size], ref), (kind, k)
+
+
 def _ext(v):
     out = bytearray()
     while v >= 255:
