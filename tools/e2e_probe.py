@@ -1,0 +1,30 @@
+"""Host-pointer path timing: compress_batch and decompress_batch separately (pinned buffers)."""
+import os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as entry
+from tools.perf_probe_lib import gen_f32
+pkg = entry.load_package()
+ctx = pkg.Context(0)
+FRAME = 262144
+total = int(os.environ.get("PROBE_BYTES", 2 << 30))
+nf = total // FRAME
+src = gen_f32(total // 4)
+h_src = torch.empty(total, dtype=torch.uint8, pin_memory=True); h_src.copy_(src)
+h_comp = torch.empty(total + 32 * nf + 64, dtype=torch.uint8, pin_memory=True)
+h_out = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+offs = np.arange(nf, dtype=np.uint64) * FRAME
+lens = np.full(nf, FRAME, dtype=np.uint32)
+a_src, a_comp, a_out = h_src.numpy(), h_comp.numpy(), h_out.numpy()
+for st in [int(x) for x in os.environ.get("PROBE_STAGES", "128").split(",")]:
+    ctx.set_option(pkg.OPT_HOST_STAGE_BYTES, st << 20)
+    tc, td = [], []
+    for it in range(4):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        _, foff, flen, stt, tot = ctx.compress_batch(a_src, offs, lens, pkg.Shuffle.Shuffle1, 4, dst=a_comp)
+        t1 = time.perf_counter()
+        _, olen, st2 = ctx.decompress_batch(a_comp, foff, flen, offs, total, dst=a_out)
+        t2 = time.perf_counter()
+        if it: tc.append(t1 - t0); td.append(t2 - t1)
+    print(f"stage {st} MiB: compress {1e3 * min(tc):.1f} ms (H2D {total / 1e6:.0f} MB, D2H {tot / 1e6:.0f} MB -> {total / min(tc) / 1e9:.1f} GB/s in), "
+          f"decompress {1e3 * min(td):.1f} ms ({total / min(td) / 1e9:.1f} GB/s out), ok={bool(torch.equal(h_out, h_src))}")
