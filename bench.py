@@ -58,6 +58,23 @@ def committed_traffic(kernel, bytes_per_gpu):
         return None
 
 
+def bind_to_gpu_numa_node(index):
+    """Best effort: run this rank on the cores NVML reports as local to its GPU, so that the pinned
+    host buffers of the e2e leg (first touch) and the DMA traffic stay on that socket."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def workload_name(total_bytes, nframes):
     return (f"C3: float32 smooth field, {total_bytes / 2**30:g} GiB per GPU = {nframes} frames x 256 KiB, "
             f"LZ4 level 5 + Shuffle1 typesize 4, compress then decompress")
@@ -219,6 +236,9 @@ def run_gpu(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    if world > 1:
+        bind_to_gpu_numa_node(local)       # pinned e2e buffers are then allocated next to this rank's GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -347,7 +367,8 @@ def run_gpu(args):
                             "shared-memory hash table), not HBM-bound: DESIGN.md section 4 and profiles/r01c_ncu_summary.md"}
         # e2e through the host-pointer C ABI with pinned host buffers
         e2e = run_e2e(torch, pkg, ctx, args, dev, src, nf, total, world)
-        # CPU baseline (oracle port), bounded sample
+        # CPU baseline (oracle port), bounded sample, on all host cores
+        os.sched_setaffinity(0, all_cpus)
         threads = os.cpu_count() or 1
         cpu = cpu_round_trip(orc, int(args.cpu_sample_mib) << 20, threads, reps=2)
         line = {
