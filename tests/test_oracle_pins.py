@@ -175,3 +175,33 @@ def test_golden_fixtures(orc):
         assert rc == item.get("decode_status", 0)
         if rc == 0:
             assert hashlib.sha256(out.tobytes()).hexdigest() == item["decoded_sha256"]
+
+
+def test_frames_produced_by_the_cuda_encoder_are_valid_go_blosc_frames():
+    """tests/golden/gpu_frames_v1.json holds frames the CUDA path (shuffle + K3 + pack) produced on a
+    B200 (generator: tests/make_gpu_golden.py).  Without a GPU: the oracle -- the restated reference
+    Decompress -- and liblz4 decode them to the formula inputs, header fields are the reference's."""
+    import hashlib
+    import json
+    from make_golden import make_input
+    import oracle as orc
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpu_frames_v1.json")) as f:
+        gold = json.load(f)
+    assert len(gold["frames"]) >= 8
+    for item in gold["frames"]:
+        data = make_input(item["input"])
+        assert hashlib.sha256(data.tobytes()).hexdigest() == item["input_sha256"]
+        fr = np.frombuffer(bytes.fromhex(item["frame_hex"]), dtype=np.uint8)
+        assert fr.size == item["frame_len"]
+        rc, ref = orc.compress(data, orc.LZ4, 5, item["shuffle"], item["typesize"])
+        assert rc == 0 and fr[:2].tobytes() == ref[:2].tobytes() and fr[3:12].tobytes() == ref[3:12].tobytes()
+        assert (fr[2] & 0x5) == (ref[2] & 0x5)
+        assert int.from_bytes(fr[12:16].tobytes(), "little") == fr.size
+        rc, back = orc.decompress(fr)
+        assert rc == 0 and np.array_equal(back, data), item["input"]
+        if not fr[2] & 0x2:
+            assert fr.size <= ref.size * 1.25 + 64, (item["input"], fr.size, ref.size)   # loose: size parity is test_gpu_parity's job
+            if orc.liblz4() is not None:
+                filt = {0: lambda d, t: d, 1: orc.shuffle, 2: orc.bitshuffle}[item["shuffle"]](data, item["typesize"])
+                got = orc.liblz4_decompress(fr[16:], data.size)
+                assert got is not None and np.array_equal(got, filt), item["input"]
