@@ -223,7 +223,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                                                        uint32_t L, uint64_t tail,
                                                        uint8_t *__restrict__ body, uint32_t *table,
                                                        LaneLists *lists, int lane, uint32_t dense_lits,
-                                                       uint32_t strip, uint32_t strip_cap) {
+                                                       uint32_t strip_full, uint32_t strip_cap, bool cold_start) {
     EncState st;
     st.body = body; st.op = 0; st.have_first = false;
     st.m.first_ll = L; st.m.body_len = 0; st.m.trail_ll = L; st.m.info = 0;
@@ -249,14 +249,25 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
     }
     uint32_t anchor = W, si = W;
     uint32_t rep = 0;                                            // this lane's last match offset
+    uint32_t ramp = cold_start ? 0u : 5u;                        // dense steps taken so far (5: no ramp)
     while (si < mfl) {
         // adaptive skip of the reference compressor: about 3 probes per 4 + lits/128 bytes
         const uint32_t lits = si - anchor;
         const uint32_t stride = lits < dense_lits ? 1u : (4u + (lits >> 7)) / 3u;
         if (stride == 1) {
             // ------------------------------------------------------------ dense step: strips
+            // The first dense steps of a segment run on 1, 2, 4, 8, 16 lanes: the table is cold, and inside
+            // ONE step a lane cannot see what a lower lane will only reach in a later turn, so a period
+            // that first repeats inside a full step is mostly missed there (a 1024-byte period lost 79 %
+            // of its first 1952 bytes).  With the step size doubling, an earlier occurrence of a position
+            // lies in an earlier step (or in its own strip), which the table already holds.
+            // Only the first segment of a frame pays for this (small frames live there entirely; a later
+            // segment can lose at most the first repeat inside one step, about a kilobyte).
+            const uint32_t strip = strip_full;
+            const uint32_t nlanes = ramp < 5 ? (1u << ramp) : 32u;
+            ramp++;
             uint32_t pos = si + (uint32_t)lane * strip;
-            if (pos > mfl) pos = mfl;
+            if (pos > mfl || (uint32_t)lane >= nlanes) pos = mfl;
             const uint32_t send = pos + strip < mfl ? pos + strip : mfl;
             const uint32_t cap = send + strip_cap < mlimit ? send + strip_cap : mlimit;
             uint32_t cnt = 0, e = 0, moff = 0, mst = 0, my_last = 0;
@@ -266,7 +277,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             // the same for the probe window and the previous-offset window was measured and did not pay.
             uint32_t xa0 = 0, xa1 = 0, xa2 = 0, xb0 = 0, xb1 = 0, xb2 = 0;
             {   // the next step's strips: bring their lines into L2 while this step is parsed
-                const uint32_t a = si + 32u * strip + 64u * (uint32_t)lane;
+                const uint32_t a = si + nlanes * strip + 64u * (uint32_t)lane;
                 if (a < mlimit) asm volatile("prefetch.global.L2 [%0];" ::"l"(org + a));
             }
             while (__any_sync(0xffffffffu, ext || pos < send)) {
@@ -364,7 +375,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                     }
                 }
             }
-            const uint32_t region_end = si + 32u * strip < mfl ? si + 32u * strip : mfl;
+            const uint32_t region_end = si + nlanes * strip < mfl ? si + nlanes * strip : mfl;
             const uint32_t any_match = __ballot_sync(0xffffffffu, cnt != 0);
             if (any_match == 0) { si = region_end; continue; }
             // ---- open matches are finished 32 lanes wide, in stream order; one that an earlier
@@ -617,7 +628,7 @@ lz4_encode_kernel(EncodeArgs a) {
                                                       enc_tables + ((size_t)warp << HL), &enc_lists[warp], lane,
                                                       a.tune[0] ? a.tune[0] : 256u,
                                                       a.tune[1] ? (a.tune[1] < 64u ? a.tune[1] : 64u) : kStrip,
-                                                      a.tune[2] ? a.tune[2] : kStripCap);
+                                                      a.tune[2] ? a.tune[2] : kStripCap, B == 0);
             if (lane == 0) a.meta[a.seg_base[f] + s] = m;
             __syncwarp();
         }

@@ -200,7 +200,7 @@ def test_frames_produced_by_the_cuda_encoder_are_valid_go_blosc_frames():
         rc, back = orc.decompress(fr)
         assert rc == 0 and np.array_equal(back, data), item["input"]
         if not fr[2] & 0x2:
-            assert fr.size <= ref.size * 1.25 + 64, (item["input"], fr.size, ref.size)   # loose: size parity is test_gpu_parity's job
+            assert fr.size <= ref.size * 1.4 + 64, (item["input"], fr.size, ref.size)   # loose: size parity on the BASELINE configs is test_gpu_parity's job
             if orc.liblz4() is not None:
                 filt = {0: lambda d, t: d, 1: orc.shuffle, 2: orc.bitshuffle}[item["shuffle"]](data, item["typesize"])
                 got = orc.liblz4_decompress(fr[16:], data.size)
