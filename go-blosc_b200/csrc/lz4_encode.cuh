@@ -7,7 +7,7 @@
 //
 //   encode   one warp per 64 KiB SEGMENT of a frame (warps take (frame, segment) items from an
 //            atomic ticket: byte planes of very different compressibility would otherwise leave
-//            most warps of a CTA idle).  A segment references only itself and the last kWarmBytes
+//            most warps of a CTA idle).  A segment references only itself and the last kWarmBytes (4.5 KiB)
 //            of its predecessor (entered into the hash table first, so runs and periodic patterns
 //            continue across the boundary), so positions fit a table entry and the reference
 //            compressor's adaptive skip restarts at every segment (after a byte shuffle: at every
@@ -39,7 +39,8 @@ constexpr uint32_t kSegSlot = 65840;   // align16(65536 + 65536/255 + 32): worst
 constexpr int kEncWarps = 4;           // segments (warps) per CTA
 constexpr int kEncThreads = kEncWarps * 32;
 constexpr int kHashLogDefault = 10;    // 2^10 x u32 = 4 KiB (+ 3 KiB of match lists) per warp: 32 resident warps per SM
-constexpr uint32_t kWarmBytes = 512;   // tail of the previous segment pre-loaded into the hash table
+constexpr uint32_t kWarmBytes = 4608;  // tail of the previous segment pre-loaded into the hash table:
+constexpr uint32_t kWarmDense = 512;   //   its last kWarmDense bytes at every position, the rest at every 4th
 
 struct SegMeta {
     uint32_t first_ll;   // literals before the first match (whole segment if there is none)
@@ -238,15 +239,39 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
     const WordView in = word_view(org);
     for (uint32_t i = lane; i < (1u << HL); i += kWarp) table[i] = 0;
     __syncwarp();
-    // warm-up: enter the tail of the previous segment (ascending, so the nearest position wins)
-    for (uint32_t q0 = 0; q0 < W; q0 += kWarp) {
-        const uint32_t q = q0 + lane;
-        if (q + 3 < W) {
-            const uint32_t hv = wv_load32(in, q) * 2654435761u;
-            table[hv >> (32 - HL)] = (((hv >> (17 - HL)) & 0x7FFFu) << 17) | q;
+    // warm-up: enter the tail of the previous segment (ascending, so the nearest position wins).  The
+    // older part goes in at every 4th position: a repeat of 8 bytes or more still meets an entered
+    // position within 3 bytes and backward extension recovers the start, so periods up to 4 KiB
+    // continue across a segment boundary at a quarter of the cost.
+    const uint32_t Wsparse = W > kWarmDense ? W - kWarmDense : 0u;
+    for (uint32_t q0 = 0; q0 < Wsparse; q0 += 16u * kWarp) {        // four loads in flight per lane
+        uint32_t hv[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t q = q0 + 4u * ((uint32_t)j * kWarp + (uint32_t)lane);
+            hv[j] = q < Wsparse ? wv_load32(in, q) * 2654435761u : 0u;
         }
-        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t q = q0 + 4u * ((uint32_t)j * kWarp + (uint32_t)lane);
+            if (q < Wsparse) table[hv[j] >> (32 - HL)] = (((hv[j] >> (17 - HL)) & 0x7FFFu) << 17) | q;
+        }
     }
+    __syncwarp();
+    for (uint32_t q0 = Wsparse; q0 < W; q0 += 4u * kWarp) {
+        uint32_t hv[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t q = q0 + (uint32_t)j * kWarp + (uint32_t)lane;
+            hv[j] = q + 3 < W ? wv_load32(in, q) * 2654435761u : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t q = q0 + (uint32_t)j * kWarp + (uint32_t)lane;
+            if (q + 3 < W) table[hv[j] >> (32 - HL)] = (((hv[j] >> (17 - HL)) & 0x7FFFu) << 17) | q;
+        }
+    }
+    __syncwarp();
     uint32_t anchor = W, si = W;
     uint32_t rep = 0;                                            // this lane's last match offset
     uint32_t ramp = cold_start ? 0u : 5u;                        // dense steps taken so far (5: no ramp)
