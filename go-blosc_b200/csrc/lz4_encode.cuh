@@ -120,6 +120,32 @@ __device__ __forceinline__ uint32_t warp_put_len_ext(uint8_t *out, uint32_t v, i
 }
 
 // ---- emission helpers ----------------------------------------------------------------------
+// A lane's output stream leaves as aligned 32-bit words: bytes collect in a 64-bit accumulator and
+// are stored four at a time once the write position is 4-byte aligned; the unaligned head and the
+// last < 4 bytes go out as single bytes (their neighbours belong to other lanes).  32 lanes writing
+// scattered single bytes cost one LSU wavefront per byte; this cuts them by about four.
+struct LaneWriter {
+    uint8_t *p;        // where the first byte still held in acc goes
+    uint32_t acc;
+    uint32_t nb;       // bytes held in acc (< 4)
+    __device__ __forceinline__ void begin(uint8_t *at) { p = at; acc = 0; nb = 0; }
+    __device__ __forceinline__ void put(uint32_t v, uint32_t n) {       // n <= 4 bytes, v clean above them
+        if ((uintptr_t)p & 3u) {                                        // unaligned head: single bytes
+            for (uint32_t i = 0; i < n; i++) {
+                if ((uintptr_t)p & 3u) { *p++ = (uint8_t)v; v >>= 8; }
+                else { acc |= (v & 0xFFu) << (8u * nb); nb++; v >>= 8; }
+            }
+            return;
+        }
+        const uint32_t s = 8u * nb;
+        const uint32_t lo = acc | (v << s), hi = __funnelshift_l(v, 0u, s);   // hi = v >> (32 - s), 0 for s = 0
+        nb += n;
+        if (nb >= 4) { *reinterpret_cast<uint32_t *>(p) = lo; p += 4; acc = hi; nb -= 4; }
+        else acc = lo;
+    }
+    __device__ __forceinline__ void flush() { while (nb) { *p++ = (uint8_t)acc; acc >>= 8; nb--; } }
+};
+
 struct EncState {
     uint8_t *body;
     uint32_t op;
@@ -224,7 +250,8 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                                                        uint32_t L, uint64_t tail,
                                                        uint8_t *__restrict__ body, uint32_t *table,
                                                        LaneLists *lists, int lane, uint32_t dense_lits,
-                                                       uint32_t strip_full, uint32_t strip_cap, bool cold_start) {
+                                                       uint32_t strip_full, uint32_t strip_cap, bool cold_start,
+                                                       uint32_t writer_min_lits) {
     EncState st;
     st.body = body; st.op = 0; st.have_first = false;
     st.m.first_ll = L; st.m.body_len = 0; st.m.trail_ll = L; st.m.info = 0;
@@ -460,7 +487,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             const bool seg_first = !st.have_first && lane == __ffs(keptm) - 1;
             // ---- backward extension over the pending literals (down to the previous surviving match,
             // possibly in another strip) and the encoded size of this lane's sequences
-            uint32_t size = 0;
+            uint32_t size = 0, lit_sum = 0, nseq = 0;          // lit_sum: literals the lanes write themselves
             {
                 uint32_t pe = prev;
                 for (uint32_t k = kf; k < cnt; k++) {
@@ -474,6 +501,8 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                     const uint32_t ll = ms - pe, mlc = len - 4;
                     if (seg_first && k == kf) size += 2u + len_ext_bytes(mlc);
                     else size += 1u + len_ext_bytes(ll) + ll + 2u + len_ext_bytes(mlc);
+                    if (ll <= kLaneLitEmit) lit_sum += ll;
+                    nseq++;
                     pe = me;
                 }
             }
@@ -484,8 +513,58 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                 if (lane >= d) incl += t;
             }
             const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const bool use_writer = __reduce_add_sync(0xffffffffu, lit_sum) >= writer_min_lits * __reduce_add_sync(0xffffffffu, nseq);
             // ---- every lane writes its own sequences; long literal runs are left to the warp
             uint32_t g_dst0 = 0, g_src0 = 0, g_len0 = 0, g_dst1 = 0, g_src1 = 0, g_len1 = 0;
+            // Two ways to write them: steps whose lanes write two or more literals per sequence on average
+            // (low-entropy data: runs of 8..30 literals between short matches) go through the aligned-word
+            // writer, which cuts the scattered single-byte stores by four (C5: 39 -> 30 ms per 8 GiB);
+            // steps of mostly token + offset, and steps whose literal runs are long enough to be copied
+            // 32 lanes wide anyway (C4), are cheaper byte by byte.
+            if (use_writer)
+            {
+                LaneWriter w;
+                w.begin(body + st.op + (incl - size));
+                uint32_t pe = prev, ng = 0;
+                for (uint32_t k = kf; k < cnt; k++) {
+                    const uint32_t a = lists->a[k][lane];
+                    const uint32_t ms = a & 0x1FFFFu;
+                    const uint32_t me = k + 1 == cnt ? my_last : ms + (a >> 17);
+                    const uint32_t offset = lists->off[k][lane];
+                    const uint32_t ll = ms - pe, mlc = me - ms - 4;
+                    if (seg_first && k == kf) {
+                        st.m.first_ll = ll;
+                        st.m.info = 0x100u | (mlc < 15 ? mlc : 15u);
+                    } else {
+                        w.put(((ll < 15 ? ll : 15u) << 4) | (mlc < 15 ? mlc : 15u), 1);
+                        if (ll >= 15) {
+                            uint32_t v = ll - 15;
+                            while (v >= 255) { w.put(255, 1); v -= 255; }
+                            w.put(v, 1);
+                        }
+                        if (ll <= kLaneLitEmit) {
+                            uint32_t i = 0;
+                            for (; i + 4 <= ll; i += 4) w.put(wv_load32(in, pe + i), 4);
+                            if (i < ll) w.put(wv_load32(in, pe + i) & (0xFFFFFFFFu >> (8u * (4u - (ll - i)))), ll - i);
+                        } else {
+                            w.flush();                                  // the run is copied 32 lanes wide below
+                            if (ng == 0) { g_dst0 = (uint32_t)(w.p - body); g_src0 = pe; g_len0 = ll; }
+                            else { g_dst1 = (uint32_t)(w.p - body); g_src1 = pe; g_len1 = ll; }
+                            ng++;
+                            w.p += ll;
+                        }
+                    }
+                    w.put(offset, 2);
+                    if (mlc >= 15) {
+                        uint32_t v = mlc - 15;
+                        while (v >= 255) { w.put(255, 1); v -= 255; }
+                        w.put(v, 1);
+                    }
+                    pe = me;
+                }
+                w.flush();
+            }
+            else
             {
                 uint8_t *b = body + st.op + (incl - size);
                 uint32_t pe = prev, ng = 0;
@@ -653,7 +732,8 @@ lz4_encode_kernel(EncodeArgs a) {
                                                       enc_tables + ((size_t)warp << HL), &enc_lists[warp], lane,
                                                       a.tune[0] ? a.tune[0] : 256u,
                                                       a.tune[1] ? (a.tune[1] < 64u ? a.tune[1] : 64u) : kStrip,
-                                                      a.tune[2] ? a.tune[2] : kStripCap, B == 0);
+                                                      a.tune[2] ? a.tune[2] : kStripCap, B == 0,
+                                                      a.tune[3] ? a.tune[3] - 1u : 2u);
             if (lane == 0) a.meta[a.seg_base[f] + s] = m;
             __syncwarp();
         }
