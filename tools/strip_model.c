@@ -27,7 +27,7 @@ static uint32_t hashf(const uint8_t *p) {
 static size_t put_ext(uint8_t *o, size_t v) { size_t k = 0; while (v >= 255) { o[k++] = 255; v -= 255; } o[k++] = (uint8_t)v; return k; }
 
 
-static int STRIP = 64, CAPX = 2, SM = 0, NOTRIMBACK = 0, BACKX = 0, REP = 0, GROUP = 4, WAYS2 = 0, UPTO = 0, INGRP = 0, MINM = 4, PHASED = 0, RECMAX = 16, HALVES = 1, SKIPCONT = 0, NOSHIFT = 0, REPFIRST = 0, LCMP = 16, SHORTRULE = 0, SHORTLEN = 6, SHORTLL = 15, REPWIN = 0;
+static int STRIP = 64, CAPX = 2, SM = 0, NOTRIMBACK = 0, BACKX = 0, REP = 0, GROUP = 4, WAYS2 = 0, UPTO = 0, INGRP = 0, MINM = 4, MINM_TABLE_ONLY = 0, PHASED = 0, RECMAX = 16, HALVES = 1, SKIPCONT = 0, NOSHIFT = 0, REPFIRST = 0, LCMP = 16, SHORTRULE = 0, SHORTLEN = 6, SHORTLL = 15, REPWIN = 0;
 static double COST_A = 0, COST_B = 0; static long NSTEPS = 0, NOPEN = 0, NDROP = 0, NTRIM = 0;
 typedef struct { uint32_t ms, me, off; int open; } mt_t;
 
@@ -102,10 +102,11 @@ size_t model_encode(const uint8_t *src, uint32_t n, uint8_t *out, long *nseq) {
                 int maxext = 0, anyok = 0;
                 for (int l = 0; l < 32; l++) if (act[l]) {
                     lane_iters[l]++;
-                    int pick = -1; uint32_t cand = 0;
+                    int pick = -1; uint32_t cand = 0; int from_rep = 0;
+                    if (REPFIRST == 3 && REP && rep[l]) for (int k = 0; k < nv[l] && pick < 0; k++) { uint32_t p = pos[l] + k; if (p >= rep[l] && ld32(src + p - rep[l]) == sq[l][k]) { pick = k; cand = p - rep[l]; } }
                     for (int k = 0; k < nv[l] && pick < 0; k++) {
                         uint32_t p = pos[l] + k;
-                        if (REPFIRST == 1 && REP && rep[l] && p >= rep[l] && (REPWIN == 0 || pos[l] - lanch[l] < (uint32_t)REPWIN) && ld32(src + p - rep[l]) == sq[l][k]) { pick = k; cand = p - rep[l]; break; }
+                        if ((REPFIRST == 1 || REPFIRST == 3) && REP && rep[l] && p >= rep[l] && (REPWIN == 0 || pos[l] - lanch[l] < (uint32_t)REPWIN) && ld32(src + p - rep[l]) == sq[l][k]) { pick = k; cand = p - rep[l]; from_rep = 1; break; }
                         if (REPFIRST == 2) { /* longest of table / rep / fixed offsets, compared over LCMP bytes */
                             uint32_t best = 0, bc = 0; uint32_t cs[4]; int nc = 0;
                             uint32_t e_ = ent[l][k][0]; uint32_t c = e_ & 0x1FFFF;
@@ -133,7 +134,7 @@ size_t model_encode(const uint8_t *src, uint32_t n, uint8_t *out, long *nseq) {
                     int open = (e >= cap && cap < mlimit);
                     uint32_t ms = pos[l], mc = cand;
                     while (ms > lanch[l] && mc > 0 && src[ms - 1] == src[mc - 1]) { ms--; mc--; }
-                    if ((int)(e - ms) < MINM) { pos[l] += 1; continue; }
+                    if ((int)(e - ms) < MINM && !(MINM_TABLE_ONLY && from_rep)) { pos[l] += 1; continue; }
                     int ext = (int)((e - pos[l]) / 4) + (int)(pos[l] - ms); if (ext > maxext) maxext = ext;
                     lane_iters[l] += (int)((e - pos[l] - 4 + 7) / 8) + 1;
                     rep[l] = ms - mc;
@@ -246,6 +247,7 @@ int main(int argc, char **argv) {
         if (!strcmp(argv[i], "ways2")) WAYS2 = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "upto")) UPTO = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "minm")) MINM = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "minm_table_only")) MINM_TABLE_ONLY = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "phased")) PHASED = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "recmax")) RECMAX = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "halves")) HALVES = atoi(argv[i + 1]);
