@@ -20,10 +20,10 @@
 
 using namespace b2b;
 
-enum KernelId { K_FILTER = 0, K_ENCODE, K_DECODE, K_SCAN, K_PACK, K_INFO, K_FINALIZE, K_COUNT };
+enum KernelId { K_FILTER = 0, K_ENCODE, K_DECODE, K_SCAN, K_PACK, K_INFO, K_FINALIZE, K_PARSE, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"filter_batch_kernel", "lz4_encode_kernel", "lz4_decode_kernel",
                                                   "scan_offsets_kernel", "pack_frames_kernel", "frame_info_kernel",
-                                                  "finalize_frames_kernel"};
+                                                  "finalize_frames_kernel", "lz4_parse_kernel"};
 
 struct TimedLaunch { int id; cudaEvent_t a, b; };
 
@@ -60,6 +60,7 @@ struct b2b_ctx {
     int opt_filter_ctas_per_sm = 0;
     int opt_hash_log = 0;              // 0: default (kHashLogDefault)
     uint32_t opt_tune[4] = {0, 0, 0, 0};   // encoder experiment knobs (0: built-in default)
+    int opt_fused_decode = 0;          // 1: one fused decode kernel instead of parse kernel + copy kernel
     uint64_t opt_stage_bytes = 128ull << 20;
     uint64_t launches = 0;
     std::string last_err;
@@ -370,19 +371,33 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     if (!d_frames || !d_frame_off || !d_frame_len || !d_dst || !d_dst_off || !d_dst_cap ||
         !d_out_len || !d_status)
         return B2B_EINVAL;
-    const uint64_t need = align_up(total_dst + 64, 256) + align_up(8ull * nframes, 256) + 8192;
+    const bool split = !(d_index && segs_per_frame) && !ctx->opt_fused_decode;
+    const uint64_t nrec_max = total_dst / 4 + (uint64_t)(kSeqSlack + 1) * nframes + 64;   // sum of dst_cap / 4 + slack
+    const uint64_t need = align_up(total_dst + 64, 256) + align_up(8ull * nframes, 256) + 8192 +
+                          (split ? align_up(8 * nrec_max, 256) + align_up(8ull * nframes, 256) +
+                                   align_up(4ull * nframes, 256) + scan_scratch_bytes(nframes) + 1024 : 0);
     int rc = ensure_arena(ctx, need);
     if (rc) return rc;
     Arena ar(ctx);
     uint8_t *d_stage = ar.take<uint8_t>(total_dst + 64);
     FrameMeta *d_meta = ar.take<FrameMeta>(nframes);
     unsigned long long *d_ticket = ar.take<unsigned long long>(4);
+    uint64_t *d_table = nullptr, *d_table_off = nullptr;
+    uint32_t *d_nrec = nullptr;
+    uint8_t *scan_t = nullptr;
+    if (split) {
+        d_table = ar.take<uint64_t>(nrec_max);
+        d_table_off = ar.take<uint64_t>(nframes);
+        d_nrec = ar.take<uint32_t>(nframes);
+        scan_t = ar.take<uint8_t>(scan_scratch_bytes(nframes));
+    }
 
     DecodeArgs a;
     a.frames = static_cast<const uint8_t *>(d_frames); a.frame_off = d_frame_off;
     a.frame_len = d_frame_len; a.nframes = nframes; a.typesize_override = typesize_override;
     a.dst = static_cast<uint8_t *>(d_dst); a.scratch = d_stage; a.dst_off = d_dst_off;
     a.dst_cap = d_dst_cap; a.out_len = d_out_len; a.status = d_status; a.meta = d_meta;
+    a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr;
     if (d_index && segs_per_frame) {
         // one warp per (frame, segment): sub-streams between the index entries decode independently
         IndexedDecodeArgs ia; ia.d = a; ia.index = d_index; ia.segs_per_frame = segs_per_frame; ia.ticket = d_ticket;
@@ -396,9 +411,21 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         CU(ctx, cudaGetLastError());
         index_finish_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(a);
         ctx->launches++;
+    } else if (split) {
+        // parse kernel (28 registers, 48 warps per SM) -> one 8-byte record per sequence -> copy kernel
+        rc = launch_scan(ctx, d_dst_cap, nframes, d_table_off, nullptr, kScanSeqSlots, scan_t, s);
+        if (rc) return rc;
+        ParseArgs pa;
+        pa.frames = a.frames; pa.frame_off = d_frame_off; pa.frame_len = d_frame_len; pa.dst_cap = d_dst_cap;
+        pa.nframes = nframes; pa.table = d_table; pa.table_off = d_table_off; pa.nrec = d_nrec; pa.table_cap = nrec_max;
+        a.table = d_table; a.table_off = d_table_off; a.nrec = d_nrec;
+        const unsigned grid = (nframes + kCodecWarps - 1) / kCodecWarps;
+        { LaunchTimer lt(ctx, K_PARSE, s); lz4_parse_kernel<<<grid, kCodecThreads, 0, s>>>(pa); }
+        CU(ctx, cudaGetLastError());
+        { LaunchTimer lt(ctx, K_DECODE, s); lz4_decode_kernel<true><<<grid, kCodecThreads, 0, s>>>(a); }
     } else {
         LaunchTimer lt(ctx, K_DECODE, s);
-        lz4_decode_kernel<<<(nframes + kCodecWarps - 1) / kCodecWarps, kCodecThreads, 0, s>>>(a);
+        lz4_decode_kernel<false><<<(nframes + kCodecWarps - 1) / kCodecWarps, kCodecThreads, 0, s>>>(a);
     }
     CU(ctx, cudaGetLastError());
 
@@ -535,6 +562,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
             ctx->opt_hash_log = (int)value; return B2B_OK;
         case B2B_OPT_KERNEL_TIMING: ctx->opt_timing = value != 0; return B2B_OK;
         case 100: case 101: case 102: case 103: ctx->opt_tune[option - 100] = (uint32_t)value; return B2B_OK;
+        case 104: ctx->opt_fused_decode = value != 0; return B2B_OK;
         case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (128ull << 20); return B2B_OK;
         default: return B2B_EINVAL;
     }

@@ -8,6 +8,8 @@ namespace b2b {
 constexpr int kFilterThreads = 256;     // threads per filter CTA
 constexpr int kTileBytes = 16384;       // bytes of one filter tile (one CTA pass)
 constexpr int kWarp = 32;
+// sequence records of the split decoder: a frame gets dst_cap / 4 + kSeqSlack of them (lz4_kernels.cuh)
+constexpr uint32_t kSeqSlack = 40;
 
 // Per-frame filter selection (uniform for a compress batch, per frame from the header on
 // decompress).  mode: 0 none, 1 byte shuffle, 2 bit shuffle.

@@ -112,14 +112,13 @@ struct SeqTable {
     uint32_t b[32];   // (literal position - batch start in the stream) | match length << 16
 };
 
-// Copies out the `count` sequences of the table.  0: ok, -1 malformed, -2 would overrun cap.
-__device__ __forceinline__ int warp_flush_batch(const uint8_t *__restrict__ src, uint32_t batch_ip,
-                                                uint8_t *dst, uint32_t &op, uint32_t cap, uint32_t count,
-                                                const SeqTable *tab, int lane) {
-    __syncwarp();
+// Copies out `count` sequences, lane i holding sequence i as a = offset | literals << 16 and
+// b = (literal position - batch start in the stream) | match length << 16 (0 for idle lanes).
+// 0: ok, -1 malformed, -2 would overrun cap.
+__device__ __forceinline__ int warp_copy_batch(const uint8_t *__restrict__ src, uint32_t batch_ip,
+                                               uint8_t *dst, uint32_t &op, uint32_t cap, uint32_t count,
+                                               uint32_t a, uint32_t b, int lane) {
     const bool act = (uint32_t)lane < count;
-    uint32_t a = 0, b = 0;
-    if (act) { a = tab->a[lane]; b = tab->b[lane]; }
     const uint32_t off = a & 0xFFFFu, ll = a >> 16, ml = b >> 16, lrel = b & 0xFFFFu;
     const uint32_t tot = ll + ml;
     uint32_t incl = tot;
@@ -190,6 +189,16 @@ __device__ __forceinline__ int warp_flush_batch(const uint8_t *__restrict__ src,
     return 0;
 }
 
+// the same, fed from the per-warp table in shared memory
+__device__ __forceinline__ int warp_flush_batch(const uint8_t *__restrict__ src, uint32_t batch_ip,
+                                                uint8_t *dst, uint32_t &op, uint32_t cap, uint32_t count,
+                                                const SeqTable *tab, int lane) {
+    __syncwarp();
+    uint32_t a = 0, b = 0;
+    if ((uint32_t)lane < count) { a = tab->a[lane]; b = tab->b[lane]; }
+    return warp_copy_batch(src, batch_ip, dst, op, cap, count, a, b, lane);
+}
+
 // One sequence, 32 lanes wide.  1: sequence done, 0: that was the closing token (stream ends),
 // -1 malformed, -2 would overrun cap.  Strictness follows the oracle: zero offsets, offsets
 // beyond the output so far, reads past the stream, writes past cap and a final token with a
@@ -235,54 +244,43 @@ __device__ __forceinline__ int64_t warp_lz4_decode(const uint8_t *__restrict__ s
     // leave it, is decoded a sequence at a time (which also holds all end-of-stream rules).
     constexpr uint32_t kWindowReach = 306;
     for (;;) {
-        if (clen - ip < kWindowReach) {
-            if (count) {
-                const int r = warp_flush_batch(src, batch_ip, dst, op, cap, count, tab, lane);
-                if (r < 0) return r;
-                count = 0;
-                __syncwarp();
+        bool other = clen - ip < kWindowReach;             // the tail of the stream: no window, one sequence
+        if (!other) {
+            // ---- every lane decodes the token that would start at its byte of the window
+            const uint32_t p = ip + lane;
+            uint32_t nxt = 0xFFFFu, ta = 0, tb = 0;
+            {
+                const uint32_t t = src[p], e1 = src[p + 1];
+                const bool x1 = (t >> 4) == 15u;
+                const uint32_t ll = (t >> 4) + (x1 ? e1 : 0u);
+                const uint32_t lit = p + 1 + (x1 ? 1u : 0u);
+                const uint32_t oq = lit + ll;                     // offset bytes at oq, oq + 1
+                const uint32_t off = (uint32_t)src[oq] | ((uint32_t)src[oq + 1] << 8);
+                const uint32_t e2 = src[oq + 2];
+                const bool x2 = (t & 15u) == 15u;
+                const uint32_t ml = (t & 15u) + 4u + (x2 ? e2 : 0u);
+                const bool regular = !(x1 && e1 == 255u) && !(x2 && e2 == 255u);
+                if (regular) {
+                    nxt = oq + 2u + (x2 ? 1u : 0u) - ip;
+                    ta = off | (ll << 16);
+                    tb = (lit - batch_ip) | (ml << 16);
+                }
             }
-            const int r = warp_decode_one(src, clen, dst, cap, ip, op, lane, open_end);
-            if (r < 0) return r;
-            if (r == 0) break;
-            batch_ip = ip;
-            continue;
-        }
-        // ---- every lane decodes the token that would start at its byte of the window
-        const uint32_t p = ip + lane;
-        uint32_t nxt = 0xFFFFu, ta = 0, tb = 0;
-        {
-            const uint32_t t = src[p], e1 = src[p + 1];
-            const bool x1 = (t >> 4) == 15u;
-            const uint32_t ll = (t >> 4) + (x1 ? e1 : 0u);
-            const uint32_t lit = p + 1 + (x1 ? 1u : 0u);
-            const uint32_t oq = lit + ll;                     // offset bytes at oq, oq + 1
-            const uint32_t off = (uint32_t)src[oq] | ((uint32_t)src[oq + 1] << 8);
-            const uint32_t e2 = src[oq + 2];
-            const bool x2 = (t & 15u) == 15u;
-            const uint32_t ml = (t & 15u) + 4u + (x2 ? e2 : 0u);
-            const bool regular = !(x1 && e1 == 255u) && !(x2 && e2 == 255u);
-            if (regular) {
-                nxt = oq + 2u + (x2 ? 1u : 0u) - ip;
-                ta = off | (ll << 16);
-                tb = (lit - batch_ip) | (ml << 16);
+            // ---- walk the chain of real token starts inside the window
+            uint32_t starts = 0, cur = 0;
+            while (cur < 32) {
+                const uint32_t x = __shfl_sync(0xffffffffu, nxt, cur);
+                if (x == 0xFFFFu) { other = true; break; }
+                starts |= 1u << cur;
+                cur = x;
             }
+            if ((starts >> lane) & 1u) {
+                const uint32_t slot = count + __popc(starts & ((1u << lane) - 1u));
+                tab->a[slot] = ta; tab->b[slot] = tb;
+            }
+            count += __popc(starts);
+            ip += cur;
         }
-        // ---- walk the chain of real token starts inside the window
-        uint32_t starts = 0, cur = 0;
-        bool other = false;
-        while (cur < 32) {
-            const uint32_t x = __shfl_sync(0xffffffffu, nxt, cur);
-            if (x == 0xFFFFu) { other = true; break; }
-            starts |= 1u << cur;
-            cur = x;
-        }
-        if ((starts >> lane) & 1u) {
-            const uint32_t slot = count + __popc(starts & ((1u << lane) - 1u));
-            tab->a[slot] = ta; tab->b[slot] = tb;
-        }
-        count += __popc(starts);
-        ip += cur;
         if (other || count > kBatchFill) {
             if (count) {
                 const int r = warp_flush_batch(src, batch_ip, dst, op, cap, count, tab, lane);
@@ -301,6 +299,59 @@ __device__ __forceinline__ int64_t warp_lz4_decode(const uint8_t *__restrict__ s
     return (int64_t)op;
 }
 
+// K4 copy half: the records of one frame, 32 at a time
+__device__ __forceinline__ int64_t warp_lz4_copy(const uint8_t *__restrict__ src, uint32_t clen, uint8_t *dst,
+                                                 uint32_t cap, const uint64_t *__restrict__ rec, uint32_t nrec,
+                                                 int lane) {
+    if (clen == 0) return 0;
+    uint32_t ip = 0, op = 0, e = 0;
+    bool tail = nrec == 0xFFFFFFFFu;                       // no table: sequence by sequence from the start
+    for (;;) {
+        bool one = tail;                                   // decode one sequence with warp_decode_one this turn?
+        if (!tail) {
+            const uint32_t rem = nrec - e;                 // nrec >= 1: the table always ends with a tail record
+            const uint64_t r = (uint32_t)lane < rem ? rec[e + lane] : 0ull;
+            const uint32_t kind = (uint32_t)(r >> 62);
+            const uint32_t stop = __ballot_sync(0xffffffffu, (uint32_t)lane < rem && kind != 0);
+            const uint32_t count = stop ? (uint32_t)(__ffs(stop) - 1) : (rem < 32u ? rem : 32u);
+            if (count) {
+                uint32_t a = 0, b = 0, insz = 0;
+                if ((uint32_t)lane < count) {
+                    a = (uint32_t)r;                       // offset | literals << 16
+                    const uint32_t ll = a >> 16, ml = (uint32_t)(r >> 32) & 0xFFFFu;
+                    insz = 1u + (ll >= 15u ? 1u : 0u) + ll + 2u + (ml >= 19u ? 1u : 0u);
+                    b = ml << 16;
+                }
+                uint32_t incl = insz;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if ((uint32_t)lane < count) b |= incl - insz + 1u + ((a >> 16) >= 15u ? 1u : 0u);   // literal position
+                const int rc = warp_copy_batch(src, ip, dst, op, cap, count, a, b, lane);
+                if (rc < 0) return rc;
+                ip += __shfl_sync(0xffffffffu, incl, 31);
+                e += count;
+                __syncwarp();
+            }
+            if (stop) {
+                one = true;
+                tail = __shfl_sync(0xffffffffu, kind, (int)count) != 1u;
+                e += 1;
+            } else if (e >= nrec) {
+                return -1;                                 // cannot happen with a table from lz4_parse_kernel
+            }
+        }
+        if (one) {
+            const int rc = warp_decode_one(src, clen, dst, cap, ip, op, lane);
+            if (rc < 0) return rc;
+            if (rc == 0) break;
+        }
+    }
+    return (int64_t)op;
+}
+
 struct DecodeArgs {
     const uint8_t *frames;
     const uint64_t *frame_off;
@@ -314,6 +365,10 @@ struct DecodeArgs {
     uint32_t *out_len;
     uint32_t *status;
     FrameMeta *meta;    // filter still to run on frame f (mode 0: none)
+    // split decode only: the sequence records lz4_parse_kernel wrote
+    const uint64_t *table;
+    const uint64_t *table_off;
+    const uint32_t *nrec;
 };
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t *p) {
@@ -333,6 +388,7 @@ __device__ __forceinline__ uint32_t check_header(const uint8_t *fr, uint32_t fle
     return kOk;
 }
 
+template <bool kSplit>
 __global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_kernel(DecodeArgs a) {
     __shared__ SeqTable seq_tables[kCodecWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -368,7 +424,8 @@ __global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_kernel(DecodeArgs
                 else { warp_copy(out, fr + 16, plen, lane); produced = plen; }
             } else {
                 const uint32_t dcap = cap < norig ? cap : norig;
-                const int64_t got = warp_lz4_decode(fr + 16, plen, out, dcap, &seq_tables[warp], lane);
+                const int64_t got = kSplit ? warp_lz4_copy(fr + 16, plen, out, dcap, a.table + a.table_off[f], a.nrec[f], lane)
+                                           : warp_lz4_decode(fr + 16, plen, out, dcap, &seq_tables[warp], lane);
                 if (got == -1) st = kEDecompressionFailed;            // blosc.go:410-413
                 else if (got == -2) st = dcap == norig ? kEDecompressionFailed : kEDstTooSmall;
                 else if ((uint64_t)got != norig) { st = kESizeMismatch; produced = (uint32_t)got; }  // blosc.go:429-431
@@ -382,6 +439,97 @@ __global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_kernel(DecodeArgs
         a.out_len[f] = produced;
         a.meta[f] = m;
     }
+}
+
+// ---- split decode: parse kernel -> sequence table -> copy kernel ----------------------------------
+// The fused kernel above runs at 64 registers / 32 warps per SM because of its copy half; its parse
+// half needs 28.  Split, the parse runs at 48 warps per SM (the whole 8 GiB C3 batch in 4.4 ms against
+// ~7 ms inside the fused kernel) and writes one 8-byte record per sequence; the copy kernel then
+// reads 32 records per batch instead of parsing.  Records (u64), kind in bits 62..63:
+//   0  regular sequence: offset | literals << 16 | match length << 32
+//   1  a token the window parse does not handle starts at stream position (low 32 bits): the copy
+//      kernel decodes that one sequence with warp_decode_one
+//   2  from stream position (low 32 bits) on, decode sequence by sequence to the end (the last 306
+//      bytes of a stream, the closing token, anything malformed, a full table)
+// All error reporting stays in the copy kernel (offsets, capacity, end-of-stream rules).
+// a frame's table holds dst_cap / 4 + kSeqSlack records: every sequence but the last emits >= 4 bytes
+
+struct ParseArgs {
+    const uint8_t *frames;
+    const uint64_t *frame_off;
+    const uint32_t *frame_len;
+    const uint32_t *dst_cap;
+    uint32_t nframes;
+    uint64_t *table;            // all frames' records
+    const uint64_t *table_off;  // first record of frame f (exclusive scan of dst_cap / 4 + kSeqSlack)
+    uint32_t *nrec;             // records written for frame f (~0: no room in the table, decode without it)
+    uint64_t table_cap;         // records the table can hold in all
+};
+
+__global__ void __launch_bounds__(kCodecThreads, 12) lz4_parse_kernel(ParseArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t f = blockIdx.x * kCodecWarps + warp;
+    if (f >= a.nframes) return;
+    const uint8_t *fr = a.frames + a.frame_off[f];
+    uint32_t flags = 0, codec = 0, tsz = 0, norig = 0, ncomp = 0;
+    const uint32_t st = check_header(fr, a.frame_len[f], flags, codec, tsz, norig, ncomp);
+    if (st != kOk || (flags & 0x2u) || (codec != 1 && codec != 2)) { if (lane == 0) a.nrec[f] = 0; return; }
+    const uint8_t *__restrict__ src = fr + 16;
+    const uint32_t clen = ncomp - 16;
+    const uint32_t room = a.dst_cap[f] / 4u + kSeqSlack;
+    if (a.table_off[f] + room > a.table_cap) {            // capacities that overlap in dst: not sized for
+        if (lane == 0) a.nrec[f] = 0xFFFFFFFFu;
+        return;
+    }
+    uint64_t *tab = a.table + a.table_off[f];
+    uint32_t ip = 0, n = 0;
+    constexpr uint32_t kWindowReach = 306;
+    constexpr uint64_t kLong = 1ull << 62, kTail = 2ull << 62;
+    for (;;) {
+        if (clen - ip < kWindowReach || n + 14 > room) { if (lane == 0) tab[n] = kTail | ip; n++; break; }
+        const uint32_t p = ip + lane;
+        uint32_t nxt = 0xFFFFu;
+        uint64_t rec = 0;
+        {
+            const uint32_t t = src[p], e1 = src[p + 1];
+            const bool x1 = (t >> 4) == 15u;
+            const uint32_t ll = (t >> 4) + (x1 ? e1 : 0u);
+            const uint32_t oq = p + 1 + (x1 ? 1u : 0u) + ll;                  // offset bytes at oq, oq + 1
+            const uint32_t off = (uint32_t)src[oq] | ((uint32_t)src[oq + 1] << 8);
+            const uint32_t e2 = src[oq + 2];
+            const bool x2 = (t & 15u) == 15u;
+            const uint32_t ml = (t & 15u) + 4u + (x2 ? e2 : 0u);
+            if (!(x1 && e1 == 255u) && !(x2 && e2 == 255u)) {
+                nxt = oq + 2u + (x2 ? 1u : 0u) - ip;
+                rec = (uint64_t)(off | (ll << 16)) | ((uint64_t)ml << 32);
+            }
+        }
+        uint32_t starts = 0, cur = 0;
+        bool other = false;
+        while (cur < 32) {
+            const uint32_t x = __shfl_sync(0xffffffffu, nxt, cur);
+            if (x == 0xFFFFu) { other = true; break; }
+            starts |= 1u << cur;
+            cur = x;
+        }
+        if ((starts >> lane) & 1u) tab[n + __popc(starts & ((1u << lane) - 1u))] = rec;
+        n += __popc(starts);
+        ip += cur;
+        if (other) {
+            // a token with longer extensions (or the closing token, or nonsense): find its end, lengths only
+            uint32_t q = ip;
+            const uint32_t tok = src[q++];
+            uint64_t ll = tok >> 4, ml = tok & 15u;
+            bool ok = !(ll == 15 && !warp_read_len_ext(src, clen, q, ll, lane)) && ll <= (uint64_t)(clen - q);
+            if (ok) { q += (uint32_t)ll; ok = q != clen && clen - q >= 2; }
+            if (ok) { q += 2; ok = !(ml == 15 && !warp_read_len_ext(src, clen, q, ml, lane)); }
+            if (!ok) { if (lane == 0) tab[n] = kTail | ip; n++; break; }      // the copy kernel meets it and decides
+            if (lane == 0) tab[n] = kLong | ip;
+            n++;
+            ip = q;
+        }
+    }
+    if (lane == 0) a.nrec[f] = n;
 }
 
 // ---- decode with a side-car index ------------------------------------------

@@ -21,13 +21,15 @@ enum ScanOp : int {
     kScanIdentity = 0,   // x
     kScanAlign16 = 1,    // (x + 15) & ~15     packed frames start on 16-byte boundaries
     kScanSegSlot = 2,    // scratch bytes of the frame's segment slots (lz4_encode.cuh)
-    kScanSegCount = 3    // number of 64 KiB segments of the frame
+    kScanSegCount = 3,   // number of 64 KiB segments of the frame
+    kScanSeqSlots = 4    // sequence records of the split decoder for a frame of capacity x
 };
 
 __device__ __forceinline__ uint64_t scan_apply(int op, uint32_t x) {
     if (op == kScanAlign16) return ((uint64_t)x + 15ull) & ~15ull;
     if (op == kScanSegSlot) return frame_slot_bytes(x);
     if (op == kScanSegCount) return seg_count(x);
+    if (op == kScanSeqSlots) return (uint64_t)(x / 4u) + kSeqSlack;
     return x;
 }
 

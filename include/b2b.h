@@ -113,8 +113,9 @@ B2B_API int b2b_set_option(b2b_ctx *ctx, int option, int64_t value);
 B2B_API int b2b_reserve(b2b_ctx *ctx, uint64_t total_uncompressed_bytes, uint32_t nframes);
 /* number of kernel launches issued through this ctx since creation (bench's gpu_launches) */
 B2B_API uint64_t b2b_launch_count(b2b_ctx *ctx);
-/* per-kernel launch counts and (with B2B_OPT_KERNEL_TIMING) summed device time; kernel = 0..5:
- * filter, lz4 encode, lz4 decode, offsets scan, pack, frame info.  Synchronises pending events. */
+/* per-kernel launch counts and (with B2B_OPT_KERNEL_TIMING) summed device time; kernel = 0..7:
+ * filter, lz4 encode, lz4 decode (copy half), offsets scan, pack, frame info, finalize, lz4 parse
+ * (decode's parse half); B2B_EINVAL beyond.  Synchronises pending events. */
 B2B_API int b2b_kernel_stats(b2b_ctx *ctx, int kernel, const char **name, uint64_t *launches,
                              double *total_ms);
 B2B_API int b2b_kernel_stats_reset(b2b_ctx *ctx);

@@ -536,3 +536,43 @@ def test_indexed_frames_are_standard_and_decode_in_parallel(ctx, orc, torch_mod,
     torch.cuda.synchronize()
     st = d_st2.cpu().numpy()
     assert st[9] != 0 and not st[:9].any() and not st[10:].any()
+
+
+def test_split_and_fused_decoders_agree(ctx, orc):
+    """K4 runs as parse kernel + copy kernel by default and as one fused kernel under option 104: on
+    a ragged batch of valid, truncated and corrupted frames both give the same status, length and bytes
+    (and the oracle's status)."""
+    rng = np.random.default_rng(77)
+    frames, caps = [], []
+    for k, n in enumerate([1, 13, 305, 306, 307, 700, 4096, 65536, 70001, 300000, 1 << 20]):
+        for kind in ("smooth_f32", "lowent_i16", "text", "random", "zeros", "period3"):
+            data = dg.corpus(n)[kind]
+            sh, T = [(1, 4), (0, 1), (2, 8), (1, 2)][(k + len(kind)) % 4]
+            fr = np.frombuffer(ctx.compress(data, 1, 5, sh, T), dtype=np.uint8).copy()
+            frames.append(fr); caps.append(n)
+            if fr.size > 40 and not fr[2] & 2:
+                m = fr.copy(); m[int(rng.integers(16, m.size))] ^= np.uint8(rng.integers(1, 256)); frames.append(m); caps.append(n)
+                cut = int(rng.integers(17, fr.size)); t = fr[:cut].copy(); t[12:16] = np.frombuffer(struct.pack("<I", cut), dtype=np.uint8)
+                frames.append(t); caps.append(n)
+    flen = np.array([f.size for f in frames], dtype=np.uint32)
+    foff = np.concatenate([[0], np.cumsum((flen[:-1].astype(np.uint64) + 15) // 16 * 16)]).astype(np.uint64)
+    blob = np.zeros(int(foff[-1] + flen[-1]) + 64, dtype=np.uint8)
+    for o, f in zip(foff, frames):
+        blob[int(o):int(o) + f.size] = f
+    cap = np.array(caps, dtype=np.uint64)
+    doff = np.concatenate([[0], np.cumsum((cap[:-1] + 15) // 16 * 16)]).astype(np.uint64)
+    res = []
+    for fused in (0, 1):
+        ctx.set_option(104, fused)
+        try:
+            out, olen, st = ctx.decompress_batch(blob, foff, flen, doff, int(doff[-1] + cap[-1]) + 64)
+        finally:
+            ctx.set_option(104, 0)
+        res.append((out.copy(), olen.copy(), st.copy()))
+    assert np.array_equal(res[0][2], res[1][2]) and np.array_equal(res[0][1], res[1][1])
+    for k, f in enumerate(frames):
+        rc, ref = orc.decompress(f)
+        assert int(res[0][2][k]) == rc, (k, int(res[0][2][k]), rc)
+        if rc == 0:
+            for out, _, _ in res:
+                assert np.array_equal(out[int(doff[k]):int(doff[k]) + ref.size], ref), k
