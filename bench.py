@@ -46,7 +46,7 @@ def peaks():
 def committed_traffic(kernel, bytes_per_gpu):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed
     ncu --set full capture, if that capture was taken at this launch size (else None)."""
-    p = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r01d_traffic.json")
     try:
         with open(p) as f:
             t = json.load(f)
@@ -361,14 +361,17 @@ def run_gpu(args):
         kernels["lz4_decode_kernel"]["frac_of_peak"] = kernels["lz4_decode_kernel"]["achieved_gbs_algorithmic"] / peak
         for kname in ("filter_batch_kernel", "lz4_decode_kernel", "pack_frames_kernel"):
             kernels[kname]["traffic"] = committed_traffic(kname, total)
+        t_parse = committed_traffic("lz4_parse_kernel", total)
+        if kernels["lz4_decode_kernel"]["traffic"] is not None and t_parse is not None:
+            kernels["lz4_decode_kernel"]["traffic"] += t_parse                # K4 = both halves
         traffic = args.traffic_bytes if args.traffic_bytes is not None else committed_traffic("lz4_encode_kernel", total)
         roofline = {"kernel": "lz4_encode_kernel", "bound": "hbm", "achieved": algo_c / (enc_avg / 1e3) / 1e9, "peak": peak,
                     "unit": "GB/s", "frac": algo_c / (enc_avg / 1e3) / 1e9 / peak, "traffic": traffic,
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": algo_c,
-                    "traffic_source": "profiles/r01c_traffic.json (ncu --set full at this launch size)" if traffic else None,
+                    "traffic_source": "profiles/r01d_traffic.json (ncu --set full at this launch size)" if traffic else None,
                     "note": "dominant kernel of the step; it is issue/latency-bound (per-lane LZ4 match search over a "
-                            "shared-memory hash table), not HBM-bound: DESIGN.md section 4 and profiles/r01c_ncu_summary.md"}
+                            "shared-memory hash table), not HBM-bound: DESIGN.md section 4 and profiles/r01d_ncu_summary.md"}
         # e2e through the host-pointer C ABI with pinned host buffers
         e2e = run_e2e(torch, pkg, ctx, args, dev, src, nf, total, world)
         # CPU baseline (oracle port), bounded sample, on all host cores
