@@ -208,6 +208,13 @@ ABI = [
     ("b2b_decompress_batch_dev", _int, [_vp, _vp, _vp, _vp, _u32, _i64, _vp, _vp, _vp, _u64, _u32,
                                         _vp, _vp, _vp]),
     ("b2b_scan_offsets_dev", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
+    ("b2b_blocks_blocksize", _u32, [_sz, _i64, _u32]),
+    ("b2b_compress_blocks", _int, [_vp, _vp, _sz, _int, _i64, _u32, _vp, _sz, C.POINTER(_sz)]),
+    ("b2b_decompress_blocks", _int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
+    ("b2b_compress_blocks_batch_dev", _int, [_vp, _vp, _vp, _vp, _u32, _u64, _u32, _int, _i64, _u32, _vp, _u64,
+                                             _vp, _vp, _vp, _vp, _vp]),
+    ("b2b_decompress_blocks_batch_dev", _int, [_vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _u64, _u32, _u32,
+                                               _vp, _vp, _vp]),
     ("b2b_index_segments", _u32, [_u32]),
     ("b2b_compress_batch_dev_indexed", _int, [_vp, _vp, _vp, _vp, _u32, _u64, _u32, _int, _i64, _vp, _u64,
                                               _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
@@ -494,6 +501,59 @@ class Context:
                                                     total_dst_bytes, max_orig_len, _dev_ptr(d_out_len),
                                                     _dev_ptr(d_status), _dev_ptr(d_index), int(segs_per_frame),
                                                     C.c_void_p(stream))
+        if rc:
+            _raise(rc, self._h)
+
+    # ---- opt-in Blosc-1 multi-block frames (b2b.h; the reference ignores Options.BlockSize and
+    # cannot read these): int32 bstarts + one LZ4 block per block, filter per block
+    @staticmethod
+    def blocks_blocksize(n: int, typesize: int, blocksize: int = 0) -> int:
+        return int(lib().b2b_blocks_blocksize(int(n), int(typesize), int(blocksize)))
+
+    def compress_blocks(self, data, shuffle=Shuffle.Shuffle1, typesize=4, blocksize=0) -> bytes:
+        a = _as_u8(data)
+        out = np.empty(a.size + 16 + 64, dtype=np.uint8)
+        n = C.c_size_t(0)
+        rc = lib().b2b_compress_blocks(self._h, _np_ptr(a), a.size, int(shuffle), int(typesize), int(blocksize),
+                                       _np_ptr(out), out.size, C.byref(n))
+        if rc:
+            _raise(rc, self._h)
+        return out[:n.value].tobytes()
+
+    def decompress_blocks(self, frame) -> bytes:
+        a = _as_u8(frame)
+        if a.size < HEADER_SIZE:
+            raise ErrInvalidHeader(lib().b2b_strerror(EINVALID_HEADER).decode())
+        cap = int.from_bytes(a[4:8].tobytes(), "little")
+        cap_alloc = min(cap, 255 * a.size + 64)          # an LZ4 block expands at most 255x
+        out = np.empty(max(cap_alloc, 1), dtype=np.uint8)
+        n = C.c_size_t(0)
+        rc = lib().b2b_decompress_blocks(self._h, _np_ptr(a), a.size, _np_ptr(out), cap_alloc, C.byref(n))
+        if rc == EDST_TOO_SMALL and cap_alloc < cap:
+            rc = EDECOMPRESSION_FAILED
+        if rc:
+            _raise(rc, self._h)
+        return out[:n.value].tobytes()
+
+    def compress_blocks_batch_dev(self, d_src, d_src_off, d_src_len, nframes, total_src_bytes, max_frame_len,
+                                  shuffle, typesize, blocksize, d_dst, dst_cap, d_frame_off, d_frame_len,
+                                  d_status, d_total_out, stream=0):
+        rc = lib().b2b_compress_blocks_batch_dev(self._h, _dev_ptr(d_src), _dev_ptr(d_src_off),
+                                                 _dev_ptr(d_src_len), nframes, total_src_bytes, max_frame_len,
+                                                 int(shuffle), int(typesize), int(blocksize), _dev_ptr(d_dst),
+                                                 dst_cap, _dev_ptr(d_frame_off), _dev_ptr(d_frame_len),
+                                                 _dev_ptr(d_status), _dev_ptr(d_total_out), C.c_void_p(stream))
+        if rc:
+            _raise(rc, self._h)
+
+    def decompress_blocks_batch_dev(self, d_frames, d_frame_off, d_frame_len, nframes, d_dst, d_dst_off,
+                                    d_dst_cap, total_dst_bytes, max_orig_len, blocksize, d_out_len, d_status,
+                                    stream=0):
+        rc = lib().b2b_decompress_blocks_batch_dev(self._h, _dev_ptr(d_frames), _dev_ptr(d_frame_off),
+                                                   _dev_ptr(d_frame_len), nframes, _dev_ptr(d_dst),
+                                                   _dev_ptr(d_dst_off), _dev_ptr(d_dst_cap), total_dst_bytes,
+                                                   max_orig_len, int(blocksize), _dev_ptr(d_out_len),
+                                                   _dev_ptr(d_status), C.c_void_p(stream))
         if rc:
             _raise(rc, self._h)
 

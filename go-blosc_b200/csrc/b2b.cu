@@ -17,13 +17,16 @@
 #include "lz4_encode.cuh"
 #include "lz4_kernels.cuh"
 #include "scan.cuh"
+#include "blocks.cuh"
 
 using namespace b2b;
 
-enum KernelId { K_FILTER = 0, K_ENCODE, K_DECODE, K_SCAN, K_PACK, K_INFO, K_FINALIZE, K_PARSE, K_COUNT };
+enum KernelId { K_FILTER = 0, K_ENCODE, K_DECODE, K_SCAN, K_PACK, K_INFO, K_FINALIZE, K_PARSE,
+                K_BLOCKS_META, K_BLOCKS_PACK, K_BLOCKS_DECODE, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"filter_batch_kernel", "lz4_encode_kernel", "lz4_decode_kernel",
                                                   "scan_offsets_kernel", "pack_frames_kernel", "frame_info_kernel",
-                                                  "finalize_frames_kernel", "lz4_parse_kernel"};
+                                                  "finalize_frames_kernel", "lz4_parse_kernel",
+                                                  "blocks_meta_kernels", "blocks_pack_kernel", "blocks_decode_kernel"};
 
 struct TimedLaunch { int id; cudaEvent_t a, b; };
 
@@ -442,6 +445,222 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     return B2B_OK;
 }
 
+// ---- Blosc-1 multi-block frames (blocks.cuh): every block is a frame of its own to K1..K4 ----------
+int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d_src_off,
+                               const uint32_t *d_src_len, uint32_t nframes, uint64_t total_src,
+                               uint32_t max_len, int shuffle, int64_t typesize, uint32_t blocksize,
+                               void *d_dst, uint64_t dst_cap, uint64_t *d_frame_off, uint32_t *d_frame_len,
+                               uint32_t *d_status, uint64_t *d_total_out, cudaStream_t s) {
+    if (nframes == 0) {
+        if (d_total_out) CU(ctx, cudaMemsetAsync(d_total_out, 0, 8, s));
+        return B2B_OK;
+    }
+    if (!d_src || !d_src_off || !d_src_len || !d_dst || !d_frame_off || !d_frame_len || !d_status)
+        return B2B_EINVAL;
+    if (((uintptr_t)d_dst & 15u) != 0) return B2B_EINVAL;
+    if (blocksize != 0 && blocksize < kB1MinBuffer) return B2B_EINVAL;
+    if (dst_cap < total_src + 31ull * nframes) return B2B_EDST_TOO_SMALL;
+    const uint32_t T = b1_typesize(typesize);
+    const uint32_t b_full = b1_blocksize(~0ull, T, blocksize);          // what every frame of >= blocksize bytes uses
+    const uint64_t nslots64 = total_src / b_full + 2ull * nframes;      // shorter frames: one block + a partial one
+    if (nslots64 >= (1ull << 31)) return B2B_EINVAL;
+    const uint32_t nslots = (uint32_t)nslots64;
+    const uint32_t max_blk = std::min<uint32_t>(max_len, b_full);
+    const FrameMeta fm = uniform_meta(shuffle, T);
+    const bool filtered = fm.mode != 0;
+    const uint32_t base_flags = (kB1Lz4Format << 5) | kB1DontSplit |
+                                (shuffle == B2B_SHUFFLE ? B2B_FLAG_SHUFFLE : shuffle == B2B_BITSHUFFLE ? B2B_FLAG_BITSHUFFLE : 0);
+
+    const uint64_t comp_bytes = comp_scratch_bytes(total_src, nslots);
+    const uint64_t max_segs_total = total_src / kSegBytes + nslots + 1;
+    const uint64_t need = (filtered ? align_up(total_src + 64, 256) : 0) + align_up(comp_bytes, 256) +
+                          align_up(16 * max_segs_total, 256) + align_up(8 * max_segs_total, 256) +
+                          12 * align_up(8ull * (nslots + 1), 256) + 4 * align_up(8ull * nframes, 256) +
+                          3 * scan_scratch_bytes(nslots + 1) + 2 * scan_scratch_bytes(nframes) + 16384;
+    int rc = ensure_arena(ctx, need);
+    if (rc) return rc;
+    Arena ar(ctx);
+    uint8_t *d_shuf = filtered ? ar.take<uint8_t>(total_src + 64) : nullptr;
+    uint8_t *d_comp = ar.take<uint8_t>(comp_bytes);
+    SegMeta *d_meta = ar.take<SegMeta>(max_segs_total);
+    SegPlace *d_place = ar.take<SegPlace>(max_segs_total);
+    uint64_t *blk_off = ar.take<uint64_t>(nslots);
+    uint64_t *comp_off = ar.take<uint64_t>(nslots);
+    uint64_t *seg_base = ar.take<uint64_t>(nslots);
+    uint64_t *blk_pos = ar.take<uint64_t>(nslots + 1);
+    uint32_t *blk_len = ar.take<uint32_t>(nslots);
+    uint32_t *owner = ar.take<uint32_t>(nslots);
+    uint32_t *comp_len = ar.take<uint32_t>(nslots + 1);
+    uint32_t *blk_flen = ar.take<uint32_t>(nslots);
+    uint32_t *blk_flags = ar.take<uint32_t>(nslots);
+    uint32_t *final_ll = ar.take<uint32_t>(nslots);
+    uint32_t *final_off = ar.take<uint32_t>(nslots);
+    uint32_t *blk_status = ar.take<uint32_t>(nslots);
+    uint32_t *frm_bs = ar.take<uint32_t>(nframes);
+    uint32_t *frm_nblk = ar.take<uint32_t>(nframes);
+    uint64_t *blk_base = ar.take<uint64_t>(nframes);
+    uint32_t *frm_flags = ar.take<uint32_t>(nframes);
+    uint8_t *scan_a = ar.take<uint8_t>(scan_scratch_bytes(nslots + 1));
+    uint8_t *scan_b = ar.take<uint8_t>(scan_scratch_bytes(nslots + 1));
+    uint8_t *scan_c = ar.take<uint8_t>(scan_scratch_bytes(nslots + 1));
+    uint8_t *scan_d = ar.take<uint8_t>(scan_scratch_bytes(nframes));
+    uint8_t *scan_e = ar.take<uint8_t>(scan_scratch_bytes(nframes));
+    unsigned long long *d_ticket = ar.take<unsigned long long>(4);
+
+    BlocksGeomArgs ga;
+    ga.src_len = d_src_len; ga.nframes = nframes; ga.typesize = T; ga.blocksize_req = blocksize;
+    ga.bs = frm_bs; ga.nblk = frm_nblk;
+    { LaunchTimer lt(ctx, K_BLOCKS_META, s); blocks_geom_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(ga); }
+    CU(ctx, cudaGetLastError());
+    rc = launch_scan(ctx, frm_nblk, nframes, blk_base, nullptr, kScanIdentity, scan_d, s);
+    if (rc) return rc;
+    BlocksExpandArgs xa;
+    xa.blk_base = blk_base; xa.nblk = frm_nblk; xa.bs = frm_bs; xa.src_off = d_src_off; xa.src_len = d_src_len;
+    xa.nframes = nframes; xa.nslots = nslots; xa.owner = owner; xa.blk_off = blk_off; xa.blk_len = blk_len;
+    { LaunchTimer lt(ctx, K_BLOCKS_META, s); blocks_expand_kernel<<<(nslots + 127) / 128, 128, 0, s>>>(xa); }
+    CU(ctx, cudaGetLastError());
+
+    const uint8_t *in = static_cast<const uint8_t *>(d_src);
+    if (filtered) {
+        rc = launch_filter(ctx, in, d_shuf, blk_off, blk_len, 0, nslots, max_blk, nullptr, fm, nullptr, 0, s);
+        if (rc) return rc;
+        in = d_shuf;
+    }
+    rc = launch_scan(ctx, blk_len, nslots, comp_off, nullptr, kScanSegSlot, scan_a, s);
+    if (rc) return rc;
+    rc = launch_scan(ctx, blk_len, nslots, seg_base, nullptr, kScanSegCount, scan_b, s);
+    if (rc) return rc;
+    uint64_t segs_grid = std::max<uint64_t>(1, ((uint64_t)max_blk + kSegBytes - 1) / kSegBytes);
+    segs_grid = std::min<uint64_t>(segs_grid, std::max<uint64_t>(1, (1ull << 30) / nslots));
+    EncodeArgs e;
+    e.in = in; e.src_off = blk_off; e.src_len = blk_len; e.nframes = nslots;
+    e.segs_grid = (uint32_t)segs_grid; e.comp = d_comp; e.comp_off = comp_off;
+    e.seg_base = seg_base; e.meta = d_meta; e.ticket = d_ticket;
+    for (int i = 0; i < 4; i++) e.tune[i] = ctx->opt_tune[i];
+    e.independent = 0;
+    rc = launch_encode(ctx, e, s);
+    if (rc) return rc;
+    FinalizeArgs fa;
+    fa.src_len = blk_len; fa.seg_base = seg_base; fa.meta = d_meta; fa.place = d_place;
+    fa.nframes = nslots; fa.shuffle_flag = 0; fa.keep_raw = 0;
+    fa.comp_len = comp_len; fa.frame_len = blk_flen; fa.flags = blk_flags;
+    fa.final_ll = final_ll; fa.final_off = final_off; fa.status = blk_status;
+    fa.index = nullptr; fa.segs_per_frame = 0;
+    { LaunchTimer lt(ctx, K_FINALIZE, s); finalize_frames_kernel<<<(nslots + 127) / 128, 128, 0, s>>>(fa); }
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemsetAsync(comp_len + nslots, 0, 4, s));
+    rc = launch_scan(ctx, comp_len, nslots + 1, blk_pos, nullptr, kScanStream, scan_c, s);
+    if (rc) return rc;
+    BlocksFrameArgs ba;
+    ba.src_len = d_src_len; ba.nblk = frm_nblk; ba.blk_base = blk_base; ba.blk_pos = blk_pos;
+    ba.nframes = nframes; ba.base_flags = base_flags;
+    ba.frame_len = d_frame_len; ba.frame_flags = frm_flags; ba.status = d_status;
+    { LaunchTimer lt(ctx, K_BLOCKS_META, s); blocks_frame_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(ba); }
+    CU(ctx, cudaGetLastError());
+    rc = launch_scan(ctx, d_frame_len, nframes, d_frame_off, d_total_out, kScanAlign16, scan_e, s);
+    if (rc) return rc;
+
+    BlocksPackArgs pk;
+    pk.p.in = in; pk.p.raw = in; pk.p.src_off = blk_off; pk.p.src_len = blk_len; pk.p.comp = d_comp;
+    pk.p.comp_off = comp_off; pk.p.seg_base = seg_base; pk.p.meta = d_meta; pk.p.place = d_place;
+    pk.p.comp_len = comp_len; pk.p.flags = blk_flags; pk.p.final_ll = final_ll; pk.p.final_off = final_off;
+    pk.p.status = blk_status; pk.p.frame_off = nullptr; pk.p.dst = nullptr;
+    pk.p.nframes = nslots; pk.p.segs_grid = 1; pk.p.codec = B2B_LZ4; pk.p.typesize_u8 = T; pk.p.header = 0;
+    pk.orig = static_cast<const uint8_t *>(d_src); pk.owner = owner; pk.blk_base = blk_base;
+    pk.nblk = frm_nblk; pk.bs = frm_bs; pk.blk_pos = blk_pos; pk.src_off = d_src_off; pk.src_len = d_src_len;
+    pk.frame_off = d_frame_off; pk.frame_len = d_frame_len; pk.frame_flags = frm_flags; pk.frame_status = d_status;
+    pk.dst = static_cast<uint8_t *>(d_dst); pk.typesize = T;
+    { LaunchTimer lt(ctx, K_BLOCKS_PACK, s); blocks_pack_kernel<<<nslots, kFilterThreads, 0, s>>>(pk); }
+    CU(ctx, cudaGetLastError());
+    return B2B_OK;
+}
+
+int decompress_blocks_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64_t *d_frame_off,
+                                 const uint32_t *d_frame_len, uint32_t nframes, void *d_dst,
+                                 const uint64_t *d_dst_off, const uint32_t *d_dst_cap, uint64_t total_dst,
+                                 uint32_t max_orig, uint32_t blocksize, uint32_t *d_out_len,
+                                 uint32_t *d_status, cudaStream_t s) {
+    if (nframes == 0) return B2B_OK;
+    if (!d_frames || !d_frame_off || !d_frame_len || !d_dst || !d_dst_off || !d_dst_cap || !d_out_len || !d_status)
+        return B2B_EINVAL;
+    if (blocksize != 0 && blocksize < kB1MinBuffer) return B2B_EINVAL;
+    const uint32_t slice = blocksize ? blocksize : kB1DefaultBlock;
+    const uint64_t nslots64 = total_dst / slice + 2ull * nframes;
+    if (nslots64 >= (1ull << 31)) return B2B_EINVAL;
+    const uint32_t nslots = (uint32_t)nslots64;
+    const uint64_t nrec_max = total_dst / 4 + (uint64_t)(kSeqSlack + 1) * nslots + 64;
+    const uint64_t need = align_up(total_dst + 64, 256) + 9 * align_up(8ull * nslots, 256) +
+                          3 * align_up(8ull * nframes, 256) + align_up(8 * nrec_max, 256) +
+                          scan_scratch_bytes(nframes) + scan_scratch_bytes(nslots) + 8192;
+    int rc = ensure_arena(ctx, need);
+    if (rc) return rc;
+    Arena ar(ctx);
+    uint8_t *d_stage = ar.take<uint8_t>(total_dst + 64);
+    uint64_t *d_table = ar.take<uint64_t>(nrec_max);
+    uint64_t *slot_off = ar.take<uint64_t>(nslots);
+    uint64_t *strm_src = ar.take<uint64_t>(nslots);
+    uint64_t *table_off = ar.take<uint64_t>(nslots);
+    uint32_t *slot_len = ar.take<uint32_t>(nslots);
+    uint32_t *strm_clen = ar.take<uint32_t>(nslots);
+    uint32_t *strm_kind = ar.take<uint32_t>(nslots);
+    uint32_t *strm_nrec = ar.take<uint32_t>(nslots);
+    uint32_t *owner = ar.take<uint32_t>(nslots);
+    FrameMeta *slot_meta = ar.take<FrameMeta>(nslots);
+    uint64_t *blk_base = ar.take<uint64_t>(nframes);
+    uint32_t *frm_nblk = ar.take<uint32_t>(nframes);
+    uint32_t *frm_bs = ar.take<uint32_t>(nframes);
+    uint8_t *scan_a = ar.take<uint8_t>(scan_scratch_bytes(nframes));
+    uint8_t *scan_b = ar.take<uint8_t>(scan_scratch_bytes(nslots));
+
+    BlocksInfoArgs ia;
+    ia.frames = static_cast<const uint8_t *>(d_frames); ia.frame_off = d_frame_off; ia.frame_len = d_frame_len;
+    ia.dst_cap = d_dst_cap; ia.nframes = nframes; ia.slice = slice; ia.nblk = frm_nblk; ia.bs = frm_bs;
+    ia.out_len = d_out_len; ia.status = d_status;
+    { LaunchTimer lt(ctx, K_BLOCKS_META, s); blocks_info_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(ia); }
+    CU(ctx, cudaGetLastError());
+    rc = launch_scan(ctx, frm_nblk, nframes, blk_base, nullptr, kScanIdentity, scan_a, s);
+    if (rc) return rc;
+    BlocksOwnerArgs oa;
+    oa.blk_base = blk_base; oa.nblk = frm_nblk; oa.nframes = nframes; oa.nslots = nslots; oa.owner = owner;
+    { LaunchTimer lt(ctx, K_BLOCKS_META, s); blocks_owner_kernel<<<(nslots + 127) / 128, 128, 0, s>>>(oa); }
+    CU(ctx, cudaGetLastError());
+    BlocksDecodeArgs da;
+    da.frames = ia.frames; da.frame_off = d_frame_off; da.owner = owner; da.blk_base = blk_base; da.bs = frm_bs;
+    da.dst = static_cast<uint8_t *>(d_dst); da.scratch = d_stage; da.dst_off = d_dst_off; da.status = d_status;
+    da.nslots = nslots; da.strm_src = strm_src; da.strm_clen = strm_clen; da.strm_kind = strm_kind;
+    da.slot_off = slot_off; da.slot_len = slot_len; da.slot_meta = slot_meta;
+    { LaunchTimer lt(ctx, K_BLOCKS_META, s); blocks_streams_kernel<<<(nslots + 127) / 128, 128, 0, s>>>(da); }
+    CU(ctx, cudaGetLastError());
+    // K4's two halves over the block streams: parse kernel -> sequence records -> copy kernel
+    rc = launch_scan(ctx, slot_len, nslots, table_off, nullptr, kScanSeqSlots, scan_b, s);
+    if (rc) return rc;
+    StreamArgs sa;
+    sa.src = ia.frames; sa.src_off = strm_src; sa.clen = strm_clen; sa.dst = da.dst; sa.scratch = d_stage;
+    sa.dst_off = slot_off; sa.cap = slot_len; sa.kind = strm_kind; sa.owner = owner; sa.status = d_status;
+    sa.nstreams = nslots; sa.table = d_table; sa.table_off = table_off; sa.nrec = strm_nrec;
+    const unsigned sgrid = (nslots + kCodecWarps - 1) / kCodecWarps;
+    { LaunchTimer lt(ctx, K_PARSE, s); lz4_parse_streams_kernel<<<sgrid, kCodecThreads, 0, s>>>(sa); }
+    CU(ctx, cudaGetLastError());
+    { LaunchTimer lt(ctx, K_DECODE, s); lz4_copy_streams_kernel<<<sgrid, kCodecThreads, 0, s>>>(sa); }
+    CU(ctx, cudaGetLastError());
+    { LaunchTimer lt(ctx, K_BLOCKS_DECODE, s); blocks_decode_kernel<<<sgrid, kCodecThreads, 0, s>>>(da); }   // split blocks
+    CU(ctx, cudaGetLastError());
+    { LaunchTimer lt(ctx, K_BLOCKS_META, s);
+      blocks_finish_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(d_status, d_out_len, blk_base, frm_nblk, nslots, nframes); }
+    CU(ctx, cudaGetLastError());
+
+    FilterArgs fa;
+    fa.src = d_stage; fa.dst = static_cast<uint8_t *>(d_dst);
+    fa.ft.off = slot_off; fa.ft.len = slot_len; fa.ft.uniform_len = 0; fa.ft.nframes = nslots;
+    fa.ft.tiles_per_frame = tiles_for(std::min<uint32_t>(max_orig, slice), nslots, ctx);
+    fa.meta = slot_meta; fa.uniform = FrameMeta{0, 0}; fa.status = nullptr; fa.inverse = 1;
+    fa.copy_inactive = 0;
+    { LaunchTimer lt(ctx, K_FILTER, s);
+      filter_batch_kernel<<<(unsigned)((uint64_t)nslots * fa.ft.tiles_per_frame), kFilterThreads, 0, s>>>(fa); }
+    CU(ctx, cudaGetLastError());
+    return B2B_OK;
+}
+
 int shuffle_dev_locked(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, const void *d_src,
                        void *d_dst, size_t n, cudaStream_t s) {
     if (n == 0) return B2B_OK;
@@ -706,6 +925,113 @@ int b2b_decompress_batch_dev(b2b_ctx *ctx, const void *d_frames, const uint64_t 
                                        typesize_override, d_dst, d_dst_off, d_dst_cap,
                                        total_dst_bytes, max_orig_len, d_out_len, d_status,
                                        (cudaStream_t)stream);
+}
+
+// ---- Blosc-1 multi-block frames --------------------------------------------------------------------
+uint32_t b2b_blocks_blocksize(size_t n, int64_t typesize, uint32_t blocksize) {
+    return b1_blocksize(n, b1_typesize(typesize), blocksize);
+}
+
+int b2b_compress_blocks_batch_dev(b2b_ctx *ctx, const void *d_src, const uint64_t *d_src_off,
+                                  const uint32_t *d_src_len, uint32_t nframes, uint64_t total_src_bytes,
+                                  uint32_t max_frame_len, int shuffle, int64_t typesize, uint32_t blocksize,
+                                  void *d_dst, uint64_t dst_cap, uint64_t *d_frame_off, uint32_t *d_frame_len,
+                                  uint32_t *d_status, uint64_t *d_total_out, void *stream) {
+    if (!ctx) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    return compress_blocks_dev_locked(ctx, d_src, d_src_off, d_src_len, nframes, total_src_bytes, max_frame_len,
+                                      shuffle, typesize, blocksize, d_dst, dst_cap, d_frame_off, d_frame_len,
+                                      d_status, d_total_out, (cudaStream_t)stream);
+}
+
+int b2b_decompress_blocks_batch_dev(b2b_ctx *ctx, const void *d_frames, const uint64_t *d_frame_off,
+                                    const uint32_t *d_frame_len, uint32_t nframes, void *d_dst,
+                                    const uint64_t *d_dst_off, const uint32_t *d_dst_cap,
+                                    uint64_t total_dst_bytes, uint32_t max_orig_len, uint32_t blocksize,
+                                    uint32_t *d_out_len, uint32_t *d_status, void *stream) {
+    if (!ctx) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    return decompress_blocks_dev_locked(ctx, d_frames, d_frame_off, d_frame_len, nframes, d_dst, d_dst_off,
+                                        d_dst_cap, total_dst_bytes, max_orig_len, blocksize, d_out_len,
+                                        d_status, (cudaStream_t)stream);
+}
+
+int b2b_compress_blocks(b2b_ctx *ctx, const void *src, size_t n, int shuffle, int64_t typesize,
+                        uint32_t blocksize, void *dst, size_t cap, size_t *out_len) {
+    if (!ctx || !out_len || !dst) return B2B_EINVAL;
+    if (n == 0) return B2B_EINVALID_DATA;
+    if (!src) return B2B_EINVAL;
+    if (n > kB1MaxBuffer) return B2B_EDATA_TOO_LARGE;
+    if (shuffle != B2B_NOSHUFFLE && shuffle != B2B_SHUFFLE && shuffle != B2B_BITSHUFFLE) return B2B_EINVAL;
+    if (cap < n + 16) return B2B_EDST_TOO_SMALL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    uint8_t *d_in = nullptr, *d_out = nullptr, *d_tab = nullptr;
+    int rc = ensure_hbuf(ctx, 0, n + 64, &d_in);
+    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 1, n + 256, &d_out);
+    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 2, 4096, &d_tab);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    uint64_t *d_off = reinterpret_cast<uint64_t *>(d_tab);            // [0] src_off, [1] frame_off, [2] total
+    uint32_t *d_u32 = reinterpret_cast<uint32_t *>(d_tab + 256);      // [0] src_len, [1] frame_len, [2] status
+    const uint64_t h_off[3] = {0, 0, 0};
+    const uint32_t h_u32[3] = {(uint32_t)n, 0, 0};
+    CU(ctx, cudaMemcpyAsync(d_in, src, n, cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemcpyAsync(d_off, h_off, sizeof h_off, cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemcpyAsync(d_u32, h_u32, sizeof h_u32, cudaMemcpyHostToDevice, s));
+    rc = compress_blocks_dev_locked(ctx, d_in, d_off, d_u32, 1, n, (uint32_t)n, shuffle, typesize, blocksize, d_out,
+                                    n + 256, d_off + 1, d_u32 + 1, d_u32 + 2, d_off + 2, s);
+    if (rc) return rc;
+    uint32_t h_res[3] = {0, 0, 0};
+    CU(ctx, cudaMemcpyAsync(h_res, d_u32, sizeof h_res, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    if (h_res[2]) return (int)h_res[2];
+    CU(ctx, cudaMemcpyAsync(dst, d_out, h_res[1], cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    *out_len = h_res[1];
+    return B2B_OK;
+}
+
+int b2b_decompress_blocks(b2b_ctx *ctx, const void *frame, size_t len, void *dst, size_t cap, size_t *out_len) {
+    if (!ctx || !out_len || (!frame && len)) return B2B_EINVAL;
+    b2b_header h;
+    int rc = b2b_parse_header(frame, len, &h);
+    if (rc) return rc;
+    if (len > 0xFFFFFFFFull) len = 0xFFFFFFFFull;                     // cbytes is a u32: the rest is not the frame
+    if (h.nbytes_orig == 0 && h.nbytes_comp >= 16 && h.nbytes_comp <= len) { *out_len = 0; return B2B_OK; }
+    if (!dst) return B2B_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = std::min<uint64_t>(h.nbytes_orig, cap);
+    uint8_t *d_in = nullptr, *d_out = nullptr, *d_tab = nullptr;
+    rc = ensure_hbuf(ctx, 0, len + 64, &d_in);
+    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 1, n + 256, &d_out);
+    if (rc == B2B_OK) rc = ensure_hbuf(ctx, 2, 4096, &d_tab);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    uint64_t *d_off = reinterpret_cast<uint64_t *>(d_tab);            // [0] frame_off, [1] dst_off
+    uint32_t *d_u32 = reinterpret_cast<uint32_t *>(d_tab + 256);      // [0] frame_len, [1] dst_cap, [2] out_len, [3] status
+    const uint64_t h_off[2] = {0, 0};
+    const uint32_t h_u32[4] = {(uint32_t)len, (uint32_t)n, 0, 0};
+    CU(ctx, cudaMemcpyAsync(d_in, frame, len, cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemcpyAsync(d_off, h_off, sizeof h_off, cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemcpyAsync(d_u32, h_u32, sizeof h_u32, cudaMemcpyHostToDevice, s));
+    // the table is sized from the header's own block size (a stored frame is copied in 64 KiB slices)
+    uint32_t bs = (h.flags & B2B_FLAG_MEMCPY) ? 0u : std::min<uint32_t>(h.blocksize, h.nbytes_orig);
+    if (bs != 0 && bs < kB1MinBuffer) bs = kB1MinBuffer;
+    rc = decompress_blocks_dev_locked(ctx, d_in, d_off, d_u32, 1, d_out, d_off + 1, d_u32 + 1, n, (uint32_t)n, bs,
+                                      d_u32 + 2, d_u32 + 3, s);
+    if (rc) return rc;
+    uint32_t h_res[4] = {0, 0, 0, 0};
+    CU(ctx, cudaMemcpyAsync(h_res, d_u32, sizeof h_res, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    if (h_res[3]) return (int)h_res[3];
+    CU(ctx, cudaMemcpyAsync(dst, d_out, h_res[2], cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    *out_len = h_res[2];
+    return B2B_OK;
 }
 
 int b2b_scan_offsets_dev(b2b_ctx *ctx, const uint32_t *d_len, uint32_t n, uint64_t *d_off,

@@ -832,6 +832,28 @@ __device__ __forceinline__ uint32_t cta_put_token(uint8_t *dst, uint32_t lt, uin
     return 2 + full;
 }
 
+// segment s of frame f's LZ4 block, assembled at its place in `out` (the start of the block) by the whole CTA
+__device__ __forceinline__ void cta_pack_lz4_segment(const PackArgs &a, uint32_t f, uint32_t s, uint32_t n,
+                                                     uint32_t nseg, uint64_t base, uint8_t *out) {
+    const uint32_t B = s * kSegBytes;
+    const uint8_t *frame = a.in + a.src_off[f];
+    const SegMeta m = a.meta[base + s];
+    if (m.info & 0x100u) {
+        const SegPlace pl = a.place[base + s];
+        uint8_t *d = out + pl.out_off;
+        const uint32_t hdr = cta_put_token(d, pl.lit_total, m.info & 15u);
+        // carried + leading literals are one contiguous input range ending at the match start
+        cta_copy(d + hdr, frame + ((uint64_t)B + m.first_ll - pl.lit_total), pl.lit_total);
+        cta_copy(d + hdr + pl.lit_total, a.comp + a.comp_off[f] + (uint64_t)s * kSegSlot, m.body_len);
+    }
+    if (s == nseg - 1) {                                  // closing token: the last literals
+        const uint32_t lf = a.final_ll[f];
+        uint8_t *d = out + a.final_off[f];
+        const uint32_t hdr = cta_put_token(d, lf, 0);
+        cta_copy(d + hdr, frame + (n - lf), lf);
+    }
+}
+
 __global__ void __launch_bounds__(kFilterThreads) pack_frames_kernel(PackArgs a) {
     const uint64_t item = blockIdx.x;
     const uint32_t f = (uint32_t)(item / a.segs_grid), s0 = (uint32_t)(item % a.segs_grid);
@@ -851,28 +873,13 @@ __global__ void __launch_bounds__(kFilterThreads) pack_frames_kernel(PackArgs a)
     }
     const uint64_t base = a.seg_base[f];
     for (uint32_t s = s0; s < nseg; s += a.segs_grid) {
-        const uint32_t B = s * kSegBytes;
-        const uint32_t L = n - B < kSegBytes ? n - B : kSegBytes;
         if (flags & 0x2u) {                                   // memcpy frame
+            const uint32_t B = s * kSegBytes;
+            const uint32_t L = n - B < kSegBytes ? n - B : kSegBytes;
             cta_copy(out + B, a.raw + a.src_off[f] + B, L);
             continue;
         }
-        const uint8_t *frame = a.in + a.src_off[f];
-        const SegMeta m = a.meta[base + s];
-        if (m.info & 0x100u) {
-            const SegPlace pl = a.place[base + s];
-            uint8_t *d = out + pl.out_off;
-            const uint32_t hdr = cta_put_token(d, pl.lit_total, m.info & 15u);
-            // carried + leading literals are one contiguous input range ending at the match start
-            cta_copy(d + hdr, frame + ((uint64_t)B + m.first_ll - pl.lit_total), pl.lit_total);
-            cta_copy(d + hdr + pl.lit_total, a.comp + a.comp_off[f] + (uint64_t)s * kSegSlot, m.body_len);
-        }
-        if (s == nseg - 1) {                                  // closing token: the last literals
-            const uint32_t lf = a.final_ll[f];
-            uint8_t *d = out + a.final_off[f];
-            const uint32_t hdr = cta_put_token(d, lf, 0);
-            cta_copy(d + hdr, frame + (n - lf), lf);
-        }
+        cta_pack_lz4_segment(a, f, s, n, nseg, base, out);
     }
 }
 

@@ -466,22 +466,9 @@ struct ParseArgs {
     uint64_t table_cap;         // records the table can hold in all
 };
 
-__global__ void __launch_bounds__(kCodecThreads, 12) lz4_parse_kernel(ParseArgs a) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t f = blockIdx.x * kCodecWarps + warp;
-    if (f >= a.nframes) return;
-    const uint8_t *fr = a.frames + a.frame_off[f];
-    uint32_t flags = 0, codec = 0, tsz = 0, norig = 0, ncomp = 0;
-    const uint32_t st = check_header(fr, a.frame_len[f], flags, codec, tsz, norig, ncomp);
-    if (st != kOk || (flags & 0x2u) || (codec != 1 && codec != 2)) { if (lane == 0) a.nrec[f] = 0; return; }
-    const uint8_t *__restrict__ src = fr + 16;
-    const uint32_t clen = ncomp - 16;
-    const uint32_t room = a.dst_cap[f] / 4u + kSeqSlack;
-    if (a.table_off[f] + room > a.table_cap) {            // capacities that overlap in dst: not sized for
-        if (lane == 0) a.nrec[f] = 0xFFFFFFFFu;
-        return;
-    }
-    uint64_t *tab = a.table + a.table_off[f];
+// the sequence records of one LZ4 block; returns how many were written (room >= 15)
+__device__ __forceinline__ uint32_t warp_lz4_parse(const uint8_t *__restrict__ src, uint32_t clen, uint64_t *tab,
+                                                   uint32_t room, int lane) {
     uint32_t ip = 0, n = 0;
     constexpr uint32_t kWindowReach = 306;
     constexpr uint64_t kLong = 1ull << 62, kTail = 2ull << 62;
@@ -529,7 +516,64 @@ __global__ void __launch_bounds__(kCodecThreads, 12) lz4_parse_kernel(ParseArgs 
             ip = q;
         }
     }
+    return n;
+}
+
+__global__ void __launch_bounds__(kCodecThreads, 12) lz4_parse_kernel(ParseArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t f = blockIdx.x * kCodecWarps + warp;
+    if (f >= a.nframes) return;
+    const uint8_t *fr = a.frames + a.frame_off[f];
+    uint32_t flags = 0, codec = 0, tsz = 0, norig = 0, ncomp = 0;
+    const uint32_t st = check_header(fr, a.frame_len[f], flags, codec, tsz, norig, ncomp);
+    if (st != kOk || (flags & 0x2u) || (codec != 1 && codec != 2)) { if (lane == 0) a.nrec[f] = 0; return; }
+    const uint32_t room = a.dst_cap[f] / 4u + kSeqSlack;
+    if (a.table_off[f] + room > a.table_cap) {            // capacities that overlap in dst: not sized for
+        if (lane == 0) a.nrec[f] = 0xFFFFFFFFu;
+        return;
+    }
+    const uint32_t n = warp_lz4_parse(fr + 16, ncomp - 16, a.table + a.table_off[f], room, lane);
     if (lane == 0) a.nrec[f] = n;
+}
+
+// ---- the same two halves over a table of bare LZ4 streams (the blocks of blocks.cuh) ----------------
+struct StreamArgs {
+    const uint8_t *src;         // stream t: src + src_off[t], clen[t] bytes
+    const uint64_t *src_off;
+    const uint32_t *clen;
+    uint8_t *dst, *scratch;     // decodes to exactly cap[t] bytes at (kind & 4 ? scratch : dst) + dst_off[t]
+    const uint64_t *dst_off;
+    const uint32_t *cap;
+    const uint32_t *kind;       // low 2 bits: 0 nothing, 1 stored (copy cap bytes), 2 one LZ4 block, 3 not ours
+    const uint32_t *owner;      // status[owner[t]] is raised when stream t fails
+    uint32_t *status;
+    uint32_t nstreams;
+    uint64_t *table;            // sequence records
+    const uint64_t *table_off;  // exclusive scan of cap / 4 + kSeqSlack
+    uint32_t *nrec;
+};
+
+__global__ void __launch_bounds__(kCodecThreads, 12) lz4_parse_streams_kernel(StreamArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t t = blockIdx.x * kCodecWarps + warp;
+    if (t >= a.nstreams || (a.kind[t] & 3u) != 2u) return;
+    const uint32_t n = warp_lz4_parse(a.src + a.src_off[t], a.clen[t], a.table + a.table_off[t],
+                                      a.cap[t] / 4u + kSeqSlack, lane);
+    if (lane == 0) a.nrec[t] = n;
+}
+
+__global__ void __launch_bounds__(kCodecThreads, 8) lz4_copy_streams_kernel(StreamArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t t = blockIdx.x * kCodecWarps + warp;
+    if (t >= a.nstreams) return;
+    const uint32_t kind = a.kind[t];
+    if ((kind & 3u) == 0u || (kind & 3u) == 3u) return;
+    const uint8_t *src = a.src + a.src_off[t];
+    uint8_t *out = ((kind & 4u) ? a.scratch : a.dst) + a.dst_off[t];
+    const uint32_t cap = a.cap[t];
+    if ((kind & 3u) == 1u) { warp_copy(out, src, cap, lane); return; }
+    const int64_t got = warp_lz4_copy(src, a.clen[t], out, cap, a.table + a.table_off[t], a.nrec[t], lane);
+    if (got != (int64_t)cap && lane == 0) atomicMax(a.status + a.owner[t], (uint32_t)kEDecompressionFailed);
 }
 
 // ---- decode with a side-car index ------------------------------------------

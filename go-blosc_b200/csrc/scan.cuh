@@ -22,7 +22,8 @@ enum ScanOp : int {
     kScanAlign16 = 1,    // (x + 15) & ~15     packed frames start on 16-byte boundaries
     kScanSegSlot = 2,    // scratch bytes of the frame's segment slots (lz4_encode.cuh)
     kScanSegCount = 3,   // number of 64 KiB segments of the frame
-    kScanSeqSlots = 4    // sequence records of the split decoder for a frame of capacity x
+    kScanSeqSlots = 4,   // sequence records of the split decoder for a frame of capacity x
+    kScanStream = 5      // x ? x + 4 : 0     a stream of a Blosc-1 block behind its int32 size (blocks.cuh)
 };
 
 __device__ __forceinline__ uint64_t scan_apply(int op, uint32_t x) {
@@ -30,6 +31,7 @@ __device__ __forceinline__ uint64_t scan_apply(int op, uint32_t x) {
     if (op == kScanSegSlot) return frame_slot_bytes(x);
     if (op == kScanSegCount) return seg_count(x);
     if (op == kScanSeqSlots) return (uint64_t)(x / 4u) + kSeqSlack;
+    if (op == kScanStream) return x ? (uint64_t)x + 4ull : 0ull;
     return x;
 }
 

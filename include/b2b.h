@@ -69,6 +69,8 @@ enum { B2B_NOSHUFFLE = 0, B2B_SHUFFLE = 1, B2B_BITSHUFFLE = 2 };
 enum { B2B_FLAG_SHUFFLE = 0x1, B2B_FLAG_MEMCPY = 0x2, B2B_FLAG_BITSHUFFLE = 0x4 };
 #define B2B_HEADER_SIZE 16
 #define B2B_FORMAT_VERSION 2
+/* additional flag bits of the opt-in multi-block frames (b2b_*_blocks_*) */
+enum { B2B_FLAG_DONTSPLIT = 0x10, B2B_BLOCKS_LZ4_FORMAT = 1 /* flags >> 5 */ };
 
 /* 16-byte frame header, little-endian on the wire (blosc.go:154-162) */
 typedef struct b2b_header {
@@ -113,9 +115,10 @@ B2B_API int b2b_set_option(b2b_ctx *ctx, int option, int64_t value);
 B2B_API int b2b_reserve(b2b_ctx *ctx, uint64_t total_uncompressed_bytes, uint32_t nframes);
 /* number of kernel launches issued through this ctx since creation (bench's gpu_launches) */
 B2B_API uint64_t b2b_launch_count(b2b_ctx *ctx);
-/* per-kernel launch counts and (with B2B_OPT_KERNEL_TIMING) summed device time; kernel = 0..7:
+/* per-kernel launch counts and (with B2B_OPT_KERNEL_TIMING) summed device time; kernel = 0..10:
  * filter, lz4 encode, lz4 decode (copy half), offsets scan, pack, frame info, finalize, lz4 parse
- * (decode's parse half); B2B_EINVAL beyond.  Synchronises pending events. */
+ * (decode's parse half), block-frame tables, block-frame pack, block-frame decode; B2B_EINVAL
+ * beyond.  Synchronises pending events. */
 B2B_API int b2b_kernel_stats(b2b_ctx *ctx, int kernel, const char **name, uint64_t *launches,
                              double *total_ms);
 B2B_API int b2b_kernel_stats_reset(b2b_ctx *ctx);
@@ -225,6 +228,40 @@ B2B_API int b2b_decompress_batch_dev_indexed(b2b_ctx *ctx, const void *d_frames,
                                              uint32_t *d_out_len, uint32_t *d_status,
                                              const uint64_t *d_index, uint32_t segs_per_frame,
                                              void *stream);
+
+/* ---- Blosc-1 multi-block frames (opt-in, no reference counterpart) ------
+ * The reference declares Options.BlockSize and never reads it (blosc.go:227-234; every frame it
+ * writes or reads is ONE block, blosc.go:320-434), so these frames stay behind their own entry
+ * points and the reference cannot decode them.  Layout: the published Blosc-1 chunk -- 16-byte
+ * header (version 2, versionlz 1, flags 0x1 shuffle / 0x2 stored / 0x4 bitshuffle / 0x10 not
+ * split / format 1 = LZ4 in bits 5..7, typesize, nbytes, blocksize, cbytes), int32 bstarts[nblocks],
+ * then per block an int32 size and one LZ4 block (size == block length: stored raw).  The filter
+ * runs per block; the bit shuffle is the reference's own arrangement (shuffle.go:145-295), so
+ * frames with flag 0x4 are private to this library.  The encoder never splits blocks into
+ * per-byte streams (flag 0x10); the decoder also reads split blocks.  A frame is at most
+ * nbytes + 16 bytes (stored when it would not be).  blocksize: 0 = 64 KiB, otherwise >= 128;
+ * the block size used is b2b_blocks_blocksize() (whole elements, at most the buffer).
+ * typesize outside 1..255 counts as 1.  n == 0: B2B_EINVALID_DATA; n > 2^31 - 17: B2B_EDATA_TOO_LARGE.
+ * Batch calls have the conventions of b2b_compress_batch_dev / b2b_decompress_batch_dev; on
+ * decompression `blocksize` is what the frames were written with (it sizes the block table:
+ * a frame with more than nbytes / blocksize + 2 blocks reports B2B_EUNSUPPORTED). */
+B2B_API uint32_t b2b_blocks_blocksize(size_t n, int64_t typesize, uint32_t blocksize);
+B2B_API int b2b_compress_blocks(b2b_ctx *ctx, const void *src, size_t n, int shuffle, int64_t typesize,
+                                uint32_t blocksize, void *dst, size_t cap, size_t *out_len);
+B2B_API int b2b_decompress_blocks(b2b_ctx *ctx, const void *frame, size_t len, void *dst, size_t cap,
+                                  size_t *out_len);
+B2B_API int b2b_compress_blocks_batch_dev(b2b_ctx *ctx, const void *d_src, const uint64_t *d_src_off,
+                                          const uint32_t *d_src_len, uint32_t nframes,
+                                          uint64_t total_src_bytes, uint32_t max_frame_len, int shuffle,
+                                          int64_t typesize, uint32_t blocksize, void *d_dst,
+                                          uint64_t dst_cap, uint64_t *d_frame_off, uint32_t *d_frame_len,
+                                          uint32_t *d_status, uint64_t *d_total_out, void *stream);
+B2B_API int b2b_decompress_blocks_batch_dev(b2b_ctx *ctx, const void *d_frames,
+                                            const uint64_t *d_frame_off, const uint32_t *d_frame_len,
+                                            uint32_t nframes, void *d_dst, const uint64_t *d_dst_off,
+                                            const uint32_t *d_dst_cap, uint64_t total_dst_bytes,
+                                            uint32_t max_orig_len, uint32_t blocksize,
+                                            uint32_t *d_out_len, uint32_t *d_status, void *stream);
 
 /* K5 on its own: d_off = exclusive scan of d_len (u32 -> u64), d_total[0] = sum. */
 B2B_API int b2b_scan_offsets_dev(b2b_ctx *ctx, const uint32_t *d_len, uint32_t n, uint64_t *d_off,

@@ -115,6 +115,16 @@ int orc_decompress_batch_mt(const uint8_t *frames, const uint64_t *frame_off,
 int orc_shuffle_mt(int mode, int inverse, int64_t typesize, const uint8_t *src, uint8_t *dst,
                    size_t n, int threads, int fast);
 
+/* ---- opt-in Blosc-1 multi-block frames (blosc1_blocks.c) ------------
+ * No reference counterpart (the reference ignores Options.BlockSize): PARITY
+ * UNPINNED, the published Blosc-1 chunk layout restated.  blocksize_req 0 = 64 KiB;
+ * split != 0 writes typesize streams per block where Blosc-1 would. */
+enum { ORC_B1_FLAG_DONTSPLIT = 0x10, ORC_B1_LZ4_FORMAT = 1 };
+uint32_t orc_blocks_blocksize(size_t n, int64_t typesize, uint32_t blocksize_req);
+int orc_blocks_compress(const uint8_t *data, size_t n, int shuffle, int64_t typesize,
+                        uint32_t blocksize_req, int split, uint8_t *dst, size_t cap, size_t *out_len);
+int orc_blocks_decompress(const uint8_t *frame, size_t len, uint8_t *dst, size_t cap, size_t *out_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,10 +26,9 @@ MEMCPY_SHUFFLED, MEMCPY_REF_QUIRK = 0, 1
 
 def build(force: bool = False) -> str:
     """Compile oracle/liboracle.so with gcc (seconds)."""
-    src = os.path.join(_HERE, "blosc_oracle.c")
-    hdr = os.path.join(_HERE, "blosc_oracle.h")
+    deps = [os.path.join(_HERE, f) for f in ("blosc_oracle.c", "blosc1_blocks.c", "blosc_oracle.h")]
     stale = (not os.path.exists(_SO)) or any(
-        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr))
+        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in deps)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
     return _SO
@@ -64,6 +63,11 @@ def lib():
         L.orc_decompress_batch_mt.restype = C.c_int
         L.orc_shuffle_mt.argtypes = [C.c_int, C.c_int, i64, vp, vp, sz, C.c_int, C.c_int]
         L.orc_shuffle_mt.restype = C.c_int
+        L.orc_blocks_blocksize.argtypes = [sz, i64, C.c_uint32]; L.orc_blocks_blocksize.restype = C.c_uint32
+        L.orc_blocks_compress.argtypes = [vp, sz, C.c_int, i64, C.c_uint32, C.c_int, vp, sz, C.POINTER(sz)]
+        L.orc_blocks_compress.restype = C.c_int
+        L.orc_blocks_decompress.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]
+        L.orc_blocks_decompress.restype = C.c_int
         _lib = L
     return _lib
 
@@ -151,6 +155,36 @@ def decompress(frame, typesize_override=0, cap=None):
     out = C.c_size_t(0)
     rc = lib().orc_decompress(_ptr(s) if s.size else None, s.size, int(typesize_override), _ptr(d),
                               cap, C.byref(out))
+    return rc, (d[:out.value].copy() if rc == 0 else None)
+
+
+# ---- opt-in Blosc-1 multi-block frames (oracle/blosc1_blocks.c; parity unpinned) -----------
+B1_FLAG_DONTSPLIT, B1_LZ4_FORMAT = 0x10, 1
+
+
+def blocks_blocksize(n: int, typesize: int, blocksize: int = 0) -> int:
+    return int(lib().orc_blocks_blocksize(n, int(typesize), int(blocksize)))
+
+
+def blocks_compress(data, shuffle=SHUFFLE, typesize=4, blocksize=0, split=False):
+    """Returns (status, frame-or-None)."""
+    s = _u8(data)
+    d = np.empty(16 + s.size + 64, dtype=np.uint8)
+    out = C.c_size_t(0)
+    rc = lib().orc_blocks_compress(_ptr(s) if s.size else None, s.size, int(shuffle), int(typesize),
+                                   int(blocksize), int(bool(split)), _ptr(d), d.size, C.byref(out))
+    return rc, (d[:out.value].copy() if rc == 0 else None)
+
+
+def blocks_decompress(frame, cap=None):
+    """Returns (status, data-or-None)."""
+    s = _u8(frame)
+    if cap is None:
+        cap = int(np.frombuffer(s[4:8].tobytes(), dtype="<u4")[0]) if s.size >= 16 else 0
+        cap = min(cap, 1 << 31)
+    d = np.empty(max(cap, 1), dtype=np.uint8)
+    out = C.c_size_t(0)
+    rc = lib().orc_blocks_decompress(_ptr(s) if s.size else None, s.size, _ptr(d), cap, C.byref(out))
     return rc, (d[:out.value].copy() if rc == 0 else None)
 
 

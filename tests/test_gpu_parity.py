@@ -576,3 +576,162 @@ def test_split_and_fused_decoders_agree(ctx, orc):
         if rc == 0:
             for out, _, _ in res:
                 assert np.array_equal(out[int(doff[k]):int(doff[k]) + ref.size], ref), k
+
+
+# ---- opt-in Blosc-1 multi-block frames (oracle/blosc1_blocks.c, parity unpinned) ----
+from test_blocks_oracle import parse as b1_parse, walk_blocks as b1_walk  # noqa: E402
+
+
+@pytest.mark.parametrize("shuffle,T", [(0, 1), (1, 4), (1, 3), (2, 8), (1, 17)])
+def test_block_frames_cross_decode_with_oracle(ctx, orc, shuffle, T):
+    """GPU block frames: same header fields as the oracle's, every block re-derived from the wire bytes
+    (liblz4 decodes the streams), oracle decodes them; oracle frames (split and not) decode on the GPU."""
+    unfilt = {0: lambda b, t: b, 1: orc.unshuffle, 2: orc.bitunshuffle}[shuffle] if T > 1 else (lambda b, t: b)
+    for name, data in dg.corpus(200003).items():
+        for bs in (0, 4096, 100000, 1 << 20):
+            fr = np.frombuffer(ctx.compress_blocks(data, shuffle, T, bs), dtype=np.uint8)
+            rc, ref = orc.blocks_compress(data, shuffle, T, bs, False)
+            assert rc == 0 and fr.size <= data.size + 16
+            hg, hr = b1_parse(fr), b1_parse(ref)
+            assert {k: v for k, v in hg.items() if k != "cbytes"} == {k: v for k, v in hr.items() if k != "cbytes"} \
+                or (hg["flags"] ^ hr["flags"]) == 2, (name, bs, hg, hr)
+            assert hg["cbytes"] == fr.size and hg["blocksize"] == ctx.blocks_blocksize(data.size, T, bs)
+            assert fr.size <= ref.size * 1.6 + 64, (name, bs, fr.size, ref.size)   # format test; C3-shape test holds the size
+            if not hg["flags"] & 2:
+                assert b1_walk(orc, fr, data, unfilt) == -(-data.size // hg["blocksize"])
+            rc, back = orc.blocks_decompress(fr)
+            assert rc == 0 and np.array_equal(back, data), (name, bs)
+            assert ctx.decompress_blocks(fr) == data.tobytes()
+            for split in (False, True):
+                rc, ref = orc.blocks_compress(data, shuffle, T, bs, split)
+                assert rc == 0 and ctx.decompress_blocks(ref) == data.tobytes(), (name, bs, split)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 127, 128, 129, 255, 4096, 65535, 65536, 65537, 3 * 65536, (1 << 20) + 77])
+def test_block_frames_sizes(ctx, orc, n):
+    for data in (dg.ramp(n), dg.random_bytes(n, 1), np.zeros(n, dtype=np.uint8), dg.smooth_f32(n // 4 + 1, 2)[:n].copy()):
+        for bs in (0, 128, 1000):
+            fr = np.frombuffer(ctx.compress_blocks(data, 1, 4, bs), dtype=np.uint8)
+            h = b1_parse(fr)
+            assert fr.size <= n + 16 and h["nbytes"] == n and h["cbytes"] == fr.size
+            assert bool(h["flags"] & 2) or n >= 128
+            rc, back = orc.blocks_decompress(fr)
+            assert rc == 0 and np.array_equal(back, data), (n, bs)
+            assert ctx.decompress_blocks(fr) == data.tobytes()
+
+
+def test_block_frames_errors_match_oracle(ctx, orc, pkg):
+    with pytest.raises(pkg.ErrInvalidData):
+        ctx.compress_blocks(b"")
+    with pytest.raises(pkg.ErrInval):
+        ctx.compress_blocks(b"x" * 1000, 1, 4, 64)                    # block sizes below 128 are refused
+    data = dg.smooth_f32(50000, 3)
+    fr = np.frombuffer(ctx.compress_blocks(data, 1, 4, 16384), dtype=np.uint8)
+    assert not b1_parse(fr)["flags"] & 2
+    rng = np.random.default_rng(11)
+    cases = [fr[:10], fr[:-1]]
+    for byte, val in ((0, 3), (1, 2), (3, 0)):
+        bad = fr.copy(); bad[byte] = val; cases.append(bad)
+    for fmt in (0, 2, 4, 7):
+        bad = fr.copy(); bad[2] = (bad[2] & 0x1F) | (fmt << 5); cases.append(bad)
+    for field, val in ((8, 0), (4, 0x7FFFFFFF), (12, 15), (16, 8), (16, fr.size - 2), (20, 0x7FFFFFF0)):
+        bad = fr.copy(); bad[field:field + 4] = np.frombuffer(struct.pack("<I", val), dtype=np.uint8); cases.append(bad)
+    for _ in range(40):                                               # random damage anywhere
+        bad = fr.copy()
+        for _ in range(int(rng.integers(1, 4))):
+            bad[int(rng.integers(0, bad.size))] = int(rng.integers(0, 256))
+        cases.append(bad)
+    for i, bad in enumerate(cases):
+        rc, back = orc.blocks_decompress(bad)
+        try:
+            got = ctx.decompress_blocks(bad)
+            assert rc == 0 and got == back.tobytes(), (i, rc)
+        except pkg.BloscError as e:
+            assert rc == e.status or (rc != 0 and e.status in (pkg.EDECOMPRESSION_FAILED, pkg.EUNSUPPORTED)), (i, rc, e.status)
+
+
+def test_block_frames_device_batch_ragged(ctx, orc, torch_mod):
+    torch = torch_mod
+    rng = np.random.default_rng(5)
+    parts = [dg.smooth_f32(70000, 1), dg.random_bytes(5000, 2), np.zeros(0, dtype=np.uint8), dg.lowent_i16(300000, 3),
+             dg.ramp(100), dg.text_like(333333, 4), dg.smooth_f32(16384, 5), dg.random_bytes(200000, 6), dg.ramp(127)]
+    parts += [dg.smooth_f32(int(rng.integers(1, 60000)), 10 + i) for i in range(40)]
+    lens = np.array([p.size for p in parts], dtype=np.uint32)
+    offs = np.zeros(len(parts), dtype=np.uint64)
+    np.cumsum(((lens.astype(np.uint64) + 15) // 16 * 16)[:-1], out=offs[1:])
+    total = int(offs[-1] + lens[-1])
+    host = np.zeros(total + 16, dtype=np.uint8)
+    for p, o in zip(parts, offs):
+        host[int(o):int(o) + p.size] = p
+    nf = len(parts)
+    for shuffle, T, bs in ((1, 4, 0), (2, 8, 32768), (0, 1, 4096), (1, 2, 200000)):
+        d_src = torch.from_numpy(host).cuda()
+        d_off = torch.from_numpy(offs.astype(np.int64)).cuda()
+        d_len = torch.from_numpy(lens.astype(np.int32)).cuda()
+        cap = total + 32 * nf + 64
+        d_dst = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        d_foff = torch.empty(nf, dtype=torch.int64, device="cuda")
+        d_flen = torch.empty(nf, dtype=torch.int32, device="cuda")
+        d_st = torch.empty(nf, dtype=torch.int32, device="cuda")
+        d_tot = torch.empty(1, dtype=torch.int64, device="cuda")
+        s = torch.cuda.current_stream().cuda_stream
+        ctx.compress_blocks_batch_dev(d_src, d_off, d_len, nf, total, int(lens.max()), shuffle, T, bs, d_dst, cap,
+                                      d_foff, d_flen, d_st, d_tot, s)
+        torch.cuda.synchronize()
+        st, foff, flen = d_st.cpu().numpy(), d_foff.cpu().numpy(), d_flen.cpu().numpy()
+        comp = d_dst.cpu().numpy()
+        assert [int(x) for x in st] == [1 if p.size == 0 else 0 for p in parts]
+        assert np.all(foff % 16 == 0) and int(d_tot.item()) == int(((flen.astype(np.int64) + 15) // 16 * 16).sum())
+        for f, p in enumerate(parts):
+            if p.size == 0:
+                assert flen[f] == 0
+                continue
+            fr = comp[foff[f]:foff[f] + flen[f]]
+            rc, back = orc.blocks_decompress(fr)
+            assert rc == 0 and np.array_equal(back, p), (shuffle, T, bs, f)
+            assert b1_parse(fr)["blocksize"] == ctx.blocks_blocksize(p.size, T, bs)
+        d_out = torch.zeros(total + 16, dtype=torch.uint8, device="cuda")
+        d_olen = torch.empty(nf, dtype=torch.int32, device="cuda")
+        d_st2 = torch.empty(nf, dtype=torch.int32, device="cuda")
+        ctx.decompress_blocks_batch_dev(d_dst, d_foff, d_flen, nf, d_out, d_off, d_len, total, int(lens.max()),
+                                        bs, d_olen, d_st2, s)
+        torch.cuda.synchronize()
+        st2 = d_st2.cpu().numpy()
+        assert [int(x) for x in st2] == [2 if p.size == 0 else 0 for p in parts]     # an empty slot is no frame
+        assert np.array_equal(d_olen.cpu().numpy(), lens)
+        assert torch.equal(d_out[:total], d_src[:total])
+
+
+def test_block_frames_c3_shape_roundtrip(ctx, orc, torch_mod):
+    """Config C3's shape (256 KiB float32 frames, Shuffle T=4) as block frames of 64 KiB blocks."""
+    torch = torch_mod
+    nf, fl = 256, 262144
+    host = dg.smooth_f32(nf * fl // 4, 5)
+    d_src = torch.from_numpy(host).cuda()
+    d_off = torch.arange(nf, dtype=torch.int64, device="cuda") * fl
+    d_len = torch.full((nf,), fl, dtype=torch.int32, device="cuda")
+    cap = nf * fl + 32 * nf + 64
+    d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_foff = torch.empty(nf, dtype=torch.int64, device="cuda")
+    d_flen = torch.empty(nf, dtype=torch.int32, device="cuda")
+    d_st = torch.empty(nf, dtype=torch.int32, device="cuda")
+    d_tot = torch.empty(1, dtype=torch.int64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    ctx.compress_blocks_batch_dev(d_src, d_off, d_len, nf, nf * fl, fl, 1, 4, 0, d_dst, cap, d_foff, d_flen, d_st, d_tot, s)
+    torch.cuda.synchronize()
+    assert not d_st.any()
+    foff, flen = d_foff.cpu().numpy(), d_flen.cpu().numpy()
+    comp = d_dst.cpu().numpy()
+    ref_total = 0
+    for f in (0, 1, 17, nf - 1):
+        fr = comp[foff[f]:foff[f] + flen[f]]
+        rc, back = orc.blocks_decompress(fr)
+        assert rc == 0 and np.array_equal(back, host[f * fl:(f + 1) * fl])
+        ref_total += orc.blocks_compress(host[f * fl:(f + 1) * fl], 1, 4, 0, False)[1].size
+    assert sum(int(flen[f]) for f in (0, 1, 17, nf - 1)) <= 1.04 * ref_total
+    d_out = torch.zeros(nf * fl, dtype=torch.uint8, device="cuda")
+    d_olen = torch.empty(nf, dtype=torch.int32, device="cuda")
+    d_st2 = torch.empty(nf, dtype=torch.int32, device="cuda")
+    ctx.decompress_blocks_batch_dev(d_dst, d_foff, d_flen, nf, d_out, d_off, d_len, nf * fl, fl, 0, d_olen, d_st2, s)
+    torch.cuda.synchronize()
+    assert not d_st2.any() and torch.equal(d_out, d_src)

@@ -83,6 +83,11 @@ for key, hl, tune in [(k, h, t) for k in which for h in hashlogs for t in tunes]
         label += " indexed"
         comp = lambda: ctx.compress_batch_dev_indexed(data, d_off, d_len, nf, size, fl, sh, T, d_c, cap, d_foff, d_flen, d_st, d_tot, d_idx, spf, s)
         dec = lambda: ctx.decompress_batch_dev_indexed(d_c, d_foff, d_flen, nf, 0, d_out, d_off, d_len, size, fl, d_olen, d_st, d_idx, spf, s)
+    elif os.environ.get("PROBE_BLOCKS"):                 # Blosc-1 multi-block frames, PROBE_BLOCKS = block size (1 = default)
+        bsz = int(os.environ["PROBE_BLOCKS"]); bsz = 0 if bsz == 1 else bsz
+        label += f" blocks({bsz or 65536})"
+        comp = lambda: ctx.compress_blocks_batch_dev(data, d_off, d_len, nf, size, fl, sh, T, bsz, d_c, cap, d_foff, d_flen, d_st, d_tot, s)
+        dec = lambda: ctx.decompress_blocks_batch_dev(d_c, d_foff, d_flen, nf, d_out, d_off, d_len, size, fl, bsz, d_olen, d_st, s)
     else:
         comp = lambda: ctx.compress_batch_dev(data, d_off, d_len, nf, size, fl, sh, T, d_c, cap, d_foff, d_flen, d_st, d_tot, s)
         dec = lambda: ctx.decompress_batch_dev(d_c, d_foff, d_flen, nf, 0, d_out, d_off, d_len, size, fl, d_olen, d_st, s)
