@@ -117,6 +117,56 @@ func decompressBackend(data []byte, typeSize int) ([]byte, error) {
 	return dst[:int(n):int(n)], nil
 }
 
+// CompressBlocks writes a Blosc-1 MULTI-BLOCK frame: the one place where Options.BlockSize (declared and
+// never read by the reference, blosc.go:227-234) means something.  0 = 64 KiB blocks.  Such frames have
+// int32 bstarts and one LZ4 block per block; the reference's Decompress cannot read them (it decodes one
+// block per frame), DecompressBlocks does.  opts.Codec must be LZ4.
+func CompressBlocks(data []byte, opts Options) ([]byte, error) {
+	if len(data) == 0 {
+		return nil, ErrInvalidData
+	}
+	if opts.Codec != LZ4 {
+		return nil, fmt.Errorf("%w: multi-block frames are LZ4 only", ErrInvalidCodec)
+	}
+	dst := make([]byte, len(data)+16+64)
+	var n C.size_t
+	err := withCtx(func(c *gpuCtx) error {
+		rc := C.b2b_compress_blocks(c.h, unsafe.Pointer(&data[0]), C.size_t(len(data)), C.int(opts.Shuffle),
+			C.int64_t(opts.TypeSize), C.uint32_t(opts.BlockSize), unsafe.Pointer(&dst[0]), C.size_t(len(dst)), &n)
+		return statusErr(rc, "blocks")
+	})
+	if err != nil {
+		return nil, err
+	}
+	return dst[:int(n):int(n)], nil
+}
+
+// DecompressBlocks reads a Blosc-1 multi-block LZ4 frame (split or unsplit blocks, stored frames).
+func DecompressBlocks(data []byte) ([]byte, error) {
+	h, err := ParseHeader(data)
+	if err != nil {
+		return nil, err
+	}
+	capacity := int(h.NBytesOrig)
+	if reach := 255*len(data) + 64; capacity > reach {
+		capacity = reach
+	}
+	dst := make([]byte, capacity+1)
+	var n C.size_t
+	err = withCtx(func(c *gpuCtx) error {
+		rc := C.b2b_decompress_blocks(c.h, unsafe.Pointer(&data[0]), C.size_t(len(data)), unsafe.Pointer(&dst[0]),
+			C.size_t(capacity), &n)
+		if rc == C.B2B_EDST_TOO_SMALL && capacity < int(h.NBytesOrig) {
+			rc = C.B2B_EDECOMPRESSION_FAILED
+		}
+		return statusErr(rc, fmt.Sprintf("expected %d", h.NBytesOrig))
+	})
+	if err != nil {
+		return nil, err
+	}
+	return dst[:int(n):int(n)], nil
+}
+
 func filterInPlace(data []byte, typeSize int, mode Shuffle, inverse int) {
 	if len(data) == 0 || (mode != Shuffle1 && mode != BitShuffle) {
 		return // default arm of the reference's switch: untouched

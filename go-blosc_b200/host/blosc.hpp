@@ -135,6 +135,33 @@ inline Bytes DecompressWithSize(const Bytes &data, int64_t typeSize) {   // blos
 }
 inline Bytes Decompress(const Bytes &data) { return DecompressWithSize(data, 0); }   // blosc.go:291-293
 
+// Blosc-1 multi-block frames: the one place where Options.blockSize (declared, never read by the
+// reference: blosc.go:227-234) means something; 0 = 64 KiB.  The reference cannot decode these frames.
+inline Bytes CompressBlocks(const Bytes &data, const Options &o) {
+    if (data.empty()) throw ErrInvalidData();
+    if (o.codec != Codec::LZ4) raise(B2B_EINVALID_CODEC, "multi-block frames are LZ4 only");
+    Bytes out(data.size() + 16 + 64);
+    size_t n = 0;
+    if (int rc = b2b_compress_blocks(context(), data.data(), data.size(), (int)o.shuffle, o.typeSize,
+                                     (uint32_t)o.blockSize, out.data(), out.size(), &n))
+        raise(rc, "blocks");
+    out.resize(n);
+    return out;
+}
+inline Bytes DecompressBlocks(const Bytes &data) {
+    if (data.size() < (size_t)HeaderSize) throw ErrInvalidHeader();
+    Header h = ParseHeader(data);
+    size_t cap = h.nbytes_orig, reach = 255 * data.size() + 64;
+    if (cap > reach) cap = reach;
+    Bytes out(cap + 1);
+    size_t n = 0;
+    int rc = b2b_decompress_blocks(context(), data.data(), data.size(), out.data(), cap, &n);
+    if (rc == B2B_EDST_TOO_SMALL && cap < h.nbytes_orig) rc = B2B_EDECOMPRESSION_FAILED;
+    if (rc) raise(rc);
+    out.resize(n);
+    return out;
+}
+
 inline void ShuffleBuffer(Bytes &data, int64_t typeSize, Shuffle mode) {   // shuffle.go:298-309
     if (data.empty() || (mode != Shuffle::Shuffle1 && mode != Shuffle::BitShuffle)) return;
     if (int rc = b2b_shuffle(context(), (int)mode, 0, typeSize, data.data(), data.data(), data.size())) raise(rc);

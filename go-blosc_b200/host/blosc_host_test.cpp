@@ -51,6 +51,13 @@ int main(int argc, char **argv) {
     try { Decompress(bad); EXPECT(false); } catch (const Error &) {}
     Bytes mism = Compress(ramp(1000), Codec::LZ4, 5, Shuffle::NoShuffle, 1); mism[4] = 0xD0; mism[5] = 0x07;   // 2000
     try { Decompress(mism); EXPECT(false); } catch (const ErrSizeMismatch &) {}
+    // opt-in Blosc-1 multi-block frames: Options.blockSize is honoured here and only here
+    Options ob; ob.blockSize = 16384;
+    Bytes bf = CompressBlocks(f64, ob), bd = CompressBlocks(data, ob);
+    Header bh = GetInfo(bd);
+    EXPECT(bh.blocksize == 16384 && bh.nbytes_orig == 100000 && bh.nbytes_comp == bd.size() && (bh.flags & 0x10));
+    EXPECT(DecompressBlocks(bd) == data && DecompressBlocks(bf) == f64);
+    try { Decompress(bd); EXPECT(false); } catch (const Error &) {}   // the one-block decoder must not accept it
     std::printf(fails ? "blosc_host_test: %d FAILURES\n" : "blosc_host_test: all ok\n", fails);
     return fails != 0;
 }
