@@ -27,7 +27,7 @@ static uint32_t hashf(const uint8_t *p) {
 static size_t put_ext(uint8_t *o, size_t v) { size_t k = 0; while (v >= 255) { o[k++] = 255; v -= 255; } o[k++] = (uint8_t)v; return k; }
 
 
-static int STRIP = 64, CAPX = 2, SM = 0, NOTRIMBACK = 0, BACKX = 0, REP = 0, GROUP = 4, WAYS2 = 0, UPTO = 0, INGRP = 0, MINM = 4, MINM_TABLE_ONLY = 0, PHASED = 0, RECMAX = 16, HALVES = 1, SKIPCONT = 0, NOSHIFT = 0, REPFIRST = 0, LCMP = 16, SHORTRULE = 0, SHORTLEN = 6, SHORTLL = 15, REPWIN = 0;
+static int MINLL = 0; static int STRIP = 64, CAPX = 2, SM = 0, NOTRIMBACK = 0, BACKX = 0, REP = 0, GROUP = 4, WAYS2 = 0, UPTO = 0, INGRP = 0, MINM = 4, MINM_TABLE_ONLY = 0, PHASED = 0, RECMAX = 16, HALVES = 1, SKIPCONT = 0, NOSHIFT = 0, REPFIRST = 0, LCMP = 16, SHORTRULE = 0, SHORTLEN = 6, SHORTLL = 15, REPWIN = 0;
 static double COST_A = 0, COST_B = 0; static long NSTEPS = 0, NOPEN = 0, NDROP = 0, NTRIM = 0;
 typedef struct { uint32_t ms, me, off; int open; } mt_t;
 
@@ -94,7 +94,7 @@ size_t model_encode(const uint8_t *src, uint32_t n, uint8_t *out, long *nseq) {
                 int any = 0; static uint32_t ent[32][4][2], hh[32][4], sq[32][4], ck[32][4]; int act[32], nv[32];
                 const uint32_t HM = (1u << HASHLOG) - 1; (void)HM;
                 for (int l = 0; l < 32; l++) { act[l] = pos[l] < send[l]; if (act[l]) { any = 1; nv[l] = send[l] - pos[l] < (uint32_t)GROUP ? (int)(send[l] - pos[l]) : GROUP;
-                    for (int k = 0; k < nv[l]; k++) { sq[l][k] = ld32(src + pos[l] + k); uint32_t hv = sq[l][k] * 2654435761u; hh[l][k] = hv >> (32 - HASHLOG); ck[l][k] = (hv >> (17 - HASHLOG)) & 0x7FFF;
+                    for (int k = 0; k < nv[l]; k++) { sq[l][k] = ld32(src + pos[l] + k); uint32_t hv = sq[l][k] * 2654435761u; if (HASHBYTES == 5) hv = (uint32_t)(((ld64(src + pos[l] + k) << 24) * 889523592379ULL) >> 32); if (HASHBYTES == 6) hv = (uint32_t)(((ld64(src + pos[l] + k) << 16) * 227718039650203ULL) >> 32); if (HASHBYTES == 45) hv = (sq[l][k] ^ (src[pos[l] + k + 4] * 0x9E3779B1u)) * 2654435761u; hh[l][k] = hv >> (32 - HASHLOG); ck[l][k] = (hv >> (17 - HASHLOG)) & 0x7FFF;
                         if (WAYS2) { uint32_t b = hh[l][k] & ~1u; ent[l][k][0] = table[b]; ent[l][k][1] = table[b + 1]; } else { ent[l][k][0] = table[hh[l][k]]; ent[l][k][1] = 0; } } } }
                 if (!any) break;
                 for (int l = 0; l < 32; l++) if (act[l] && !UPTO) for (int k = 0; k < nv[l]; k++) { uint32_t v = (ck[l][k] << 17) | (pos[l] + k);
@@ -134,7 +134,7 @@ size_t model_encode(const uint8_t *src, uint32_t n, uint8_t *out, long *nseq) {
                     int open = (e >= cap && cap < mlimit);
                     uint32_t ms = pos[l], mc = cand;
                     while (ms > lanch[l] && mc > 0 && src[ms - 1] == src[mc - 1]) { ms--; mc--; }
-                    if ((int)(e - ms) < MINM && !(MINM_TABLE_ONLY && from_rep)) { pos[l] += 1; continue; }
+                    if ((int)(e - ms) < MINM && !(MINM_TABLE_ONLY && from_rep) && (int)(ms - lanch[l]) >= MINLL) { pos[l] += 1; continue; }
                     int ext = (int)((e - pos[l]) / 4) + (int)(pos[l] - ms); if (ext > maxext) maxext = ext;
                     lane_iters[l] += (int)((e - pos[l] - 4 + 7) / 8) + 1;
                     rep[l] = ms - mc;
@@ -247,6 +247,7 @@ int main(int argc, char **argv) {
         if (!strcmp(argv[i], "ways2")) WAYS2 = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "upto")) UPTO = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "minm")) MINM = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "minll")) MINLL = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "minm_table_only")) MINM_TABLE_ONLY = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "phased")) PHASED = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "recmax")) RECMAX = atoi(argv[i + 1]);
