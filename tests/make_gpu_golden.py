@@ -43,6 +43,25 @@ def main():
         json.dump(out, f, indent=0)
     print("wrote", len(frames), "frames,", sum(fr["frame_len"] for fr in frames), "bytes")
 
+    # the opt-in Blosc-1 multi-block frames (b2b_compress_blocks), same idea: gpu_block_frames_v1.json
+    bspecs = [({"kind": "ramp", "n": 100000}, 1, 4, 16384), ({"kind": "f32_ramp", "n": 40000, "k": 0.001}, 1, 4, 0),
+              ({"kind": "f64_ramp", "n": 8000}, 2, 8, 4096), ({"kind": "i16mod8", "n": 70000}, 1, 2, 32768),
+              ({"kind": "lcg", "n": 4096}, 1, 4, 1024), ({"kind": "zeros", "n": 200000}, 0, 1, 0),
+              ({"kind": "period3", "n": 4096}, 0, 1, 1000), ({"kind": "ramp", "n": 100}, 1, 4, 0),
+              ({"kind": "f32_ramp", "n": 14000, "k": 0.001}, 1, 3, 5000)]
+    bframes = []
+    for spec, sh, T, bs in bspecs:
+        data = make_input(spec)
+        fr = ctx.compress_blocks(data, sh, T, bs)
+        assert ctx.decompress_blocks(fr) == data.tobytes()
+        bframes.append({"input": spec, "shuffle": sh, "typesize": T, "blocksize": bs, "frame_len": len(fr),
+                        "input_sha256": hashlib.sha256(data.tobytes()).hexdigest(), "frame_hex": bytes(fr).hex()})
+    out = {"note": "Blosc-1 multi-block frames produced by the CUDA path of this repository on a B200 "
+                   "(b2b_compress_blocks; see tests/make_gpu_golden.py)", "frames": bframes}
+    with open(os.path.join(ROOT, "gpurun_out", "gpu_block_frames_v1.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("wrote", len(bframes), "block frames,", sum(fr["frame_len"] for fr in bframes), "bytes")
+
 
 if __name__ == "__main__":
     main()

@@ -113,3 +113,38 @@ def test_errors(orc):
     assert orc.blocks_decompress(np.concatenate([stored, stored[:4]]))[0] == 0   # trailing bytes are not the frame
     bad = stored.copy(); bad[12:16] = np.frombuffer(struct.pack("<I", 1000 + 15), dtype=np.uint8)
     assert orc.blocks_decompress(bad)[0] == orc.ESIZE_MISMATCH
+
+
+def test_block_frames_produced_by_the_cuda_path_hold_to_the_format(orc):
+    """tests/golden/gpu_block_frames_v1.json: multi-block frames that b2b_compress_blocks produced on a
+    B200 (generator: tests/make_gpu_golden.py).  Without a GPU: every block is re-derived from the wire
+    bytes (liblz4 on the streams), the oracle decodes the frames, header fields are the oracle's."""
+    import hashlib
+    import json
+    import os
+    from make_golden import make_input
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpu_block_frames_v1.json")) as f:
+        gold = json.load(f)
+    assert len(gold["frames"]) >= 8
+    stored = 0
+    for item in gold["frames"]:
+        data = make_input(item["input"])
+        assert hashlib.sha256(data.tobytes()).hexdigest() == item["input_sha256"]
+        fr = np.frombuffer(bytes.fromhex(item["frame_hex"]), dtype=np.uint8)
+        sh, T = item["shuffle"], item["typesize"]
+        h = parse(fr)
+        rc, ref = orc.blocks_compress(data, sh, T, item["blocksize"], False)
+        hr = parse(ref)
+        assert rc == 0 and fr.size == item["frame_len"] == h["cbytes"] and fr.size <= data.size + 16
+        assert all(h[k] == hr[k] for k in ("version", "versionlz", "typesize", "nbytes", "blocksize"))
+        assert (h["flags"] | 2) == (hr["flags"] | 2)
+        rc, back = orc.blocks_decompress(fr)
+        assert rc == 0 and np.array_equal(back, data), item["input"]
+        if h["flags"] & 2:
+            stored += 1
+            assert np.array_equal(fr[16:], data)
+        else:
+            unfilt = {0: lambda b, t: b, 1: orc.unshuffle, 2: orc.bitunshuffle}[sh] if T > 1 else (lambda b, t: b)
+            assert walk_blocks(orc, fr, data, unfilt) == -(-data.size // h["blocksize"])
+            assert fr.size <= ref.size * 1.5 + 64
+    assert stored >= 2          # the incompressible input and the 100-byte buffer
