@@ -585,7 +585,9 @@ int decompress_blocks_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint6
         return B2B_EINVAL;
     if (blocksize != 0 && blocksize < kB1MinBuffer) return B2B_EINVAL;
     const uint32_t slice = blocksize ? blocksize : kB1DefaultBlock;
-    const uint64_t nslots64 = total_dst / slice + 2ull * nframes;
+    // a frame written with this block size has blocks of whole elements: at least slice - 254 bytes
+    const uint32_t slice_min = slice - std::min<uint32_t>(254u, slice / 2);
+    const uint64_t nslots64 = total_dst / slice_min + 2ull * nframes;
     if (nslots64 >= (1ull << 31)) return B2B_EINVAL;
     const uint32_t nslots = (uint32_t)nslots64;
     const uint64_t nrec_max = total_dst / 4 + (uint64_t)(kSeqSlack + 1) * nslots + 64;
@@ -614,7 +616,7 @@ int decompress_blocks_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint6
 
     BlocksInfoArgs ia;
     ia.frames = static_cast<const uint8_t *>(d_frames); ia.frame_off = d_frame_off; ia.frame_len = d_frame_len;
-    ia.dst_cap = d_dst_cap; ia.nframes = nframes; ia.slice = slice; ia.nblk = frm_nblk; ia.bs = frm_bs;
+    ia.dst_cap = d_dst_cap; ia.nframes = nframes; ia.slice = slice; ia.slice_min = slice_min; ia.nblk = frm_nblk; ia.bs = frm_bs;
     ia.out_len = d_out_len; ia.status = d_status;
     { LaunchTimer lt(ctx, K_BLOCKS_META, s); blocks_info_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(ia); }
     CU(ctx, cudaGetLastError());

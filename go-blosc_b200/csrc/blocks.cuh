@@ -180,7 +180,8 @@ struct BlocksInfoArgs {
     const uint8_t *frames;
     const uint64_t *frame_off;
     const uint32_t *frame_len, *dst_cap;
-    uint32_t nframes, slice;    // slice: the caller's block size (sizes the slot table; stored frames are copied in slices of it)
+    uint32_t nframes, slice;    // slice: the caller's block size (stored frames are copied in slices of it)
+    uint32_t slice_min;         // smallest block size a frame written with `slice` can have (whole elements): sizes the slot table
     uint32_t *nblk, *bs;        // out: slots of frame f, bytes per slot
     uint32_t *out_len, *status;
 };
@@ -206,7 +207,7 @@ __global__ void blocks_info_kernel(BlocksInfoArgs a) {
             else {
                 b = bsz; k = (uint32_t)(((uint64_t)n + b - 1) / b);
                 if (16ull + 4ull * k > ncomp) st = kEInvalidData;
-                else if (k > n / a.slice + 2u) st = kEUnsupported;      // blocks smaller than the table was sized for
+                else if (k > n / a.slice_min + 2u) st = kEUnsupported;  // blocks smaller than the table was sized for
             }
         }
         if (st == kOk && a.dst_cap[f] < n) st = kEDstTooSmall;

@@ -244,7 +244,8 @@ B2B_API int b2b_decompress_batch_dev_indexed(b2b_ctx *ctx, const void *d_frames,
  * typesize outside 1..255 counts as 1.  n == 0: B2B_EINVALID_DATA; n > 2^31 - 17: B2B_EDATA_TOO_LARGE.
  * Batch calls have the conventions of b2b_compress_batch_dev / b2b_decompress_batch_dev; on
  * decompression `blocksize` is what the frames were written with (it sizes the block table:
- * a frame with more than nbytes / blocksize + 2 blocks reports B2B_EUNSUPPORTED). */
+ * a frame whose blocks are smaller than that block size rounded down to whole elements
+ * reports B2B_EUNSUPPORTED). */
 B2B_API uint32_t b2b_blocks_blocksize(size_t n, int64_t typesize, uint32_t blocksize);
 B2B_API int b2b_compress_blocks(b2b_ctx *ctx, const void *src, size_t n, int shuffle, int64_t typesize,
                                 uint32_t blocksize, void *dst, size_t cap, size_t *out_len);

@@ -620,6 +620,21 @@ def test_block_frames_sizes(ctx, orc, n):
             assert ctx.decompress_blocks(fr) == data.tobytes()
 
 
+def test_block_frames_typesize_255_many_blocks(ctx, orc):
+    """Blocks hold whole elements: with typesize 255 a 256-byte block size means 255-byte blocks, more of
+    them than nbytes / 256 -- the block table has to be sized for that on both sides."""
+    data = dg.smooth_f32(1 << 18, 9)
+    for T, bs in ((255, 256), (255, 128), (200, 1000), (7, 130)):
+        fr = np.frombuffer(ctx.compress_blocks(data, 1, T, bs), dtype=np.uint8)
+        h = b1_parse(fr)
+        assert h["blocksize"] == max(bs // T * T, T) and h["typesize"] == T
+        rc, back = orc.blocks_decompress(fr)
+        assert rc == 0 and np.array_equal(back, data)
+        assert ctx.decompress_blocks(fr) == data.tobytes()
+        rc, ref = orc.blocks_compress(data, 1, T, bs, True)
+        assert rc == 0 and ctx.decompress_blocks(ref) == data.tobytes()
+
+
 def test_block_frames_errors_match_oracle(ctx, orc, pkg):
     with pytest.raises(pkg.ErrInvalidData):
         ctx.compress_blocks(b"")
