@@ -211,6 +211,9 @@ ABI = [
     ("b2b_blocks_blocksize", _u32, [_sz, _i64, _u32]),
     ("b2b_compress_blocks", _int, [_vp, _vp, _sz, _int, _i64, _u32, _vp, _sz, C.POINTER(_sz)]),
     ("b2b_decompress_blocks", _int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
+    ("b2b_compress_blocks_batch", _int, [_vp, _vp, _vp, _vp, _u32, _int, _i64, _u32, _vp, _u64, _vp, _vp, _vp,
+                                         C.POINTER(_u64)]),
+    ("b2b_decompress_blocks_batch", _int, [_vp, _vp, _vp, _vp, _u32, _u32, _vp, _u64, _vp, _vp, _vp]),
     ("b2b_compress_blocks_batch_dev", _int, [_vp, _vp, _vp, _vp, _u32, _u64, _u32, _int, _i64, _u32, _vp, _u64,
                                              _vp, _vp, _vp, _vp, _vp]),
     ("b2b_decompress_blocks_batch_dev", _int, [_vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _u64, _u32, _u32,
@@ -534,6 +537,44 @@ class Context:
         if rc:
             _raise(rc, self._h)
         return out[:n.value].tobytes()
+
+    def compress_blocks_batch(self, src, src_off, src_len, shuffle=Shuffle.Shuffle1, typesize=4, blocksize=0, dst=None):
+        """Host-pointer batch of multi-block frames. Returns (dst, frame_off, frame_len, status, total)."""
+        a = _as_u8(src)
+        src_off = np.ascontiguousarray(src_off, dtype=np.uint64)
+        src_len = np.ascontiguousarray(src_len, dtype=np.uint32)
+        nf = len(src_len)
+        span = int((src_off + src_len).max() - src_off.min()) if nf else 0
+        if dst is None:
+            dst = np.empty(span + 32 * nf + 64, dtype=np.uint8)
+        frame_off = np.zeros(nf, dtype=np.uint64)
+        frame_len = np.zeros(nf, dtype=np.uint32)
+        status = np.zeros(nf, dtype=np.uint32)
+        total = C.c_uint64(0)
+        rc = lib().b2b_compress_blocks_batch(self._h, _np_ptr(a), _np_ptr(src_off), _np_ptr(src_len), nf,
+                                             int(shuffle), int(typesize), int(blocksize), _np_ptr(dst), dst.size,
+                                             _np_ptr(frame_off), _np_ptr(frame_len), _np_ptr(status), C.byref(total))
+        if rc:
+            _raise(rc, self._h)
+        return dst, frame_off, frame_len, status, total.value
+
+    def decompress_blocks_batch(self, frames, frame_off, frame_len, dst_off, dst_total, blocksize=0, dst=None):
+        """Returns (dst, out_len, status)."""
+        a = _as_u8(frames)
+        frame_off = np.ascontiguousarray(frame_off, dtype=np.uint64)
+        frame_len = np.ascontiguousarray(frame_len, dtype=np.uint32)
+        dst_off = np.ascontiguousarray(dst_off, dtype=np.uint64)
+        nf = len(frame_len)
+        if dst is None:
+            dst = np.empty(max(int(dst_total), 1), dtype=np.uint8)
+        out_len = np.zeros(nf, dtype=np.uint32)
+        status = np.zeros(nf, dtype=np.uint32)
+        rc = lib().b2b_decompress_blocks_batch(self._h, _np_ptr(a), _np_ptr(frame_off), _np_ptr(frame_len), nf,
+                                               int(blocksize), _np_ptr(dst), int(dst_total), _np_ptr(dst_off),
+                                               _np_ptr(out_len), _np_ptr(status))
+        if rc:
+            _raise(rc, self._h)
+        return dst, out_len, status
 
     def compress_blocks_batch_dev(self, d_src, d_src_off, d_src_len, nframes, total_src_bytes, max_frame_len,
                                   shuffle, typesize, blocksize, d_dst, dst_cap, d_frame_off, d_frame_len,

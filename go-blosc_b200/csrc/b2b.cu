@@ -1110,9 +1110,11 @@ static int sync_pipeline(b2b_ctx *ctx, cudaError_t e, int rc) {
     return rc;
 }
 
-int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, const uint32_t *src_len,
-                       uint32_t nframes, int shuffle, int64_t typesize, void *dst, uint64_t dst_cap,
-                       uint64_t *frame_off, uint32_t *frame_len, uint32_t *status, uint64_t *total_out) {
+// blocks: Blosc-1 multi-block frames (blocks.cuh) of `blocksize` instead of the reference's one-block frames
+static int host_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, const uint32_t *src_len,
+                               uint32_t nframes, int shuffle, int64_t typesize, void *dst, uint64_t dst_cap,
+                               uint64_t *frame_off, uint32_t *frame_len, uint32_t *status, uint64_t *total_out,
+                               bool blocks, uint32_t blocksize) {
     if (!ctx) return B2B_EINVAL;
     if (nframes == 0) { if (total_out) *total_out = 0; return B2B_OK; }
     if (!src || !src_off || !src_len || !dst || !frame_off || !frame_len || !status) return B2B_EINVAL;
@@ -1189,8 +1191,11 @@ int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, c
         if (e == cudaSuccess && k >= (size_t)S) e = cudaStreamWaitEvent(sk, ctx->ev_out_free[slot], 0);
         if (e != cudaSuccess) break;
         select_arena(ctx, 1 + slot);
-        rc = compress_batch_dev_locked(ctx, d_in, d_src_off, d_src_len, n, span, c.max_len, shuffle, typesize,
-                                       d_out[slot], out_cap, d_frame_off, d_frame_len, d_status, d_total, sk);
+        rc = blocks ? compress_blocks_dev_locked(ctx, d_in, d_src_off, d_src_len, n, span, c.max_len, shuffle, typesize,
+                                                 blocksize, d_out[slot], out_cap, d_frame_off, d_frame_len, d_status,
+                                                 d_total, sk)
+                    : compress_batch_dev_locked(ctx, d_in, d_src_off, d_src_len, n, span, c.max_len, shuffle, typesize,
+                                                d_out[slot], out_cap, d_frame_off, d_frame_len, d_status, d_total, sk);
         select_arena(ctx, 0);
         if (rc) break;
         e = cudaEventRecord(ctx->ev_done[slot], sk);
@@ -1210,10 +1215,26 @@ int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, c
     return rc;
 }
 
-int b2b_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame_off,
-                         const uint32_t *frame_len, uint32_t nframes, int64_t typesize_override,
-                         void *dst, uint64_t dst_cap, const uint64_t *dst_off, uint32_t *out_len,
-                         uint32_t *status) {
+int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, const uint32_t *src_len,
+                       uint32_t nframes, int shuffle, int64_t typesize, void *dst, uint64_t dst_cap,
+                       uint64_t *frame_off, uint32_t *frame_len, uint32_t *status, uint64_t *total_out) {
+    return host_compress_batch(ctx, src, src_off, src_len, nframes, shuffle, typesize, dst, dst_cap, frame_off,
+                               frame_len, status, total_out, false, 0);
+}
+
+int b2b_compress_blocks_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off, const uint32_t *src_len,
+                              uint32_t nframes, int shuffle, int64_t typesize, uint32_t blocksize, void *dst,
+                              uint64_t dst_cap, uint64_t *frame_off, uint32_t *frame_len, uint32_t *status,
+                              uint64_t *total_out) {
+    if (blocksize != 0 && blocksize < kB1MinBuffer) return B2B_EINVAL;
+    return host_compress_batch(ctx, src, src_off, src_len, nframes, shuffle, typesize, dst, dst_cap, frame_off,
+                               frame_len, status, total_out, true, blocksize);
+}
+
+static int host_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame_off,
+                                 const uint32_t *frame_len, uint32_t nframes, int64_t typesize_override,
+                                 void *dst, uint64_t dst_cap, const uint64_t *dst_off, uint32_t *out_len,
+                                 uint32_t *status, bool blocks, uint32_t blocksize) {
     if (!ctx) return B2B_EINVAL;
     if (nframes == 0) return B2B_OK;
     if (!frames || !frame_off || !frame_len || !dst_off || !out_len || !status) return B2B_EINVAL;
@@ -1292,8 +1313,10 @@ int b2b_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame
         if (e == cudaSuccess && k >= (size_t)S) e = cudaStreamWaitEvent(sk, ctx->ev_out_free[slot], 0);
         if (e != cudaSuccess) break;
         select_arena(ctx, 1 + slot);
-        rc = decompress_batch_dev_locked(ctx, d_in, d_frame_off, d_frame_len, n, typesize_override, d_out,
-                                         d_dst_off, d_cap, out_span, max_cap, d_out_len, d_status, sk);
+        rc = blocks ? decompress_blocks_dev_locked(ctx, d_in, d_frame_off, d_frame_len, n, d_out, d_dst_off, d_cap,
+                                                   out_span, max_cap, blocksize, d_out_len, d_status, sk)
+                    : decompress_batch_dev_locked(ctx, d_in, d_frame_off, d_frame_len, n, typesize_override, d_out,
+                                                  d_dst_off, d_cap, out_span, max_cap, d_out_len, d_status, sk);
         select_arena(ctx, 0);
         if (rc) break;
         e = cudaEventRecord(ctx->ev_done[slot], sk);
@@ -1310,6 +1333,22 @@ int b2b_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame
     }
     while (rc == B2B_OK && e == cudaSuccess && retired < launched) rc = retire(retired++);
     return sync_pipeline(ctx, e, rc);
+}
+
+int b2b_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame_off,
+                         const uint32_t *frame_len, uint32_t nframes, int64_t typesize_override,
+                         void *dst, uint64_t dst_cap, const uint64_t *dst_off, uint32_t *out_len,
+                         uint32_t *status) {
+    return host_decompress_batch(ctx, frames, frame_off, frame_len, nframes, typesize_override, dst, dst_cap,
+                                 dst_off, out_len, status, false, 0);
+}
+
+int b2b_decompress_blocks_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame_off,
+                                const uint32_t *frame_len, uint32_t nframes, uint32_t blocksize, void *dst,
+                                uint64_t dst_cap, const uint64_t *dst_off, uint32_t *out_len, uint32_t *status) {
+    if (blocksize != 0 && blocksize < kB1MinBuffer) return B2B_EINVAL;
+    return host_decompress_batch(ctx, frames, frame_off, frame_len, nframes, 0, dst, dst_cap, dst_off, out_len,
+                                 status, true, blocksize);
 }
 
 int b2b_compress(b2b_ctx *ctx, const void *src, size_t n, int codec, int level, int shuffle,

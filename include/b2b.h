@@ -251,6 +251,16 @@ B2B_API int b2b_compress_blocks(b2b_ctx *ctx, const void *src, size_t n, int shu
                                 uint32_t blocksize, void *dst, size_t cap, size_t *out_len);
 B2B_API int b2b_decompress_blocks(b2b_ctx *ctx, const void *frame, size_t len, void *dst, size_t cap,
                                   size_t *out_len);
+/* host-pointer batches: the same pipeline as b2b_compress_batch / b2b_decompress_batch */
+B2B_API int b2b_compress_blocks_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off,
+                                      const uint32_t *src_len, uint32_t nframes, int shuffle,
+                                      int64_t typesize, uint32_t blocksize, void *dst, uint64_t dst_cap,
+                                      uint64_t *frame_off, uint32_t *frame_len, uint32_t *status,
+                                      uint64_t *total_out);
+B2B_API int b2b_decompress_blocks_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame_off,
+                                        const uint32_t *frame_len, uint32_t nframes, uint32_t blocksize,
+                                        void *dst, uint64_t dst_cap, const uint64_t *dst_off,
+                                        uint32_t *out_len, uint32_t *status);
 B2B_API int b2b_compress_blocks_batch_dev(b2b_ctx *ctx, const void *d_src, const uint64_t *d_src_off,
                                           const uint32_t *d_src_len, uint32_t nframes,
                                           uint64_t total_src_bytes, uint32_t max_frame_len, int shuffle,

@@ -750,3 +750,40 @@ def test_block_frames_c3_shape_roundtrip(ctx, orc, torch_mod):
     ctx.decompress_blocks_batch_dev(d_dst, d_foff, d_flen, nf, d_out, d_off, d_len, nf * fl, fl, 0, d_olen, d_st2, s)
     torch.cuda.synchronize()
     assert not d_st2.any() and torch.equal(d_out, d_src)
+
+
+@pytest.mark.parametrize("stage", [0, 1 << 20, 100000])
+def test_block_frames_host_batch_pipeline(ctx, orc, stage):
+    """Host-pointer batches of multi-block frames through the same H2D / kernels / D2H pipeline as the
+    one-block frames; small stage sizes force several chunks."""
+    ctx.set_option(3, stage)
+    try:
+        sizes = [32768, 65536, 1000, 131072, 13, 262144, 524288, 1, 99999, 2 << 20, 127, 128]
+        frames = [dg.random_bytes(s, i) if i % 3 == 0 else dg.lowent_i16((s + 1) // 2, i)[:s].copy() if i % 3 == 1
+                  else dg.smooth_f32(s // 4 + 1, i)[:s].copy() for i, s in enumerate(sizes)]
+        src = np.concatenate(frames)
+        lens = np.array(sizes, dtype=np.uint32)
+        offs = np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.uint64)
+        for bs in (0, 20000):
+            dst, foff, flen, status, total = ctx.compress_blocks_batch(src, offs, lens, shuffle=1, typesize=2, blocksize=bs)
+            assert not status.any()
+            assert np.array_equal(foff, np.concatenate([[0], np.cumsum((flen.astype(np.uint64) + 15) // 16 * 16)[:-1]]))
+            assert total == int(foff[-1]) + (int(flen[-1]) + 15) // 16 * 16
+            for f, data in enumerate(frames):
+                fr = dst[int(foff[f]):int(foff[f]) + int(flen[f])]
+                assert b1_parse(fr)["blocksize"] == ctx.blocks_blocksize(data.size, 2, bs) and fr.size <= data.size + 16
+                rc, back = orc.blocks_decompress(fr)
+                assert rc == 0 and np.array_equal(back, data), (bs, f)
+            out, out_len, st = ctx.decompress_blocks_batch(dst, foff, flen, offs, src.size, blocksize=bs)
+            assert not st.any() and np.array_equal(out_len, lens) and np.array_equal(out, src)
+            broken = dst.copy()
+            broken[int(foff[3])] = 9                                          # bad version
+            assert not b1_parse(dst[int(foff[1]):])["flags"] & 2                # frame 1 (low-entropy) is not stored
+            broken[int(foff[1]) + 16:int(foff[1]) + 20] = 0xFF               # its first bstart out of range
+            out, out_len, st = ctx.decompress_blocks_batch(broken, foff, flen, offs, src.size, blocksize=bs)
+            good = [f for f in range(len(sizes)) if f not in (3, 1)]
+            assert st[3] == 3 and st[1] == 8 and not st[good].any()
+            for f in good:
+                assert np.array_equal(out[int(offs[f]):int(offs[f]) + sizes[f]], frames[f])
+    finally:
+        ctx.set_option(3, 0)

@@ -16,14 +16,22 @@ h_out = torch.empty(total, dtype=torch.uint8, pin_memory=True)
 offs = np.arange(nf, dtype=np.uint64) * FRAME
 lens = np.full(nf, FRAME, dtype=np.uint32)
 a_src, a_comp, a_out = h_src.numpy(), h_comp.numpy(), h_out.numpy()
+blocks = os.environ.get("PROBE_BLOCKS")          # Blosc-1 multi-block frames of this block size (1 = default)
+if blocks:
+    bsz = 0 if int(blocks) == 1 else int(blocks)
+    comp = lambda: ctx.compress_blocks_batch(a_src, offs, lens, pkg.Shuffle.Shuffle1, 4, bsz, dst=a_comp)
+    dec = lambda foff, flen: ctx.decompress_blocks_batch(a_comp, foff, flen, offs, total, bsz, dst=a_out)
+else:
+    comp = lambda: ctx.compress_batch(a_src, offs, lens, pkg.Shuffle.Shuffle1, 4, dst=a_comp)
+    dec = lambda foff, flen: ctx.decompress_batch(a_comp, foff, flen, offs, total, dst=a_out)
 for st in [int(x) for x in os.environ.get("PROBE_STAGES", "128").split(",")]:
     ctx.set_option(pkg.OPT_HOST_STAGE_BYTES, st << 20)
     tc, td = [], []
     for it in range(4):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        _, foff, flen, stt, tot = ctx.compress_batch(a_src, offs, lens, pkg.Shuffle.Shuffle1, 4, dst=a_comp)
+        _, foff, flen, stt, tot = comp()
         t1 = time.perf_counter()
-        _, olen, st2 = ctx.decompress_batch(a_comp, foff, flen, offs, total, dst=a_out)
+        _, olen, st2 = dec(foff, flen)
         t2 = time.perf_counter()
         if it: tc.append(t1 - t0); td.append(t2 - t1)
     print(f"stage {st} MiB: compress {1e3 * min(tc):.1f} ms (H2D {total / 1e6:.0f} MB, D2H {tot / 1e6:.0f} MB -> {total / min(tc) / 1e9:.1f} GB/s in), "
