@@ -140,7 +140,7 @@ __device__ __forceinline__ void wr32(uint8_t *p, uint32_t v) {
     p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
 }
 // one CTA per block slot
-__global__ void __launch_bounds__(kFilterThreads) blocks_pack_kernel(BlocksPackArgs a) {
+__global__ void __launch_bounds__(kFilterThreads, 8) blocks_pack_kernel(BlocksPackArgs a) {
     const uint32_t t = blockIdx.x;
     const uint32_t f = a.owner[t];
     if (f == kNoOwner || a.frame_status[f] != 0) return;

@@ -854,7 +854,7 @@ __device__ __forceinline__ void cta_pack_lz4_segment(const PackArgs &a, uint32_t
     }
 }
 
-__global__ void __launch_bounds__(kFilterThreads) pack_frames_kernel(PackArgs a) {
+__global__ void __launch_bounds__(kFilterThreads, 8) pack_frames_kernel(PackArgs a) {
     const uint64_t item = blockIdx.x;
     const uint32_t f = (uint32_t)(item / a.segs_grid), s0 = (uint32_t)(item % a.segs_grid);
     if (f >= a.nframes || a.status[f] != 0) return;
