@@ -787,3 +787,64 @@ def test_block_frames_host_batch_pipeline(ctx, orc, stage):
                 assert np.array_equal(out[int(offs[f]):int(offs[f]) + sizes[f]], frames[f])
     finally:
         ctx.set_option(3, 0)
+
+
+@pytest.mark.parametrize("kind", ["smooth_f32", "lowent_i16", "text"])
+def test_block_frames_decoder_fuzz_matches_oracle(ctx, orc, kind):
+    """The fuzz contract on multi-block frames: GPU-written (unsplit) and oracle-written split frames with
+    bytes flipped, 0xFF runs, truncation, nbytes / blocksize / bstarts / stream-size fields changed go
+    through the GPU batch decoder in one call; every mutant must get the oracle's status and, when it
+    decodes, the oracle's bytes."""
+    rng = np.random.default_rng({"smooth_f32": 21, "lowent_i16": 22, "text": 23}[kind])
+    sh, T = {"smooth_f32": (1, 4), "lowent_i16": (1, 2), "text": (0, 1)}[kind]
+    bs = 4096
+    frames = []
+    for n in (3000, 20000, 70001):
+        data = dg.corpus(n)[kind]
+        bases = [np.frombuffer(ctx.compress_blocks(data, sh, T, bs), dtype=np.uint8), orc.blocks_compress(data, sh, T, bs, True)[1]]
+        for base in bases:
+            if base[2] & 2:
+                continue
+            nblocks = -(-n // int(b1_parse(base)["blocksize"]))
+            for _ in range(30):
+                m = base.copy()
+                what = int(rng.integers(0, 8))
+                if what == 0:                     # flip 1..4 bytes after the header
+                    for _ in range(int(rng.integers(1, 5))):
+                        m[int(rng.integers(16, m.size))] ^= np.uint8(rng.integers(1, 256))
+                elif what == 1:                   # a short run of 0xFF
+                    p0 = int(rng.integers(16, m.size)); m[p0:p0 + int(rng.integers(1, 6))] = 255
+                elif what == 2:                   # truncate (cbytes follows)
+                    cut = int(rng.integers(17, m.size)); m = m[:cut].copy(); m[12:16] = np.frombuffer(struct.pack("<I", cut), dtype=np.uint8)
+                elif what == 3:                   # nbytes off by a little
+                    m[4:8] = np.frombuffer(struct.pack("<I", max(n + int(rng.integers(-3, 4)), 1)), dtype=np.uint8)
+                elif what == 4:                   # a bstarts entry moved
+                    b = int(rng.integers(0, nblocks)); v = struct.unpack("<I", m[16 + 4 * b:20 + 4 * b].tobytes())[0]
+                    m[16 + 4 * b:20 + 4 * b] = np.frombuffer(struct.pack("<I", max(v + int(rng.integers(-40, 41)), 0)), dtype=np.uint8)
+                elif what == 5:                   # the size prefix of a block's first stream changed
+                    b = int(rng.integers(0, nblocks)); p0 = struct.unpack("<I", m[16 + 4 * b:20 + 4 * b].tobytes())[0]
+                    v = struct.unpack("<I", m[p0:p0 + 4].tobytes())[0]
+                    m[p0:p0 + 4] = np.frombuffer(struct.pack("<I", max(v + int(rng.integers(-3, 4)), 0)), dtype=np.uint8)
+                elif what == 6:                   # flags: split bit / filter bits toggled
+                    m[2] ^= np.uint8([0x10, 0x01, 0x04][int(rng.integers(0, 3))])
+                else:                             # block size doubled (fewer, longer blocks announced)
+                    m[8:12] = np.frombuffer(struct.pack("<I", 2 * int(b1_parse(base)["blocksize"])), dtype=np.uint8)
+                frames.append(m)
+    assert len(frames) >= 60
+    want = [orc.blocks_decompress(f) for f in frames]
+    caps = [max(int(b1_parse(f)["nbytes"]), 1) for f in frames]
+    flen = np.array([f.size for f in frames], dtype=np.uint32)
+    foff = np.concatenate([[0], np.cumsum((flen[:-1].astype(np.uint64) + 15) // 16 * 16)]).astype(np.uint64)
+    blob = np.zeros(int(foff[-1] + flen[-1]) + 64, dtype=np.uint8)
+    for o, f in zip(foff, frames):
+        blob[int(o):int(o) + f.size] = f
+    cap = np.array(caps, dtype=np.uint64)
+    doff = np.concatenate([[0], np.cumsum((cap[:-1] + 15) // 16 * 16)]).astype(np.uint64)
+    out, olen, st = ctx.decompress_blocks_batch(blob, foff, flen, doff, int(doff[-1] + cap[-1]) + 64, blocksize=bs)
+    nok = 0
+    for k, (rc, ref) in enumerate(want):
+        assert int(st[k]) == rc, (kind, k, int(st[k]), rc, frames[k][:16].tobytes().hex())
+        if rc == 0:
+            nok += 1
+            assert int(olen[k]) == ref.size and np.array_equal(out[int(doff[k]):int(doff[k]) + ref.size], ref), (kind, k)
+    assert nok < len(frames)                      # the mutations do break frames
