@@ -63,3 +63,40 @@ def global_frame_table(ctx, local_frame_len, group=None, stream=0):
     ctx.scan_offsets_dev(all_len.contiguous(), n, all_off, total, stream)
     rank = dist.get_rank(group)
     return all_len, all_off, total, sum(counts[:rank])
+
+
+def gather_packed_frames(local_buf, local_total: int, local_frame_off, local_frame_len, dst: int = 0, group=None):
+    """Materialise ONE packed buffer with every rank's frames on rank `dst` (optional peer
+    copies).  Each rank holds its own packed output of compress_batch_dev: `local_buf[:local_total]`
+    with frames at `local_frame_off` (16-byte aligned) of `local_frame_len` bytes.  The ranks' buffers
+    are laid end to end in rank order (every local total is a multiple of 16, so frames stay aligned);
+    the bytes travel point to point (NCCL send/recv over NVLink on the GPU box, gloo in the CPU tests),
+    the tables with two all-gathers.  Returns (buf, frame_off, frame_len): the global offsets / lengths
+    of all frames on every rank, and the packed bytes on `dst` (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = local_buf.device
+    tot = torch.tensor([int(local_total)], dtype=torch.int64, device=dev)
+    tots = [torch.zeros_like(tot) for _ in range(world)]
+    dist.all_gather(tots, tot, group=group)
+    tots = [int(t.item()) for t in tots]
+    bases = [sum(tots[:r]) for r in range(world)]
+    all_len, counts = allgather_frame_sizes(local_frame_len, group)
+    all_off_local, _ = allgather_frame_sizes(local_frame_off.to(torch.int64), group)
+    base_per_frame = torch.cat([torch.full((c,), b, dtype=torch.int64, device=dev) for c, b in zip(counts, bases)]) \
+        if sum(counts) else torch.zeros(0, dtype=torch.int64, device=dev)
+    frame_off = all_off_local + base_per_frame
+    buf, ops = None, []
+    if rank == dst:
+        buf = torch.empty(max(sum(tots), 1), dtype=torch.uint8, device=dev)
+        buf[bases[rank]:bases[rank] + tots[rank]] = local_buf[:tots[rank]]
+        ops = [dist.P2POp(dist.irecv, buf[bases[r]:bases[r] + tots[r]], r, group) for r in range(world)
+               if r != dst and tots[r]]
+    elif tots[rank]:
+        ops = [dist.P2POp(dist.isend, local_buf[:tots[rank]].contiguous(), dst, group)]
+    if ops:                                       # one batch: the receives of all peers run concurrently
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
+    return buf, frame_off, all_len

@@ -97,3 +97,58 @@ def test_shard_range_properties():
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
     with pytest.raises(ValueError):
         par.shard_range(10, 2, 2)
+
+
+def _gather_worker(rank, world, port, nframes, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import __graft_entry__ as entry
+    entry.load_package()
+    import go_blosc_b200.parallel as par
+    orc = entry.load_oracle()
+    frames = _frames(nframes)
+    lo, hi = par.shard_range(nframes, rank, world)
+    # this rank's packed output, laid out like compress_batch_dev's: frames on 16-byte boundaries
+    parts, offs, lens, pos = [], [], [], 0
+    for f in range(lo, hi):
+        rc, fr = orc.compress(frames[f], orc.LZ4, 5, orc.SHUFFLE, 2)
+        assert rc == 0
+        offs.append(pos); lens.append(fr.size)
+        pad = (-fr.size) % 16
+        parts.append(np.concatenate([fr, np.zeros(pad, dtype=np.uint8)]))
+        pos += fr.size + pad
+    local = torch.from_numpy(np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8))
+    buf, g_off, g_len = par.gather_packed_frames(local, pos, torch.tensor(offs, dtype=torch.int64),
+                                                 torch.tensor(lens, dtype=torch.int32), dst=0)
+    ok = True
+    if rank == 0:
+        blob = buf.numpy()
+        assert g_off.numel() == nframes and g_len.numel() == nframes
+        for f in range(nframes):                              # every rank's frames, in global frame order
+            o, n = int(g_off[f]), int(g_len[f])
+            assert o % 16 == 0
+            rc, back = orc.decompress(blob[o:o + n])
+            ok = ok and rc == 0 and np.array_equal(back, frames[f])
+    else:
+        assert buf is None
+    q.put((rank, ok, g_off.tolist(), g_len.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nframes", [37, 3, 1])
+def test_gather_packed_frames_world2(nframes):
+    """K6 + peer copies: the ranks' packed buffers end to end on rank 0, global offsets on every rank."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, nframes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in results)
+    assert results[0][2] == results[1][2] and results[0][3] == results[1][3]     # the same table everywhere
