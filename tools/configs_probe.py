@@ -84,3 +84,15 @@ for _ in range(3):
     tc.append(e[0].elapsed_time(e[1])); td.append(e[1].elapsed_time(e[2]))
 print(f"C5 mixed with decode index ({spf} entries per frame): ratio {int(d_tot.item()) / acc:.4f}, compress {acc / min(tc) / 1e6:.1f} GB/s, "
       f"decompress {acc / min(td) / 1e6:.1f} GB/s, exact={torch.equal(d_out, src)}, status ok={not bool(d_st.any())}")
+
+# ---- the same C5 batch as Blosc-1 multi-block frames (64 KiB blocks: every block an independent stream, no side-car)
+compb = lambda: ctx.compress_blocks_batch_dev(src, d_off, d_len, nf, acc, mx, 1, 2, 0, d_c, cap, d_foff, d_flen, d_st, d_tot, s)
+decb = lambda: ctx.decompress_blocks_batch_dev(d_c, d_foff, d_flen, nf, d_out, d_off, d_len, acc, mx, 0, d_olen, d_st, s)
+compb(); d_out.zero_(); decb(); torch.cuda.synchronize()
+tc, td = [], []
+for _ in range(3):
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record(); compb(); e[1].record(); decb(); e[2].record(); torch.cuda.synchronize()
+    tc.append(e[0].elapsed_time(e[1])); td.append(e[1].elapsed_time(e[2]))
+print(f"C5 mixed as multi-block frames (64 KiB blocks): ratio {int(d_tot.item()) / acc:.4f}, compress {acc / min(tc) / 1e6:.1f} GB/s, "
+      f"decompress {acc / min(td) / 1e6:.1f} GB/s, exact={torch.equal(d_out, src)}, status ok={not bool(d_st.any())}")
