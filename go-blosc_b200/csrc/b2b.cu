@@ -333,6 +333,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     e.seg_base = d_seg_base; e.meta = d_meta; e.ticket = d_ticket;
     for (int i = 0; i < 4; i++) e.tune[i] = ctx->opt_tune[i];
     e.independent = d_index ? 1u : 0u;
+    e.planes = fm.mode == 1 ? fm.typesize : 0u;
     rc = launch_encode(ctx, e, s);
     if (rc) return rc;
 
@@ -537,7 +538,7 @@ int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *
     e.segs_grid = (uint32_t)segs_grid; e.comp = d_comp; e.comp_off = comp_off;
     e.seg_base = seg_base; e.meta = d_meta; e.ticket = d_ticket;
     for (int i = 0; i < 4; i++) e.tune[i] = ctx->opt_tune[i];
-    e.independent = 0;
+    e.independent = 0; e.planes = 0;
     rc = launch_encode(ctx, e, s);
     if (rc) return rc;
     FinalizeArgs fa;

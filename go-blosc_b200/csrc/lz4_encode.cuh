@@ -702,6 +702,7 @@ struct EncodeArgs {
     unsigned long long *ticket; // zero before launch
     uint32_t tune[4];           // experiment knobs (0: default)
     uint32_t independent;       // 1: no warm-up window, segments never reference each other (decode index)
+    uint32_t planes;            // typesize when the input went through the byte shuffle (plane = len / typesize), else 0
 };
 
 template <int HL>
@@ -726,7 +727,10 @@ lz4_encode_kernel(EncodeArgs a) {
         for (uint32_t s = s0; s < nseg; s += a.segs_grid) {
             const uint32_t B = s * kSegBytes;
             const uint32_t L = n - B < kSegBytes ? n - B : kSegBytes;
-            const uint32_t W = a.independent ? 0u : (B < kWarmBytes ? B : kWarmBytes);
+            // after a byte shuffle a segment that starts on a plane boundary has nothing to learn from the
+            // tail of the previous plane (another byte of the element): no warm-up window there
+            const bool plane_start = a.planes > 1 && B % (n / a.planes) == 0;
+            const uint32_t W = (a.independent || plane_start) ? 0u : (B < kWarmBytes ? B : kWarmBytes);
             const SegMeta m = warp_encode_segment<HL>(frame + B - W, W, L, (uint64_t)n - B - L,
                                                       a.comp + a.comp_off[f] + (uint64_t)s * kSegSlot,
                                                       enc_tables + ((size_t)warp << HL), &enc_lists[warp], lane,

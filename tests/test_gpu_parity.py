@@ -633,6 +633,11 @@ def test_block_frames_typesize_255_many_blocks(ctx, orc):
         assert ctx.decompress_blocks(fr) == data.tobytes()
         rc, ref = orc.blocks_compress(data, 1, T, bs, True)
         assert rc == 0 and ctx.decompress_blocks(ref) == data.tobytes()
+    for T in (0, -3, 256, 300, 1 << 40):                  # Blosc-1: a typesize outside 1..255 counts as 1
+        fr = np.frombuffer(ctx.compress_blocks(data, 1, T, 0), dtype=np.uint8)
+        rc, ref = orc.blocks_compress(data, 1, T, 0, False)
+        assert rc == 0 and b1_parse(fr)["typesize"] == 1 == b1_parse(ref)["typesize"] and fr[:12].tobytes() == ref[:12].tobytes()
+        assert ctx.decompress_blocks(fr) == data.tobytes()
 
 
 def test_block_frames_errors_match_oracle(ctx, orc, pkg):
