@@ -640,7 +640,7 @@ int decompress_blocks_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint6
     StreamArgs sa;
     sa.src = ia.frames; sa.src_off = strm_src; sa.clen = strm_clen; sa.dst = da.dst; sa.scratch = d_stage;
     sa.dst_off = slot_off; sa.cap = slot_len; sa.kind = strm_kind; sa.owner = owner; sa.status = d_status;
-    sa.nstreams = nslots; sa.table = d_table; sa.table_off = table_off; sa.nrec = strm_nrec;
+    sa.nstreams = nslots; sa.table = d_table; sa.table_off = table_off; sa.nrec = strm_nrec; sa.table_cap = nrec_max;
     const unsigned sgrid = (nslots + kCodecWarps - 1) / kCodecWarps;
     { LaunchTimer lt(ctx, K_PARSE, s); lz4_parse_streams_kernel<<<sgrid, kCodecThreads, 0, s>>>(sa); }
     CU(ctx, cudaGetLastError());

@@ -550,15 +550,17 @@ struct StreamArgs {
     uint32_t nstreams;
     uint64_t *table;            // sequence records
     const uint64_t *table_off;  // exclusive scan of cap / 4 + kSeqSlack
-    uint32_t *nrec;
+    uint32_t *nrec;             // ~0: no room in the table (outputs that overlap in dst), decoded without it
+    uint64_t table_cap;         // records the table can hold in all
 };
 
 __global__ void __launch_bounds__(kCodecThreads, 12) lz4_parse_streams_kernel(StreamArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t t = blockIdx.x * kCodecWarps + warp;
     if (t >= a.nstreams || (a.kind[t] & 3u) != 2u) return;
-    const uint32_t n = warp_lz4_parse(a.src + a.src_off[t], a.clen[t], a.table + a.table_off[t],
-                                      a.cap[t] / 4u + kSeqSlack, lane);
+    const uint32_t room = a.cap[t] / 4u + kSeqSlack;
+    if (a.table_off[t] + room > a.table_cap) { if (lane == 0) a.nrec[t] = 0xFFFFFFFFu; return; }
+    const uint32_t n = warp_lz4_parse(a.src + a.src_off[t], a.clen[t], a.table + a.table_off[t], room, lane);
     if (lane == 0) a.nrec[t] = n;
 }
 

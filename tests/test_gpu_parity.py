@@ -853,3 +853,31 @@ def test_block_frames_decoder_fuzz_matches_oracle(ctx, orc, kind):
             nok += 1
             assert int(olen[k]) == ref.size and np.array_equal(out[int(doff[k]):int(doff[k]) + ref.size], ref), (kind, k)
     assert nok < len(frames)                      # the mutations do break frames
+
+
+def test_block_frames_overlapping_outputs_do_not_overrun_the_record_table(ctx, orc, torch_mod):
+    """Every frame decoded to the SAME place with total_dst_bytes = one frame: the sequence-record table is
+    sized from total_dst_bytes, so the streams that do not fit it must fall back to table-less decoding."""
+    torch = torch_mod
+    nf, fl = 64, 262144
+    data = dg.lowent_i16(fl // 2, 3)
+    fr = np.frombuffer(ctx.compress_blocks(data, 1, 2, 0), dtype=np.uint8)
+    stride = (fr.size + 15) // 16 * 16
+    blob = np.zeros(stride * nf + 64, dtype=np.uint8)
+    for f in range(nf):
+        blob[f * stride:f * stride + fr.size] = fr
+    d_c = torch.from_numpy(blob).cuda()
+    d_foff = torch.arange(nf, dtype=torch.int64, device="cuda") * stride
+    d_flen = torch.full((nf,), fr.size, dtype=torch.int32, device="cuda")
+    d_off = torch.zeros(nf, dtype=torch.int64, device="cuda")
+    d_cap = torch.full((nf,), fl, dtype=torch.int32, device="cuda")
+    d_out = torch.zeros(fl + 64, dtype=torch.uint8, device="cuda")
+    d_olen = torch.empty(nf, dtype=torch.int32, device="cuda")
+    d_st = torch.empty(nf, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    ctx.decompress_blocks_batch_dev(d_c, d_foff, d_flen, nf, d_out, d_off, d_cap, fl, fl, 0, d_olen, d_st, s)
+    torch.cuda.synchronize()
+    st = d_st.cpu().numpy()
+    # the block table is sized from total_dst_bytes too: frames beyond it are refused, none is decoded wrongly
+    assert set(int(x) for x in st) <= {0, 11} and st[0] == 0
+    assert np.array_equal(d_out[:fl].cpu().numpy(), data)
