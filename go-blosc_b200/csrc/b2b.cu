@@ -334,6 +334,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     for (int i = 0; i < 4; i++) e.tune[i] = ctx->opt_tune[i];
     e.independent = d_index ? 1u : 0u;
     e.planes = fm.mode == 1 ? fm.typesize : 0u;
+    e.comp_cap = comp_bytes; e.seg_cap = max_segs_total;
     rc = launch_encode(ctx, e, s);
     if (rc) return rc;
 
@@ -343,6 +344,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     fa.comp_len = d_comp_len; fa.frame_len = d_frame_len; fa.flags = d_flags;
     fa.final_ll = d_final_ll; fa.final_off = d_final_off; fa.status = d_status;
     fa.index = d_index; fa.segs_per_frame = segs_per_frame;
+    fa.comp_off = d_comp_off; fa.comp_cap = comp_bytes; fa.seg_cap = max_segs_total;
     { LaunchTimer lt(ctx, K_FINALIZE, s); finalize_frames_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(fa); }
     CU(ctx, cudaGetLastError());
 
@@ -539,6 +541,7 @@ int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *
     e.seg_base = seg_base; e.meta = d_meta; e.ticket = d_ticket;
     for (int i = 0; i < 4; i++) e.tune[i] = ctx->opt_tune[i];
     e.independent = 0; e.planes = 0;
+    e.comp_cap = comp_bytes; e.seg_cap = max_segs_total;
     rc = launch_encode(ctx, e, s);
     if (rc) return rc;
     FinalizeArgs fa;
@@ -547,6 +550,7 @@ int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *
     fa.comp_len = comp_len; fa.frame_len = blk_flen; fa.flags = blk_flags;
     fa.final_ll = final_ll; fa.final_off = final_off; fa.status = blk_status;
     fa.index = nullptr; fa.segs_per_frame = 0;
+    fa.comp_off = comp_off; fa.comp_cap = comp_bytes; fa.seg_cap = max_segs_total;
     { LaunchTimer lt(ctx, K_FINALIZE, s); finalize_frames_kernel<<<(nslots + 127) / 128, 128, 0, s>>>(fa); }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemsetAsync(comp_len + nslots, 0, 4, s));
@@ -554,7 +558,7 @@ int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *
     if (rc) return rc;
     BlocksFrameArgs ba;
     ba.src_len = d_src_len; ba.nblk = frm_nblk; ba.blk_base = blk_base; ba.blk_pos = blk_pos;
-    ba.nframes = nframes; ba.base_flags = base_flags;
+    ba.nframes = nframes; ba.base_flags = base_flags; ba.nslots = nslots; ba.blk_status = blk_status;
     ba.frame_len = d_frame_len; ba.frame_flags = frm_flags; ba.status = d_status;
     { LaunchTimer lt(ctx, K_BLOCKS_META, s); blocks_frame_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(ba); }
     CU(ctx, cudaGetLastError());
@@ -1081,24 +1085,39 @@ int b2b_shuffle(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, const voi
 // for a bulk copy, so H2D of chunk k+1, the kernels of chunk k and D2H of chunk k-1 overlap and
 // both PCIe directions stay busy.  Pinned caller buffers are DMA'd directly; pageable ones make
 // the bulk copies synchronous (still correct).
-struct HostChunk { uint32_t f0, f1; uint64_t lo, hi; uint32_t max_len; };
+struct HostChunk { uint32_t f0, f1; uint64_t lo, hi; uint32_t max_len; uint64_t sum; };   // sum: bytes of all frames (> hi - lo when they overlap)
 
 static std::vector<HostChunk> split_chunks(const uint64_t *off, const uint32_t *len, uint32_t nframes,
                                            uint64_t stage_bytes) {
     std::vector<HostChunk> out;
     uint32_t f = 0;
     while (f < nframes) {
-        HostChunk c{f, f, ~0ull, 0, 0};
+        HostChunk c{f, f, ~0ull, 0, 0, 0};
         uint64_t bytes = 0;
         while (c.f1 < nframes && (c.f1 == c.f0 || bytes + len[c.f1] <= stage_bytes)) {
             c.lo = std::min(c.lo, off[c.f1]); c.hi = std::max(c.hi, off[c.f1] + len[c.f1]);
             c.max_len = std::max(c.max_len, len[c.f1]);
             bytes += len[c.f1]; c.f1++;
         }
+        c.sum = bytes;
         out.push_back(c);
         f = c.f1;
     }
     return out;
+}
+
+// The filter writes frame f's transformed bytes at f's own source offset in scratch, so source ranges that
+// overlap would clobber each other: such a batch is refused (frames in offset order are checked in one pass).
+static bool ranges_disjoint(const uint64_t *off, const uint32_t *len, uint32_t n) {
+    bool ordered = true;
+    for (uint32_t f = 1; f < n && ordered; f++) ordered = off[f] >= off[f - 1] + len[f - 1];
+    if (ordered) return true;
+    std::vector<std::pair<uint64_t, uint32_t>> v(n);
+    for (uint32_t f = 0; f < n; f++) v[f] = {off[f], len[f]};
+    std::sort(v.begin(), v.end());
+    for (uint32_t f = 1; f < n; f++)
+        if (v[f].second != 0 && v[f].first < v[f - 1].first + v[f - 1].second) return false;
+    return true;
 }
 
 static int sync_pipeline(b2b_ctx *ctx, cudaError_t e, int rc) {
@@ -1119,6 +1138,7 @@ static int host_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *sr
     if (!ctx) return B2B_EINVAL;
     if (nframes == 0) { if (total_out) *total_out = 0; return B2B_OK; }
     if (!src || !src_off || !src_len || !dst || !frame_off || !frame_len || !status) return B2B_EINVAL;
+    if (!ranges_disjoint(src_off, src_len, nframes)) return B2B_EINVAL;
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
     constexpr int S = b2b_ctx::kSlots;
@@ -1160,7 +1180,8 @@ static int host_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *sr
         const HostChunk &c = chunks[k];
         const int slot = (int)(k % S);
         const uint32_t n = c.f1 - c.f0;
-        const uint64_t span = c.hi - c.lo, out_cap = span + 31ull * n + 64;
+        // scratch and output are sized for the bytes of all frames, which is more than the span when frames overlap
+        const uint64_t span = c.hi - c.lo, work = std::max<uint64_t>(span, c.sum), out_cap = work + 31ull * n + 64;
         uint64_t a8, a4; layout(n, a8, a4);
         const uint64_t tab_bytes = 2 * a8 + 3 * a4 + 256;
         uint8_t *d_in = nullptr, *d_tab = nullptr, *h_tab = nullptr;
@@ -1192,10 +1213,10 @@ static int host_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *sr
         if (e == cudaSuccess && k >= (size_t)S) e = cudaStreamWaitEvent(sk, ctx->ev_out_free[slot], 0);
         if (e != cudaSuccess) break;
         select_arena(ctx, 1 + slot);
-        rc = blocks ? compress_blocks_dev_locked(ctx, d_in, d_src_off, d_src_len, n, span, c.max_len, shuffle, typesize,
+        rc = blocks ? compress_blocks_dev_locked(ctx, d_in, d_src_off, d_src_len, n, work, c.max_len, shuffle, typesize,
                                                  blocksize, d_out[slot], out_cap, d_frame_off, d_frame_len, d_status,
                                                  d_total, sk)
-                    : compress_batch_dev_locked(ctx, d_in, d_src_off, d_src_len, n, span, c.max_len, shuffle, typesize,
+                    : compress_batch_dev_locked(ctx, d_in, d_src_off, d_src_len, n, work, c.max_len, shuffle, typesize,
                                                 d_out[slot], out_cap, d_frame_off, d_frame_len, d_status, d_total, sk);
         select_arena(ctx, 0);
         if (rc) break;

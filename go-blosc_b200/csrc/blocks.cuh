@@ -104,6 +104,8 @@ struct BlocksFrameArgs {
     const uint64_t *blk_base;
     const uint64_t *blk_pos;    // exclusive scan of (4 + stored bytes) over nslots + 1 slots
     uint32_t nframes, base_flags;
+    uint32_t nslots;            // slots the table holds (sized from the caller's total_src_bytes)
+    const uint32_t *blk_status; // per slot: kEDstTooSmall when the block did not fit the scratch
     uint32_t *frame_len, *frame_flags, *status;
 };
 __global__ void blocks_frame_kernel(BlocksFrameArgs a) {
@@ -113,11 +115,15 @@ __global__ void blocks_frame_kernel(BlocksFrameArgs a) {
     uint32_t st = kOk, len = 0, flags = a.base_flags;
     if (n == 0) st = kEInvalidData;                       // as blosc.go:269-271 for the one-block frame
     else if (n > kB1MaxBuffer) st = kEDataTooLarge;
+    else if (a.blk_base[f] + a.nblk[f] > a.nslots) st = kEDstTooSmall;   // total_src_bytes was not a bound
     else {
         const uint64_t b0 = a.blk_base[f], k = a.nblk[f];
-        const uint64_t total = 16ull + 4ull * k + (a.blk_pos[b0 + k] - a.blk_pos[b0]);
-        const bool stored = n < kB1MinBuffer || total > (uint64_t)n + 16ull;   // Blosc-1's bound: nbytes + 16
-        if (stored) { flags |= 0x2u; len = n + 16u; } else len = (uint32_t)total;
+        for (uint64_t i = 0; i < k; i++) if (a.blk_status[b0 + i] == kEDstTooSmall) st = kEDstTooSmall;
+        if (st == kOk) {
+            const uint64_t total = 16ull + 4ull * k + (a.blk_pos[b0 + k] - a.blk_pos[b0]);
+            const bool stored = n < kB1MinBuffer || total > (uint64_t)n + 16ull;   // Blosc-1's bound: nbytes + 16
+            if (stored) { flags |= 0x2u; len = n + 16u; } else len = (uint32_t)total;
+        }
     }
     a.frame_len[f] = len; a.frame_flags[f] = flags; a.status[f] = st;
 }

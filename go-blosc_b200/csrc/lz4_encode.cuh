@@ -703,7 +703,15 @@ struct EncodeArgs {
     uint32_t tune[4];           // experiment knobs (0: default)
     uint32_t independent;       // 1: no warm-up window, segments never reference each other (decode index)
     uint32_t planes;            // typesize when the input went through the byte shuffle (plane = len / typesize), else 0
+    uint64_t comp_cap, seg_cap; // bytes of `comp`, entries of `meta`: sized from the caller's total_src_bytes; a frame
+                                // that does not fit (sources that overlap, a bound that was not one) is skipped
 };
+
+// scratch was sized from host-known bounds; a frame beyond them gets B2B_EDST_TOO_SMALL instead of a wild write
+__device__ __forceinline__ bool frame_fits_scratch(uint64_t comp_off, uint64_t seg_base, uint32_t n, uint64_t comp_cap,
+                                                   uint64_t seg_cap) {
+    return comp_off + frame_slot_bytes(n) <= comp_cap && seg_base + seg_count(n) <= seg_cap;
+}
 
 template <int HL>
 __global__ void __launch_bounds__(kEncThreads, HL <= 10 ? 7 : (HL == 11 ? 5 : (HL == 12 ? 2 : 1)))
@@ -724,6 +732,7 @@ lz4_encode_kernel(EncodeArgs a) {
         const uint32_t n = a.src_len[f];
         const uint32_t nseg = seg_count(n);
         const uint8_t *frame = a.in + a.src_off[f];
+        if (!frame_fits_scratch(a.comp_off[f], a.seg_base[f], n, a.comp_cap, a.seg_cap)) continue;
         for (uint32_t s = s0; s < nseg; s += a.segs_grid) {
             const uint32_t B = s * kSegBytes;
             const uint32_t L = n - B < kSegBytes ? n - B : kSegBytes;
@@ -763,6 +772,8 @@ struct FinalizeArgs {
     // s's sequences | output position of that token's first literal << 32; ~0 if the segment has none
     uint64_t *index;
     uint32_t segs_per_frame;
+    const uint64_t *comp_off;   // with comp_cap / seg_cap: the same capacity check as the encoder's
+    uint64_t comp_cap, seg_cap;
 };
 
 __global__ void finalize_frames_kernel(FinalizeArgs a) {
@@ -774,7 +785,10 @@ __global__ void finalize_frames_kernel(FinalizeArgs a) {
         for (uint32_t s = 0; s < a.segs_per_frame; s++) a.index[(uint64_t)f * a.segs_per_frame + s] = ~0ull;
     if (n == 0) st = 1;                                   // ErrInvalidData, blosc.go:269-271
     else if (n > 0xFFFFFFFFu - 16u) st = 6;               // header fields are u32
-    else {
+    else if (!frame_fits_scratch(a.comp_off[f], a.seg_base[f], n, a.comp_cap, a.seg_cap)) {
+        st = 11;                                          // B2B_EDST_TOO_SMALL: the scratch bound was not one
+        if (a.index) for (uint32_t s = 0; s < a.segs_per_frame; s++) a.index[(uint64_t)f * a.segs_per_frame + s] = ~0ull;
+    } else {
         const uint32_t nseg = seg_count(n);
         const uint64_t base = a.seg_base[f];
         uint64_t out = 0, carry = 0;

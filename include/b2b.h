@@ -156,7 +156,8 @@ B2B_API int b2b_lz4_block_decompress(b2b_ctx *ctx, const void *src, size_t n, vo
  * nframes independent frames; frame f is src[src_off[f] .. +src_len[f]).  Output frames are
  * packed back to back into dst; frame_off/frame_len (host arrays, nframes entries) receive
  * the packed-offsets table, status[f] the per-frame B2B_* status.  Pinned (cudaHostAlloc /
- * cudaHostRegister) buffers are DMA'd directly, pageable ones are staged. */
+ * cudaHostRegister) buffers are DMA'd directly, pageable ones are staged.  The source ranges of a
+ * compress batch must not overlap (B2B_EINVAL): a frame is filtered in scratch at its own offset. */
 B2B_API int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off,
                                const uint32_t *src_len, uint32_t nframes, int shuffle,
                                int64_t typesize, void *dst, uint64_t dst_cap, uint64_t *frame_off,
@@ -176,7 +177,10 @@ B2B_API int b2b_shuffle_dev(b2b_ctx *ctx, int mode, int inverse, int64_t typesiz
  * size scratch: the extent max(d_src_off[f] + d_src_len[f]) and max(d_src_len[f]).
  * Output is PACKED: frame f is written at d_dst + d_frame_off[f] (exclusive scan of d_frame_len, built on the device by a
  * single-pass decoupled-look-back scan), d_total_out[0] = total bytes.  dst_cap must be
- * >= total_src_bytes + 32*nframes (frames start on 16-byte boundaries).  d_status[f] is a B2B_* code. */
+ * >= total_src_bytes + 32*nframes (frames start on 16-byte boundaries).  d_status[f] is a B2B_* code.
+ * The source ranges must not overlap (a frame is filtered in scratch at its own offset); a frame that
+ * does not fit the scratch sized from total_src_bytes reports B2B_EDST_TOO_SMALL, nothing is written
+ * out of bounds. */
 B2B_API int b2b_compress_batch_dev(b2b_ctx *ctx, const void *d_src, const uint64_t *d_src_off,
                                    const uint32_t *d_src_len, uint32_t nframes,
                                    uint64_t total_src_bytes, uint32_t max_frame_len, int shuffle,

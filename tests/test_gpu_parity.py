@@ -881,3 +881,42 @@ def test_block_frames_overlapping_outputs_do_not_overrun_the_record_table(ctx, o
     # the block table is sized from total_dst_bytes too: frames beyond it are refused, none is decoded wrongly
     assert set(int(x) for x in st) <= {0, 11} and st[0] == 0
     assert np.array_equal(d_out[:fl].cpu().numpy(), data)
+
+
+def test_batches_with_overlapping_or_understated_sources_are_refused_not_corrupted(ctx, pkg, orc, torch_mod):
+    """A frame is filtered in scratch at its own source offset, so overlapping source ranges cannot be served:
+    the host batch refuses them; the device batch (which cannot see the tables) reports B2B_EDST_TOO_SMALL for
+    the frames that do not fit the scratch sized from total_src_bytes and writes nothing out of bounds."""
+    torch = torch_mod
+    data = dg.lowent_i16(100000, 1)
+    n = data.size
+    with pytest.raises(pkg.ErrInval):
+        ctx.compress_batch(data, [0, 50000], [100000, 100000], shuffle=1, typesize=2)
+    with pytest.raises(pkg.ErrInval):
+        ctx.compress_blocks_batch(data, [0, 0], [n, n], shuffle=1, typesize=2)
+    dst, foff, flen, st, _ = ctx.compress_batch(data, [100000, 0], [100000, 100000], shuffle=1, typesize=2)   # any order is fine
+    assert not st.any() and orc.decompress(dst[int(foff[0]):int(foff[0]) + int(flen[0])])[1].tobytes() == data[100000:].tobytes()
+    # device batch: 64 frames that all read the same 200 000 bytes, total_src_bytes says 200 000
+    nf = 64
+    d_src = torch.from_numpy(data).cuda()
+    d_off = torch.zeros(nf, dtype=torch.int64, device="cuda")
+    d_len = torch.full((nf,), n, dtype=torch.int32, device="cuda")
+    cap = nf * (n + 32) + 64
+    for blocks in (False, True):
+        d_dst = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        d_foff = torch.empty(nf, dtype=torch.int64, device="cuda")
+        d_flen = torch.empty(nf, dtype=torch.int32, device="cuda")
+        d_st = torch.empty(nf, dtype=torch.int32, device="cuda")
+        d_tot = torch.empty(1, dtype=torch.int64, device="cuda")
+        s = torch.cuda.current_stream().cuda_stream
+        if blocks:
+            ctx.compress_blocks_batch_dev(d_src, d_off, d_len, nf, n, n, 1, 2, 0, d_dst, cap, d_foff, d_flen, d_st, d_tot, s)
+        else:
+            ctx.compress_batch_dev(d_src, d_off, d_len, nf, n, n, 1, 2, d_dst, cap, d_foff, d_flen, d_st, d_tot, s)
+        torch.cuda.synchronize()
+        st = d_st.cpu().numpy()
+        assert set(int(x) for x in st) <= {0, 11} and (st == 11).any(), st
+        flen = d_flen.cpu().numpy()
+        assert all(flen[f] == 0 for f in range(nf) if st[f] == 11)
+    # the context is still healthy
+    assert ctx.decompress(ctx.compress(data, 1, 5, 1, 2)) == data.tobytes()
