@@ -379,7 +379,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         return B2B_EINVAL;
     const bool split = !(d_index && segs_per_frame) && !ctx->opt_fused_decode;
     const uint64_t nrec_max = total_dst / 4 + (uint64_t)(kSeqSlack + 1) * nframes + 64;   // sum of dst_cap / 4 + slack
-    const uint64_t need = align_up(total_dst + 64, 256) + align_up(8ull * nframes, 256) + 8192 +
+    const uint64_t need = align_up(total_dst + 64, 256) + align_up(8ull * nframes, 256) + align_up(4ull * nframes, 256) + 8192 +
                           (split ? align_up(8 * nrec_max, 256) + align_up(8ull * nframes, 256) +
                                    align_up(4ull * nframes, 256) + scan_scratch_bytes(nframes) + 1024 : 0);
     int rc = ensure_arena(ctx, need);
@@ -387,7 +387,12 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     Arena ar(ctx);
     uint8_t *d_stage = ar.take<uint8_t>(total_dst + 64);
     FrameMeta *d_meta = ar.take<FrameMeta>(nframes);
+    uint32_t *d_cap_eff = ar.take<uint32_t>(nframes);
     unsigned long long *d_ticket = ar.take<unsigned long long>(4);
+    clip_caps_kernel<<<(nframes + 255) / 256, 256, 0, s>>>(d_dst_off, d_dst_cap, total_dst, nframes, d_cap_eff);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    d_dst_cap = d_cap_eff;
     uint64_t *d_table = nullptr, *d_table_off = nullptr;
     uint32_t *d_nrec = nullptr;
     uint8_t *scan_t = nullptr;
@@ -597,7 +602,7 @@ int decompress_blocks_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint6
     const uint32_t nslots = (uint32_t)nslots64;
     const uint64_t nrec_max = total_dst / 4 + (uint64_t)(kSeqSlack + 1) * nslots + 64;
     const uint64_t need = align_up(total_dst + 64, 256) + 9 * align_up(8ull * nslots, 256) +
-                          3 * align_up(8ull * nframes, 256) + align_up(8 * nrec_max, 256) +
+                          4 * align_up(8ull * nframes, 256) + align_up(8 * nrec_max, 256) +
                           scan_scratch_bytes(nframes) + scan_scratch_bytes(nslots) + 8192;
     int rc = ensure_arena(ctx, need);
     if (rc) return rc;
@@ -618,6 +623,11 @@ int decompress_blocks_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint6
     uint32_t *frm_bs = ar.take<uint32_t>(nframes);
     uint8_t *scan_a = ar.take<uint8_t>(scan_scratch_bytes(nframes));
     uint8_t *scan_b = ar.take<uint8_t>(scan_scratch_bytes(nslots));
+    uint32_t *d_cap_eff = ar.take<uint32_t>(nframes);
+    clip_caps_kernel<<<(nframes + 255) / 256, 256, 0, s>>>(d_dst_off, d_dst_cap, total_dst, nframes, d_cap_eff);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    d_dst_cap = d_cap_eff;
 
     BlocksInfoArgs ia;
     ia.frames = static_cast<const uint8_t *>(d_frames); ia.frame_off = d_frame_off; ia.frame_len = d_frame_len;

@@ -672,6 +672,16 @@ __global__ void index_finish_kernel(DecodeArgs a) {
     a.meta[f] = m;
 }
 
+// The staging buffer of a decompress batch is sized from the caller's total_dst_bytes: an output slot that
+// reaches beyond it gets capacity 0 (the frame then reports B2B_EDST_TOO_SMALL) instead of a wild write.
+__global__ void clip_caps_kernel(const uint64_t *dst_off, const uint32_t *dst_cap, uint64_t total_dst, uint32_t nframes,
+                                 uint32_t *cap_eff) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    const uint64_t o = dst_off[f];
+    cap_eff[f] = (o <= total_dst && dst_cap[f] <= total_dst - o) ? dst_cap[f] : 0u;
+}
+
 // header-only pass for b2b_frame_info_batch_dev
 __global__ void frame_info_kernel(const uint8_t *frames, const uint64_t *frame_off,
                                   const uint32_t *frame_len, uint32_t nframes, uint32_t *orig_len,

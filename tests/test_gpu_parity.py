@@ -918,5 +918,29 @@ def test_batches_with_overlapping_or_understated_sources_are_refused_not_corrupt
         assert set(int(x) for x in st) <= {0, 11} and (st == 11).any(), st
         flen = d_flen.cpu().numpy()
         assert all(flen[f] == 0 for f in range(nf) if st[f] == 11)
+    # decompress side: 16 frames at distinct output offsets, total_dst_bytes understated as two frames' worth
+    nf = 16
+    d_off = torch.arange(nf, dtype=torch.int64, device="cuda") * n
+    d_len = torch.full((nf,), n, dtype=torch.int32, device="cuda")
+    d_big = torch.from_numpy(np.tile(data, nf)).cuda()
+    cap = nf * (n + 32) + 64
+    for blocks in (False, True):
+        d_dst = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        d_foff = torch.empty(nf, dtype=torch.int64, device="cuda")
+        d_flen = torch.empty(nf, dtype=torch.int32, device="cuda")
+        d_st = torch.empty(nf, dtype=torch.int32, device="cuda")
+        d_tot = torch.empty(1, dtype=torch.int64, device="cuda")
+        d_out = torch.zeros(nf * n, dtype=torch.uint8, device="cuda")
+        d_olen = torch.empty(nf, dtype=torch.int32, device="cuda")
+        if blocks:
+            ctx.compress_blocks_batch_dev(d_big, d_off, d_len, nf, nf * n, n, 1, 2, 0, d_dst, cap, d_foff, d_flen, d_st, d_tot, s)
+            ctx.decompress_blocks_batch_dev(d_dst, d_foff, d_flen, nf, d_out, d_off, d_len, 2 * n, n, 0, d_olen, d_st, s)
+        else:
+            ctx.compress_batch_dev(d_big, d_off, d_len, nf, nf * n, n, 1, 2, d_dst, cap, d_foff, d_flen, d_st, d_tot, s)
+            ctx.decompress_batch_dev(d_dst, d_foff, d_flen, nf, 0, d_out, d_off, d_len, 2 * n, n, d_olen, d_st, s)
+        torch.cuda.synchronize()
+        st = d_st.cpu().numpy()
+        assert list(st[:2]) == [0, 0] and all(int(x) == 11 for x in st[2:]), (blocks, st)
+        assert torch.equal(d_out[:2 * n], d_big[:2 * n]) and not d_out[2 * n:].any()
     # the context is still healthy
     assert ctx.decompress(ctx.compress(data, 1, 5, 1, 2)) == data.tobytes()
