@@ -1,8 +1,8 @@
 """Compressed size of the CUDA encoder vs the oracle over a corpus x size x filter grid: worst offenders first."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import __graft_entry__ as entry
 import datagen as dg
 pkg = entry.load_package(); orc = entry.load_oracle()

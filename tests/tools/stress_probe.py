@@ -1,6 +1,7 @@
 import os, sys, time
 import numpy as np, torch
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import __graft_entry__ as entry
 import datagen as dg
 pkg = entry.load_package(); orc = entry.load_oracle()

@@ -3,7 +3,7 @@
  * NOT part of the product and not a fallback: it replays the kernel's parse on the CPU, lane
  * by lane, so that match-finder parameters (hash width, table size, skip schedule) can be
  * compared with the oracle's pierrec-style compressor without spending GPU time.
- * Build: gcc -O2 -o /tmp/encoder_model tools/encoder_model.c oracle/blosc_oracle.c -lm -pthread
+ * Build: gcc -O2 -o /tmp/strip_model tests/tools/strip_model.c oracle/blosc_oracle.c -lm -pthread
  */
 #include <math.h>
 #include <stdint.h>
@@ -11,7 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "../oracle/blosc_oracle.h"
+#include "../../oracle/blosc_oracle.h"
 
 static int INSERT_AFTER = 0, LAZY = 0, WAYS = 1, LAZYCAP = 1 << 30, SEG = 0, FIXD = 0, NOBACK = 0; static int HASHLOG = 12, HASHBYTES = 4, SKIPLOG = 7, SKIPDIV = 3, INSERT_END = 0, PREFER_TABLE = 0;
 
