@@ -84,6 +84,36 @@ __device__ __forceinline__ void warp_match_copy(uint8_t *dst, uint32_t off, uint
     }
 }
 
+// Lean variants for the batch loop (n <= 288: regular tokens): plain byte loops, no 16-byte realigning path,
+// so that the loop's register footprint is not set by a copy routine it hardly ever needs at that size.
+__device__ __forceinline__ void warp_copy_short(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
+    for (uint32_t i = lane; i < n; i += 2 * kWarp) {       // two loads in flight (the ranges never overlap)
+        const bool p1 = i + kWarp < n;
+        const uint8_t v0 = src[i];
+        uint8_t v1 = 0;
+        if (p1) v1 = src[i + kWarp];
+        dst[i] = v0;
+        if (p1) dst[i + kWarp] = v1;
+    }
+}
+__device__ __forceinline__ void warp_match_copy_short(uint8_t *dst, uint32_t off, uint32_t ml, int lane) {
+    const uint8_t *base = dst - off;
+    if (off >= ml) { warp_copy_short(dst, base, ml, lane); return; }
+    if (off == 1) {                                        // a run
+        const uint8_t v = base[0];
+        for (uint32_t i = lane; i < ml; i += kWarp) dst[i] = v;
+        return;
+    }
+    uint32_t written = 0;                                  // general overlap: the written region doubles every round
+    while (written < ml) {
+        uint32_t len = off + written;
+        if (len > ml - written) len = ml - written;
+        warp_copy_short(dst + written, base, len, lane);
+        written += len;
+        __syncwarp();
+    }
+}
+
 // ---- batched decode -----------------------------------------------------------------------
 // A "regular" token carries at most one length-extension byte per field (literals <= 269,
 // match <= 273).  The decoder parses such tokens 32 stream positions at a time: every lane
@@ -101,7 +131,7 @@ __device__ __forceinline__ void warp_match_copy(uint8_t *dst, uint32_t off, uint
 #define B2B_LANE_LIT 16
 #endif
 #ifndef B2B_LANE_MATCH
-#define B2B_LANE_MATCH 24
+#define B2B_LANE_MATCH 16
 #endif
 constexpr uint32_t kLaneLit = B2B_LANE_LIT;       // literal bytes a lane copies by itself
 constexpr uint32_t kLaneMatch = B2B_LANE_MATCH;   // longest match a lane copies by itself
@@ -153,7 +183,7 @@ __device__ __forceinline__ int warp_copy_batch(const uint8_t *__restrict__ src, 
         tails &= tails - 1;
         const uint32_t dj = __shfl_sync(0xffffffffu, excl, j), sj = __shfl_sync(0xffffffffu, lrel, j);
         const uint32_t lj = __shfl_sync(0xffffffffu, ll, j);
-        warp_copy(dst + op + dj + kLaneLit, src + batch_ip + sj + kLaneLit, lj - kLaneLit, lane);
+        warp_copy_short(dst + op + dj + kLaneLit, src + batch_ip + sj + kLaneLit, lj - kLaneLit, lane);
     }
     __syncwarp();
     // ---- matches
@@ -166,14 +196,16 @@ __device__ __forceinline__ int warp_copy_batch(const uint8_t *__restrict__ src, 
     {
         uint8_t *m0 = dst + mpos;
         const uint8_t *ms = m0 - off;                     // all reads stay inside [ms, m0)
-        uint32_t k = 0;
-        for (uint32_t i0 = 0; i0 < maxpm; i0 += 4) {
-            uint32_t v[4];
+        {
+            uint32_t k = 0;
+            for (uint32_t i0 = 0; i0 < maxpm; i0 += 4) {
+                uint32_t v[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (i0 + q < pm) { v[q] = ms[k]; k = (k + 1 == off) ? 0u : k + 1; }
+                for (int q = 0; q < 4; q++)
+                    if (i0 + q < pm) { v[q] = ms[k]; k = (k + 1 == off) ? 0u : k + 1; }
 #pragma unroll
-            for (int q = 0; q < 4; q++) if (i0 + q < pm) m0[i0 + q] = (uint8_t)v[q];
+                for (int q = 0; q < 4; q++) if (i0 + q < pm) m0[i0 + q] = (uint8_t)v[q];
+            }
         }
     }
     uint32_t rest = __ballot_sync(0xffffffffu, act && !indep);
@@ -183,7 +215,7 @@ __device__ __forceinline__ int warp_copy_batch(const uint8_t *__restrict__ src, 
         const uint32_t pj = __shfl_sync(0xffffffffu, mpos, j), oj = __shfl_sync(0xffffffffu, off, j);
         const uint32_t mj = __shfl_sync(0xffffffffu, ml, j);
         __syncwarp();
-        warp_match_copy(dst + pj, oj, mj, lane);
+        warp_match_copy_short(dst + pj, oj, mj, lane);
     }
     op += total;
     return 0;
