@@ -46,7 +46,7 @@ def peaks():
 def committed_traffic(kernel, bytes_per_gpu):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed
     ncu --set full capture, if that capture was taken at this launch size (else None)."""
-    p = os.path.join(ROOT, "profiles", "r01d_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r01g_traffic.json")
     try:
         with open(p) as f:
             t = json.load(f)
@@ -369,9 +369,9 @@ def run_gpu(args):
                     "unit": "GB/s", "frac": algo_c / (enc_avg / 1e3) / 1e9 / peak, "traffic": traffic,
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": algo_c,
-                    "traffic_source": "profiles/r01d_traffic.json (ncu --set full at this launch size)" if traffic else None,
+                    "traffic_source": "profiles/r01g_traffic.json (ncu --set full at this launch size)" if traffic else None,
                     "note": "dominant kernel of the step; it is issue/latency-bound (per-lane LZ4 match search over a "
-                            "shared-memory hash table), not HBM-bound: DESIGN.md section 4 and profiles/r01d_ncu_summary.md"}
+                            "shared-memory hash table), not HBM-bound: DESIGN.md section 4 and profiles/r01g_ncu_summary.md"}
         # e2e through the host-pointer C ABI with pinned host buffers
         e2e = run_e2e(torch, pkg, ctx, args, dev, src, nf, total, world)
         # CPU baseline (oracle port), bounded sample, on all host cores
