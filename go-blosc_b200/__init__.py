@@ -36,7 +36,7 @@ MIN_HEADER_SIZE = 16
 (OK, EINVALID_DATA, EINVALID_HEADER, EINVALID_VERSION, EINVALID_CODEC, ESIZE_MISMATCH,
  EDATA_TOO_LARGE, ECOMPRESSION_FAILED, EDECOMPRESSION_FAILED, ECUDA, EUNSUPPORTED,
  EDST_TOO_SMALL, EINVAL) = range(13)
-OPT_REF_MEMCPY_QUIRK, OPT_FILTER_CTAS_PER_SM, OPT_HOST_STAGE_BYTES, OPT_HASH_LOG, OPT_KERNEL_TIMING = 1, 2, 3, 4, 5
+OPT_REF_MEMCPY_QUIRK, OPT_FILTER_CTAS_PER_SM, OPT_HOST_STAGE_BYTES, OPT_HASH_LOG, OPT_KERNEL_TIMING, OPT_HASH_BYTES = 1, 2, 3, 4, 5, 6
 
 
 class Codec(enum.IntEnum):   # blosc.go:55-64

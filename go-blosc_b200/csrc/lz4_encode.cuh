@@ -32,6 +32,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef B2B_TRACE
+#define B2B_TRACE(...) ((void)0)      // tests/emu only: event hook of the CPU shim, nothing in the CUDA build
+#endif
+
 namespace b2b {
 
 constexpr uint32_t kSegBytes = 65536;
@@ -99,6 +103,16 @@ __device__ __forceinline__ void wv_load64(const WordView &v, uint32_t p, uint32_
     hi = __funnelshift_r(w1, w2, a << 3);
 }
 
+// 8 bytes at position p and the byte after them (still three aligned loads)
+__device__ __forceinline__ void wv_load72(const WordView &v, uint32_t p, uint32_t &lo, uint32_t &hi, uint32_t &b8) {
+    const uint32_t a = p + v.sh;
+    const uint32_t *q = v.w + (a >> 2);
+    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+    lo = __funnelshift_r(w0, w1, a << 3);
+    hi = __funnelshift_r(w1, w2, a << 3);
+    b8 = (w2 >> ((a & 3u) << 3)) & 0xFFu;
+}
+
 // the same in two halves, so that the loads can be issued one turn before their use
 __device__ __forceinline__ void wv_issue64(const WordView &v, uint32_t p, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
     const uint32_t *q = v.w + ((p + v.sh) >> 2);
@@ -109,6 +123,20 @@ __device__ __forceinline__ void wv_finish64(const WordView &v, uint32_t p, uint3
     const uint32_t a = (p + v.sh) << 3;
     lo = __funnelshift_r(w0, w1, a);
     hi = __funnelshift_r(w1, w2, a);
+}
+
+// Hash of the window at a position: lo = its first 4 bytes, hi = the bytes after them.  HB = bytes hashed:
+//   4  typed arrays behind a byte shuffle (short matches count; the default)
+//   5  unshuffled input: a 4-byte context is too ambiguous in text and in low-entropy integers (the most recent
+//      occurrence is rarely the longest one); the reference compressor hashes 6 bytes
+//   6  the reference's own width
+// phase: position inside a bit-shuffle group (0 otherwise): after the bit shuffle byte k of group g is only
+// comparable with byte k of an earlier group, so the place is part of the key (candidates at offsets 8T * j).
+template <int HB>
+__device__ __forceinline__ uint32_t enc_hash(uint32_t lo, uint32_t hi, uint32_t phase) {
+    if constexpr (HB == 4) return (lo ^ (phase * 0x9E3779B1u)) * 2654435761u;
+    else if constexpr (HB == 5) return (lo ^ (((hi & 0xFFu) | (phase << 8)) * 0x9E3779B1u)) * 2654435761u;
+    else return (lo ^ (((hi & 0xFFFFu) | (phase << 16)) * 0x9E3779B1u)) * 2654435761u;
 }
 
 // writes a length extension (value already reduced by 15) at out, returns bytes written
@@ -259,13 +287,16 @@ struct LaneLists {
 // is resolved with shuffles, and the selected sequences are written by their own lanes at
 // offsets from a warp prefix sum.  Only the first sequence of a step (its literals may reach
 // far back) and a match longer than the per-lane bound go through the 32-lane-wide path.
-template <int HL>
+template <int HL, int HB, bool PH>
 __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict__ org, uint32_t W,
                                                        uint32_t L, uint64_t tail,
                                                        uint8_t *__restrict__ body, uint32_t *table,
                                                        LaneLists *lists, int lane, uint32_t dense_lits,
                                                        uint32_t strip_full, uint32_t strip_cap, bool cold_start,
-                                                       uint32_t writer_min_lits) {
+                                                       uint32_t writer_min_lits, uint32_t ph0_, uint32_t phmask_) {
+    // PH: the input is bit-shuffled and the frame is long enough for it to matter: ph0 = place of org inside a
+    // group, phmask = group size - 1 (a power of two); both zero (and folded away) otherwise
+    const uint32_t ph0 = PH ? ph0_ : 0u, phmask = PH ? phmask_ : 0u;
     EncState st;
     st.body = body; st.op = 0; st.have_first = false;
     st.m.first_ll = L; st.m.body_len = 0; st.m.trail_ll = L; st.m.info = 0;
@@ -290,7 +321,9 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t q = q0 + 4u * ((uint32_t)j * kWarp + (uint32_t)lane);
-            hv[j] = q < Wsparse ? wv_load32(in, q) * 2654435761u : 0u;
+            uint32_t wlo = 0, whi = 0;
+            if (q < Wsparse) wv_load64(in, q, wlo, whi);
+            hv[j] = enc_hash<HB>(wlo, whi, (ph0 + q) & phmask);
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -304,7 +337,9 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t q = q0 + (uint32_t)j * kWarp + (uint32_t)lane;
-            hv[j] = q + 3 < W ? wv_load32(in, q) * 2654435761u : 0u;
+            uint32_t wlo = 0, whi = 0;
+            if (q + 3 < W) wv_load64(in, q, wlo, whi);
+            hv[j] = enc_hash<HB>(wlo, whi, (ph0 + q) & phmask);
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -344,14 +379,23 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             uint32_t xa0 = 0, xa1 = 0, xa2 = 0, xb0 = 0, xb1 = 0, xb2 = 0;
             {   // the next step's strips: bring their lines into L2 while this step is parsed
                 const uint32_t a = si + nlanes * strip + 64u * (uint32_t)lane;
+#ifdef __CUDA_ARCH__
                 if (a < mlimit) asm volatile("prefetch.global.L2 [%0];" ::"l"(org + a));
+#else
+                (void)a;
+#endif
             }
             while (__any_sync(0xffffffffu, ext || pos < send)) {
                 if (!ext) {
+#ifdef B2B_EXP_DEAD
+                    if (pos < send && phmask) { const uint32_t phs = (ph0 + pos) & phmask; if (phs + 3 < B2B_EXP_DEAD) { pos += B2B_EXP_DEAD - 3 - phs; if (pos > send) pos = send; } }
+#endif
                     if (pos < send) {
                         // ---- four consecutive positions per turn: one 12-byte window, four probes in flight
                         uint32_t v0, v1;
-                        wv_load64(in, pos, v0, v1);
+                        uint32_t v2 = 0;
+                        if constexpr (HB == 6) wv_load72(in, pos, v0, v1, v2);
+                        else wv_load64(in, pos, v0, v1);
                         uint32_t seq[4], ent[4], chk[4];
                         seq[0] = v0; seq[1] = __funnelshift_r(v0, v1, 8);
                         seq[2] = __funnelshift_r(v0, v1, 16); seq[3] = __funnelshift_r(v0, v1, 24);
@@ -359,7 +403,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                         uint32_t hh[4];
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
-                            const uint32_t hv = seq[k] * 2654435761u;
+                            const uint32_t hv = enc_hash<HB>(seq[k], __funnelshift_r(v1, v2, 8 * k), (ph0 + pos + k) & phmask);
                             hh[k] = hv >> (32 - HL); chk[k] = (hv >> (17 - HL)) & 0x7FFFu;
                             ent[k] = table[hh[k]];
                         }
@@ -407,6 +451,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                             if (nv > 1 && (seq[1] == seq[0])) { pick = 1; pc = pos; }
                             sure = true;
                         }
+                        B2B_TRACE(1, ph0 + pos, nv, pick, pick >= 0 ? pos + pick - pc : 0, sure);
                         if (pick >= 0) {
                             ext = true; mst = pos + pick; moff = mst - pc; e = sure ? mst + 4 : mst;
                             if (e + 8 <= cap) { wv_issue64(in, e, xa0, xa1, xa2); wv_issue64(in, e - moff, xb0, xb1, xb2); }
@@ -650,8 +695,9 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
         }
         const uint32_t p = si + (uint32_t)lane * stride;
         const bool valid = p < mfl;
-        const uint32_t seq = valid ? wv_load32(in, p) : 0u;
-        const uint32_t hv = seq * 2654435761u;
+        uint32_t seq = 0, seq_hi = 0;
+        if (valid) wv_load64(in, p, seq, seq_hi);
+        const uint32_t hv = enc_hash<HB>(seq, seq_hi, (ph0 + p) & phmask);
         const uint32_t h = hv >> (32 - HL);
         const uint32_t chk = (hv >> (17 - HL)) & 0x7FFFu;
         const uint32_t ent = table[h];
@@ -716,6 +762,8 @@ struct EncodeArgs {
     unsigned long long *ticket; // zero before launch
     uint32_t tune[4];           // experiment knobs (0: default)
     uint32_t independent;       // 1: no warm-up window, segments never reference each other (decode index)
+    uint32_t phase_mask;        // 8 * typesize - 1 when the input went through the bit shuffle and that is a power of two
+                                // (candidates are then looked for at the same place of an earlier group only), else 0
     uint32_t planes;            // typesize when the input went through the byte shuffle (plane = len / typesize), else 0
     uint64_t comp_cap, seg_cap; // bytes of `comp`, entries of `meta`: sized from the caller's total_src_bytes; a frame
                                 // that does not fit (sources that overlap, a bound that was not one) is skipped
@@ -727,10 +775,14 @@ __device__ __forceinline__ bool frame_fits_scratch(uint64_t comp_off, uint64_t s
     return comp_off + frame_slot_bytes(n) <= comp_cap && seg_base + seg_count(n) <= seg_cap;
 }
 
-template <int HL>
+template <int HL, int HB, bool PH>
 __global__ void __launch_bounds__(kEncThreads, HL <= 10 ? 7 : (HL == 11 ? 5 : (HL == 12 ? 2 : 1)))
 lz4_encode_kernel(EncodeArgs a) {
+#ifndef B2B_EMU
     extern __shared__ __align__(16) uint32_t enc_tables[];   // kEncWarps x 2^HL entries
+#else
+    static uint32_t enc_tables[kEncWarps << 13];             // tests/emu: the CPU shim has no dynamic shared memory
+#endif
     __shared__ LaneLists enc_lists[kEncWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t items = (uint64_t)a.nframes * a.segs_grid;
@@ -747,6 +799,8 @@ lz4_encode_kernel(EncodeArgs a) {
         const uint32_t nseg = seg_count(n);
         const uint8_t *frame = a.in + a.src_off[f];
         if (!frame_fits_scratch(a.comp_off[f], a.seg_base[f], n, a.comp_cap, a.seg_cap)) continue;
+        // short frames are mostly the raw tail the bit shuffle leaves alone: no place in the key there
+        const uint32_t pmask = (PH && n >= 32u * (a.phase_mask + 1u)) ? a.phase_mask : 0u;
         for (uint32_t s = s0; s < nseg; s += a.segs_grid) {
             const uint32_t B = s * kSegBytes;
             const uint32_t L = n - B < kSegBytes ? n - B : kSegBytes;
@@ -754,13 +808,13 @@ lz4_encode_kernel(EncodeArgs a) {
             // tail of the previous plane (another byte of the element): no warm-up window there
             const bool plane_start = a.planes > 1 && B % (n / a.planes) == 0;
             const uint32_t W = (a.independent || plane_start) ? 0u : (B < kWarmBytes ? B : kWarmBytes);
-            const SegMeta m = warp_encode_segment<HL>(frame + B - W, W, L, (uint64_t)n - B - L,
+            const SegMeta m = warp_encode_segment<HL, HB, PH>(frame + B - W, W, L, (uint64_t)n - B - L,
                                                       a.comp + a.comp_off[f] + (uint64_t)s * kSegSlot,
                                                       enc_tables + ((size_t)warp << HL), &enc_lists[warp], lane,
                                                       a.tune[0] ? a.tune[0] : 256u,
                                                       a.tune[1] ? (a.tune[1] < 64u ? a.tune[1] : 64u) : kStrip,
                                                       a.tune[2] ? a.tune[2] : kStripCap, B == 0,
-                                                      a.tune[3] ? a.tune[3] - 1u : 2u);
+                                                      a.tune[3] ? a.tune[3] - 1u : 2u, (B - W) & pmask, pmask);
             if (lane == 0) a.meta[a.seg_base[f] + s] = m;
             __syncwarp();
         }

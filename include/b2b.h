@@ -104,11 +104,17 @@ enum {
     B2B_OPT_FILTER_CTAS_PER_SM = 2,
     /* host batch path: bytes of uncompressed data per pipeline chunk (0 = default 128 MiB; 4 chunks in flight) */
     B2B_OPT_HOST_STAGE_BYTES = 3,
-    /* log2 of the LZ4 match-finder's shared-memory hash table, 11..14 (0 = default 12).  Larger
-     * tables find more matches (ratio) and cost occupancy (speed). */
+    /* log2 of the LZ4 match-finder's per-warp shared-memory hash table: 10..13, or 0 = automatic
+     * (10 behind a byte or bit shuffle; 12 for unshuffled input, where the history has to reach
+     * further).  Larger tables find more matches (ratio) and cost resident warps (speed). */
     B2B_OPT_HASH_LOG = 4,
     /* 1: bracket every kernel launch with CUDA events on its stream (see b2b_kernel_stats) */
-    B2B_OPT_KERNEL_TIMING = 5
+    B2B_OPT_KERNEL_TIMING = 5,
+    /* bytes of input the match finder hashes per position: 4, 5 or 6, or 0 = automatic (4 behind a
+     * shuffle, 5 for unshuffled input: the most recent occurrence of a 4-byte context is rarely the
+     * longest one in text or low-entropy integers; the reference compressor hashes 6).  5 needs
+     * B2B_OPT_HASH_LOG >= 11 and 6 needs >= 12 (smaller tables are raised to that). */
+    B2B_OPT_HASH_BYTES = 6
 };
 B2B_API int b2b_set_option(b2b_ctx *ctx, int option, int64_t value);
 /* pre-size the device scratch arena so that later calls do not allocate */

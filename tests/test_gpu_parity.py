@@ -238,6 +238,7 @@ def test_compressed_size_within_one_percent_of_oracle(ctx, orc):
         "C1 ramp + Shuffle T=4": (dg.ramp(100000), 1, 4),
         "f32 i*0.001 + Shuffle T=4": (dg.f32_ramp(n // 4, 0.001), 1, 4),
         "text NoShuffle": (dg.text_like(n, 9), 0, 1),
+        "lowent int16 NoShuffle": (dg.lowent_i16(n // 2, 3), 0, 1),
     }
     report = {}
     for name, (data, sh, T) in cases.items():
@@ -245,13 +246,14 @@ def test_compressed_size_within_one_percent_of_oracle(ctx, orc):
         rc, ref = orc.compress(data, orc.LZ4, 5, sh, T)
         report[name] = (mine, int(ref.size), mine / ref.size)
     print("\ncompressed size gpu vs oracle:", json.dumps(report, indent=1))
-    # north_star bar: within 1% of the reference (here: of the restated compressor).  Met at the
-    # default table size (2^10 entries) on C1/C3/C5 and beaten by 1.5-8% with B2B_OPT_HASH_LOG = 11.
-    # The bit-shuffled C4 field (one 8..19-byte match per 64-byte group, found at offset 64*j) pays
-    # ~3.5% for the small shared-memory table and the strip-parallel parse; a larger table narrows
-    # it a little at the cost of resident warps.  DESIGN.md has the numbers.  Text (NoShuffle, not a
-    # BASELINE config) is reported, loosely bounded.
-    bound = {"C4 smooth f64 + BitShuffle T=8": 1.04, "text NoShuffle": 1.25, "f32 i*0.001 + Shuffle T=4": 1.10}
+    # north_star bar: within 1% of the reference (here: of the restated compressor).  Met on C1/C3/C5.
+    # Not met on the bit-shuffled C4 field (1.030): the oracle's second match of a 64-byte group comes from
+    # up to 64 KiB back (half of them from more than 1 KiB), which needs its 2^16-entry table and 6-byte hash
+    # (a scalar greedy parse with this kernel's 2^10 entries and 4-byte hash gives the same 1.03; DESIGN.md
+    # section 4 has the sweep), and a table of that reach does not fit a warp's share of shared memory.
+    # Unshuffled input (not a BASELINE config) runs with a 2^12 table and a 5-byte hash by default.
+    bound = {"C4 smooth f64 + BitShuffle T=8": 1.032, "text NoShuffle": 1.09, "f32 i*0.001 + Shuffle T=4": 1.01,
+             "lowent int16 NoShuffle": 1.06}
     for name, (mine, ref, ratio) in report.items():
         assert mine <= ref * bound.get(name, 1.01) + 16, (name, mine, ref)
     ctx.set_option(4, 13)
@@ -261,7 +263,7 @@ def test_compressed_size_within_one_percent_of_oracle(ctx, orc):
     finally:
         ctx.set_option(4, 0)
     print("C4 with hash_log=13:", mine, report["C4 smooth f64 + BitShuffle T=8"][1])
-    assert mine <= report["C4 smooth f64 + BitShuffle T=8"][1] * 1.035
+    assert mine <= report["C4 smooth f64 + BitShuffle T=8"][1] * 1.03
 
 
 # ---- K4: oracle / liblz4 frames into the GPU decoder ------------------------------------------------
