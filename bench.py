@@ -33,6 +33,7 @@ import __graft_entry__ as entry  # noqa: E402
 FRAME = 262144
 METRIC = "shuffle+LZ4 compress+decompress round trip, uncompressed GB/s (device resident)"
 UNIT = "GB/s"
+TRAFFIC_FILE = "r01g_traffic.json"      # dram bytes per launch from the committed ncu --set full capture
 
 
 def peaks():
@@ -46,7 +47,7 @@ def peaks():
 def committed_traffic(kernel, bytes_per_gpu):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed
     ncu --set full capture, if that capture was taken at this launch size (else None)."""
-    p = os.path.join(ROOT, "profiles", "r01g_traffic.json")
+    p = os.path.join(ROOT, "profiles", TRAFFIC_FILE)
     try:
         with open(p) as f:
             t = json.load(f)
@@ -222,6 +223,278 @@ def run_reference(args):
     return 0
 
 
+
+# ---------------------------------------------------------------------------------------------
+# The other BASELINE.json configs (C1, C2, C4 on one GPU; C5 sharded over the ranks)
+# ---------------------------------------------------------------------------------------------
+def timed(torch, fn, warm=3, reps=10):
+    """best / median device ms of fn() (CUDA events on the current stream)."""
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[0], ts[len(ts) // 2]
+
+
+def config_c1(pkg, ctx, orc):
+    """C1 README example: 100 000 B ramp, LZ4 level 5, Shuffle1 typesize 4, ONE call of Compress / Decompress with
+    host slices (b2b_compress / b2b_decompress): a latency config."""
+    data = (np.arange(100000) % 256).astype(np.uint8)
+    fr = ctx.compress(data, pkg.Codec.LZ4, 5, pkg.Shuffle.Shuffle1, 4)
+    back = ctx.decompress(fr)
+    tc, td = [], []
+    for _ in range(30):
+        t0 = time.perf_counter(); fr = ctx.compress(data, pkg.Codec.LZ4, 5, pkg.Shuffle.Shuffle1, 4); t1 = time.perf_counter()
+        back = ctx.decompress(fr); t2 = time.perf_counter()
+        tc.append(t1 - t0); td.append(t2 - t1)
+    rc, ref = orc.compress(data, orc.LZ4, 5, orc.SHUFFLE, 4)
+    rc2, via_oracle = orc.decompress(np.frombuffer(fr, dtype=np.uint8))
+    t0 = time.perf_counter()
+    for _ in range(20):
+        orc.compress(data, orc.LZ4, 5, orc.SHUFFLE, 4)
+    cpu_c = (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(20):
+        orc.decompress(ref)
+    cpu_d = (time.perf_counter() - t0) / 20
+    ok = back == data.tobytes() and rc2 == 0 and np.array_equal(via_oracle, data) and bytes(fr[:12]) == ref[:12].tobytes()
+    tc.sort(); td.sort()
+    return {"workload": "C1: README example, 100 000 B ramp, LZ4 level 5 + Shuffle1 typesize 4, one Compress / Decompress call "
+                        "with host buffers (b2b_compress / b2b_decompress)",
+            "frame_bytes": len(fr), "oracle_frame_bytes": int(ref.size), "header": bytes(fr[:16]).hex(),
+            "compress_us": 1e6 * tc[0], "decompress_us": 1e6 * td[0], "compress_us_median": 1e6 * tc[len(tc) // 2],
+            "decompress_us_median": 1e6 * td[len(td) // 2], "round_trip_us": 1e6 * (tc[0] + td[0]),
+            "cpu_port_one_thread_us": {"compress": 1e6 * cpu_c, "decompress": 1e6 * cpu_d},
+            "verified": bool(ok)}
+
+
+def latency_curve(pkg, ctx, orc, sizes=(4 << 10, 64 << 10, 1 << 20, 16 << 20, 256 << 20)):
+    """Single-call latency / throughput of b2b_compress + b2b_decompress against the CPU port on one thread."""
+    out = []
+    for n in sizes:
+        data = gen_field_host(n // 4, seed=n)
+        reps = 10 if n <= (1 << 20) else 3
+        fr = ctx.compress(data, pkg.Codec.LZ4, 5, pkg.Shuffle.Shuffle1, 4)
+        best_c = best_d = 1e9
+        for _ in range(reps):
+            t0 = time.perf_counter(); fr = ctx.compress(data, pkg.Codec.LZ4, 5, pkg.Shuffle.Shuffle1, 4); t1 = time.perf_counter()
+            back = ctx.decompress(fr); t2 = time.perf_counter()
+            best_c, best_d = min(best_c, t1 - t0), min(best_d, t2 - t1)
+        ok = back == data.tobytes()
+        creps = 3 if n <= (16 << 20) else 1
+        t0 = time.perf_counter()
+        for _ in range(creps):
+            rc, ref = orc.compress(data, orc.LZ4, 5, orc.SHUFFLE, 4)
+        t1 = time.perf_counter()
+        for _ in range(creps):
+            orc.decompress(ref)
+        t2 = time.perf_counter()
+        out.append({"bytes": n, "gpu_compress_us": 1e6 * best_c, "gpu_decompress_us": 1e6 * best_d,
+                    "cpu_compress_us": 1e6 * (t1 - t0) / creps, "cpu_decompress_us": 1e6 * (t2 - t1) / creps,
+                    "gpu_round_trip_gbs": n / (best_c + best_d) / 1e9, "cpu_round_trip_gbs": n / ((t2 - t0) / creps) / 1e9,
+                    "verified": bool(ok)})
+    return out
+
+
+def config_c2(torch, pkg, ctx, orc, dev, stream, peak, nbytes=4 << 30):
+    """C2: Shuffle1 / unshuffle only (ShuffleBuffer / UnshuffleBuffer semantics: whole-buffer transform, plane stride
+    n / T), typesize 1, 2, 4, 8, 16 on the SAME 4 GiB float buffer.  Checked on the whole buffer against an independent
+    torch transpose (+ a 64-bit checksum of both) and on 64 random 1 MiB source windows against the oracle."""
+    src = gen_field_device(torch, nbytes // 4, dev, seed=0xC2)
+    dst = torch.empty_like(src)
+    back = torch.empty_like(src)
+    rng = np.random.default_rng(2)
+    res = {"workload": f"C2: Shuffle1 / unshuffle only over typesize 1,2,4,8,16 on one {nbytes / 2**30:g} GiB float32 buffer "
+                       "(whole-buffer transform, plane stride n/T), b2b_shuffle_dev", "bytes": nbytes,
+           "algorithmic_bytes_per_launch": 2 * nbytes, "typesizes": {}}
+    all_ok = True
+    for T in (1, 2, 4, 8, 16):
+        E = nbytes // T
+        fwd = lambda: ctx.shuffle_dev(pkg.Shuffle.Shuffle1, 0, T, src, dst, nbytes, stream)
+        inv = lambda: ctx.shuffle_dev(pkg.Shuffle.Shuffle1, 1, T, dst, back, nbytes, stream)
+        f_best, f_med = timed(torch, fwd)
+        i_best, i_med = timed(torch, inv)
+        torch.cuda.synchronize()
+        # whole buffer: independent torch transpose, byte for byte, and a wrapping 64-bit word sum of both
+        ref = src.view(E, T).t().contiguous().view(-1) if T > 1 else src
+        ok = bool(torch.equal(dst, ref)) and bool(torch.equal(back, src))
+        csum = int(dst.view(torch.int64).sum().item()) & 0xFFFFFFFFFFFFFFFF
+        csum_ref = int(ref.view(torch.int64).sum().item()) & 0xFFFFFFFFFFFFFFFF
+        ok = ok and csum == csum_ref
+        del ref
+        # 64 random windows of 1 MiB of source: the oracle's shuffle of the window is T plane slices of dst
+        m = (1 << 20) // T
+        for _ in range(64 if T > 1 else 4):
+            i0 = int(rng.integers(0, E - m))
+            win = src[i0 * T:(i0 + m) * T].cpu().numpy()
+            want = orc.shuffle(win, T) if T > 1 else win
+            got = torch.cat([dst[j * E + i0:j * E + i0 + m] for j in range(T)]).cpu().numpy()
+            ok = ok and np.array_equal(got, want)
+            ok = ok and np.array_equal(orc.unshuffle(got, T) if T > 1 else got, back[i0 * T:(i0 + m) * T].cpu().numpy())
+        all_ok = all_ok and ok
+        ent = {"shuffle_ms": f_best, "unshuffle_ms": i_best, "shuffle_ms_median": f_med, "unshuffle_ms_median": i_med,
+               "shuffle_gbs_uncompressed": nbytes / f_best / 1e6, "unshuffle_gbs_uncompressed": nbytes / i_best / 1e6,
+               "checksum64": f"{csum:016x}", "verified": bool(ok)}
+        if T > 1:
+            ent["roofline"] = {"bound": "hbm", "unit": "GB/s", "peak": peak,
+                               "shuffle": {"achieved": 2 * nbytes / f_best / 1e6, "frac": 2 * nbytes / f_best / 1e6 / peak},
+                               "unshuffle": {"achieved": 2 * nbytes / i_best / 1e6, "frac": 2 * nbytes / i_best / 1e6 / peak}}
+        else:
+            ent["note"] = "typesize 1 is the identity (shuffle.go:17-19): a device copy, outside the roofline"
+        res["typesizes"][str(T)] = ent
+    res["verified"] = bool(all_ok)
+    del src, dst, back
+    torch.cuda.empty_cache()
+    return res
+
+
+def config_c4(torch, pkg, ctx, orc, dev, stream, peak, want_bytes=16 << 30):
+    """C4: float64 field, LZ4 + BitShuffle typesize 8, 256 KiB frames, at 16 GiB if the device has room (6x the
+    input: source, frames, output, scratch), else the largest power of two that fits.  Throughput on the full set,
+    cross-decode both ways on a sample of frames."""
+    free_b, _ = torch.cuda.mem_get_info()
+    total = want_bytes
+    while total * 6.6 > free_b and total > (1 << 30):
+        total //= 2
+    nf = total // FRAME
+    src = torch.empty(total, dtype=torch.uint8, device=dev)
+    chunk = 1 << 24
+    g = torch.Generator(device=dev); g.manual_seed(0xC4)
+    v = src.view(torch.float64)
+    for lo in range(0, total // 8, chunk):
+        hi = min(total // 8, lo + chunk)
+        i = torch.arange(lo, hi, device=dev, dtype=torch.float64)
+        u = torch.rand(hi - lo, device=dev, generator=g, dtype=torch.float64) * 2 - 1
+        v[lo:hi] = torch.sin(2 * torch.pi * i / 4096) + 0.25 * torch.sin(2 * torch.pi * i / 333.3) + 1e-3 * u
+    d_off = torch.arange(nf, dtype=torch.int64, device=dev) * FRAME
+    d_len = torch.full((nf,), FRAME, dtype=torch.int32, device=dev)
+    cap = total + 32 * nf + 64
+    d_c = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_foff = torch.empty(nf, dtype=torch.int64, device=dev); d_flen = torch.empty(nf, dtype=torch.int32, device=dev)
+    d_st = torch.empty(nf, dtype=torch.int32, device=dev); d_st2 = torch.empty(nf, dtype=torch.int32, device=dev)
+    d_tot = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_out = torch.empty(total, dtype=torch.uint8, device=dev); d_olen = torch.empty(nf, dtype=torch.int32, device=dev)
+    comp = lambda: ctx.compress_batch_dev(src, d_off, d_len, nf, total, FRAME, pkg.Shuffle.BitShuffle, 8, d_c, cap, d_foff,
+                                          d_flen, d_st, d_tot, stream)
+    dec = lambda: ctx.decompress_batch_dev(d_c, d_foff, d_flen, nf, 0, d_out, d_off, d_len, total, FRAME, d_olen, d_st2, stream)
+    tc, _ = timed(torch, comp, warm=1, reps=3)
+    td, _ = timed(torch, dec, warm=1, reps=3)
+    torch.cuda.synchronize()
+    ctot = int(d_tot.item())
+    ok = bool((d_st == 0).all()) and bool((d_st2 == 0).all()) and bool(torch.equal(d_out, src))
+    # sampled cross-decode: GPU frames through the oracle (= reference Decompress); oracle frames through the GPU
+    foff, flen = d_foff.cpu().numpy(), d_flen.cpu().numpy()
+    sample = sorted({int(k * (nf - 1) / 31) for k in range(32)})
+    gpu_sz = ref_sz = 0
+    ref_frames = []
+    for f in sample:
+        fr = d_c[int(foff[f]):int(foff[f]) + int(flen[f])].cpu().numpy()
+        raw = src[f * FRAME:(f + 1) * FRAME].cpu().numpy()
+        rc, back = orc.decompress(fr)
+        ok = ok and rc == 0 and np.array_equal(back, raw)
+        rc, ref = orc.compress(raw, orc.LZ4, 5, orc.BITSHUFFLE, 8)
+        ok = ok and fr[:12].tobytes() == ref[:12].tobytes()
+        gpu_sz += fr.size; ref_sz += ref.size
+        ref_frames.append((raw, ref))
+    blob = np.concatenate([r for _, r in ref_frames])
+    r_len = np.array([r.size for _, r in ref_frames], dtype=np.uint32)
+    r_off = np.concatenate([[0], np.cumsum(r_len[:-1], dtype=np.uint64)]).astype(np.uint64)
+    o_off = np.arange(len(ref_frames), dtype=np.uint64) * FRAME
+    out, olen, st = ctx.decompress_batch(blob, r_off, r_len, o_off, len(ref_frames) * FRAME)
+    ok = ok and not st.any() and np.array_equal(out, np.concatenate([r for r, _ in ref_frames]))
+    algo = total + ctot                                               # n + (16 + c) per frame
+    res = {"workload": f"C4: float64 smooth field, {total / 2**30:g} GiB = {nf} frames x 256 KiB, LZ4 + BitShuffle typesize 8 "
+                       f"({want_bytes / 2**30:g} GiB named; sized to the free device memory)", "bytes": total,
+           "compress_gbs": total / tc / 1e6, "decompress_gbs": total / td / 1e6, "compress_ms": tc, "decompress_ms": td,
+           "round_trip_gbs": total / (tc + td) / 1e6, "compressed_fraction": ctot / total,
+           "size_vs_oracle_32_frames": gpu_sz / ref_sz,
+           "cross_decode": f"{len(sample)} GPU frames decoded by the oracle (reference Decompress semantics), "
+                           f"{len(sample)} oracle frames decoded by the GPU",
+           "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "algorithmic_bytes_per_pass": algo,
+                        "compress": {"achieved": algo / tc / 1e6, "frac": algo / tc / 1e6 / peak},
+                        "decompress": {"achieved": algo / td / 1e6, "frac": algo / td / 1e6 / peak}},
+           "verified": bool(ok)}
+    del src, d_c, d_out
+    torch.cuda.empty_cache()
+    return res
+
+
+C5_SIZES_KIB = (32, 64, 128, 256, 512, 1024, 2048)
+
+
+def config_c5(torch, dist, pkg, ctx, orc, par, dev, stream, peak, rank, world, per_gpu_bytes=2 << 30):
+    """C5: mixed workload, Shuffle1 typesize 2, frame sizes cycling 32 KiB .. 2 MiB, random bytes (-> memcpy flag)
+    alternating with low-entropy int16; the GLOBAL frame list is sharded contiguously over the ranks."""
+    lens = []
+    acc = 0
+    i = 0
+    while acc + (C5_SIZES_KIB[i % 7] << 10) <= per_gpu_bytes * world:
+        lens.append(C5_SIZES_KIB[i % 7] << 10); acc += lens[-1]; i += 1
+    lo, hi = par.shard_range(len(lens), rank, world)
+    mine = np.array(lens[lo:hi], dtype=np.uint32)
+    nf = len(mine)
+    total = int(mine.sum())
+    offs = np.concatenate([[0], np.cumsum(mine[:-1], dtype=np.uint64)]).astype(np.uint64)
+    g = torch.Generator(device=dev); g.manual_seed(0xC5 + rank)
+    src = torch.randint(0, 8, (total // 2,), device=dev, generator=g, dtype=torch.int16).view(torch.uint8)
+    for k in range(nf):
+        if (lo + k) % 2 == 0:                                          # even global frames: random bytes
+            a = int(offs[k])
+            src[a:a + int(mine[k])] = torch.randint(0, 256, (int(mine[k]),), device=dev, generator=g, dtype=torch.uint8)
+    d_off = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    d_len = torch.from_numpy(mine.astype(np.int32)).to(dev)
+    cap = total + 32 * nf + 64
+    d_c = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_foff = torch.empty(nf, dtype=torch.int64, device=dev); d_flen = torch.empty(nf, dtype=torch.int32, device=dev)
+    d_st = torch.empty(nf, dtype=torch.int32, device=dev); d_st2 = torch.empty(nf, dtype=torch.int32, device=dev)
+    d_tot = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_out = torch.empty(total, dtype=torch.uint8, device=dev); d_olen = torch.empty(nf, dtype=torch.int32, device=dev)
+    mx = int(mine.max())
+    comp = lambda: ctx.compress_batch_dev(src, d_off, d_len, nf, total, mx, pkg.Shuffle.Shuffle1, 2, d_c, cap, d_foff, d_flen,
+                                          d_st, d_tot, stream)
+    dec = lambda: ctx.decompress_batch_dev(d_c, d_foff, d_flen, nf, 0, d_out, d_off, d_len, total, mx, d_olen, d_st2, stream)
+    comp(); dec(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    tc, _ = timed(torch, comp, warm=1, reps=3)
+    td, _ = timed(torch, dec, warm=1, reps=3)
+    torch.cuda.synchronize()
+    ctot = int(d_tot.item())
+    ok = bool((d_st == 0).all()) and bool((d_st2 == 0).all()) and bool(torch.equal(d_out, src))
+    foff, flen = d_foff.cpu().numpy(), d_flen.cpu().numpy()
+    for f in sorted({int(k * (nf - 1) / 7) for k in range(8)}):          # memcpy flag on the random frames, oracle decode
+        fr = d_c[int(foff[f]):int(foff[f]) + int(flen[f])].cpu().numpy()
+        ok = ok and bool(fr[2] & 2) == ((lo + f) % 2 == 0)
+        rc, back = orc.decompress(fr)
+        ok = ok and rc == 0 and np.array_equal(back, src[int(offs[f]):int(offs[f]) + int(mine[f])].cpu().numpy())
+    t = torch.tensor([tc, td, float(total), float(ctot), 1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+    per_rank = None
+    if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [[float(x) for x in a.tolist()] for a in allt]
+    else:
+        per_rank = [[float(x) for x in t.tolist()]]
+    tc_max = max(p[0] for p in per_rank); td_max = max(p[1] for p in per_rank)
+    bytes_all = sum(p[2] for p in per_rank); c_all = sum(p[3] for p in per_rank)
+    algo = bytes_all + c_all
+    return {"workload": f"C5: mixed, Shuffle1 typesize 2, frames cycling 32 KiB..2 MiB, random (memcpy flag) alternating with "
+                        f"low-entropy int16, {bytes_all / 2**30:.2f} GiB over {world} GPU(s), global frame list sharded "
+                        "contiguously (no data-path collective)",
+            "bytes": bytes_all, "frames": len(lens), "compress_gbs": bytes_all / tc_max / 1e6, "decompress_gbs": bytes_all / td_max / 1e6,
+            "round_trip_gbs": bytes_all / (tc_max + td_max) / 1e6, "compressed_fraction": c_all / bytes_all,
+            "per_rank": [{"bytes": p[2], "compress_ms": p[0], "decompress_ms": p[1]} for p in per_rank],
+            "imbalance": {"compress_max_over_mean": tc_max / (sum(p[0] for p in per_rank) / world),
+                          "decompress_max_over_mean": td_max / (sum(p[1] for p in per_rank) / world)},
+            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak * world, "algorithmic_bytes_per_pass": algo,
+                         "compress": {"achieved": algo / tc_max / 1e6, "frac": algo / tc_max / 1e6 / (peak * world)},
+                         "decompress": {"achieved": algo / td_max / 1e6, "frac": algo / td_max / 1e6 / (peak * world)}},
+            "verified": all(p[4] > 0.5 for p in per_rank)}
+
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
@@ -326,10 +599,11 @@ def run_gpu(args):
     bytes_all = float(total) * world
     value = bytes_all / (ms_step / 1e3) / 1e9
 
-    line = None
+    orc = entry.load_oracle()          # the checker: sampled cross-checks below, outside every timed region
+    orc.build()
+    sizes = None
     if rank == 0:
-        # oracle cross-check of a few frames of this rank (outside the timed region)
-        orc = entry.load_oracle()
+        # oracle cross-check of a few frames of this rank
         foff, flen = d_foff.cpu().numpy(), d_flen.cpu().numpy()
         gpu_sz = ref_sz = 0
         for f in sorted({int(k * (nf - 1) / 63) for k in range(64)}):   # 64 frames spread over the batch
@@ -341,7 +615,25 @@ def run_gpu(args):
             ok = ok and fr[:12].tobytes() == ref[:12].tobytes()          # identical header fields
             gpu_sz += fr.size; ref_sz += ref.size
         sizes = gpu_sz / ref_sz
-        peak, peak_src = peaks()
+    # e2e through the host-pointer C ABI (every rank: the ranks share the host's PCIe / memory path)
+    e2e = run_e2e(torch, pkg, ctx, args, dev, src, nf, total, world)
+    peak, peak_src = peaks()
+    # the other BASELINE configs: C5 sharded over the ranks; C1 / C2 / C4 are one-GPU configs
+    del src, d_c, d_out
+    torch.cuda.empty_cache()
+    configs = {}
+    if not args.no_configs:
+        configs["C5"] = config_c5(torch, dist, pkg, ctx, orc, par, dev, stream, peak, rank, world,
+                                  per_gpu_bytes=int(args.c5_gib * 2**30))
+        if world == 1:
+            configs["C1"] = config_c1(pkg, ctx, orc)
+            configs["C1"]["latency_curve"] = latency_curve(pkg, ctx, orc)
+            configs["C2"] = config_c2(torch, pkg, ctx, orc, dev, stream, peak, nbytes=int(args.c2_gib * 2**30))
+            configs["C4"] = config_c4(torch, pkg, ctx, orc, dev, stream, peak, want_bytes=int(args.c4_gib * 2**30))
+        for c in configs.values():
+            ok = ok and bool(c.get("verified", False))
+    line = None
+    if rank == 0:
         enc_n, enc_ms = stats["lz4_encode_kernel"]
         dec_n, dec_ms = stats["lz4_decode_kernel"]
         par_n, par_ms = stats.get("lz4_parse_kernel", (0, 0.0))          # K4 = parse kernel + copy kernel
@@ -360,7 +652,8 @@ def run_gpu(args):
         kernels["lz4_decode_kernel"]["achieved_gbs_algorithmic"] = (comp_total + total) / (dec_ms / dec_n / 1e3) / 1e9
         kernels["lz4_decode_kernel"]["frac_of_peak"] = kernels["lz4_decode_kernel"]["achieved_gbs_algorithmic"] / peak
         for kname in ("filter_batch_kernel", "lz4_decode_kernel", "pack_frames_kernel"):
-            kernels[kname]["traffic"] = committed_traffic(kname, total)
+            if kname in kernels:
+                kernels[kname]["traffic"] = committed_traffic(kname, total)
         t_parse = committed_traffic("lz4_parse_kernel", total)
         if kernels["lz4_decode_kernel"]["traffic"] is not None and t_parse is not None:
             kernels["lz4_decode_kernel"]["traffic"] += t_parse                # K4 = both halves
@@ -369,11 +662,9 @@ def run_gpu(args):
                     "unit": "GB/s", "frac": algo_c / (enc_avg / 1e3) / 1e9 / peak, "traffic": traffic,
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": algo_c,
-                    "traffic_source": "profiles/r01g_traffic.json (ncu --set full at this launch size)" if traffic else None,
+                    "traffic_source": f"profiles/{TRAFFIC_FILE} (ncu --set full at this launch size)" if traffic else None,
                     "note": "dominant kernel of the step; it is issue/latency-bound (per-lane LZ4 match search over a "
-                            "shared-memory hash table), not HBM-bound: DESIGN.md section 4 and profiles/r01g_ncu_summary.md"}
-        # e2e through the host-pointer C ABI with pinned host buffers
-        e2e = run_e2e(torch, pkg, ctx, args, dev, src, nf, total, world)
+                            "shared-memory hash table), not HBM-bound: DESIGN.md section 4 and the ncu summaries under profiles/"}
         # CPU baseline (oracle port), bounded sample, on all host cores
         os.sched_setaffinity(0, all_cpus)
         threads = os.cpu_count() or 1
@@ -395,12 +686,10 @@ def run_gpu(args):
                                        f"per task on {threads} pthreads, best of 2",
                              "compress_gbs": cpu["compress_gbs"], "decompress_gbs": cpu["decompress_gbs"],
                              "ratio": cpu["ratio"]},
-            "e2e": e2e, "clocks": clk.summary(),
+            "e2e": e2e, "clocks": clk.summary(), "configs": configs,
         }
         if gather_ms is not None:
             line["allgather_sizes_ms"] = gather_ms
-    else:
-        run_e2e(torch, pkg, ctx, args, dev, src, nf, total, world)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -459,6 +748,10 @@ def main():
     ap.add_argument("--cpu-sample-mib", type=int, default=int(os.environ.get("BENCH_CPU_SAMPLE_MIB", 1024)))
     ap.add_argument("--hash-log", type=int, default=0)
     ap.add_argument("--e2e-stage-mib", type=int, default=int(os.environ.get("BENCH_E2E_STAGE_MIB", 0)))
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs object (C1, C2, C4, C5)")
+    ap.add_argument("--c2-gib", type=float, default=float(os.environ.get("BENCH_C2_GIB", 4)))
+    ap.add_argument("--c4-gib", type=float, default=float(os.environ.get("BENCH_C4_GIB", 16)))
+    ap.add_argument("--c5-gib", type=float, default=float(os.environ.get("BENCH_C5_GIB", 2)), help="C5 bytes per GPU")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture")
     args = ap.parse_args()
