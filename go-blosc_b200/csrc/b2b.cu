@@ -68,6 +68,10 @@ struct b2b_ctx {
     uint64_t opt_stage_bytes = 128ull << 20;
     uint64_t launches = 0;
     std::string last_err;
+    // arena 0 is shared by every device-pointer call: a call on another stream than the previous one waits for it
+    cudaEvent_t ev_arena = nullptr;
+    cudaStream_t arena_stream = nullptr;
+    bool arena_busy = false;
 };
 
 namespace {
@@ -111,6 +115,22 @@ void fold_timings(b2b_ctx *ctx) {
     }
     ctx->pending.clear();
 }
+
+// Device-pointer calls carve their scratch from offset 0 of arena 0 and only enqueue work.  Two calls on the SAME
+// stream are ordered by the stream; a call on a DIFFERENT stream than the previous one first waits for the event the
+// previous call left behind, so that two streams never work in the same scratch at once (ctx->mu held).
+struct ArenaGuard {
+    b2b_ctx *ctx; cudaStream_t s;
+    ArenaGuard(b2b_ctx *c, cudaStream_t st) : ctx(c), s(st) {
+        if (ctx->cur_arena != 0) return;                   // pipeline slots own their arena and stream
+        if (ctx->arena_busy && ctx->arena_stream != s) cudaStreamWaitEvent(s, ctx->ev_arena, 0);
+    }
+    ~ArenaGuard() {
+        if (ctx->cur_arena != 0) return;
+        cudaEventRecord(ctx->ev_arena, s);
+        ctx->arena_stream = s; ctx->arena_busy = true;
+    }
+};
 
 // bump allocator over the ctx arena
 struct Arena {
@@ -212,14 +232,14 @@ int launch_scan(b2b_ctx *ctx, const uint32_t *d_len, uint32_t n, uint64_t *d_off
 int launch_filter(b2b_ctx *ctx, const uint8_t *src, uint8_t *dst, const uint64_t *off,
                   const uint32_t *len, uint64_t uniform_len, uint32_t nframes, uint64_t max_len,
                   const FrameMeta *meta, FrameMeta uniform, const uint32_t *status, int inverse,
-                  cudaStream_t s) {
+                  cudaStream_t s, uint64_t limit = 0) {
     if (nframes == 0) return B2B_OK;
     FilterArgs a;
     a.src = src; a.dst = dst;
     a.ft.off = off; a.ft.len = len; a.ft.uniform_len = uniform_len; a.ft.nframes = nframes;
     a.ft.tiles_per_frame = tiles_for(max_len, nframes, ctx);
     a.meta = meta; a.uniform = uniform; a.status = status; a.inverse = inverse;
-    a.copy_inactive = 1;
+    a.copy_inactive = 1; a.limit = limit;
     const uint64_t grid = (uint64_t)nframes * a.ft.tiles_per_frame;
     { LaunchTimer lt(ctx, K_FILTER, s); filter_batch_kernel<<<(unsigned)grid, kFilterThreads, 0, s>>>(a); }
     CU(ctx, cudaGetLastError());
@@ -296,6 +316,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
                               uint64_t dst_cap, uint64_t *d_frame_off, uint32_t *d_frame_len,
                               uint32_t *d_status, uint64_t *d_total_out, cudaStream_t s,
                               bool raw_block = false, uint64_t *d_index = nullptr, uint32_t segs_per_frame = 0) {
+    ArenaGuard arena_guard(ctx, s);
     if (nframes == 0) {
         if (d_total_out) CU(ctx, cudaMemsetAsync(d_total_out, 0, 8, s));
         return B2B_OK;
@@ -337,7 +358,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     const uint8_t *in = static_cast<const uint8_t *>(d_src);
     if (filtered) {
         rc = launch_filter(ctx, in, d_shuf, d_src_off, d_src_len, 0, nframes, max_len, nullptr, fm,
-                           nullptr, 0, s);
+                           nullptr, 0, s, total_src);
         if (rc) return rc;
         in = d_shuf;
     }
@@ -358,7 +379,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     e.planes = fm.mode == 1 ? fm.typesize : 0u;
     // bit shuffle: the place inside the 8 * typesize group is part of the hash key (lz4_encode.cuh, enc_hash)
     e.phase_mask = (fm.mode == 2 && (fm.typesize & (fm.typesize - 1)) == 0 && fm.typesize <= 512) ? 8u * fm.typesize - 1u : 0u;
-    e.comp_cap = comp_bytes; e.seg_cap = max_segs_total;
+    e.comp_cap = comp_bytes; e.seg_cap = max_segs_total; e.src_cap = filtered ? total_src : ~0ull;
     rc = launch_encode(ctx, e, !filtered, s);
     if (rc) return rc;
 
@@ -369,6 +390,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     fa.final_ll = d_final_ll; fa.final_off = d_final_off; fa.status = d_status;
     fa.index = d_index; fa.segs_per_frame = segs_per_frame;
     fa.comp_off = d_comp_off; fa.comp_cap = comp_bytes; fa.seg_cap = max_segs_total;
+    fa.src_off = d_src_off; fa.src_cap = filtered ? total_src : ~0ull;
     { LaunchTimer lt(ctx, K_FINALIZE, s); finalize_frames_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(fa); }
     CU(ctx, cudaGetLastError());
 
@@ -384,7 +406,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     p.frame_off = d_frame_off; p.dst = static_cast<uint8_t *>(d_dst);
     p.nframes = nframes; p.segs_grid = (uint32_t)segs_grid;
     p.codec = B2B_LZ4; p.typesize_u8 = (uint32_t)(uint8_t)typesize;     // blosc.go:362
-    p.header = raw_block ? 0 : 1;
+    p.header = raw_block ? 0 : 1; p.dst_cap = dst_cap;
     { LaunchTimer lt(ctx, K_PACK, s);
       pack_frames_kernel<<<(unsigned)((uint64_t)nframes * segs_grid), kFilterThreads, 0, s>>>(p); }
     CU(ctx, cudaGetLastError());
@@ -397,6 +419,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
                                 const uint32_t *d_dst_cap, uint64_t total_dst, uint32_t max_orig,
                                 uint32_t *d_out_len, uint32_t *d_status, cudaStream_t s,
                                 const uint64_t *d_index = nullptr, uint32_t segs_per_frame = 0) {
+    ArenaGuard arena_guard(ctx, s);
     if (nframes == 0) return B2B_OK;
     if (!d_frames || !d_frame_off || !d_frame_len || !d_dst || !d_dst_off || !d_dst_cap ||
         !d_out_len || !d_status)
@@ -483,6 +506,7 @@ int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *
                                uint32_t max_len, int shuffle, int64_t typesize, uint32_t blocksize,
                                void *d_dst, uint64_t dst_cap, uint64_t *d_frame_off, uint32_t *d_frame_len,
                                uint32_t *d_status, uint64_t *d_total_out, cudaStream_t s) {
+    ArenaGuard arena_guard(ctx, s);
     if (nframes == 0) {
         if (d_total_out) CU(ctx, cudaMemsetAsync(d_total_out, 0, 8, s));
         return B2B_OK;
@@ -554,7 +578,7 @@ int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *
 
     const uint8_t *in = static_cast<const uint8_t *>(d_src);
     if (filtered) {
-        rc = launch_filter(ctx, in, d_shuf, blk_off, blk_len, 0, nslots, max_blk, nullptr, fm, nullptr, 0, s);
+        rc = launch_filter(ctx, in, d_shuf, blk_off, blk_len, 0, nslots, max_blk, nullptr, fm, nullptr, 0, s, total_src);
         if (rc) return rc;
         in = d_shuf;
     }
@@ -571,7 +595,7 @@ int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *
     for (int i = 0; i < 4; i++) e.tune[i] = ctx->opt_tune[i];
     e.independent = 0; e.planes = 0;
     e.phase_mask = (fm.mode == 2 && (fm.typesize & (fm.typesize - 1)) == 0 && fm.typesize <= 512) ? 8u * fm.typesize - 1u : 0u;
-    e.comp_cap = comp_bytes; e.seg_cap = max_segs_total;
+    e.comp_cap = comp_bytes; e.seg_cap = max_segs_total; e.src_cap = filtered ? total_src : ~0ull;
     rc = launch_encode(ctx, e, !filtered, s);
     if (rc) return rc;
     FinalizeArgs fa;
@@ -581,6 +605,7 @@ int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *
     fa.final_ll = final_ll; fa.final_off = final_off; fa.status = blk_status;
     fa.index = nullptr; fa.segs_per_frame = 0;
     fa.comp_off = comp_off; fa.comp_cap = comp_bytes; fa.seg_cap = max_segs_total;
+    fa.src_off = blk_off; fa.src_cap = filtered ? total_src : ~0ull;
     { LaunchTimer lt(ctx, K_FINALIZE, s); finalize_frames_kernel<<<(nslots + 127) / 128, 128, 0, s>>>(fa); }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemsetAsync(comp_len + nslots, 0, 4, s));
@@ -600,7 +625,7 @@ int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *
     pk.p.comp_off = comp_off; pk.p.seg_base = seg_base; pk.p.meta = d_meta; pk.p.place = d_place;
     pk.p.comp_len = comp_len; pk.p.flags = blk_flags; pk.p.final_ll = final_ll; pk.p.final_off = final_off;
     pk.p.status = blk_status; pk.p.frame_off = nullptr; pk.p.dst = nullptr;
-    pk.p.nframes = nslots; pk.p.segs_grid = 1; pk.p.codec = B2B_LZ4; pk.p.typesize_u8 = T; pk.p.header = 0;
+    pk.p.nframes = nslots; pk.p.segs_grid = 1; pk.p.codec = B2B_LZ4; pk.p.typesize_u8 = T; pk.p.header = 0; pk.p.dst_cap = 0;
     pk.orig = static_cast<const uint8_t *>(d_src); pk.owner = owner; pk.blk_base = blk_base;
     pk.nblk = frm_nblk; pk.bs = frm_bs; pk.blk_pos = blk_pos; pk.src_off = d_src_off; pk.src_len = d_src_len;
     pk.frame_off = d_frame_off; pk.frame_len = d_frame_len; pk.frame_flags = frm_flags; pk.frame_status = d_status;
@@ -615,6 +640,7 @@ int decompress_blocks_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint6
                                  const uint64_t *d_dst_off, const uint32_t *d_dst_cap, uint64_t total_dst,
                                  uint32_t max_orig, uint32_t blocksize, uint32_t *d_out_len,
                                  uint32_t *d_status, cudaStream_t s) {
+    ArenaGuard arena_guard(ctx, s);
     if (nframes == 0) return B2B_OK;
     if (!d_frames || !d_frame_off || !d_frame_len || !d_dst || !d_dst_off || !d_dst_cap || !d_out_len || !d_status)
         return B2B_EINVAL;
@@ -716,6 +742,7 @@ int shuffle_dev_locked(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, co
         if (src != dst) CU(ctx, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s));
         return B2B_OK;
     }
+    ArenaGuard arena_guard(ctx, s);
     uint8_t *out = dst;
     if (src == dst) {  // in place (ShuffleBuffer semantics): transform into scratch, copy back
         int rc = ensure_arena(ctx, n + 4096);
@@ -773,6 +800,7 @@ int b2b_init(int device, b2b_ctx **out) {
               cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_tab, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_arena, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < b2b_ctx::kSlots && ok; i++)
         ok = cudaStreamCreateWithFlags(&ctx->s_k[i], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_in_ready[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -807,6 +835,7 @@ void b2b_destroy(b2b_ctx *ctx) {
         if (ctx->ev_out_free[i]) cudaEventDestroy(ctx->ev_out_free[i]);
     }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->ev_arena) cudaEventDestroy(ctx->ev_arena);
     delete ctx;
 }
 
@@ -949,6 +978,7 @@ int b2b_frame_info_batch_dev(b2b_ctx *ctx, const void *d_frames, const uint64_t 
     cudaStream_t s = (cudaStream_t)stream;
     if (nframes == 0) { if (d_total) CU(ctx, cudaMemsetAsync(d_total, 0, 8, s)); return B2B_OK; }
     if (!d_frames || !d_frame_off || !d_frame_len || !d_orig_len || !d_dst_off || !d_status) return B2B_EINVAL;
+    ArenaGuard arena_guard(ctx, s);
     int rc = ensure_arena(ctx, scan_scratch_bytes(nframes) + 4096);
     if (rc) return rc;
     { LaunchTimer lt(ctx, K_INFO, s);
@@ -1085,6 +1115,7 @@ int b2b_scan_offsets_dev(b2b_ctx *ctx, const uint32_t *d_len, uint32_t n, uint64
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
     if (n && (!d_len || !d_off)) return B2B_EINVAL;
+    ArenaGuard arena_guard(ctx, (cudaStream_t)stream);
     int rc = ensure_arena(ctx, scan_scratch_bytes(n) + 4096);
     if (rc) return rc;
     return launch_scan(ctx, d_len, n, d_off, d_total, kScanIdentity, ctx->arena, (cudaStream_t)stream);
@@ -1291,6 +1322,13 @@ int b2b_compress_blocks_batch(b2b_ctx *ctx, const void *src, const uint64_t *src
                                frame_len, status, total_out, true, blocksize);
 }
 
+// Output slots may come in any order and with gaps between them: frames are processed in the order of their
+// output offsets, slots that overlap are refused (B2B_EINVAL), and only the bytes a frame produced are ever
+// written to dst (a gap between two slots, or the slot of a failed frame, keeps what the caller had there).
+// Adjacent slots form a RUN that is laid out on the device exactly as in dst, so that a run of good frames
+// goes back in one copy; the input side is gathered the same way (runs of nearby frames, one H2D each).
+struct HostRun { uint64_t host, dev, len; uint32_t i0, i1; };
+
 static int host_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_t *frame_off,
                                  const uint32_t *frame_len, uint32_t nframes, int64_t typesize_override,
                                  void *dst, uint64_t dst_cap, const uint64_t *dst_off, uint32_t *out_len,
@@ -1317,55 +1355,138 @@ static int host_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_
         const uint64_t reach = 255ull * frame_len[f] + 64;
         cap[f] = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(norig, room), reach);
     }
-    // chunks by OUTPUT bytes (the larger side)
-    const std::vector<HostChunk> chunks = split_chunks(dst_off, cap.data(), nframes, ctx->opt_stage_bytes);
+    // processing order = order of the output slots
+    std::vector<uint32_t> ord;
+    bool mono = true;
+    for (uint32_t f = 1; f < nframes && mono; f++) mono = dst_off[f] >= dst_off[f - 1] + cap[f - 1];
+    if (!mono) {
+        ord.resize(nframes);
+        for (uint32_t f = 0; f < nframes; f++) ord[f] = f;
+        std::stable_sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return dst_off[x] < dst_off[y]; });
+        uint64_t end = 0;
+        for (uint32_t i = 0; i < nframes; i++) {
+            const uint32_t f = ord[i];
+            if (cap[f] == 0) continue;
+            if (dst_off[f] < end) return B2B_EINVAL;          // two output slots overlap
+            end = dst_off[f] + cap[f];
+        }
+    }
+    auto F = [&](uint32_t i) { return mono ? i : ord[i]; };
+    // chunks by OUTPUT bytes (the larger side), in processing order
+    struct Chunk { uint32_t i0, i1, max_cap; uint64_t out_bytes; };
+    std::vector<Chunk> chunks;
+    for (uint32_t i = 0; i < nframes;) {
+        Chunk c{i, i, 0, 0};
+        while (c.i1 < nframes && (c.i1 == c.i0 || c.out_bytes + cap[F(c.i1)] <= ctx->opt_stage_bytes)) {
+            c.out_bytes += cap[F(c.i1)]; c.max_cap = std::max(c.max_cap, cap[F(c.i1)]); c.i1++;
+        }
+        chunks.push_back(c);
+        i = c.i1;
+    }
     int rc = B2B_OK;
     cudaError_t e = cudaSuccess;
+    std::vector<HostRun> out_runs[S];
+    std::vector<uint64_t> dev_dst_off[S];
+    uint8_t *d_out_slot[S] = {};
     // table block: [frame_off u64 n][dst_off u64 n][frame_len u32 n][cap u32 n][out_len u32 n][status u32 n]
     auto retire = [&](size_t k) -> int {
-        const HostChunk &c = chunks[k];
+        const Chunk &c = chunks[k];
         const int slot = (int)(k % S);
-        const uint32_t n = c.f1 - c.f0;
+        const uint32_t n = c.i1 - c.i0;
         const uint64_t a8 = align_up(8ull * n, 256), a4 = align_up(4ull * n, 256);
         CU(ctx, cudaEventSynchronize(ctx->ev_tab[slot]));
         const uint8_t *t = ctx->ptab[slot];
-        memcpy(out_len + c.f0, t + 2 * a8 + 2 * a4, 4ull * n);
-        memcpy(status + c.f0, t + 2 * a8 + 3 * a4, 4ull * n);
+        const uint32_t *h_out_len = (const uint32_t *)(t + 2 * a8 + 2 * a4);
+        const uint32_t *h_status = (const uint32_t *)(t + 2 * a8 + 3 * a4);
+        for (uint32_t j = 0; j < n; j++) { out_len[F(c.i0 + j)] = h_out_len[j]; status[F(c.i0 + j)] = h_status[j]; }
+        // bytes back: a run whose frames all filled their slots goes in one copy, else frame by frame, and
+        // only what a frame produced (status OK, or the short output of a size mismatch)
+        for (const HostRun &r : out_runs[slot]) {
+            bool whole = true;
+            for (uint32_t i = r.i0; i < r.i1 && whole; i++)
+                whole = h_status[i - c.i0] == B2B_OK && h_out_len[i - c.i0] == cap[F(i)];
+            if (whole) {
+                if (r.len) CU(ctx, cudaMemcpyAsync(hdst + r.host, d_out_slot[slot] + r.dev, r.len, cudaMemcpyDeviceToHost, ctx->s_out));
+                continue;
+            }
+            for (uint32_t i = r.i0; i < r.i1; i++) {
+                const uint32_t st = h_status[i - c.i0], got = std::min(h_out_len[i - c.i0], cap[F(i)]);
+                if ((st == B2B_OK || st == B2B_ESIZE_MISMATCH) && got)
+                    CU(ctx, cudaMemcpyAsync(hdst + dst_off[F(i)], d_out_slot[slot] + dev_dst_off[slot][i - c.i0], got,
+                                            cudaMemcpyDeviceToHost, ctx->s_out));
+            }
+        }
+        CU(ctx, cudaEventRecord(ctx->ev_out_free[slot], ctx->s_out));
         return B2B_OK;
     };
     size_t launched = 0, retired = 0;
+    std::vector<HostRun> in_runs;
     for (size_t k = 0; k < chunks.size() && rc == B2B_OK; k++) {
-        const HostChunk &c = chunks[k];
+        const Chunk &c = chunks[k];
         const int slot = (int)(k % S);
-        const uint32_t n = c.f1 - c.f0;
+        const uint32_t n = c.i1 - c.i0;
         while (retired + S <= k && rc == B2B_OK) rc = retire(retired++);
         if (rc) break;
-        uint64_t in_lo = ~0ull, in_hi = 0; uint32_t max_cap = 0;
-        for (uint32_t f = c.f0; f < c.f1; f++) {
-            in_lo = std::min(in_lo, frame_off[f]); in_hi = std::max(in_hi, frame_off[f] + frame_len[f]);
-            max_cap = std::max(max_cap, cap[f]);
+        // input runs: frames that follow each other in `frames` (or nearly: a gap of up to 4 KiB is carried along)
+        in_runs.clear();
+        uint64_t in_bytes = 0;
+        std::vector<uint64_t> dev_frame_off(n);
+        for (uint32_t i = c.i0; i < c.i1; i++) {
+            const uint64_t o = frame_off[F(i)], l = frame_len[F(i)];
+            if (!in_runs.empty()) {
+                HostRun &r = in_runs.back();
+                if (o >= r.host && o <= r.host + r.len + 4096) {
+                    r.len = std::max(r.len, o + l - r.host); r.i1 = i + 1;
+                    dev_frame_off[i - c.i0] = r.dev + (o - r.host);
+                    continue;
+                }
+                in_bytes = align_up(r.dev + r.len, 16);
+            }
+            in_runs.push_back(HostRun{o, in_bytes, l, i, i + 1});
+            dev_frame_off[i - c.i0] = in_bytes;
         }
-        const uint64_t in_span = in_hi - in_lo, out_span = c.hi - c.lo;
+        if (!in_runs.empty()) in_bytes = in_runs.back().dev + in_runs.back().len;
+        // output runs: slots that touch; the device image of a run keeps the layout it has in dst
+        out_runs[slot].clear();
+        dev_dst_off[slot].assign(n, 0);
+        uint64_t out_bytes = 0;
+        for (uint32_t i = c.i0; i < c.i1; i++) {
+            const uint64_t o = dst_off[F(i)], l = cap[F(i)];
+            if (!out_runs[slot].empty()) {
+                HostRun &r = out_runs[slot].back();
+                if (o == r.host + r.len) {
+                    dev_dst_off[slot][i - c.i0] = r.dev + r.len; r.len += l; r.i1 = i + 1;
+                    continue;
+                }
+                out_bytes = align_up(r.dev + r.len, 16);
+            }
+            out_runs[slot].push_back(HostRun{o, out_bytes, l, i, i + 1});
+            dev_dst_off[slot][i - c.i0] = out_bytes;
+        }
+        if (!out_runs[slot].empty()) out_bytes = out_runs[slot].back().dev + out_runs[slot].back().len;
         const uint64_t a8 = align_up(8ull * n, 256), a4 = align_up(4ull * n, 256);
         const uint64_t tab_bytes = 2 * a8 + 4 * a4 + 256;
         uint8_t *d_in = nullptr, *d_out = nullptr, *d_tab = nullptr, *h_tab = nullptr;
-        rc = ensure_hbuf(ctx, 3 * slot + 0, in_span + 64, &d_in);
-        if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 1, out_span + 64, &d_out);
+        rc = ensure_hbuf(ctx, 3 * slot + 0, in_bytes + 64, &d_in);
+        if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 1, out_bytes + 64, &d_out);
         if (rc == B2B_OK) rc = ensure_hbuf(ctx, 3 * slot + 2, tab_bytes, &d_tab);
         if (rc == B2B_OK) rc = ensure_ptab(ctx, slot, tab_bytes, &h_tab);
         if (rc) break;
+        d_out_slot[slot] = d_out;
         uint64_t *d_frame_off = (uint64_t *)d_tab, *d_dst_off = (uint64_t *)(d_tab + a8);
         uint32_t *d_frame_len = (uint32_t *)(d_tab + 2 * a8), *d_cap = (uint32_t *)(d_tab + 2 * a8 + a4);
         uint32_t *d_out_len = (uint32_t *)(d_tab + 2 * a8 + 2 * a4), *d_status = (uint32_t *)(d_tab + 2 * a8 + 3 * a4);
         uint64_t *h_frame_off = (uint64_t *)h_tab, *h_dst_off = (uint64_t *)(h_tab + a8);
-        for (uint32_t i = 0; i < n; i++) {
-            h_frame_off[i] = frame_off[c.f0 + i] - in_lo;
-            h_dst_off[i] = dst_off[c.f0 + i] - c.lo;
+        uint32_t *h_frame_len = (uint32_t *)(h_tab + 2 * a8), *h_cap = (uint32_t *)(h_tab + 2 * a8 + a4);
+        for (uint32_t j = 0; j < n; j++) {
+            h_frame_off[j] = dev_frame_off[j];
+            h_dst_off[j] = dev_dst_off[slot][j];
+            h_frame_len[j] = frame_len[F(c.i0 + j)];
+            h_cap[j] = cap[F(c.i0 + j)];
         }
-        memcpy(h_tab + 2 * a8, frame_len + c.f0, 4ull * n);
-        memcpy(h_tab + 2 * a8 + a4, cap.data() + c.f0, 4ull * n);
         if (k >= (size_t)S) e = cudaStreamWaitEvent(ctx->s_in, ctx->ev_in_free[slot], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, hf + in_lo, in_span, cudaMemcpyHostToDevice, ctx->s_in);
+        for (const HostRun &r : in_runs)
+            if (e == cudaSuccess && r.len) e = cudaMemcpyAsync(d_in + r.dev, hf + r.host, r.len, cudaMemcpyHostToDevice, ctx->s_in);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab, h_tab, 2 * a8 + 2 * a4, cudaMemcpyHostToDevice, ctx->s_in);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_ready[slot], ctx->s_in);
         cudaStream_t sk = ctx->s_k[slot];
@@ -1374,22 +1495,22 @@ static int host_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_
         if (e != cudaSuccess) break;
         select_arena(ctx, 1 + slot);
         rc = blocks ? decompress_blocks_dev_locked(ctx, d_in, d_frame_off, d_frame_len, n, d_out, d_dst_off, d_cap,
-                                                   out_span, max_cap, blocksize, d_out_len, d_status, sk)
+                                                   out_bytes, c.max_cap, blocksize, d_out_len, d_status, sk)
                     : decompress_batch_dev_locked(ctx, d_in, d_frame_off, d_frame_len, n, typesize_override, d_out,
-                                                  d_dst_off, d_cap, out_span, max_cap, d_out_len, d_status, sk);
+                                                  d_dst_off, d_cap, out_bytes, c.max_cap, d_out_len, d_status, sk);
         select_arena(ctx, 0);
         if (rc) break;
         e = cudaEventRecord(ctx->ev_done[slot], sk);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_free[slot], sk);
-        // bytes out on s_out, result tables on s_tab
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[slot], 0);
-        if (e == cudaSuccess && out_span) e = cudaMemcpyAsync(hdst + c.lo, d_out, out_span, cudaMemcpyDeviceToHost, ctx->s_out);
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_out_free[slot], ctx->s_out);
+        // result tables -> pinned block; the bytes follow when the tables are on the host (retire)
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_tab, ctx->ev_done[slot], 0);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_tab + 2 * a8 + 2 * a4, d_tab + 2 * a8 + 2 * a4, 2 * a4, cudaMemcpyDeviceToHost, ctx->s_tab);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_tab[slot], ctx->s_tab);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[slot], 0);
         if (e != cudaSuccess) break;
         launched = k + 1;
+        // while this chunk is in flight, ship the one before it
+        while (retired + 1 < launched && rc == B2B_OK) rc = retire(retired++);
     }
     while (rc == B2B_OK && e == cudaSuccess && retired < launched) rc = retire(retired++);
     return sync_pipeline(ctx, e, rc);

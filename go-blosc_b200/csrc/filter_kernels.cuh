@@ -304,6 +304,7 @@ struct FilterArgs {
     const uint32_t *status;  // optional: frames whose status != 0 are skipped
     int inverse;
     int copy_inactive;       // frames without an active filter: 1 = copy src->dst, 0 = leave
+    uint64_t limit = 0;      // bytes of src / dst (0: not checked): a frame that reaches beyond is left alone
 };
 
 template <int T>
@@ -585,6 +586,7 @@ __global__ void __launch_bounds__(kFilterThreads, 6) filter_batch_kernel(FilterA
     if (a.status && a.status[f] != 0) return;
     const FrameMeta m = a.meta ? a.meta[f] : a.uniform;
     const uint64_t n = frame_len(a.ft, f), off = frame_off(a.ft, f);
+    if (a.limit && (off > a.limit || n > a.limit - off)) return;   // the caller's bound was not one: K3 reports the frame
     const uint8_t *s = a.src + off;
     uint8_t *d = a.dst + off;
     const uint64_t T = m.typesize;

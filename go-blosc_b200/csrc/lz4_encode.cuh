@@ -767,12 +767,14 @@ struct EncodeArgs {
     uint32_t planes;            // typesize when the input went through the byte shuffle (plane = len / typesize), else 0
     uint64_t comp_cap, seg_cap; // bytes of `comp`, entries of `meta`: sized from the caller's total_src_bytes; a frame
                                 // that does not fit (sources that overlap, a bound that was not one) is skipped
+    uint64_t src_cap = ~0ull;   // bytes of `in` (the filter scratch is exactly that large): same rule
 };
 
 // scratch was sized from host-known bounds; a frame beyond them gets B2B_EDST_TOO_SMALL instead of a wild write
 __device__ __forceinline__ bool frame_fits_scratch(uint64_t comp_off, uint64_t seg_base, uint32_t n, uint64_t comp_cap,
-                                                   uint64_t seg_cap) {
-    return comp_off + frame_slot_bytes(n) <= comp_cap && seg_base + seg_count(n) <= seg_cap;
+                                                   uint64_t seg_cap, uint64_t src_off = 0, uint64_t src_cap = ~0ull) {
+    return comp_off + frame_slot_bytes(n) <= comp_cap && seg_base + seg_count(n) <= seg_cap &&
+           src_off <= src_cap && n <= src_cap - src_off;
 }
 
 template <int HL, int HB, bool PH>
@@ -798,7 +800,7 @@ lz4_encode_kernel(EncodeArgs a) {
         const uint32_t n = a.src_len[f];
         const uint32_t nseg = seg_count(n);
         const uint8_t *frame = a.in + a.src_off[f];
-        if (!frame_fits_scratch(a.comp_off[f], a.seg_base[f], n, a.comp_cap, a.seg_cap)) continue;
+        if (!frame_fits_scratch(a.comp_off[f], a.seg_base[f], n, a.comp_cap, a.seg_cap, a.src_off[f], a.src_cap)) continue;
         // short frames are mostly the raw tail the bit shuffle leaves alone: no place in the key there
         const uint32_t pmask = (PH && n >= 32u * (a.phase_mask + 1u)) ? a.phase_mask : 0u;
         for (uint32_t s = s0; s < nseg; s += a.segs_grid) {
@@ -840,8 +842,10 @@ struct FinalizeArgs {
     // s's sequences | output position of that token's first literal << 32; ~0 if the segment has none
     uint64_t *index;
     uint32_t segs_per_frame;
-    const uint64_t *comp_off;   // with comp_cap / seg_cap: the same capacity check as the encoder's
+    const uint64_t *comp_off;   // with comp_cap / seg_cap / src_off / src_cap: the same capacity check as the encoder's
     uint64_t comp_cap, seg_cap;
+    const uint64_t *src_off = nullptr;
+    uint64_t src_cap = ~0ull;
 };
 
 __global__ void finalize_frames_kernel(FinalizeArgs a) {
@@ -853,7 +857,7 @@ __global__ void finalize_frames_kernel(FinalizeArgs a) {
         for (uint32_t s = 0; s < a.segs_per_frame; s++) a.index[(uint64_t)f * a.segs_per_frame + s] = ~0ull;
     if (n == 0) st = 1;                                   // ErrInvalidData, blosc.go:269-271
     else if (n > 0xFFFFFFFFu - 16u) st = 6;               // header fields are u32
-    else if (!frame_fits_scratch(a.comp_off[f], a.seg_base[f], n, a.comp_cap, a.seg_cap)) {
+    else if (!frame_fits_scratch(a.comp_off[f], a.seg_base[f], n, a.comp_cap, a.seg_cap, a.src_off ? a.src_off[f] : 0, a.src_cap)) {
         st = 11;                                          // B2B_EDST_TOO_SMALL: the scratch bound was not one
         if (a.index) for (uint32_t s = 0; s < a.segs_per_frame; s++) a.index[(uint64_t)f * a.segs_per_frame + s] = ~0ull;
     } else {
@@ -901,7 +905,9 @@ struct PackArgs {
     const uint64_t *seg_base;
     const SegMeta *meta;
     const SegPlace *place;
-    const uint32_t *comp_len, *flags, *final_ll, *final_off, *status;
+    const uint32_t *comp_len, *flags, *final_ll, *final_off;
+    uint32_t *status;
+    uint64_t dst_cap = 0;       // bytes of dst (0: not checked): a frame that would reach beyond gets B2B_EDST_TOO_SMALL
     const uint64_t *frame_off;  // packed offsets (16-byte aligned)
     uint8_t *dst;
     uint32_t nframes, segs_grid, codec, typesize_u8;
@@ -946,6 +952,11 @@ __global__ void __launch_bounds__(kFilterThreads, 8) pack_frames_kernel(PackArgs
     if (f >= a.nframes || a.status[f] != 0) return;
     const uint32_t n = a.src_len[f], c = a.comp_len[f], flags = a.flags[f];
     const uint32_t nseg = seg_count(n);
+    if (a.dst_cap && (a.frame_off[f] > a.dst_cap || (uint64_t)c + (a.header ? 16u : 0u) > a.dst_cap - a.frame_off[f])) {
+        // only reachable when total_src_bytes understated the batch; every CTA of the frame takes this exit
+        if (s0 == 0 && threadIdx.x == 0) a.status[f] = 11;
+        return;
+    }
     uint8_t *out = a.dst + a.frame_off[f];
     if (a.header) {
         if (s0 == 0 && threadIdx.x == 0) {

@@ -946,3 +946,89 @@ def test_batches_with_overlapping_or_understated_sources_are_refused_not_corrupt
         assert torch.equal(d_out[:2 * n], d_big[:2 * n]) and not d_out[2 * n:].any()
     # the context is still healthy
     assert ctx.decompress(ctx.compress(data, 1, 5, 1, 2)) == data.tobytes()
+
+
+# ---- round 2: host decompress batches with permuted / gapped output slots, two streams on one context -------
+@pytest.mark.parametrize("stage", [0, 200000])
+def test_host_decompress_batch_permuted_gapped_outputs_keep_the_gaps(ctx, orc, stage):
+    """Output slots in any order with gaps between them: every frame lands in ITS slot, bytes between the slots
+    and the slots of failed frames keep what the caller had there, overlapping slots are refused."""
+    rng = np.random.default_rng(21)
+    sizes = [70000, 1, 4096, 262144, 999, 131072, 50, 65536]
+    datas = [dg.smooth_f32((s + 3) // 4, i)[:s].copy() if i % 2 else dg.lowent_i16((s + 1) // 2, i)[:s].copy()
+             for i, s in enumerate(sizes)]
+    frames = [np.frombuffer(ctx.compress(d, 1, 5, 1, 4), dtype=np.uint8) for d in datas]
+    flen = np.array([f.size for f in frames], dtype=np.uint32)
+    foff = np.concatenate([[0], np.cumsum(flen[:-1].astype(np.uint64) + 3)]).astype(np.uint64)      # odd gaps in the input too
+    blob = np.zeros(int(foff[-1]) + int(flen[-1]), dtype=np.uint8)
+    for f, o in zip(frames, foff):
+        blob[int(o):int(o) + f.size] = f
+    order = rng.permutation(len(sizes))                                  # slot order != frame order
+    doff = np.zeros(len(sizes), dtype=np.uint64)
+    pos = 17
+    for f in order:
+        doff[f] = pos
+        pos += sizes[f] + int(rng.integers(0, 3)) * 37                  # some slots touch, some leave a gap
+    total = pos + 5
+    ctx.set_option(3, stage)
+    try:
+        dst = np.full(total, 0xA5, dtype=np.uint8)
+        out, olen, st = ctx.decompress_batch(blob, foff, flen, doff, total, dst=dst)
+        assert not st.any() and np.array_equal(olen, np.array(sizes, dtype=np.uint32))
+        covered = np.zeros(total, dtype=bool)
+        for f, d in enumerate(datas):
+            assert np.array_equal(dst[int(doff[f]):int(doff[f]) + sizes[f]], d), f
+            covered[int(doff[f]):int(doff[f]) + sizes[f]] = True
+        assert (dst[~covered] == 0xA5).all(), "bytes outside the output slots were written"
+        # a failed frame leaves its slot alone
+        bad = blob.copy()
+        bad[int(foff[3]) + 16:int(foff[3]) + int(flen[3])] ^= 0xFF
+        dst = np.full(total, 0x5A, dtype=np.uint8)
+        out, olen, st = ctx.decompress_batch(bad, foff, flen, doff, total, dst=dst)
+        assert st[3] in (5, 8) and not np.delete(st, 3).any()
+        rc, want = orc.decompress(bad[int(foff[3]):int(foff[3]) + int(flen[3])])
+        assert rc == st[3]
+        if st[3] == 8:
+            assert (dst[int(doff[3]):int(doff[3]) + sizes[3]] == 0x5A).all()
+        for f, d in enumerate(datas):
+            if f != 3:
+                assert np.array_equal(dst[int(doff[f]):int(doff[f]) + sizes[f]], d), f
+        # overlapping output slots are refused
+        clash = doff.copy()
+        clash[order[1]] = doff[order[0]] + 1
+        with pytest.raises(Exception):
+            ctx.decompress_batch(blob, foff, flen, clash, total, dst=np.zeros(total, dtype=np.uint8))
+    finally:
+        ctx.set_option(3, 0)
+
+
+def test_two_streams_on_one_context_do_not_share_scratch(ctx, torch_mod):
+    """Device-pointer calls carve their scratch from one arena: a call on another stream than the previous one
+    has to wait for it.  Alternate compress / decompress batches between two streams without any
+    host synchronisation in between and check every result."""
+    torch = torch_mod
+    n, fl = 64 << 20, 262144
+    nf = n // fl
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    srcs = [torch.randint(0, 8, (n // 2,), device="cuda", generator=g, dtype=torch.int16).view(torch.uint8) for _ in range(2)]
+    d_off = torch.arange(nf, dtype=torch.int64, device="cuda") * fl
+    d_len = torch.full((nf,), fl, dtype=torch.int32, device="cuda")
+    cap = n + 32 * nf + 64
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    bufs = []
+    for k in range(2):
+        bufs.append(dict(c=torch.empty(cap, dtype=torch.uint8, device="cuda"), foff=torch.empty(nf, dtype=torch.int64, device="cuda"),
+                         flen=torch.empty(nf, dtype=torch.int32, device="cuda"), st=torch.empty(nf, dtype=torch.int32, device="cuda"),
+                         st2=torch.empty(nf, dtype=torch.int32, device="cuda"), tot=torch.zeros(1, dtype=torch.int64, device="cuda"),
+                         out=torch.zeros(n, dtype=torch.uint8, device="cuda"), olen=torch.empty(nf, dtype=torch.int32, device="cuda")))
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for k in range(2):                       # compress on stream k while the other stream still decompresses
+            b, s = bufs[k], streams[k].cuda_stream
+            ctx.compress_batch_dev(srcs[k], d_off, d_len, nf, n, fl, 1, 2, b["c"], cap, b["foff"], b["flen"], b["st"], b["tot"], s)
+            ctx.decompress_batch_dev(b["c"], b["foff"], b["flen"], nf, 0, b["out"], d_off, d_len, n, fl, b["olen"], b["st2"], s)
+    torch.cuda.synchronize()
+    for k in range(2):
+        b = bufs[k]
+        assert not bool(b["st"].any()) and not bool(b["st2"].any())
+        assert torch.equal(b["out"], srcs[k])
