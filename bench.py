@@ -592,8 +592,22 @@ def run_gpu(args):
         b.record(); torch.cuda.synchronize()
         gather_ms = a.elapsed_time(b)
         assert all_len.numel() == nf * world and int(gtotal.item()) == int(all_len.sum().item())
+        # the same through the C ABI alone (b2b_allgather_sizes: one ncclAllGather + one scan kernel, no host sync)
+        gather_native_ms = None
+        try:
+            comm = par.NcclComm(rank, world, local)
+            par.global_frame_table_native(ctx, comm, d_flen, False, stream)          # warm-up (NCCL channel setup)
+            torch.cuda.synchronize(); dist.barrier()
+            a.record()
+            n_len, n_off, n_total = par.global_frame_table_native(ctx, comm, d_flen, False, stream)
+            b.record(); torch.cuda.synchronize()
+            gather_native_ms = a.elapsed_time(b)
+            assert torch.equal(n_len, all_len) and torch.equal(n_off, all_off) and int(n_total.item()) == int(gtotal.item())
+            comm.close()
+        except Exception as ex:                                                          # reported, never fatal
+            gather_native_ms = f"failed: {ex}"
     else:
-        comp_all, gather_ms = float(comp_total), None
+        comp_all, gather_ms, gather_native_ms = float(comp_total), None, None
     t_total, t_c, t_d = (float(x) for x in tt.tolist())
     ms_step = t_total / args.steps
     bytes_all = float(total) * world
@@ -690,6 +704,7 @@ def run_gpu(args):
         }
         if gather_ms is not None:
             line["allgather_sizes_ms"] = gather_ms
+            line["allgather_sizes_c_abi_ms"] = gather_native_ms
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -208,6 +208,7 @@ ABI = [
     ("b2b_decompress_batch_dev", _int, [_vp, _vp, _vp, _vp, _u32, _i64, _vp, _vp, _vp, _u64, _u32,
                                         _vp, _vp, _vp]),
     ("b2b_scan_offsets_dev", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
+    ("b2b_allgather_sizes", _int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _int, _vp]),
     ("b2b_blocks_blocksize", _u32, [_sz, _i64, _u32]),
     ("b2b_compress_blocks", _int, [_vp, _vp, _sz, _int, _i64, _u32, _vp, _sz, C.POINTER(_sz)]),
     ("b2b_decompress_blocks", _int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
@@ -595,6 +596,14 @@ class Context:
                                                    _dev_ptr(d_dst_off), _dev_ptr(d_dst_cap), total_dst_bytes,
                                                    max_orig_len, int(blocksize), _dev_ptr(d_out_len),
                                                    _dev_ptr(d_status), C.c_void_p(stream))
+        if rc:
+            _raise(rc, self._h)
+
+    def allgather_sizes(self, nccl_comm, d_local_len, n_local, world, d_all_len, d_all_off, d_total, align16=False, stream=0):
+        """One ncclAllGather of the per-frame sizes + the K5 scan, all on `stream` (include/b2b.h)."""
+        rc = lib().b2b_allgather_sizes(self._h, C.c_void_p(nccl_comm), _dev_ptr(d_local_len), n_local, world,
+                                       _dev_ptr(d_all_len), _dev_ptr(d_all_off), _dev_ptr(d_total), int(bool(align16)),
+                                       C.c_void_p(stream))
         if rc:
             _raise(rc, self._h)
 

@@ -3,6 +3,9 @@
 #include "../../include/b2b.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges around every stage, free when no tool listens
+
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -94,16 +97,23 @@ struct LaunchTimer {
     LaunchTimer(b2b_ctx *c, int kid, cudaStream_t st) : ctx(c), id(kid), s(st), on(c->opt_timing != 0) {
         ctx->launches++;
         ctx->kernel_launches[id]++;
+        nvtxRangePushA(kKernelNames[id]);
         if (!on) return;
         auto get = [&]() { cudaEvent_t e; if (!ctx->event_pool.empty()) { e = ctx->event_pool.back(); ctx->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
         t.id = id; t.a = get(); t.b = get();
         cudaEventRecord(t.a, s);
     }
     ~LaunchTimer() {
+        nvtxRangePop();
         if (!on) return;
         cudaEventRecord(t.b, s);
         ctx->pending.push_back(t);
     }
+};
+
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 void fold_timings(b2b_ctx *ctx) {
@@ -316,6 +326,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
                               uint64_t dst_cap, uint64_t *d_frame_off, uint32_t *d_frame_len,
                               uint32_t *d_status, uint64_t *d_total_out, cudaStream_t s,
                               bool raw_block = false, uint64_t *d_index = nullptr, uint32_t segs_per_frame = 0) {
+    NvtxRange nvtx_range("b2b.compress_batch_dev");
     ArenaGuard arena_guard(ctx, s);
     if (nframes == 0) {
         if (d_total_out) CU(ctx, cudaMemsetAsync(d_total_out, 0, 8, s));
@@ -419,6 +430,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
                                 const uint32_t *d_dst_cap, uint64_t total_dst, uint32_t max_orig,
                                 uint32_t *d_out_len, uint32_t *d_status, cudaStream_t s,
                                 const uint64_t *d_index = nullptr, uint32_t segs_per_frame = 0) {
+    NvtxRange nvtx_range("b2b.decompress_batch_dev");
     ArenaGuard arena_guard(ctx, s);
     if (nframes == 0) return B2B_OK;
     if (!d_frames || !d_frame_off || !d_frame_len || !d_dst || !d_dst_off || !d_dst_cap ||
@@ -506,6 +518,7 @@ int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *
                                uint32_t max_len, int shuffle, int64_t typesize, uint32_t blocksize,
                                void *d_dst, uint64_t dst_cap, uint64_t *d_frame_off, uint32_t *d_frame_len,
                                uint32_t *d_status, uint64_t *d_total_out, cudaStream_t s) {
+    NvtxRange nvtx_range("b2b.compress_blocks_dev");
     ArenaGuard arena_guard(ctx, s);
     if (nframes == 0) {
         if (d_total_out) CU(ctx, cudaMemsetAsync(d_total_out, 0, 8, s));
@@ -640,6 +653,7 @@ int decompress_blocks_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint6
                                  const uint64_t *d_dst_off, const uint32_t *d_dst_cap, uint64_t total_dst,
                                  uint32_t max_orig, uint32_t blocksize, uint32_t *d_out_len,
                                  uint32_t *d_status, cudaStream_t s) {
+    NvtxRange nvtx_range("b2b.decompress_blocks_dev");
     ArenaGuard arena_guard(ctx, s);
     if (nframes == 0) return B2B_OK;
     if (!d_frames || !d_frame_off || !d_frame_len || !d_dst || !d_dst_off || !d_dst_cap || !d_out_len || !d_status)
@@ -742,6 +756,7 @@ int shuffle_dev_locked(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, co
         if (src != dst) CU(ctx, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s));
         return B2B_OK;
     }
+    NvtxRange nvtx_range("b2b.shuffle_dev");
     ArenaGuard arena_guard(ctx, s);
     uint8_t *out = dst;
     if (src == dst) {  // in place (ShuffleBuffer semantics): transform into scratch, copy back
@@ -1121,6 +1136,39 @@ int b2b_scan_offsets_dev(b2b_ctx *ctx, const uint32_t *d_len, uint32_t n, uint64
     return launch_scan(ctx, d_len, n, d_off, d_total, kScanIdentity, ctx->arena, (cudaStream_t)stream);
 }
 
+// ---- multi-GPU: sizes all-gather + global offsets (the only exchange of the sharded path) ---------------
+int b2b_allgather_sizes(b2b_ctx *ctx, void *nccl_comm, const uint32_t *d_local_len, uint32_t n_local, uint32_t world,
+                        uint32_t *d_all_len, uint64_t *d_all_off, uint64_t *d_total, int align16, void *stream) {
+    if (!ctx || !nccl_comm || world == 0) return B2B_EINVAL;
+    if ((uint64_t)n_local * world >= (1ull << 32)) return B2B_EINVAL;
+    if (n_local && (!d_local_len || !d_all_len || !d_all_off)) return B2B_EINVAL;
+    // ncclResult_t ncclAllGather(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t); ncclUint32 = 3
+    typedef int (*allgather_fn)(const void *, void *, size_t, int, void *, cudaStream_t);
+    static allgather_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);          // the copy the process already uses
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) fn = reinterpret_cast<allgather_fn>(dlsym(h, "ncclAllGather"));
+        if (!fn) fn = reinterpret_cast<allgather_fn>(dlsym(RTLD_DEFAULT, "ncclAllGather"));
+    });
+    if (!fn) return B2B_EUNSUPPORTED;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    NvtxRange nvtx_range("b2b.allgather_sizes");
+    ArenaGuard arena_guard(ctx, s);
+    const uint32_t n = n_local * world;
+    int rc = ensure_arena(ctx, scan_scratch_bytes(n) + 4096);
+    if (rc) return rc;
+    if (n_local) {
+        const int nrc = fn(d_local_len, d_all_len, n_local, 3, nccl_comm, s);
+        if (nrc != 0) { ctx->last_err = "ncclAllGather failed with ncclResult_t " + std::to_string(nrc); return B2B_ECUDA; }
+    }
+    return launch_scan(ctx, d_all_len, n, d_all_off, d_total, align16 ? kScanAlign16 : kScanIdentity, ctx->arena, s);
+}
+
 // ---- host-pointer entry points ----------------------------------------------------------
 int b2b_shuffle(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, const void *src, void *dst,
                 size_t n) {
@@ -1204,6 +1252,7 @@ static int host_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *sr
                                uint32_t nframes, int shuffle, int64_t typesize, void *dst, uint64_t dst_cap,
                                uint64_t *frame_off, uint32_t *frame_len, uint32_t *status, uint64_t *total_out,
                                bool blocks, uint32_t blocksize) {
+    NvtxRange nvtx_range("b2b.compress_batch (host pipeline)");
     if (!ctx) return B2B_EINVAL;
     if (nframes == 0) { if (total_out) *total_out = 0; return B2B_OK; }
     if (!src || !src_off || !src_len || !dst || !frame_off || !frame_len || !status) return B2B_EINVAL;
@@ -1333,6 +1382,7 @@ static int host_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_
                                  const uint32_t *frame_len, uint32_t nframes, int64_t typesize_override,
                                  void *dst, uint64_t dst_cap, const uint64_t *dst_off, uint32_t *out_len,
                                  uint32_t *status, bool blocks, uint32_t blocksize) {
+    NvtxRange nvtx_range("b2b.decompress_batch (host pipeline)");
     if (!ctx) return B2B_EINVAL;
     if (nframes == 0) return B2B_OK;
     if (!frames || !frame_off || !frame_len || !dst_off || !out_len || !status) return B2B_EINVAL;

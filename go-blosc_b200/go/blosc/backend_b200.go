@@ -19,31 +19,67 @@ import (
 	"unsafe"
 )
 
-// A cgo call pins an OS thread for its duration and a b2b_ctx serialises its callers, so
-// concurrent goroutines draw contexts from a pool (one stream + scratch arena each).
-var ctxPool = sync.Pool{New: func() any {
-	var h *C.b2b_ctx
-	if rc := C.b2b_init(C.int(deviceIndex()), &h); rc != C.B2B_OK {
-		return fmt.Errorf("b2b_init: %s (no CPU fallback)", C.GoString(C.b2b_strerror(rc)))
-	}
-	c := &gpuCtx{h: h}
-	runtime.SetFinalizer(c, func(c *gpuCtx) { C.b2b_destroy(c.h) })
-	return c
-}}
+// A cgo call pins an OS thread for its duration and a b2b_ctx serialises its callers, so concurrent
+// goroutines draw contexts from a bounded free list (one stream + scratch arena + pinned staging ring
+// each).  Contexts are created on demand up to maxContexts and then reused for the life of the process:
+// a sync.Pool would let the garbage collector drop a context -- and its device arena -- between two calls.
+const maxContexts = 4
 
 type gpuCtx struct{ h *C.b2b_ctx }
 
+var (
+	ctxFree    = make(chan *gpuCtx, maxContexts)
+	ctxMu      sync.Mutex
+	ctxCreated int
+)
+
 func deviceIndex() int { return 0 } // one process per GPU: set CUDA_VISIBLE_DEVICES per rank
 
-func withCtx(f func(*gpuCtx) error) error {
-	switch c := ctxPool.Get().(type) {
-	case *gpuCtx:
-		defer ctxPool.Put(c)
-		return f(c)
-	case error:
-		return c
+func acquireCtx() (*gpuCtx, error) {
+	select {
+	case c := <-ctxFree:
+		return c, nil
+	default:
 	}
-	return fmt.Errorf("b2b: no context")
+	ctxMu.Lock()
+	if ctxCreated < maxContexts {
+		var h *C.b2b_ctx
+		if rc := C.b2b_init(C.int(deviceIndex()), &h); rc != C.B2B_OK {
+			ctxMu.Unlock()
+			return nil, fmt.Errorf("b2b_init: %s (no CPU fallback)", C.GoString(C.b2b_strerror(rc)))
+		}
+		ctxCreated++
+		ctxMu.Unlock()
+		return &gpuCtx{h: h}, nil
+	}
+	ctxMu.Unlock()
+	return <-ctxFree, nil // all contexts are busy: wait for one
+}
+
+func withCtx(f func(*gpuCtx) error) error {
+	c, err := acquireCtx()
+	if err != nil {
+		return err
+	}
+	defer func() { ctxFree <- c }()
+	runtime.LockOSThread() // the CUDA calls of one batch stay on one thread
+	defer runtime.UnlockOSThread()
+	return f(c)
+}
+
+// Shutdown destroys the idle contexts (device arenas, pinned staging); call it when no call is in flight.
+func Shutdown() {
+	for {
+		select {
+		case c := <-ctxFree:
+			C.b2b_destroy(c.h)
+			ctxMu.Lock()
+			ctxCreated--
+			ctxMu.Unlock()
+		default:
+			return
+		}
+	}
 }
 
 // statusErr maps a B2B_* status to the reference's sentinel, bare or wrapped as the
@@ -222,6 +258,10 @@ func (GPULZ4Codec) Decompress(data []byte, expectedSize int) ([]byte, error) {
 
 // CompressChunks / DecompressChunks: many independent frames per call (no reference
 // counterpart; SURVEY 8(f) rank 1).  Frames come back as sub-slices of one packed buffer.
+// The chunks are gathered into one slice first: cgo does not allow a Go slice of Go pointers to cross
+// the boundary, and one contiguous source is what b2b_compress_batch pipelines (its pinned staging ring
+// takes pageable memory at full PCIe speed).  Callers that already hold one buffer should use
+// CompressPacked, which skips the gather.
 func CompressChunks(chunks [][]byte, shuffle Shuffle, typeSize int) ([][]byte, error) {
 	n := len(chunks)
 	if n == 0 {
@@ -258,4 +298,84 @@ func CompressChunks(chunks [][]byte, shuffle Shuffle, typeSize int) ([][]byte, e
 		frames[i] = dst[foff[i] : uint64(foff[i])+uint64(flen[i])]
 	}
 	return frames, nil
+}
+
+// CompressPacked compresses the frames src[off[i] : off[i]+ln[i]] of ONE buffer (no gather copy) and returns the
+// packed output with its offsets table.
+func CompressPacked(src []byte, off []uint64, ln []uint32, shuffle Shuffle, typeSize int) (dst []byte, frameOff []uint64, frameLen []uint32, err error) {
+	n := len(off)
+	if n == 0 || len(ln) != n {
+		return nil, nil, nil, nil
+	}
+	dst = make([]byte, uint64(len(src))+uint64(32*n)+64)
+	frameOff = make([]uint64, n)
+	frameLen = make([]uint32, n)
+	st := make([]C.uint32_t, n)
+	var out C.uint64_t
+	err = withCtx(func(c *gpuCtx) error {
+		return statusErr(C.b2b_compress_batch(c.h, unsafe.Pointer(&src[0]), (*C.uint64_t)(unsafe.Pointer(&off[0])),
+			(*C.uint32_t)(unsafe.Pointer(&ln[0])), C.uint32_t(n), C.int(shuffle), C.int64_t(typeSize), unsafe.Pointer(&dst[0]),
+			C.uint64_t(len(dst)), (*C.uint64_t)(unsafe.Pointer(&frameOff[0])), (*C.uint32_t)(unsafe.Pointer(&frameLen[0])), &st[0], &out), "batch")
+	})
+	if err != nil {
+		return nil, nil, nil, err
+	}
+	for i := range st {
+		if st[i] != 0 {
+			return nil, nil, nil, statusErr(C.int(st[i]), fmt.Sprintf("chunk %d", i))
+		}
+	}
+	return dst[:out], frameOff, frameLen, nil
+}
+
+// DecompressChunks decompresses many frames in one call; the results are sub-slices of one buffer.  Frames of
+// other codecs than LZ4 / LZ4HC (or malformed headers) are reported per frame like Decompress would.
+func DecompressChunks(frames [][]byte) ([][]byte, error) {
+	n := len(frames)
+	if n == 0 {
+		return nil, nil
+	}
+	var total, outTotal uint64
+	foff := make([]C.uint64_t, n)
+	flen := make([]C.uint32_t, n)
+	doff := make([]C.uint64_t, n)
+	want := make([]uint64, n)
+	for i, f := range frames {
+		h, err := ParseHeader(f)
+		if err != nil {
+			return nil, fmt.Errorf("chunk %d: %w", i, err)
+		}
+		if !h.IsMemcpy() && h.VersionLZ != uint8(LZ4) && h.VersionLZ != uint8(LZ4HC) {
+			return nil, fmt.Errorf("chunk %d: %w: DecompressChunks is the LZ4 path", i, ErrInvalidCodec)
+		}
+		foff[i], flen[i], doff[i] = C.uint64_t(total), C.uint32_t(len(f)), C.uint64_t(outTotal)
+		want[i] = uint64(h.NBytesOrig)
+		if reach := 255*uint64(len(f)) + 64; want[i] > reach { // an LZ4 block cannot expand more than 255x
+			want[i] = reach
+		}
+		total += uint64(len(f))
+		outTotal += (want[i] + 15) &^ 15
+	}
+	src := make([]byte, total)
+	for i, f := range frames {
+		copy(src[foff[i]:], f)
+	}
+	dst := make([]byte, outTotal+1)
+	olen := make([]C.uint32_t, n)
+	st := make([]C.uint32_t, n)
+	err := withCtx(func(c *gpuCtx) error {
+		return statusErr(C.b2b_decompress_batch(c.h, unsafe.Pointer(&src[0]), &foff[0], &flen[0], C.uint32_t(n), 0,
+			unsafe.Pointer(&dst[0]), C.uint64_t(outTotal), &doff[0], &olen[0], &st[0]), "batch")
+	})
+	if err != nil {
+		return nil, err
+	}
+	out := make([][]byte, n)
+	for i := range out {
+		if st[i] != 0 {
+			return nil, statusErr(C.int(st[i]), fmt.Sprintf("chunk %d", i))
+		}
+		out[i] = dst[doff[i] : uint64(doff[i])+uint64(olen[i]) : uint64(doff[i])+uint64(olen[i])]
+	}
+	return out, nil
 }

@@ -1,3 +1,5 @@
-module github.com/example/go-blosc-b200
+// Same module path as the reference (/root/reference/go.mod:1): an application switches with a `replace`
+// directive or by vendoring this directory, its import lines stay as they are.
+module github.com/mrjoshuak/go-blosc
 
-go 1.22
+go 1.23

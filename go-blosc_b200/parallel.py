@@ -100,3 +100,62 @@ def gather_packed_frames(local_buf, local_total: int, local_frame_off, local_fra
         for q in dist.batch_isend_irecv(ops):
             q.wait()
     return buf, frame_off, all_len
+
+
+class NcclComm:
+    """A raw ncclComm_t for the C ABI (b2b_allgather_sizes takes one; torch does not hand its own out).  Created
+    through ctypes on the NCCL library the process already uses; the unique id travels over torch.distributed
+    (any backend) when world > 1."""
+
+    def __init__(self, rank: int, world: int, device: int, group=None):
+        import ctypes
+        import torch
+        self._nccl = ctypes.CDLL("libnccl.so.2")
+
+        class UniqueId(ctypes.Structure):          # ncclUniqueId: passed BY VALUE to ncclCommInitRank
+            _fields_ = [("internal", ctypes.c_byte * 128)]
+
+        uid = UniqueId()
+        if rank == 0:
+            self._check(self._nccl.ncclGetUniqueId(ctypes.byref(uid)))
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor(list(bytes(uid)), dtype=torch.uint8)
+            if dist.get_backend(group) == "nccl":
+                t = t.cuda(device)
+            dist.broadcast(t, 0, group=group)
+            ctypes.memmove(ctypes.byref(uid), bytes(t.cpu().tolist()), 128)
+        torch.cuda.set_device(device)
+        self.comm = ctypes.c_void_p()
+        self._nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+        self._check(self._nccl.ncclCommInitRank(ctypes.byref(self.comm), world, uid, rank))
+        self.world, self.rank = world, rank
+
+    @staticmethod
+    def _check(rc):
+        if rc != 0:
+            raise RuntimeError(f"NCCL call failed with ncclResult_t {rc}")
+
+    @property
+    def ptr(self) -> int:
+        return self.comm.value
+
+    def close(self):
+        import ctypes
+        if self.comm:
+            self._nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+            self._nccl.ncclCommDestroy(self.comm)
+            self.comm = None
+
+
+def global_frame_table_native(ctx, comm: NcclComm, local_frame_len, align16=False, stream=0):
+    """Global packed-offsets table through the C ABI alone: one ncclAllGather + one scan kernel on `stream`, no
+    host synchronisation (equal frame counts per rank).  Returns (all_len, all_off, total)."""
+    import torch
+    n = local_frame_len.numel()
+    dev = local_frame_len.device
+    all_len = torch.empty(n * comm.world, dtype=torch.int32, device=dev)
+    all_off = torch.empty(n * comm.world, dtype=torch.int64, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    ctx.allgather_sizes(comm.ptr, local_frame_len, n, comm.world, all_len, all_off, total, align16, stream)
+    return all_len, all_off, total

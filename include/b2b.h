@@ -162,8 +162,11 @@ B2B_API int b2b_lz4_block_decompress(b2b_ctx *ctx, const void *src, size_t n, vo
  * nframes independent frames; frame f is src[src_off[f] .. +src_len[f]).  Output frames are
  * packed back to back into dst; frame_off/frame_len (host arrays, nframes entries) receive
  * the packed-offsets table, status[f] the per-frame B2B_* status.  Pinned (cudaHostAlloc /
- * cudaHostRegister) buffers are DMA'd directly, pageable ones are staged.  The source ranges of a
- * compress batch must not overlap (B2B_EINVAL): a frame is filtered in scratch at its own offset. */
+ * cudaHostRegister) buffers are DMA'd directly, pageable ones go through the context's pinned staging
+ * ring.  The source ranges of a compress batch must not overlap (B2B_EINVAL): a frame is filtered in
+ * scratch at its own offset.  The output slots of a decompress batch (dst_off[f], NBytesOrig of frame f)
+ * may come in any order and with gaps; slots that overlap are refused (B2B_EINVAL); only the bytes a
+ * frame produced are written to dst (gaps and the slots of failed frames keep the caller's bytes). */
 B2B_API int b2b_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *src_off,
                                const uint32_t *src_len, uint32_t nframes, int shuffle,
                                int64_t typesize, void *dst, uint64_t dst_cap, uint64_t *frame_off,
@@ -175,15 +178,19 @@ B2B_API int b2b_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_
 
 /* ---- device-pointer entry points (the measured path; `stream` is a cudaStream_t) ---------
  * All pointers prefixed d_ are device pointers.  Work is enqueued on `stream`; nothing is
- * synchronised unless the scratch arena has to grow (avoid with b2b_reserve). */
+ * synchronised unless the scratch arena has to grow (avoid with b2b_reserve).  The calls of one
+ * context share one scratch arena: a call on a different stream than the previous call first waits
+ * (on the device) for that call to finish; use one context per stream for concurrent batches. */
 B2B_API int b2b_shuffle_dev(b2b_ctx *ctx, int mode, int inverse, int64_t typesize,
                             const void *d_src, void *d_dst, size_t n, void *stream);
 
 /* Compress nframes frames.  total_src_bytes / max_frame_len are host-known bounds used to
  * size scratch: the extent max(d_src_off[f] + d_src_len[f]) and max(d_src_len[f]).
  * Output is PACKED: frame f is written at d_dst + d_frame_off[f] (exclusive scan of d_frame_len, built on the device by a
- * single-pass decoupled-look-back scan), d_total_out[0] = total bytes.  dst_cap must be
- * >= total_src_bytes + 32*nframes (frames start on 16-byte boundaries).  d_status[f] is a B2B_* code.
+ * single-pass decoupled-look-back scan of the frame lengths ROUNDED UP TO 16: frames start on 16-byte
+ * boundaries), d_total_out[0] = total bytes incl. that padding.  dst_cap must be
+ * >= total_src_bytes + 31*nframes (16 header bytes + at most 15 of padding per frame) and d_dst 16-byte aligned.
+ * d_status[f] is a B2B_* code.
  * The source ranges must not overlap (a frame is filtered in scratch at its own offset); a frame that
  * does not fit the scratch sized from total_src_bytes reports B2B_EDST_TOO_SMALL, nothing is written
  * out of bounds. */
@@ -195,7 +202,9 @@ B2B_API int b2b_compress_batch_dev(b2b_ctx *ctx, const void *d_src, const uint64
                                    uint32_t *d_status, uint64_t *d_total_out, void *stream);
 
 /* Parse nframes headers on the device: d_orig_len[f] = NBytesOrig (0 on a bad header),
- * d_dst_off = exclusive scan of d_orig_len, d_total[0] = sum, d_status[f] = header status. */
+ * d_dst_off = exclusive scan of d_orig_len ROUNDED UP TO 16 (output slots start on 16-byte boundaries, which keeps the
+ * un-shuffle on its vector path), d_total[0] = their sum (the bytes a destination laid out that way needs),
+ * d_status[f] = header status. */
 B2B_API int b2b_frame_info_batch_dev(b2b_ctx *ctx, const void *d_frames,
                                      const uint64_t *d_frame_off, const uint32_t *d_frame_len,
                                      uint32_t nframes, uint32_t *d_orig_len, uint64_t *d_dst_off,
@@ -210,6 +219,19 @@ B2B_API int b2b_decompress_batch_dev(b2b_ctx *ctx, const void *d_frames,
                                      const uint64_t *d_dst_off, const uint32_t *d_dst_cap,
                                      uint64_t total_dst_bytes, uint32_t max_orig_len,
                                      uint32_t *d_out_len, uint32_t *d_status, void *stream);
+
+/* ---- multi-GPU: all-gather of the per-frame sizes + global packed-offsets table ----------
+ * Frames are sharded over the ranks with no collective on the data path; this is the one exchange, needed only
+ * when a table over EVERY rank's frames is wanted (a device-resident multi-rank container).  nccl_comm is an
+ * ncclComm_t of `world` ranks; every rank contributes n_local sizes (equal counts: pad with zeros).  d_all_len
+ * receives world * n_local sizes in rank order, d_all_off their exclusive scan (of the sizes rounded up to 16 when
+ * align16 != 0, as b2b_compress_batch_dev packs frames), d_total[0] the sum.  ONE ncclAllGather and one scan
+ * kernel on `stream`, no host synchronisation.  libb2b.so does not link NCCL: ncclAllGather is resolved at run
+ * time from the NCCL library already loaded in the process (the one that created nccl_comm), else from
+ * libnccl.so.2; B2B_EUNSUPPORTED when there is none. */
+B2B_API int b2b_allgather_sizes(b2b_ctx *ctx, void *nccl_comm, const uint32_t *d_local_len, uint32_t n_local,
+                                uint32_t world, uint32_t *d_all_len, uint64_t *d_all_off, uint64_t *d_total,
+                                int align16, void *stream);
 
 /* ---- side-car decode index (no reference counterpart) ------------------
  * The reference's wire format has ONE LZ4 block per frame (blosc.go:393), so a frame decodes on one

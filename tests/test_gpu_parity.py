@@ -1032,3 +1032,26 @@ def test_two_streams_on_one_context_do_not_share_scratch(ctx, torch_mod):
         b = bufs[k]
         assert not bool(b["st"].any()) and not bool(b["st2"].any())
         assert torch.equal(b["out"], srcs[k])
+
+
+def test_allgather_sizes_through_the_c_abi(ctx, torch_mod):
+    """b2b_allgather_sizes with a one-rank NCCL communicator: the gather is a copy, the offsets are the K5 scan
+    (plain and 16-byte aligned), everything on one stream without a host synchronisation inside the call."""
+    torch = torch_mod
+    import go_blosc_b200.parallel as par
+    comm = par.NcclComm(0, 1, 0)
+    try:
+        g = torch.Generator(device="cuda"); g.manual_seed(1)
+        lens = torch.randint(16, 300000, (5000,), device="cuda", generator=g, dtype=torch.int32)
+        s = torch.cuda.current_stream().cuda_stream
+        all_len, all_off, total = par.global_frame_table_native(ctx, comm, lens, False, s)
+        torch.cuda.synchronize()
+        want = torch.cumsum(lens.to(torch.int64), 0)
+        assert torch.equal(all_len, lens) and int(total.item()) == int(want[-1].item())
+        assert torch.equal(all_off[1:], want[:-1]) and int(all_off[0].item()) == 0
+        all_len, all_off, total = par.global_frame_table_native(ctx, comm, lens, True, s)
+        torch.cuda.synchronize()
+        want = torch.cumsum((lens.to(torch.int64) + 15) // 16 * 16, 0)
+        assert torch.equal(all_off[1:], want[:-1]) and int(total.item()) == int(want[-1].item())
+    finally:
+        comm.close()
