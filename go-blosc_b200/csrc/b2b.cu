@@ -20,16 +20,19 @@
 #include "lz4_encode.cuh"
 #include "lz4_kernels.cuh"
 #include "scan.cuh"
+#include "lz4_decode2.cuh"
 #include "blocks.cuh"
 
 using namespace b2b;
 
 enum KernelId { K_FILTER = 0, K_ENCODE, K_DECODE, K_SCAN, K_PACK, K_INFO, K_FINALIZE, K_PARSE,
-                K_BLOCKS_META, K_BLOCKS_PACK, K_BLOCKS_DECODE, K_COUNT };
+                K_BLOCKS_META, K_BLOCKS_PACK, K_BLOCKS_DECODE, K_PREP2, K_PARSE2, K_STITCH2, K_COPY2, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"filter_batch_kernel", "lz4_encode_kernel", "lz4_decode_kernel",
                                                   "scan_offsets_kernel", "pack_frames_kernel", "frame_info_kernel",
                                                   "finalize_frames_kernel", "lz4_parse_kernel",
-                                                  "blocks_meta_kernels", "blocks_pack_kernel", "blocks_decode_kernel"};
+                                                  "blocks_meta_kernels", "blocks_pack_kernel", "blocks_decode_kernel",
+                                                  "frame_prep_kernel", "lz4_chunk_parse_kernel", "lz4_stitch_kernel",
+                                                  "lz4_copy2_kernel"};
 
 struct TimedLaunch { int id; cudaEvent_t a, b; };
 
@@ -67,7 +70,8 @@ struct b2b_ctx {
     int opt_hash_log = 0;              // 0: automatic (launch_encode)
     int opt_hash_bytes = 0;            // 0: automatic
     uint32_t opt_tune[4] = {0, 0, 0, 0};   // encoder experiment knobs (0: built-in default)
-    int opt_fused_decode = 0;          // 1: one fused decode kernel instead of parse kernel + copy kernel
+    int opt_fused_decode = 2;          // K4 variant: 0 chunk-parallel decoder (lz4_decode2.cuh), 1 the first design's fused
+                                       // kernel (one warp per frame), 2 the first design's parse kernel + copy kernel
     uint64_t opt_stage_bytes = 128ull << 20;
     uint64_t launches = 0;
     std::string last_err;
@@ -436,11 +440,19 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     if (!d_frames || !d_frame_off || !d_frame_len || !d_dst || !d_dst_off || !d_dst_cap ||
         !d_out_len || !d_status)
         return B2B_EINVAL;
-    const bool split = !(d_index && segs_per_frame) && !ctx->opt_fused_decode;
+    const bool indexed = d_index && segs_per_frame;
+    const bool v2 = !indexed && ctx->opt_fused_decode == 0;
+    const bool split = !indexed && ctx->opt_fused_decode == 2;
     const uint64_t nrec_max = total_dst / 4 + (uint64_t)(kSeqSlack + 1) * nframes + 64;   // sum of dst_cap / 4 + slack
+    // chunk-parallel decoder: an LZ4 block that decodes to n bytes has at most n + n / 255 + 16 bytes (longer ones
+    // are refused by the prep kernel), so the chunks of a batch are bounded by its output size
+    const uint64_t table_chunks = total_dst / kChunkBytes + total_dst / (255ull * kChunkBytes) + 2ull * nframes + 16;
     const uint64_t need = align_up(total_dst + 64, 256) + align_up(8ull * nframes, 256) + align_up(4ull * nframes, 256) + 8192 +
                           (split ? align_up(8 * nrec_max, 256) + align_up(8ull * nframes, 256) +
-                                   align_up(4ull * nframes, 256) + scan_scratch_bytes(nframes) + 1024 : 0);
+                                   align_up(4ull * nframes, 256) + scan_scratch_bytes(nframes) + 1024 : 0) +
+                          (v2 ? align_up(sizeof(FrameDec) * (uint64_t)nframes, 256) + 3 * align_up(4ull * nframes, 256) +
+                                align_up(8ull * nframes, 256) + scan_scratch_bytes(nframes) +
+                                align_up(8ull * kChunkSlot * table_chunks, 256) + 2 * align_up(32ull * table_chunks, 256) + 2048 : 0);
     int rc = ensure_arena(ctx, need);
     if (rc) return rc;
     Arena ar(ctx);
@@ -467,8 +479,53 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     a.frame_len = d_frame_len; a.nframes = nframes; a.typesize_override = typesize_override;
     a.dst = static_cast<uint8_t *>(d_dst); a.scratch = d_stage; a.dst_off = d_dst_off;
     a.dst_cap = d_dst_cap; a.out_len = d_out_len; a.status = d_status; a.meta = d_meta;
-    a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr;
-    if (d_index && segs_per_frame) {
+    a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr; a.only = nullptr;
+    if (v2) {
+        // prep -> K5 (chunks per frame) -> one thread per chunk parses -> one thread per frame stitches ->
+        // one CTA per frame copies (lz4_decode2.cuh); frames the table has no room for (output slots that
+        // overlap in dst) go through the first design's fused kernel afterwards
+        FrameDec *d_fd = ar.take<FrameDec>(nframes);
+        uint32_t *d_plen = ar.take<uint32_t>(nframes);
+        uint32_t *d_last = ar.take<uint32_t>(nframes);
+        uint32_t *d_fallback = ar.take<uint32_t>(nframes);
+        uint64_t *d_chunk_base = ar.take<uint64_t>(nframes);
+        uint64_t *d_total_chunks = ar.take<uint64_t>(1);
+        uint8_t *scan_c = ar.take<uint8_t>(scan_scratch_bytes(nframes));
+        uint2 *d_rec = ar.take<uint2>((uint64_t)kChunkSlot * table_chunks);
+        ChunkMeta *d_cmeta = ar.take<ChunkMeta>(table_chunks);
+        ChunkDesc *d_cdesc = ar.take<ChunkDesc>(table_chunks);
+        Prep2Args pa;
+        pa.frames = a.frames; pa.frame_off = d_frame_off; pa.frame_len = d_frame_len; pa.dst_cap = d_dst_cap;
+        pa.nframes = nframes; pa.typesize_override = typesize_override; pa.fd = d_fd; pa.plen_eff = d_plen;
+        pa.out_len = d_out_len; pa.status = d_status; pa.meta = d_meta;
+        { LaunchTimer lt(ctx, K_PREP2, s); frame_prep_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(pa); }
+        CU(ctx, cudaGetLastError());
+        rc = launch_scan(ctx, d_plen, nframes, d_chunk_base, d_total_chunks, kScanChunks, scan_c, s);
+        if (rc) return rc;
+        Parse2Args pp;
+        pp.frames = a.frames; pp.frame_off = d_frame_off; pp.fd = d_fd; pp.nframes = nframes;
+        pp.chunk_base = d_chunk_base; pp.total_chunks = d_total_chunks; pp.table = d_rec; pp.meta = d_cmeta;
+        pp.table_chunks = table_chunks;
+        const unsigned pgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((table_chunks + kParse2Threads - 1) / kParse2Threads,
+                                                                          (uint64_t)ctx->sm_count * 16));
+        { LaunchTimer lt(ctx, K_PARSE2, s); lz4_chunk_parse_kernel<<<pgrid, kParse2Threads, 0, s>>>(pp); }
+        CU(ctx, cudaGetLastError());
+        Stitch2Args sa;
+        sa.frames = a.frames; sa.frame_off = d_frame_off; sa.fd = d_fd; sa.nframes = nframes; sa.chunk_base = d_chunk_base;
+        sa.table = d_rec; sa.meta = d_cmeta; sa.desc = d_cdesc; sa.last_chunk = d_last; sa.fallback = d_fallback;
+        sa.table_chunks = table_chunks;
+        { LaunchTimer lt(ctx, K_STITCH2, s); lz4_stitch_kernel<<<(nframes + 63) / 64, 64, 0, s>>>(sa); }
+        CU(ctx, cudaGetLastError());
+        Copy2Args ca;
+        ca.frames = a.frames; ca.frame_off = d_frame_off; ca.fd = d_fd; ca.nframes = nframes; ca.dst = a.dst; ca.scratch = d_stage;
+        ca.dst_off = d_dst_off; ca.chunk_base = d_chunk_base; ca.desc = d_cdesc; ca.last_chunk = d_last; ca.table = d_rec;
+        ca.fallback = d_fallback; ca.out_len = d_out_len; ca.status = d_status; ca.meta = d_meta;
+        { LaunchTimer lt(ctx, K_COPY2, s); lz4_copy2_kernel<<<nframes, kCopy2Threads, 0, s>>>(ca); }
+        CU(ctx, cudaGetLastError());
+        a.only = d_fallback;
+        { LaunchTimer lt(ctx, K_DECODE, s);
+          lz4_decode_kernel<false><<<(nframes + kCodecWarps - 1) / kCodecWarps, kCodecThreads, 0, s>>>(a); }
+    } else if (d_index && segs_per_frame) {
         // one warp per (frame, segment): sub-streams between the index entries decode independently
         IndexedDecodeArgs ia; ia.d = a; ia.index = d_index; ia.segs_per_frame = segs_per_frame; ia.ticket = d_ticket;
         const uint64_t items = (uint64_t)nframes * segs_per_frame;
@@ -870,7 +927,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
             if (value != 0 && (value < 4 || value > 6)) return B2B_EINVAL;
             ctx->opt_hash_bytes = (int)value; return B2B_OK;
         case 100: case 101: case 102: case 103: ctx->opt_tune[option - 100] = (uint32_t)value; return B2B_OK;
-        case 104: ctx->opt_fused_decode = value != 0; return B2B_OK;
+        case 104: if (value < 0 || value > 2) return B2B_EINVAL; ctx->opt_fused_decode = (int)value; return B2B_OK;
         case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (128ull << 20); return B2B_OK;
         default: return B2B_EINVAL;
     }

@@ -1,0 +1,747 @@
+// lz4_decode2.cuh -- K4, second design: chunk-parallel token parse, per-frame stitch, tile copy engine.
+//
+// Replaces lz4Codec.Decompress (codec.go:77-84 -> pierrec UncompressBlock) and the frame checks of
+// decompressBackend (blosc.go:377-434) for batches of frames.  The wire format is the reference's: one
+// raw LZ4 block per frame, so a frame is ONE serial token chain.  The first design (lz4_kernels.cuh)
+// walked that chain with one warp per frame; here the work is cut so that the unit of SIMD work is a
+// thread, not a warp:
+//
+//   prep     one thread per frame: header checks in the reference's order, FrameDec, payload length
+//   K5       exclusive scan of ceil(payload / kChunkBytes): chunk slots of every frame
+//   parse    one THREAD per 8 KiB chunk of the stream.  It starts kChunkWarm bytes before its chunk,
+//            walks tokens without recording until it enters the chunk (LZ4 chains started at a wrong
+//            byte usually merge with the true chain within a few tokens), then writes one 8-byte
+//            record (token position, output position relative to its start) per token that starts in
+//            the chunk, plus where it entered and where it left.
+//   stitch   one thread per frame walks the chunks in order with the TRUE position: a chunk whose
+//            speculative entry equals the true one is adopted as it is; otherwise the thread walks from
+//            the true position until it meets the speculative chain (its records are sorted by
+//            position) and writes the few missing records in front of it -- or, when the chains never
+//            meet, re-parses the chunk.  Worst case (every chunk wrong) = one thread per frame walking
+//            the whole stream, which is what a scalar decoder does.  Output: one descriptor per chunk
+//            (record range, absolute output base), i.e. every record now knows its input AND output
+//            position: the copy stage is position independent.
+//   copy     one CTA (4 warps) per frame, one THREAD per sequence.  Output is staged in shared memory
+//            (two 4 KiB tiles used as a ring: the tile being filled and the one before it as history)
+//            and leaves as 16-byte vectors.  Per group of 128 records: every thread decodes its token
+//            and copies its literals (runs over 64 bytes: the whole CTA, word-wise); then matches run
+//            in WAVES: a match whose source bytes are all written is copied by its thread (over 32
+//            bytes: by its warp), the others wait for the next wave.  "Written" is tracked exactly, one
+//            bit per pending match byte of the tile, so only true dependencies serialise.
+//
+// Error rules are the first design's (warp_decode_one): every token is checked in stream order --
+// literal length beyond the stream (-1), beyond the capacity (-2), closing token with a match nibble
+// (-1), offset missing / zero / beyond the output so far (-1), match beyond the capacity (-2) -- and
+// the first failing record decides the status.
+#pragma once
+#include "common.cuh"
+#include "lz4_kernels.cuh"
+
+#ifndef B2B_STAT
+#define B2B_STAT(i, v) ((void)0)
+#endif
+
+namespace b2b {
+
+constexpr uint32_t kChunkBytes = 8192;                  // stream bytes per parse chunk
+constexpr uint32_t kChunkWarm = 1024;                   // bytes walked before the chunk to find the chain
+constexpr uint32_t kChunkHead = 64;                     // free records in front of a chunk's records (stitch prefix)
+constexpr uint32_t kChunkCap = kChunkBytes / 3 + 3;     // a token that opens a match takes >= 3 bytes
+constexpr uint32_t kChunkSlot = kChunkHead + kChunkCap + 1;   // records per chunk slot (+ the closing record)
+
+// how a chain of tokens ended
+enum : uint32_t {
+    kEndCont = 0,        // ran into the next chunk
+    kEndFinal = 1,       // closing token (literals only, ends the stream)
+    kEndBadA = 2,        // malformed before its literals (length bytes / literals beyond the stream, or no token at all)
+    kEndBadB = 3,        // malformed after its literals (offset missing, closing token with a match nibble, length bytes beyond the stream)
+    kEndOverrun = 4,     // match longer than any capacity (after its literals and offset)
+    kEndOverrunLit = 5,  // literals beyond any capacity
+    kEndDead = 6         // the speculative chain never reached the chunk
+};
+
+struct FrameDec {
+    uint32_t kind;       // 0: nothing to decode (status final), 1: stored (memcpy flag), 2: LZ4 block
+    uint32_t plen;       // payload bytes
+    uint32_t norig;      // NBytesOrig
+    uint32_t dcap;       // min(capacity, NBytesOrig)
+    uint32_t mode;       // filter still to run (0 none, 1 byte shuffle, 2 bit shuffle)
+    uint32_t typesize;
+};
+
+struct ChunkMeta {       // written by the parse kernel
+    uint32_t entry;      // first token position >= chunk start on the speculative chain (~0: none)
+    uint32_t exit;       // position the chain left the chunk at (or of the token that ended it)
+    uint32_t count;      // records (without the closing one)
+    uint32_t end;        // kEnd*
+    uint32_t out;        // output bytes of those records
+    uint32_t pad[3];
+};
+
+struct ChunkDesc {       // written by the stitch kernel
+    long long base_a;    // absolute output position of relative position 0, records [0, split)
+    long long base_b;    // the same for records [split, count]
+    uint32_t start;      // first record, relative to the chunk slot
+    uint32_t count;      // 0: no token of the true chain starts in this chunk
+    uint32_t split;
+    uint32_t end;
+};
+
+// ---- one token, one thread ----------------------------------------------------------------------------
+// kEndCont: a sequence (ll literals at lit, ml match bytes, next token at next); kEndFinal: closing token;
+// kEndBadA / kEndBadB: malformed (B: ll / lit are valid and inside the stream).  Written without early
+// returns: the callers keep the lanes of a warp converged across tokens (one vote per token), and only the
+// rare length-extension loops diverge.
+__device__ __forceinline__ uint32_t tok_step(const uint8_t *__restrict__ s, uint32_t clen, uint32_t p, uint32_t &ll,
+                                             uint32_t &lit, uint64_t &ml, uint32_t &next) {
+    ll = 0; lit = p; ml = 0; next = p;
+    uint32_t kind = kEndCont;
+    if (p >= clen) {
+        kind = kEndBadA;
+    } else {
+        const uint32_t tok = s[p++];
+        uint64_t l = tok >> 4;
+        if (l == 15) {
+            bool more = true;
+            while (more) {
+                if (p >= clen) { kind = kEndBadA; more = false; }
+                else { const uint32_t b = s[p++]; l += b; more = b == 255u; }
+            }
+        }
+        if (kind == kEndCont && l > (uint64_t)(clen - p)) kind = kEndBadA;
+        if (kind == kEndCont) {
+            ll = (uint32_t)l; lit = p;
+            p += ll;
+            uint64_t m = tok & 15u;
+            if (p == clen) kind = m != 0 ? kEndBadB : kEndFinal;
+            else if (clen - p < 2) kind = kEndBadB;
+            else {
+                p += 2;
+                if (m == 15) {
+                    bool more = true;
+                    while (more) {
+                        if (p >= clen) { kind = kEndBadB; more = false; }
+                        else { const uint32_t b = s[p++]; m += b; more = b == 255u; }
+                    }
+                    if (m > 0xFFFFFFFFull) kind = kEndBadB;
+                }
+                if (kind == kEndCont) { ml = m + 4; next = p; }
+            }
+        }
+    }
+    return kind;
+}
+
+struct Walk { uint32_t pos, n, end; uint64_t rel; };
+
+// one step of a walk: the token at w.pos; record (kEmit) at out[w.n].  Returns false when the chain ended
+// (w.end says how).  rel counts output bytes from the start of the walk and never passes 2^32 - 1.
+template <bool kEmit>
+__device__ __forceinline__ bool walk_step(const uint8_t *__restrict__ s, uint32_t clen, Walk &w, uint2 *out) {
+    uint32_t ll, lit, next; uint64_t ml;
+    const uint32_t kind = tok_step(s, clen, w.pos, ll, lit, ml, next);
+    if (kEmit) out[w.n] = make_uint2(w.pos, (uint32_t)w.rel);
+    w.n++;
+    bool go = false;
+    if (kind == kEndBadA) w.end = kEndBadA;
+    else if (w.rel + ll > 0xFFFFFFFFull) w.end = kEndOverrunLit;
+    else if (kind != kEndCont) { w.rel += ll; w.end = kind; }
+    else if (w.rel + ll + ml > 0xFFFFFFFFull) { w.rel += ll; w.end = kEndOverrun; }
+    else { w.rel += ll + ml; w.pos = next; go = true; }
+    return go;
+}
+
+// Walks the chain from pos while pos < cend, at most max_n tokens (single thread: the stitch kernel)
+template <bool kEmit>
+__device__ __forceinline__ Walk chain_walk(const uint8_t *__restrict__ s, uint32_t clen, uint32_t pos, uint32_t cend,
+                                           uint32_t max_n, uint2 *out) {
+    Walk w; w.pos = pos; w.n = 0; w.end = kEndCont; w.rel = 0;
+    bool go = w.pos < cend && w.n < max_n;
+    while (go) go = walk_step<kEmit>(s, clen, w, out) && w.pos < cend && w.n < max_n;
+    return w;
+}
+
+// ---- prep: header checks (blosc.go:296-303, 165-185, 385-390, 393-407, 417-431) ---------------------------
+struct Prep2Args {
+    const uint8_t *frames;
+    const uint64_t *frame_off;
+    const uint32_t *frame_len;
+    const uint32_t *dst_cap;
+    uint32_t nframes;
+    int64_t typesize_override;
+    FrameDec *fd;
+    uint32_t *plen_eff;     // payload bytes of the frames that hold an LZ4 block, else 0 (input of the chunk scan)
+    uint32_t *out_len, *status;
+    FrameMeta *meta;
+};
+
+__global__ void frame_prep_kernel(Prep2Args a) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.nframes) return;
+    const uint8_t *fr = a.frames + a.frame_off[f];
+    uint32_t flags = 0, codec = 0, tsz = 0, norig = 0, ncomp = 0;
+    uint32_t st = check_header(fr, a.frame_len[f], flags, codec, tsz, norig, ncomp);
+    FrameDec d; d.kind = 0; d.plen = 0; d.norig = norig; d.dcap = 0; d.mode = 0; d.typesize = 0;
+    if (st == kOk) {
+        const bool is_memcpy = (flags & 0x2u) != 0;
+        if (!is_memcpy) {
+            if (codec < 1 || codec > 5) st = kEInvalidCodec;          // blosc.go:403-407
+            else if (codec != 1 && codec != 2) st = kEUnsupported;    // Snappy/ZLIB/ZSTD: host side
+        }
+        if (st == kOk) {
+            d.plen = ncomp - 16;
+            const uint64_t T = a.typesize_override > 0 ? (uint64_t)a.typesize_override : (uint64_t)tsz;
+            const uint32_t mode = (flags & 0x4u) ? 2u : ((flags & 0x1u) ? 1u : 0u);
+            const bool active = mode != 0 && T > 1 && (uint64_t)norig >= T;
+            d.mode = active ? mode : 0u;
+            d.typesize = active ? (uint32_t)T : 0u;
+            const uint32_t cap = a.dst_cap[f];
+            d.dcap = cap < norig ? cap : norig;
+            if (is_memcpy) {
+                if (d.plen != norig) st = kESizeMismatch;             // blosc.go:398-400, 429-431
+                else if (cap < norig) st = kEDstTooSmall;
+                else d.kind = 1;
+            } else {
+                // a block that decodes to n bytes is at most n + n / 255 + 16 bytes long: a longer one
+                // runs over the capacity or is malformed, whichever comes first
+                const uint64_t bound = (uint64_t)d.dcap + d.dcap / 255u + 16u;
+                if ((uint64_t)d.plen > bound) st = d.dcap == norig ? kEDecompressionFailed : kEDstTooSmall;
+                else d.kind = 2;
+            }
+        }
+    }
+    a.fd[f] = d;
+    a.plen_eff[f] = d.kind == 2 ? d.plen : 0u;
+    a.status[f] = st;
+    a.out_len[f] = 0;
+    FrameMeta m; m.mode = 0; m.typesize = 0;
+    a.meta[f] = m;
+}
+
+// ---- parse: one thread per chunk ---------------------------------------------------------------------------
+struct Parse2Args {
+    const uint8_t *frames;
+    const uint64_t *frame_off;
+    const FrameDec *fd;
+    uint32_t nframes;
+    const uint64_t *chunk_base;     // exclusive scan of the chunks per frame
+    const uint64_t *total_chunks;
+    uint2 *table;                   // kChunkSlot records per chunk
+    ChunkMeta *meta;
+    uint64_t table_chunks;          // chunks the table has room for
+};
+
+constexpr int kParse2Threads = 128;
+
+// The lanes of a warp take 32 consecutive chunks and walk them in lockstep, one token per turn (a vote per
+// turn keeps them converged whatever the tokens are).  A lane whose token runs over whole following chunks
+// (a long literal run: the incompressible byte planes of a shuffled frame) tells the lanes of those chunks,
+// which then stop walking what can only be the inside of that run.  The hint may come from a speculative
+// chain that is itself wrong; the stitch kernel re-parses such a chunk, so it costs time, never correctness.
+__global__ void __launch_bounds__(kParse2Threads) lz4_chunk_parse_kernel(Parse2Args a) {
+    __shared__ uint32_t s_dead[kParse2Threads];
+    uint64_t total = *a.total_chunks;
+    if (total > a.table_chunks) total = a.table_chunks;
+    const uint32_t tid = threadIdx.x;
+    for (uint64_t g0 = (uint64_t)blockIdx.x * kParse2Threads; g0 < total; g0 += (uint64_t)gridDim.x * kParse2Threads) {
+        __syncthreads();
+        s_dead[tid] = 0;
+        __syncthreads();
+        const uint64_t g = g0 + tid;
+        ChunkMeta m; m.entry = 0xFFFFFFFFu; m.exit = 0; m.count = 0; m.end = kEndDead; m.out = 0;
+        m.pad[0] = m.pad[1] = m.pad[2] = 0;
+        const uint8_t *s = nullptr;
+        uint32_t plen = 0, cbeg = 0, cend = 0, k = 0, nch = 0;
+        uint2 *rec = nullptr;
+        int phase = 2;                                        // 0 warm-up, 1 recording, 2 done
+        Walk w; w.pos = 0; w.n = 0; w.end = kEndCont; w.rel = 0;
+        if (g < total) {
+            uint32_t lo = 0, hi = a.nframes;                  // last frame whose first chunk is <= g
+            while (hi - lo > 1) {
+                const uint32_t mid = lo + (hi - lo) / 2;
+                if (a.chunk_base[mid] <= g) lo = mid; else hi = mid;
+            }
+            const uint32_t f = lo;
+            k = (uint32_t)(g - a.chunk_base[f]);
+            plen = a.fd[f].plen;
+            nch = (plen + kChunkBytes - 1) / kChunkBytes;
+            if (a.fd[f].kind == 2 && k < nch) {
+                s = a.frames + a.frame_off[f] + 16;
+                cbeg = k * kChunkBytes;
+                cend = k + 1 == nch ? plen + 1 : cbeg + kChunkBytes;   // the last chunk owns position plen
+                w.pos = cbeg > kChunkWarm ? cbeg - kChunkWarm : 0u;
+                rec = a.table + g * kChunkSlot + kChunkHead;
+                phase = w.pos < cbeg ? 0 : 1;
+                if (phase == 1) m.entry = w.pos;
+            }
+        }
+        while (__any_sync(0xffffffffu, phase != 2)) {
+            if (phase != 2 && s_dead[tid]) { phase = 2; m.entry = 0xFFFFFFFFu; m.count = 0; m.end = kEndDead; w.n = 0; }
+            if (phase == 0) {
+                const uint32_t before = w.pos;
+                const bool go = walk_step<false>(s, plen, w, nullptr);
+                if (!go) phase = 2;                           // the speculative chain died before the chunk
+                else if (w.pos >= cbeg) {
+                    // (a token that jumps over whole chunks from the warm-up zone says nothing certain: no hint)
+                    phase = w.pos < cend ? 1 : 2;
+                    m.entry = w.pos; m.exit = w.pos; m.end = kEndCont;
+                    w.n = 0; w.rel = 0;
+                }
+                (void)before;
+            } else if (phase == 1) {
+                const uint32_t before = w.pos;
+                const bool go = walk_step<true>(s, plen, w, rec);
+                if (go && w.pos >= cbeg + 2 * kChunkBytes) {
+                    // this token covers the chunks up to the one that holds w.pos: nothing starts inside them
+                    const uint32_t k1 = w.pos / kChunkBytes < nch ? w.pos / kChunkBytes : nch;
+                    for (uint32_t j = k + 1; j < k1 && tid + (j - k) < (uint32_t)kParse2Threads; j++) s_dead[tid + (j - k)] = 1;
+                }
+                if (!go || w.pos >= cend) {
+                    rec[w.n] = make_uint2(w.pos, (uint32_t)w.rel);
+                    m.exit = w.pos; m.count = w.n; m.end = w.end; m.out = (uint32_t)w.rel;
+                    phase = 2;
+                }
+                (void)before;
+            }
+        }
+        if (g < total) a.meta[g] = m;
+    }
+}
+
+// ---- stitch: one thread per frame ----------------------------------------------------------------------------
+struct Stitch2Args {
+    const uint8_t *frames;
+    const uint64_t *frame_off;
+    const FrameDec *fd;
+    uint32_t nframes;
+    const uint64_t *chunk_base;
+    uint2 *table;
+    const ChunkMeta *meta;
+    ChunkDesc *desc;
+    uint32_t *last_chunk;           // last chunk with a descriptor (~0: the frame has no chunk)
+    uint32_t *fallback;             // 1: no room in the table, the frame is decoded by the first design's kernel
+    uint64_t table_chunks;
+};
+
+__global__ void lz4_stitch_kernel(Stitch2Args a) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.nframes) return;
+    a.fallback[f] = 0;
+    a.last_chunk[f] = 0xFFFFFFFFu;
+    const FrameDec d = a.fd[f];
+    if (d.kind != 2) return;
+    const uint32_t plen = d.plen;
+    const uint32_t nch = (plen + kChunkBytes - 1) / kChunkBytes;
+    if (nch == 0) return;
+    const uint64_t cb = a.chunk_base[f];
+    if (cb + nch > a.table_chunks) { a.fallback[f] = 1; return; }
+    const uint8_t *s = a.frames + a.frame_off[f] + 16;
+    uint32_t e = 0, knext = 0;
+    long long op = 0;
+    for (;;) {
+        uint32_t k = e / kChunkBytes;
+        if (k >= nch) k = nch - 1;
+        for (uint32_t j = knext; j < k; j++) a.desc[cb + j].count = 0;    // chunks inside one long token
+        knext = k + 1;
+        const ChunkMeta m = a.meta[cb + k];
+        uint2 *slot = a.table + (cb + k) * kChunkSlot;
+        const uint32_t cend = k + 1 == nch ? plen + 1 : (k + 1) * kChunkBytes;
+        ChunkDesc D;
+        uint32_t endk;
+        if (m.entry == e) {
+            D.base_a = 0; D.base_b = op; D.start = kChunkHead; D.count = m.count; D.split = 0; D.end = m.end;
+            op += m.out; e = m.exit; endk = m.end;
+        } else {
+            // walk from the true position until the speculative chain is met (its records are sorted)
+            B2B_STAT(20, 1);
+            const uint2 *spec = slot + kChunkHead;
+            const uint32_t sc = m.entry == 0xFFFFFFFFu ? 0u : m.count;
+            uint32_t j = 0, spec_tok = sc ? spec[0].x : 0xFFFFFFFFu;
+            uint32_t pos = e, mc = 0, wend = kEndCont;
+            uint64_t rel = 0;
+            bool sync = false;
+            while (pos < cend) {
+                while (j < sc && spec_tok < pos) { j++; spec_tok = j < sc ? spec[j].x : 0xFFFFFFFFu; }
+                if (j < sc && spec_tok == pos && mc <= kChunkHead + j) { sync = true; break; }
+                const Walk w = chain_walk<false>(s, plen, pos, cend, 1u, nullptr);
+                mc++;
+                if (w.end != kEndCont) { wend = w.end; break; }
+                if (rel + w.rel > 0xFFFFFFFFull) {
+                    // the chain passes 2^32 bytes of output inside this chunk: it ends at this token
+                    uint32_t ll, lit, next; uint64_t ml;
+                    tok_step(s, plen, pos, ll, lit, ml, next);
+                    wend = rel + ll > 0xFFFFFFFFull ? kEndOverrunLit : kEndOverrun;
+                    break;
+                }
+                rel += w.rel; pos = w.pos;
+            }
+            if (sync) {
+                // mc records in front of spec[j]; they count from the true position (base_a)
+                uint2 *dstrec = slot + kChunkHead + j - mc;
+                chain_walk<true>(s, plen, e, cend, mc, dstrec);
+                const uint32_t spec_rel = spec[j].y;
+                D.base_a = op; D.base_b = op + (long long)rel - (long long)spec_rel;
+                D.start = kChunkHead + j - mc; D.count = mc + (m.count - j); D.split = mc; D.end = m.end;
+                op += (long long)rel + (long long)(m.out - spec_rel);
+                e = m.exit; endk = m.end;
+            } else {
+                // the chains never meet inside the chunk: re-parse it from the true position
+                B2B_STAT(21, 1);
+                uint2 *dstrec = slot + kChunkHead;
+                const Walk w = chain_walk<true>(s, plen, e, cend, 0xFFFFFFFFu, dstrec);
+                dstrec[w.n] = make_uint2(w.pos, (uint32_t)w.rel);
+                D.base_a = 0; D.base_b = op; D.start = kChunkHead; D.count = w.n; D.split = 0; D.end = w.end;
+                op += (long long)w.rel; e = w.pos; endk = w.end;
+                (void)wend;
+            }
+        }
+        a.desc[cb + k] = D;
+        if (endk != kEndCont || op > (long long)d.dcap) { a.last_chunk[f] = k; break; }
+    }
+}
+
+// ---- copy: one CTA per frame, one thread per sequence ---------------------------------------------------------
+constexpr int kCopy2Threads = 128;
+constexpr uint32_t kTile2 = 4096;                 // output bytes of one tile
+constexpr uint32_t kRing2 = 2 * kTile2;           // the tile being filled + the one before it
+constexpr uint32_t kLit2 = 64;                    // longest literal run a thread copies by itself
+constexpr uint32_t kMatch2 = 32;                  // longest match a thread copies by itself
+
+struct Copy2Args {
+    const uint8_t *frames;
+    const uint64_t *frame_off;
+    const FrameDec *fd;
+    uint32_t nframes;
+    uint8_t *dst, *scratch;
+    const uint64_t *dst_off;
+    const uint64_t *chunk_base;
+    const ChunkDesc *desc;
+    const uint32_t *last_chunk;
+    const uint2 *table;
+    const uint32_t *fallback;
+    uint32_t *out_len, *status;
+    FrameMeta *meta;
+};
+
+struct CoopLit { uint32_t dst, n; const uint8_t *src; };
+// a record that does not end inside the tile it was decoded for: kept for the next tile (a literal run of
+// 100 KB has hundreds of length bytes; they are read once)
+struct Carry { uint32_t tag, chunk, idx, ll, lit, off, flags; uint64_t vL, ml; };
+
+__device__ __forceinline__ uint32_t bits_mask(uint32_t w, uint32_t a, uint32_t b) {   // bits of [a, b) inside word w
+    uint32_t mask = 0xFFFFFFFFu;
+    if (w == (a >> 5)) mask &= 0xFFFFFFFFu << (a & 31u);
+    if (w == ((b - 1) >> 5)) mask &= 0xFFFFFFFFu >> (31u - ((b - 1) & 31u));
+    return mask;
+}
+// pending-match bits of the tile: [a, b) set / cleared / tested (a < b)
+__device__ __forceinline__ void pend_set(uint32_t *pend, uint32_t a, uint32_t b) {
+    for (uint32_t w = a >> 5; w <= ((b - 1) >> 5); w++) atomicOr(&pend[w], bits_mask(w, a, b));
+}
+__device__ __forceinline__ void pend_clear(uint32_t *pend, uint32_t a, uint32_t b) {
+    for (uint32_t w = a >> 5; w <= ((b - 1) >> 5); w++) atomicAnd(&pend[w], ~bits_mask(w, a, b));
+}
+__device__ __forceinline__ bool pend_any(const volatile uint32_t *pend, uint32_t a, uint32_t b) {
+    bool any = false;
+    for (uint32_t w = a >> 5; w <= ((b - 1) >> 5); w++) any = any || (pend[w] & bits_mask(w, a, b)) != 0;
+    return any;
+}
+
+// all threads of the CTA: tile bytes [0, upto) of the tile at v-position T0 go to outv (16-byte aligned); bytes
+// before v-position a0 do not exist
+__device__ __forceinline__ void flush_tile(const uint8_t *ring, uint8_t *outv, uint64_t T0, uint32_t upto, uint32_t a0) {
+    const uint32_t rb = (uint32_t)T0 & (kRing2 - 1u);
+    const uint32_t nvec = upto >> 4;
+    for (uint32_t i = threadIdx.x; i < nvec; i += kCopy2Threads) {
+        const uint64_t v = T0 + 16ull * i;
+        if (v < a0) {                                     // the frame's first vector, output not 16-byte aligned
+            for (uint32_t b = (uint32_t)(a0 - v); b < 16u; b++) outv[v + b] = ring[rb + 16u * i + b];
+        } else {
+            stg128(outv + v, *reinterpret_cast<const uint4 *>(ring + rb + 16u * i));
+        }
+    }
+    const uint32_t tail = upto & 15u;
+    if (threadIdx.x < tail) {
+        const uint64_t v = T0 + 16ull * nvec + threadIdx.x;
+        if (v >= a0) outv[v] = ring[rb + 16u * nvec + threadIdx.x];
+    }
+}
+
+__global__ void __launch_bounds__(kCopy2Threads, 12) lz4_copy2_kernel(Copy2Args a) {
+    __shared__ __align__(16) uint8_t ring[kRing2];
+    __shared__ uint32_t pend[kTile2 / 32];
+    __shared__ CoopLit s_coop[kCopy2Threads];
+    __shared__ Carry s_carry[2];
+    __shared__ uint32_t s_ncoop[3], s_bulk[3], s_err[3];   // per-group flags, three slots in rotation (a fast warp is at most one group ahead)
+    __shared__ const uint8_t *s_bulk_src[3];
+    __shared__ unsigned long long s_total;
+    const uint32_t f = blockIdx.x;
+    const uint32_t tid = threadIdx.x;
+    const int lane = (int)(tid & 31u);
+    const FrameDec d = a.fd[f];
+    if (d.kind == 0 || a.fallback[f]) return;             // status is final (prep) / the fallback kernel's
+    uint8_t *out = (d.mode ? a.scratch : a.dst) + a.dst_off[f];
+    const uint8_t *fr = a.frames + a.frame_off[f];
+    if (d.kind == 1) {                                    // stored frame (memcpy flag, blosc.go:393-401)
+        cta_copy(out, fr + 16, d.plen);
+        if (tid == 0) {
+            FrameMeta m; m.mode = d.mode; m.typesize = d.typesize;
+            a.status[f] = kOk; a.out_len[f] = d.norig; a.meta[f] = m;
+        }
+        return;
+    }
+    const uint8_t *__restrict__ src = fr + 16;
+    const uint32_t a0 = (uint32_t)((uintptr_t)out & 15u);
+    uint8_t *outv = out - a0;                             // v-space: v = output position + a0; outv + v is 16-byte aligned at v % 16 == 0
+    const uint64_t vlimit = (uint64_t)a0 + d.dcap;
+    for (uint32_t i = tid; i < kTile2 / 32; i += kCopy2Threads) pend[i] = 0;
+    if (tid == 0) {
+        s_ncoop[0] = s_ncoop[1] = s_ncoop[2] = 0; s_bulk[0] = s_bulk[1] = s_bulk[2] = 0;
+        s_err[0] = s_err[1] = s_err[2] = 0xFFFFFFFFu; s_total = ~0ull; s_carry[0].tag = s_carry[1].tag = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    uint64_t T0 = 0;                                      // v-position of the tile being filled
+    int32_t W0 = (int32_t)a0;                             // ring holds the positions [T0 + W0, T0 + kTile2) (W0 <= 0 after the first tile)
+    const uint32_t last = a.last_chunk[f];
+    const uint64_t cb = a.chunk_base[f];
+    uint32_t code = 0;                                    // 0 running, 1 malformed, 2 over capacity, 3 complete
+    uint32_t it = 0;                                      // group counter (tags the carry, picks the flag slots)
+    if (last == 0xFFFFFFFFu) { code = 3; if (tid == 0) s_total = 0; }
+    for (uint32_t k = 0; code == 0 && k <= last; k++) {
+        const ChunkDesc D = a.desc[cb + k];
+        if (D.count == 0) continue;
+        const uint2 *rec = a.table + (cb + k) * kChunkSlot + D.start;
+        uint32_t r = 0;
+        while (r < D.count) {
+            it++;
+            const uint32_t slot = it % 3u;
+            // ---- my record: positions, token, checks in stream order
+            const uint32_t i = r + tid;
+            const bool have = i < D.count;
+            uint64_t vL = 0, vM = 0, vE = 0;                  // literal start / match start / end, v-space
+            uint32_t ll = 0, lit = 0, off = 0, err = 0;
+            uint64_t ml = 0;
+            bool lit_ok = false, match_ok = false;
+            if (have) {
+                const Carry &c = s_carry[(it - 1u) & 1u];
+                if (tid == 0 && c.tag == it - 1u && c.chunk == k && c.idx == i) {
+                    vL = c.vL; ll = c.ll; lit = c.lit; off = c.off; ml = c.ml;
+                    lit_ok = (c.flags & 1u) != 0; match_ok = (c.flags & 2u) != 0; err = c.flags >> 2;
+                    vM = vL + ll; vE = vM + ml;
+                } else {
+                    const uint2 rc = rec[i], nx = rec[i + 1];
+                    const long long o = (i < D.split ? D.base_a : D.base_b) + (long long)rc.y;
+                    const long long on = (i + 1 < D.split ? D.base_a : D.base_b) + (long long)nx.y;
+                    const uint32_t kind = i + 1 == D.count ? D.end : (uint32_t)kEndCont;
+                    vL = (uint64_t)o + a0;
+                    if (kind == kEndBadA) { err = 1; vM = vE = vL; }
+                    else if (kind == kEndOverrunLit) { err = 2; vM = vE = vL; }
+                    else {
+                        uint32_t p = rc.x;
+                        const uint32_t tok = src[p++];
+                        ll = tok >> 4;
+                        if (ll == 15u) { uint32_t b; do { b = src[p++]; ll += b; } while (b == 255u); }
+                        lit = p;
+                        vM = vL + ll;
+                        ml = (uint64_t)(on - o) - ll;
+                        vE = vM + ml;
+                        if (vM > vlimit) err = 2;
+                        else if (kind == kEndBadB) { err = 1; lit_ok = true; }
+                        else if (kind == kEndFinal) { lit_ok = true; s_total = (uint64_t)o + ll; }
+                        else {
+                            lit_ok = true;
+                            off = (uint32_t)src[lit + ll] | ((uint32_t)src[lit + ll + 1] << 8);
+                            if (off == 0 || (uint64_t)off > (uint64_t)o + ll) err = 1;
+                            else if (kind == kEndOverrun || vE > vlimit) err = 2;
+                            else match_ok = true;
+                        }
+                    }
+                }
+                if (err) atomicMin(&s_err[slot], (tid << 2) | err);
+            }
+            // ---- clip to the tile [T0, T0 + kTile2): everything below is 32-bit and relative to T0
+            const uint64_t T1 = T0 + kTile2;
+            auto clip = [&](uint64_t v) -> uint32_t {
+                if (v > vlimit) v = vlimit;
+                if (v <= T0) return 0u;
+                return v >= T1 ? kTile2 : (uint32_t)(v - T0);
+            };
+            const uint32_t rb = (uint32_t)T0 & (kRing2 - 1u);      // the tile's place in the ring
+            const uint32_t la = have ? clip(vL) : kTile2, lb = have ? clip(vM) : kTile2, mb = have ? clip(vE) : kTile2;
+            const bool fin = have && (err != 0 || vE <= T1);
+            // a literal run that covers this tile and at least the next one: whole tiles go straight from the
+            // stream to the output
+            const bool bulk = lit_ok && vL <= T0 && vM >= T1 + kTile2;
+            if (bulk) { s_bulk[slot] = (uint32_t)((vM - T0) / kTile2); s_bulk_src[slot] = src + lit + (uint32_t)(T0 - vL); }
+            // ---- literals: no ordering, the source is the stream
+            if (lit_ok && lb > la && !bulk) {
+                const uint32_t n = lb - la;
+                const uint8_t *sp = src + lit + (uint32_t)(T0 + la - vL);
+                if (n <= kLit2) {
+                    uint8_t *dp = ring + rb + la;
+                    for (uint32_t q = 0; q < n; q++) dp[q] = sp[q];
+                } else {
+                    const uint32_t cs = atomicAdd(&s_ncoop[slot], 1u);
+                    s_coop[cs].dst = rb + la; s_coop[cs].n = n; s_coop[cs].src = sp;
+                }
+            }
+            const bool mine = match_ok && mb > lb;
+            if (mine) pend_set(pend, lb, mb);
+            if (have && !fin && vL < T1) {                        // at most one record starts in the tile and ends behind it
+                Carry &c = s_carry[it & 1u];
+                c.chunk = k; c.idx = i; c.ll = ll; c.lit = lit; c.off = off; c.vL = vL; c.ml = ml;
+                c.flags = (lit_ok ? 1u : 0u) | (match_ok ? 2u : 0u) | (err << 2);
+                c.tag = it;
+            }
+            const uint32_t nfin = (uint32_t)__syncthreads_count(fin ? 1 : 0);
+            // ---- (barrier passed: pending bits, literals, flags of this group are visible)
+            if (tid == 0) { s_ncoop[(it + 2u) % 3u] = 0; s_bulk[(it + 2u) % 3u] = 0; s_err[(it + 2u) % 3u] = 0xFFFFFFFFu; }
+            const uint32_t gerr = s_err[slot];
+            if (gerr != 0xFFFFFFFFu) { code = gerr & 3u; break; }
+            const uint32_t nbulk = s_bulk[slot];
+            if (nbulk) {
+                cta_copy(outv + T0, s_bulk_src[slot], (uint64_t)nbulk * kTile2);
+                T0 += (uint64_t)nbulk * kTile2;
+                W0 = 0;                                           // the ring holds nothing of what was just written
+                __syncthreads();                                  // the copy is visible to later match reads of the CTA
+                continue;                                         // same record again (from the carry)
+            }
+            const uint32_t nc = s_ncoop[slot];
+            if (nc) {   // literal runs over kLit2 bytes: the whole CTA, 4 bytes per thread and step
+                for (uint32_t c = 0; c < nc; c++) {
+                    uint32_t dd = s_coop[c].dst, n = s_coop[c].n;
+                    const uint8_t *sp = s_coop[c].src;
+                    uint32_t head = (4u - (dd & 3u)) & 3u;
+                    if (head > n) head = n;
+                    if (tid < head) ring[dd + tid] = sp[tid];
+                    dd += head; sp += head; n -= head;
+                    const uint32_t nw = n >> 2;
+                    const uint32_t sh = (uint32_t)((uintptr_t)sp & 3u);
+                    const uint32_t *al = reinterpret_cast<const uint32_t *>(sp - sh);
+                    uint32_t *dw = reinterpret_cast<uint32_t *>(ring + dd);
+                    if (sh == 0) {
+                        for (uint32_t w = tid; w < nw; w += kCopy2Threads) dw[w] = al[w];
+                    } else {
+                        for (uint32_t w = tid; w < nw; w += kCopy2Threads)
+                            dw[w] = __funnelshift_r(al[w], al[w + 1], 8u * sh);
+                    }
+                    if (tid < (n & 3u)) ring[dd + 4u * nw + tid] = sp[4u * nw + tid];
+                }
+                __syncthreads();
+            }
+            // ---- matches: a match runs when none of its source bytes is a pending match byte.  Each warp
+            // spins over its own lanes; other warps' progress shows in the pending bits.
+            {
+                bool pending = mine;
+                const uint32_t mn = mine ? mb - lb : 0u;          // bytes of my match inside the tile
+                const bool ovl = (uint64_t)off < ml;
+                // bytes of this match before the tile (a match that began in an earlier tile); for a periodic
+                // match only their place inside the period matters
+                uint32_t skip = 0;
+                if (mine) {
+                    const uint64_t sk = T0 + lb - vM;
+                    skip = ovl ? (uint32_t)(sk % off) : 0u;
+                }
+                // source, relative to T0: [s0, s0 + mn) without overlap, else the period [s0, s0 + off)
+                const int32_t s0 = (int32_t)lb - (int32_t)skip - (int32_t)off;
+                uint32_t sa = 0, sb = 0;                          // its part inside the tile
+                if (mine) {
+                    const int32_t s1 = s0 + (int32_t)(ovl ? off : mn);
+                    if (s1 > 0) { sa = s0 > 0 ? (uint32_t)s0 : 0u; sb = (uint32_t)s1; }
+                }
+                while (__any_sync(0xffffffffu, pending)) {
+                    if (pending && mn <= kMatch2 && (sb <= sa || !pend_any(pend, sa, sb))) {
+                        uint8_t *dp = ring + rb + lb;
+                        if (s0 >= W0) {                           // the source is in the ring
+                            if (!ovl) {
+                                for (uint32_t q = 0; q < mn; q++) dp[q] = ring[(rb + (uint32_t)s0 + q) & (kRing2 - 1u)];
+                            } else {
+                                uint32_t rem = skip;
+                                for (uint32_t q = 0; q < mn; q++) {
+                                    dp[q] = ring[(rb + (uint32_t)s0 + rem) & (kRing2 - 1u)];
+                                    rem = rem + 1u == off ? 0u : rem + 1u;
+                                }
+                            }
+                        } else {                                  // (partly) behind the ring: from the output itself
+                            uint32_t rem = skip;
+                            for (uint32_t q = 0; q < mn; q++) {
+                                const int32_t sp = s0 + (int32_t)(ovl ? rem : q);
+                                dp[q] = sp >= W0 ? ring[(rb + (uint32_t)sp) & (kRing2 - 1u)] : __ldcg(outv + (T0 + (int64_t)sp));
+                                rem = rem + 1u == off ? 0u : rem + 1u;
+                            }
+                        }
+                        __threadfence_block();
+                        pend_clear(pend, lb, mb);
+                        pending = false;
+                    }
+                    // matches over kMatch2 bytes: 32 lanes wide
+                    uint32_t longs = __ballot_sync(0xffffffffu, pending && mn > kMatch2);
+                    while (longs) {
+                        const int j = __ffs(longs) - 1;
+                        longs &= longs - 1;
+                        const uint32_t jsa = __shfl_sync(0xffffffffu, sa, j), jsb = __shfl_sync(0xffffffffu, sb, j);
+                        bool busy = false;
+                        if (jsb > jsa) {
+                            for (uint32_t w0 = jsa >> 5; w0 <= ((jsb - 1) >> 5); w0 += 32) {
+                                const uint32_t w = w0 + lane;
+                                const bool b = w <= ((jsb - 1) >> 5) &&
+                                               (((volatile uint32_t *)pend)[w] & bits_mask(w, jsa, jsb)) != 0;
+                                if (__any_sync(0xffffffffu, b)) { busy = true; break; }
+                            }
+                        }
+                        if (busy) continue;
+                        const uint32_t jlb = __shfl_sync(0xffffffffu, lb, j), jmn = __shfl_sync(0xffffffffu, mn, j);
+                        const int32_t js0 = __shfl_sync(0xffffffffu, s0, j);
+                        const uint32_t joff = __shfl_sync(0xffffffffu, off, j), jskip = __shfl_sync(0xffffffffu, skip, j);
+                        const bool jov = __shfl_sync(0xffffffffu, (uint32_t)ovl, j) != 0;
+                        uint8_t *dp = ring + rb + jlb;
+                        uint32_t rem = jov ? (jskip + (uint32_t)lane) % joff : 0u;   // place of my byte inside the period
+                        const uint32_t step = jov ? 32u % joff : 0u;
+                        for (uint32_t q = lane; q < jmn; q += 32) {
+                            const int32_t sp = js0 + (int32_t)(jov ? rem : q);
+                            dp[q] = sp >= W0 ? ring[(rb + (uint32_t)sp) & (kRing2 - 1u)] : __ldcg(outv + (T0 + (int64_t)sp));
+                            rem += step;
+                            if (rem >= joff) rem -= joff;
+                        }
+                        __threadfence_block();
+                        __syncwarp();
+                        for (uint32_t w = (jlb >> 5) + lane; w <= ((jlb + jmn - 1) >> 5); w += 32)
+                            atomicAnd(&pend[w], ~bits_mask(w, jlb, jlb + jmn));
+                        if (lane == j) pending = false;
+                    }
+                }
+            }
+            // ---- progress; a full tile leaves
+            const uint32_t nhave = D.count - r < (uint32_t)kCopy2Threads ? D.count - r : (uint32_t)kCopy2Threads;
+            r += nfin;
+            if (nfin < nhave) {
+                __syncthreads();                                  // every match of the tile is done
+                flush_tile(ring, outv, T0, kTile2, a0);
+                T0 += kTile2;
+                W0 = T0 - kTile2 > a0 ? -(int32_t)kTile2 : (int32_t)a0 - (int32_t)kTile2;
+                if (W0 < -(int32_t)kTile2) W0 = -(int32_t)kTile2;
+            }
+        }
+        if (code == 0 && D.end != kEndCont) code = D.end == kEndFinal ? 3u : 1u;
+    }
+    __syncthreads();
+    uint32_t st, produced = 0;
+    if (code == 3 && s_total != ~0ull) {
+        const uint64_t total = s_total;                               // <= dcap
+        const uint64_t vend = a0 + total;
+        if (vend > T0) flush_tile(ring, outv, T0, (uint32_t)(vend - T0), a0);
+        produced = (uint32_t)total;
+        st = total == d.norig ? (uint32_t)kOk : (uint32_t)kESizeMismatch;      // blosc.go:429-431
+    } else if (code == 2) {
+        st = d.dcap == d.norig ? (uint32_t)kEDecompressionFailed : (uint32_t)kEDstTooSmall;
+    } else {
+        st = kEDecompressionFailed;                                   // blosc.go:410-413
+    }
+    if (tid == 0) {
+        FrameMeta m; m.mode = 0; m.typesize = 0;
+        if (st == kOk) { m.mode = d.mode; m.typesize = d.typesize; }
+        a.status[f] = st; a.out_len[f] = produced; a.meta[f] = m;
+    }
+}
+
+}  // namespace b2b

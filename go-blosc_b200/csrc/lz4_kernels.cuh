@@ -401,6 +401,9 @@ struct DecodeArgs {
     const uint64_t *table;
     const uint64_t *table_off;
     const uint32_t *nrec;
+    // fused kernel only: when not null, only the frames with only[f] != 0 are decoded (the frames the
+    // chunk-parallel decoder of lz4_decode2.cuh had no table room for)
+    const uint32_t *only;
 };
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t *p) {
@@ -426,6 +429,7 @@ __global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_kernel(DecodeArgs
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t f = blockIdx.x * kCodecWarps + warp;
     if (f >= a.nframes) return;
+    if (!kSplit && a.only && !a.only[f]) return;
     const uint8_t *fr = a.frames + a.frame_off[f];
     const uint32_t flen = a.frame_len[f];
     uint32_t flags = 0, codec = 0, tsz = 0, norig = 0, ncomp = 0;

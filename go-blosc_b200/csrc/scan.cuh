@@ -23,7 +23,8 @@ enum ScanOp : int {
     kScanSegSlot = 2,    // scratch bytes of the frame's segment slots (lz4_encode.cuh)
     kScanSegCount = 3,   // number of 64 KiB segments of the frame
     kScanSeqSlots = 4,   // sequence records of the split decoder for a frame of capacity x
-    kScanStream = 5      // x ? x + 4 : 0     a stream of a Blosc-1 block behind its int32 size (blocks.cuh)
+    kScanStream = 5,     // x ? x + 4 : 0     a stream of a Blosc-1 block behind its int32 size (blocks.cuh)
+    kScanChunks = 6      // ceil(x / 8192)     parse chunks of an LZ4 block of x bytes (lz4_decode2.cuh)
 };
 
 __device__ __forceinline__ uint64_t scan_apply(int op, uint32_t x) {
@@ -32,6 +33,7 @@ __device__ __forceinline__ uint64_t scan_apply(int op, uint32_t x) {
     if (op == kScanSegCount) return seg_count(x);
     if (op == kScanSeqSlots) return (uint64_t)(x / 4u) + kSeqSlack;
     if (op == kScanStream) return x ? (uint64_t)x + 4ull : 0ull;
+    if (op == kScanChunks) return ((uint64_t)x + 8191ull) / 8192ull;
     return x;
 }
 

@@ -44,6 +44,7 @@ struct Warp {
 };
 struct Cta {
     uint32_t arrived = 0, live = 0, gen = 0;
+    uint32_t red[2] = {0, 0};   // predicate counts of __syncthreads_count / _or, by generation parity
 };
 struct Thread {
     ucontext_t ctx;
@@ -93,11 +94,29 @@ static inline void __syncthreads() {
     const uint32_t g = c->gen;
     c->arrived++;
     while (c->gen == g) {
-        if (c->arrived == c->live) { c->arrived = 0; c->gen = g + 1; break; }
+        if (c->arrived == c->live) { c->arrived = 0; c->red[(g + 1) & 1] = 0; c->gen = g + 1; break; }
         emu::yield();
     }
 }
 static inline void __threadfence() {}
+static inline void __threadfence_block() {}
+// CTA-wide barrier + reduction of a predicate
+static inline int emu_syncthreads_reduce(int pred, int op) {
+    emu::Cta *c = emu::cur->cta;
+    const uint32_t g = c->gen;
+    if (pred) c->red[g & 1]++;
+    c->arrived++;
+    while (c->gen == g) {
+        if (c->arrived == c->live) { c->arrived = 0; c->red[(g + 1) & 1] = 0; c->gen = g + 1; break; }
+        emu::yield();
+    }
+    const int n = (int)c->red[g & 1];
+    return op == 0 ? n : (n != 0);
+}
+static inline int __syncthreads_count(int pred) { return emu_syncthreads_reduce(pred, 0); }
+static inline int __syncthreads_or(int pred) { return emu_syncthreads_reduce(pred, 1); }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcg(const T *p) { return *p; }
 static inline uint32_t __ballot_sync(uint32_t, int pred) {
     const uint32_t live = emu::live_mask();
     const uint64_t *in = emu::warp_collective(pred ? 1 : 0);
@@ -203,6 +222,7 @@ template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + 
 template <typename T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <typename T> static inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <typename T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
+template <typename T> static inline T atomicAnd(T *p, T v) { T o = *p; *p = o & v; return o; }
 template <typename T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
 template <typename T> static inline T atomicCAS(T *p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
 template <typename T> static inline T min(T a, T b) { return a < b ? a : b; }

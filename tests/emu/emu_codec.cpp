@@ -29,6 +29,7 @@ inline void tr(int tag, int64_t a, int64_t b, int64_t c, int64_t d, int64_t e) {
 #include "../../go-blosc_b200/csrc/lz4_encode.cuh"
 #include "../../go-blosc_b200/csrc/lz4_kernels.cuh"
 #include "../../go-blosc_b200/csrc/scan.cuh"
+#include "../../go-blosc_b200/csrc/lz4_decode2.cuh"
 
 using namespace b2b;
 
@@ -167,6 +168,9 @@ int emu_compress_frame(const uint8_t *src, uint32_t n, int shuffle, int64_t type
     return (int)status;
 }
 
+static uint32_t g_dst_misalign = 0;
+void emu_set_dst_misalign(uint32_t m) { g_dst_misalign = m & 15u; }
+
 // one frame through K4 (split = parse kernel + copy kernel, else the fused kernel) and the inverse filter,
 // like decompress_batch_dev_locked with nframes = 1.  Returns the frame's status word.
 int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_override, int split, uint8_t *dst,
@@ -176,19 +180,51 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         posix_memalign(&p_dst, 256, (uint64_t)cap + 512)) return -1;
     memset(p_fr, 0, (uint64_t)len + 512);
     memcpy(p_fr, frame, len);
-    const uint64_t frame_off = 0, dst_off = 0;
+    const uint64_t frame_off = 0, dst_off = g_dst_misalign;
     uint32_t out = 0, status = 0, cap_eff = 0, nrec = 0;
     uint64_t table_off = 0;
     FrameMeta meta{0, 0};
-    emu::launch(1, 256, [&] { clip_caps_kernel(&dst_off, &cap, cap, 1, &cap_eff); });
+    emu::launch(1, 256, [&] { clip_caps_kernel(&dst_off, &cap, (uint64_t)cap + 16, 1, &cap_eff); });
     const uint64_t nrec_max = (uint64_t)cap / 4 + (kSeqSlack + 1) + 64;
     std::vector<uint64_t> table(nrec_max);
     DecodeArgs a;
     a.frames = (const uint8_t *)p_fr; a.frame_off = &frame_off; a.frame_len = &len; a.nframes = 1;
     a.typesize_override = typesize_override; a.dst = (uint8_t *)p_dst; a.scratch = (uint8_t *)p_stage; a.dst_off = &dst_off;
     a.dst_cap = &cap_eff; a.out_len = &out; a.status = &status; a.meta = &meta;
-    a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr;
-    if (split) {
+    a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr; a.only = nullptr;
+    if (split == 2) {
+        // chunk-parallel decoder (lz4_decode2.cuh): prep -> K5 -> chunk parse -> stitch -> tile copy (+ fallback)
+        FrameDec fd;
+        uint32_t plen_eff = 0, last_chunk = 0, fallback = 0;
+        uint64_t chunk_base = 0, total_chunks = 0;
+        Prep2Args pa;
+        pa.frames = a.frames; pa.frame_off = &frame_off; pa.frame_len = &len; pa.dst_cap = &cap_eff; pa.nframes = 1;
+        pa.typesize_override = typesize_override; pa.fd = &fd; pa.plen_eff = &plen_eff; pa.out_len = &out; pa.status = &status;
+        pa.meta = &meta;
+        emu::launch(1, 128, [&] { frame_prep_kernel(pa); });
+        run_scan(&plen_eff, 1, &chunk_base, &total_chunks, kScanChunks);
+        const uint64_t table_chunks = (uint64_t)cap / kChunkBytes + (uint64_t)cap / (255ull * kChunkBytes) + 2 + 16;
+        std::vector<uint2> tab(table_chunks * kChunkSlot);
+        std::vector<ChunkMeta> cmeta(table_chunks);
+        std::vector<ChunkDesc> cdesc(table_chunks);
+        Parse2Args pp;
+        pp.frames = a.frames; pp.frame_off = &frame_off; pp.fd = &fd; pp.nframes = 1; pp.chunk_base = &chunk_base;
+        pp.total_chunks = &total_chunks; pp.table = tab.data(); pp.meta = cmeta.data(); pp.table_chunks = table_chunks;
+        emu::launch((uint32_t)std::max<uint64_t>(1, (total_chunks + kParse2Threads - 1) / kParse2Threads), kParse2Threads,
+                    [&] { lz4_chunk_parse_kernel(pp); });
+        Stitch2Args sa;
+        sa.frames = a.frames; sa.frame_off = &frame_off; sa.fd = &fd; sa.nframes = 1; sa.chunk_base = &chunk_base;
+        sa.table = tab.data(); sa.meta = cmeta.data(); sa.desc = cdesc.data(); sa.last_chunk = &last_chunk;
+        sa.fallback = &fallback; sa.table_chunks = table_chunks;
+        emu::launch(1, 128, [&] { lz4_stitch_kernel(sa); });
+        Copy2Args ca;
+        ca.frames = a.frames; ca.frame_off = &frame_off; ca.fd = &fd; ca.nframes = 1; ca.dst = a.dst; ca.scratch = a.scratch;
+        ca.dst_off = &dst_off; ca.chunk_base = &chunk_base; ca.desc = cdesc.data(); ca.last_chunk = &last_chunk;
+        ca.table = tab.data(); ca.fallback = &fallback; ca.out_len = &out; ca.status = &status; ca.meta = &meta;
+        emu::launch(1, kCopy2Threads, [&] { lz4_copy2_kernel(ca); });
+        a.only = &fallback;
+        emu::launch(1, kCodecThreads, [&] { lz4_decode_kernel<false>(a); });
+    } else if (split) {
         run_scan(&cap_eff, 1, &table_off, nullptr, kScanSeqSlots);
         ParseArgs pa;
         pa.frames = a.frames; pa.frame_off = &frame_off; pa.frame_len = &len; pa.dst_cap = &cap_eff; pa.nframes = 1;
@@ -205,7 +241,7 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
     fa.ft.tiles_per_frame = (uint32_t)std::max<uint64_t>(1, ((uint64_t)cap + kTileBytes - 1) / kTileBytes);
     fa.meta = &meta; fa.uniform = FrameMeta{0, 0}; fa.status = &status; fa.inverse = 1; fa.copy_inactive = 0;
     emu::launch(fa.ft.tiles_per_frame, kFilterThreads, [&] { filter_batch_kernel(fa); });
-    if (out) memcpy(dst, p_dst, out);
+    if (out) memcpy(dst, (uint8_t *)p_dst + dst_off, out);
     *out_len = out;
     free(p_fr); free(p_stage); free(p_dst);
     return (int)status;
