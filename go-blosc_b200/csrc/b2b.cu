@@ -70,8 +70,9 @@ struct b2b_ctx {
     int opt_hash_log = 0;              // 0: automatic (launch_encode)
     int opt_hash_bytes = 0;            // 0: automatic
     uint32_t opt_tune[4] = {0, 0, 0, 0};   // encoder experiment knobs (0: built-in default)
-    int opt_fused_decode = 2;          // K4 variant: 0 chunk-parallel decoder (lz4_decode2.cuh), 1 the first design's fused
-                                       // kernel (one warp per frame), 2 the first design's parse kernel + copy kernel
+    int opt_fused_decode = -1;         // K4 variant: -1 automatic (by frame size, see decompress_batch_dev_locked), 0 chunk-parallel
+                                       // decoder (lz4_decode2.cuh: a frame is spread over many threads), 1 the first design's fused
+                                       // kernel (one warp per frame), 2 the first design's parse kernel + copy kernel (one warp per frame)
     uint64_t opt_stage_bytes = 128ull << 20;
     uint64_t launches = 0;
     std::string last_err;
@@ -441,8 +442,15 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         !d_out_len || !d_status)
         return B2B_EINVAL;
     const bool indexed = d_index && segs_per_frame;
-    const bool v2 = !indexed && ctx->opt_fused_decode == 0;
-    const bool split = !indexed && ctx->opt_fused_decode == 2;
+    // Automatic choice: the first design gives every frame ONE warp, which is the faster arrangement when a batch
+    // has thousands of small frames (C3: 32 768 x 256 KiB) and a poor one when frames are large or few (a 2 MiB
+    // frame keeps one warp busy for milliseconds while the rest of the device idles; C5 mixed: 138 -> 298 GB/s
+    // with the chunk-parallel decoder, whose parse runs on one thread per 8 KiB of stream and whose copy stage
+    // gives a frame a whole CTA).
+    int variant = ctx->opt_fused_decode;
+    if (variant < 0) variant = (max_orig > (512u << 10) || nframes < 4u * (uint32_t)ctx->sm_count) ? 0 : 2;
+    const bool v2 = !indexed && variant == 0;
+    const bool split = !indexed && variant == 2;
     const uint64_t nrec_max = total_dst / 4 + (uint64_t)(kSeqSlack + 1) * nframes + 64;   // sum of dst_cap / 4 + slack
     // chunk-parallel decoder: an LZ4 block that decodes to n bytes has at most n + n / 255 + 16 bytes (longer ones
     // are refused by the prep kernel), so the chunks of a batch are bounded by its output size
@@ -452,7 +460,8 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
                                    align_up(4ull * nframes, 256) + scan_scratch_bytes(nframes) + 1024 : 0) +
                           (v2 ? align_up(sizeof(FrameDec) * (uint64_t)nframes, 256) + 3 * align_up(4ull * nframes, 256) +
                                 align_up(8ull * nframes, 256) + scan_scratch_bytes(nframes) +
-                                align_up(8ull * kChunkSlot * table_chunks, 256) + 2 * align_up(32ull * table_chunks, 256) + 2048 : 0);
+                                align_up(8ull * kChunkSlot * table_chunks, 256) + 2 * align_up(32ull * table_chunks, 256) +
+                                align_up(4ull * table_chunks + 16, 256) + 2048 : 0);
     int rc = ensure_arena(ctx, need);
     if (rc) return rc;
     Arena ar(ctx);
@@ -494,6 +503,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         uint2 *d_rec = ar.take<uint2>((uint64_t)kChunkSlot * table_chunks);
         ChunkMeta *d_cmeta = ar.take<ChunkMeta>(table_chunks);
         ChunkDesc *d_cdesc = ar.take<ChunkDesc>(table_chunks);
+        uint32_t *d_dead = ar.take<uint32_t>(table_chunks + 4);      // + the parse ticket behind it
         Prep2Args pa;
         pa.frames = a.frames; pa.frame_off = d_frame_off; pa.frame_len = d_frame_len; pa.dst_cap = d_dst_cap;
         pa.nframes = nframes; pa.typesize_override = typesize_override; pa.fd = d_fd; pa.plen_eff = d_plen;
@@ -506,8 +516,10 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         pp.frames = a.frames; pp.frame_off = d_frame_off; pp.fd = d_fd; pp.nframes = nframes;
         pp.chunk_base = d_chunk_base; pp.total_chunks = d_total_chunks; pp.table = d_rec; pp.meta = d_cmeta;
         pp.table_chunks = table_chunks;
+        pp.dead = d_dead; pp.ticket = reinterpret_cast<unsigned long long *>(d_dead + ((table_chunks + 1) & ~1ull));
+        CU(ctx, cudaMemsetAsync(d_dead, 0, 4ull * (table_chunks + 4), s));
         const unsigned pgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((table_chunks + kParse2Threads - 1) / kParse2Threads,
-                                                                          (uint64_t)ctx->sm_count * 16));
+                                                                          (uint64_t)ctx->sm_count * 12));
         { LaunchTimer lt(ctx, K_PARSE2, s); lz4_chunk_parse_kernel<<<pgrid, kParse2Threads, 0, s>>>(pp); }
         CU(ctx, cudaGetLastError());
         Stitch2Args sa;
@@ -927,7 +939,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
             if (value != 0 && (value < 4 || value > 6)) return B2B_EINVAL;
             ctx->opt_hash_bytes = (int)value; return B2B_OK;
         case 100: case 101: case 102: case 103: ctx->opt_tune[option - 100] = (uint32_t)value; return B2B_OK;
-        case 104: if (value < 0 || value > 2) return B2B_EINVAL; ctx->opt_fused_decode = (int)value; return B2B_OK;
+        case 104: if (value < -1 || value > 2) return B2B_EINVAL; ctx->opt_fused_decode = (int)value; return B2B_OK;
         case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (128ull << 20); return B2B_OK;
         default: return B2B_EINVAL;
     }

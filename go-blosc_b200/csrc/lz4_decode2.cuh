@@ -40,6 +40,11 @@
 #ifndef B2B_STAT
 #define B2B_STAT(i, v) ((void)0)
 #endif
+#ifdef B2B_EMU
+#define B2B_NANOSLEEP(ns) ((void)0)
+#else
+#define B2B_NANOSLEEP(ns) __nanosleep(ns)
+#endif
 
 namespace b2b {
 
@@ -229,82 +234,92 @@ struct Parse2Args {
     uint2 *table;                   // kChunkSlot records per chunk
     ChunkMeta *meta;
     uint64_t table_chunks;          // chunks the table has room for
+    uint32_t *dead;                 // one word per chunk, zero before launch: "inside a long literal run, do not walk"
+    unsigned long long *ticket;     // zero before launch: next chunk to hand out
 };
 
 constexpr int kParse2Threads = 128;
 
-// The lanes of a warp take 32 consecutive chunks and walk them in lockstep, one token per turn (a vote per
-// turn keeps them converged whatever the tokens are).  A lane whose token runs over whole following chunks
-// (a long literal run: the incompressible byte planes of a shuffled frame) tells the lanes of those chunks,
-// which then stop walking what can only be the inside of that run.  The hint may come from a speculative
-// chain that is itself wrong; the stitch kernel re-parses such a chunk, so it costs time, never correctness.
-__global__ void __launch_bounds__(kParse2Threads) lz4_chunk_parse_kernel(Parse2Args a) {
-    __shared__ uint32_t s_dead[kParse2Threads];
+// Persistent lanes: every lane walks one chunk at a time, one token per turn, in lockstep with the other lanes of
+// its warp (a vote per turn keeps them converged whatever the tokens are); a lane that is done takes the next
+// chunk from a ticket as soon as a quarter of the warp is idle.  A lane whose token runs over whole following
+// chunks (a long literal run: the incompressible byte planes of a shuffled frame) flags those chunks, and whoever
+// holds them stops walking what can only be the inside of that run.  The flag may come from a speculative chain
+// that is itself wrong; the stitch kernel re-parses such a chunk, so it costs time, never correctness.
+__global__ void __launch_bounds__(kParse2Threads, 12) lz4_chunk_parse_kernel(Parse2Args a) {
     uint64_t total = *a.total_chunks;
     if (total > a.table_chunks) total = a.table_chunks;
-    const uint32_t tid = threadIdx.x;
-    for (uint64_t g0 = (uint64_t)blockIdx.x * kParse2Threads; g0 < total; g0 += (uint64_t)gridDim.x * kParse2Threads) {
-        __syncthreads();
-        s_dead[tid] = 0;
-        __syncthreads();
-        const uint64_t g = g0 + tid;
-        ChunkMeta m; m.entry = 0xFFFFFFFFu; m.exit = 0; m.count = 0; m.end = kEndDead; m.out = 0;
-        m.pad[0] = m.pad[1] = m.pad[2] = 0;
-        const uint8_t *s = nullptr;
-        uint32_t plen = 0, cbeg = 0, cend = 0, k = 0, nch = 0;
-        uint2 *rec = nullptr;
-        int phase = 2;                                        // 0 warm-up, 1 recording, 2 done
-        Walk w; w.pos = 0; w.n = 0; w.end = kEndCont; w.rel = 0;
-        if (g < total) {
-            uint32_t lo = 0, hi = a.nframes;                  // last frame whose first chunk is <= g
-            while (hi - lo > 1) {
-                const uint32_t mid = lo + (hi - lo) / 2;
-                if (a.chunk_base[mid] <= g) lo = mid; else hi = mid;
-            }
-            const uint32_t f = lo;
-            k = (uint32_t)(g - a.chunk_base[f]);
-            plen = a.fd[f].plen;
-            nch = (plen + kChunkBytes - 1) / kChunkBytes;
-            if (a.fd[f].kind == 2 && k < nch) {
-                s = a.frames + a.frame_off[f] + 16;
-                cbeg = k * kChunkBytes;
-                cend = k + 1 == nch ? plen + 1 : cbeg + kChunkBytes;   // the last chunk owns position plen
-                w.pos = cbeg > kChunkWarm ? cbeg - kChunkWarm : 0u;
-                rec = a.table + g * kChunkSlot + kChunkHead;
-                phase = w.pos < cbeg ? 0 : 1;
-                if (phase == 1) m.entry = w.pos;
-            }
-        }
-        while (__any_sync(0xffffffffu, phase != 2)) {
-            if (phase != 2 && s_dead[tid]) { phase = 2; m.entry = 0xFFFFFFFFu; m.count = 0; m.end = kEndDead; w.n = 0; }
-            if (phase == 0) {
-                const uint32_t before = w.pos;
-                const bool go = walk_step<false>(s, plen, w, nullptr);
-                if (!go) phase = 2;                           // the speculative chain died before the chunk
-                else if (w.pos >= cbeg) {
-                    // (a token that jumps over whole chunks from the warm-up zone says nothing certain: no hint)
-                    phase = w.pos < cend ? 1 : 2;
-                    m.entry = w.pos; m.exit = w.pos; m.end = kEndCont;
-                    w.n = 0; w.rel = 0;
+    const int lane = (int)(threadIdx.x & 31u);
+    ChunkMeta m; m.pad[0] = m.pad[1] = m.pad[2] = 0;
+    m.entry = 0xFFFFFFFFu; m.exit = 0; m.count = 0; m.end = kEndDead; m.out = 0;
+    const uint8_t *s = nullptr;
+    uint32_t plen = 0, cbeg = 0, cend = 0, k = 0, nch = 0;
+    uint64_t g = 0;
+    uint2 *rec = nullptr;
+    int phase = 2;                                            // 0 warm-up, 1 recording, 2 idle, 3 no chunks left
+    Walk w; w.pos = 0; w.n = 0; w.end = kEndCont; w.rel = 0;
+    for (;;) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, phase == 2);
+        const uint32_t busy = __ballot_sync(0xffffffffu, phase == 0 || phase == 1);
+        if (idle == 0 && busy == 0) break;
+        if (idle && (__popc(idle) >= 8 || busy == 0)) {
+            unsigned long long base = 0;
+            if (lane == __ffs(idle) - 1) base = atomicAdd(a.ticket, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, __ffs(idle) - 1);
+            if (phase == 2) {
+                g = base + __popc(idle & ((1u << lane) - 1u));
+                if (g >= total) phase = 3;
+                else {
+                    uint32_t lo = 0, hi = a.nframes;          // last frame whose first chunk is <= g
+                    while (hi - lo > 1) {
+                        const uint32_t mid = lo + (hi - lo) / 2;
+                        if (a.chunk_base[mid] <= g) lo = mid; else hi = mid;
+                    }
+                    const uint32_t f = lo;
+                    k = (uint32_t)(g - a.chunk_base[f]);
+                    plen = a.fd[f].plen;
+                    nch = (plen + kChunkBytes - 1) / kChunkBytes;
+                    m.entry = 0xFFFFFFFFu; m.exit = 0; m.count = 0; m.end = kEndDead; m.out = 0;
+                    w.n = 0; w.end = kEndCont; w.rel = 0;
+                    if (a.fd[f].kind == 2 && k < nch && !__ldcg(a.dead + g)) {
+                        s = a.frames + a.frame_off[f] + 16;
+                        cbeg = k * kChunkBytes;
+                        cend = k + 1 == nch ? plen + 1 : cbeg + kChunkBytes;   // the last chunk owns position plen
+                        w.pos = cbeg > kChunkWarm ? cbeg - kChunkWarm : 0u;
+                        rec = a.table + g * kChunkSlot + kChunkHead;
+                        phase = w.pos < cbeg ? 0 : 1;
+                        if (phase == 1) m.entry = w.pos;
+                    } else {
+                        a.meta[g] = m;                        // nothing to walk
+                    }
                 }
-                (void)before;
-            } else if (phase == 1) {
-                const uint32_t before = w.pos;
-                const bool go = walk_step<true>(s, plen, w, rec);
-                if (go && w.pos >= cbeg + 2 * kChunkBytes) {
-                    // this token covers the chunks up to the one that holds w.pos: nothing starts inside them
-                    const uint32_t k1 = w.pos / kChunkBytes < nch ? w.pos / kChunkBytes : nch;
-                    for (uint32_t j = k + 1; j < k1 && tid + (j - k) < (uint32_t)kParse2Threads; j++) s_dead[tid + (j - k)] = 1;
-                }
-                if (!go || w.pos >= cend) {
-                    rec[w.n] = make_uint2(w.pos, (uint32_t)w.rel);
-                    m.exit = w.pos; m.count = w.n; m.end = w.end; m.out = (uint32_t)w.rel;
-                    phase = 2;
-                }
-                (void)before;
             }
         }
-        if (g < total) a.meta[g] = m;
+        if (phase == 0) {
+            if (!walk_step<false>(s, plen, w, nullptr)) { phase = 2; a.meta[g] = m; }   // the speculative chain died before the chunk
+            else if (w.pos >= cbeg) {
+                // (a token that jumps over whole chunks from the warm-up zone says nothing certain: no flags)
+                m.entry = w.pos; m.exit = w.pos; m.end = kEndCont;
+                w.n = 0; w.rel = 0;
+                if (w.pos < cend && !__ldcg(a.dead + g)) phase = 1;
+                else { if (w.pos < cend) { m.entry = 0xFFFFFFFFu; m.end = kEndDead; } phase = 2; a.meta[g] = m; }
+            }
+        } else if (phase == 1) {
+            const bool go = walk_step<true>(s, plen, w, rec);
+            if (go && w.pos >= cbeg + 2 * kChunkBytes) {
+                // this token covers the chunks up to the one that holds w.pos: nothing starts inside them
+                const uint32_t k1 = w.pos / kChunkBytes < nch ? w.pos / kChunkBytes : nch;
+                for (uint32_t j = k + 1; j < k1; j++) a.dead[g + (j - k)] = 1u;
+            }
+            if (!go || w.pos >= cend) {
+                rec[w.n] = make_uint2(w.pos, (uint32_t)w.rel);
+                m.exit = w.pos; m.count = w.n; m.end = w.end; m.out = (uint32_t)w.rel;
+                phase = 2; a.meta[g] = m;
+            } else if ((w.n & 31u) == 0u && __ldcg(a.dead + g)) {
+                m.entry = 0xFFFFFFFFu; m.count = 0; m.end = kEndDead; m.out = 0;
+                phase = 2; a.meta[g] = m;
+            }
+        }
     }
 }
 
@@ -323,80 +338,104 @@ struct Stitch2Args {
     uint64_t table_chunks;
 };
 
-__global__ void lz4_stitch_kernel(Stitch2Args a) {
+// A state machine per lane, one small step per turn, so that the lanes of a warp stay together whatever their
+// frames need: 0 look at the next chunk, 1 walk from the true position towards the speculative chain, 2 write the
+// records that walk found missing (or the whole chunk), 3 done.
+__global__ void __launch_bounds__(64) lz4_stitch_kernel(Stitch2Args a) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= a.nframes) return;
-    a.fallback[f] = 0;
-    a.last_chunk[f] = 0xFFFFFFFFu;
-    const FrameDec d = a.fd[f];
-    if (d.kind != 2) return;
-    const uint32_t plen = d.plen;
-    const uint32_t nch = (plen + kChunkBytes - 1) / kChunkBytes;
-    if (nch == 0) return;
-    const uint64_t cb = a.chunk_base[f];
-    if (cb + nch > a.table_chunks) { a.fallback[f] = 1; return; }
-    const uint8_t *s = a.frames + a.frame_off[f] + 16;
-    uint32_t e = 0, knext = 0;
+    int mode = 3;
+    FrameDec d; d.kind = 0; d.plen = 0; d.dcap = 0;
+    uint32_t plen = 0, nch = 0;
+    uint64_t cb = 0;
+    const uint8_t *s = nullptr;
+    if (f < a.nframes) {
+        a.fallback[f] = 0;
+        a.last_chunk[f] = 0xFFFFFFFFu;
+        d = a.fd[f];
+        plen = d.plen;
+        nch = (plen + kChunkBytes - 1) / kChunkBytes;
+        if (d.kind == 2 && nch != 0) {
+            cb = a.chunk_base[f];
+            if (cb + nch > a.table_chunks) a.fallback[f] = 1;
+            else { s = a.frames + a.frame_off[f] + 16; mode = 0; }
+        }
+    }
+    uint32_t e = 0, knext = 0, k = 0, cend = 0;
     long long op = 0;
-    for (;;) {
-        uint32_t k = e / kChunkBytes;
-        if (k >= nch) k = nch - 1;
-        for (uint32_t j = knext; j < k; j++) a.desc[cb + j].count = 0;    // chunks inside one long token
-        knext = k + 1;
-        const ChunkMeta m = a.meta[cb + k];
-        uint2 *slot = a.table + (cb + k) * kChunkSlot;
-        const uint32_t cend = k + 1 == nch ? plen + 1 : (k + 1) * kChunkBytes;
-        ChunkDesc D;
-        uint32_t endk;
-        if (m.entry == e) {
-            D.base_a = 0; D.base_b = op; D.start = kChunkHead; D.count = m.count; D.split = 0; D.end = m.end;
-            op += m.out; e = m.exit; endk = m.end;
-        } else {
-            // walk from the true position until the speculative chain is met (its records are sorted)
-            B2B_STAT(20, 1);
-            const uint2 *spec = slot + kChunkHead;
-            const uint32_t sc = m.entry == 0xFFFFFFFFu ? 0u : m.count;
-            uint32_t j = 0, spec_tok = sc ? spec[0].x : 0xFFFFFFFFu;
-            uint32_t pos = e, mc = 0, wend = kEndCont;
-            uint64_t rel = 0;
-            bool sync = false;
-            while (pos < cend) {
-                while (j < sc && spec_tok < pos) { j++; spec_tok = j < sc ? spec[j].x : 0xFFFFFFFFu; }
-                if (j < sc && spec_tok == pos && mc <= kChunkHead + j) { sync = true; break; }
-                const Walk w = chain_walk<false>(s, plen, pos, cend, 1u, nullptr);
-                mc++;
-                if (w.end != kEndCont) { wend = w.end; break; }
-                if (rel + w.rel > 0xFFFFFFFFull) {
-                    // the chain passes 2^32 bytes of output inside this chunk: it ends at this token
-                    uint32_t ll, lit, next; uint64_t ml;
-                    tok_step(s, plen, pos, ll, lit, ml, next);
-                    wend = rel + ll > 0xFFFFFFFFull ? kEndOverrunLit : kEndOverrun;
-                    break;
-                }
-                rel += w.rel; pos = w.pos;
-            }
-            if (sync) {
-                // mc records in front of spec[j]; they count from the true position (base_a)
-                uint2 *dstrec = slot + kChunkHead + j - mc;
-                chain_walk<true>(s, plen, e, cend, mc, dstrec);
-                const uint32_t spec_rel = spec[j].y;
-                D.base_a = op; D.base_b = op + (long long)rel - (long long)spec_rel;
-                D.start = kChunkHead + j - mc; D.count = mc + (m.count - j); D.split = mc; D.end = m.end;
-                op += (long long)rel + (long long)(m.out - spec_rel);
-                e = m.exit; endk = m.end;
+    ChunkMeta m; m.entry = 0; m.exit = 0; m.count = 0; m.end = 0; m.out = 0;
+    uint2 *slot = nullptr;
+    // mode 1
+    uint32_t pos = 0, j = 0, sc = 0, spec_tok = 0, mc = 0;
+    uint64_t rel = 0;
+    // mode 2
+    Walk w; w.pos = 0; w.n = 0; w.end = kEndCont; w.rel = 0;
+    uint2 *dstrec = nullptr;
+    uint32_t limit = 0;
+    bool full = false;
+    while (__any_sync(0xffffffffu, mode != 3)) {
+        ChunkDesc D; D.count = 0xFFFFFFFFu;                   // set: a descriptor is ready this turn
+        uint32_t endk = kEndCont;
+        if (mode == 0) {
+            k = e / kChunkBytes;
+            if (k >= nch) k = nch - 1;
+            for (uint32_t q = knext; q < k; q++) a.desc[cb + q].count = 0;    // chunks inside one long token
+            knext = k + 1;
+            m = a.meta[cb + k];
+            slot = a.table + (cb + k) * kChunkSlot;
+            cend = k + 1 == nch ? plen + 1 : (k + 1) * kChunkBytes;
+            if (m.entry == e) {
+                D.base_a = 0; D.base_b = op; D.start = kChunkHead; D.count = m.count; D.split = 0; D.end = m.end;
+                op += m.out; e = m.exit; endk = m.end;
             } else {
-                // the chains never meet inside the chunk: re-parse it from the true position
-                B2B_STAT(21, 1);
-                uint2 *dstrec = slot + kChunkHead;
-                const Walk w = chain_walk<true>(s, plen, e, cend, 0xFFFFFFFFu, dstrec);
-                dstrec[w.n] = make_uint2(w.pos, (uint32_t)w.rel);
-                D.base_a = 0; D.base_b = op; D.start = kChunkHead; D.count = w.n; D.split = 0; D.end = w.end;
-                op += (long long)w.rel; e = w.pos; endk = w.end;
-                (void)wend;
+                B2B_STAT(20, 1);
+                sc = m.entry == 0xFFFFFFFFu ? 0u : m.count;
+                j = 0; spec_tok = sc ? slot[kChunkHead].x : 0xFFFFFFFFu;
+                pos = e; mc = 0; rel = 0;
+                mode = 1;
+            }
+        } else if (mode == 1) {
+            bool to_full = false, to_prefix = false;
+            if (pos >= cend) to_full = true;
+            else if (j < sc && spec_tok < pos) { j++; spec_tok = j < sc ? slot[kChunkHead + j].x : 0xFFFFFFFFu; }
+            else if (j < sc && spec_tok == pos && mc <= kChunkHead + j) to_prefix = true;
+            else {
+                Walk t; t.pos = pos; t.n = 0; t.end = kEndCont; t.rel = 0;
+                const bool go = walk_step<false>(s, plen, t, nullptr);
+                mc++;
+                if (!go || rel + t.rel > 0xFFFFFFFFull) to_full = true;    // the chain ends inside the chunk
+                else { rel += t.rel; pos = t.pos; }
+            }
+            if (to_full || to_prefix) {
+                full = to_full;
+                if (full) B2B_STAT(21, 1);
+                w.pos = e; w.n = 0; w.end = kEndCont; w.rel = 0;
+                limit = full ? 0xFFFFFFFFu : mc;
+                dstrec = full ? slot + kChunkHead : slot + kChunkHead + j - mc;
+                mode = 2;
+            }
+        } else if (mode == 2) {
+            bool fin = !(w.pos < cend && w.n < limit);
+            if (!fin) fin = !walk_step<true>(s, plen, w, dstrec);
+            if (fin) {
+                if (full) {
+                    dstrec[w.n] = make_uint2(w.pos, (uint32_t)w.rel);
+                    D.base_a = 0; D.base_b = op; D.start = kChunkHead; D.count = w.n; D.split = 0; D.end = w.end;
+                    op += (long long)w.rel; e = w.pos; endk = w.end;
+                } else {
+                    // mc records in front of spec[j]; they count from the true position (base_a)
+                    const uint32_t spec_rel = slot[kChunkHead + j].y;
+                    D.base_a = op; D.base_b = op + (long long)rel - (long long)spec_rel;
+                    D.start = kChunkHead + j - mc; D.count = mc + (m.count - j); D.split = mc; D.end = m.end;
+                    op += (long long)rel + (long long)(m.out - spec_rel);
+                    e = m.exit; endk = m.end;
+                }
+                mode = 0;
             }
         }
-        a.desc[cb + k] = D;
-        if (endk != kEndCont || op > (long long)d.dcap) { a.last_chunk[f] = k; break; }
+        if (D.count != 0xFFFFFFFFu) {
+            a.desc[cb + k] = D;
+            if (endk != kEndCont || op > (long long)d.dcap) { a.last_chunk[f] = k; mode = 3; }
+        }
     }
 }
 
@@ -434,14 +473,31 @@ __device__ __forceinline__ uint32_t bits_mask(uint32_t w, uint32_t a, uint32_t b
     if (w == ((b - 1) >> 5)) mask &= 0xFFFFFFFFu >> (31u - ((b - 1) & 31u));
     return mask;
 }
-// pending-match bits of the tile: [a, b) set / cleared / tested (a < b)
+// pending-match bits of the tile: [a, b) set / cleared / tested (a < b).  Ranges of up to 32 bits (every match a
+// thread handles alone) touch two words, addressed without a loop; pend[] has one word of padding behind it.
 __device__ __forceinline__ void pend_set(uint32_t *pend, uint32_t a, uint32_t b) {
-    for (uint32_t w = a >> 5; w <= ((b - 1) >> 5); w++) atomicOr(&pend[w], bits_mask(w, a, b));
+    if (b - a <= 32u) {
+        const uint32_t m = b - a == 32u ? 0xFFFFFFFFu : (1u << (b - a)) - 1u, sh = a & 31u;
+        atomicOr(&pend[a >> 5], m << sh);
+        if (sh && (m >> (32u - sh))) atomicOr(&pend[(a >> 5) + 1], m >> (32u - sh));
+    } else {
+        for (uint32_t w = a >> 5; w <= ((b - 1) >> 5); w++) atomicOr(&pend[w], bits_mask(w, a, b));
+    }
 }
 __device__ __forceinline__ void pend_clear(uint32_t *pend, uint32_t a, uint32_t b) {
-    for (uint32_t w = a >> 5; w <= ((b - 1) >> 5); w++) atomicAnd(&pend[w], ~bits_mask(w, a, b));
+    if (b - a <= 32u) {
+        const uint32_t m = b - a == 32u ? 0xFFFFFFFFu : (1u << (b - a)) - 1u, sh = a & 31u;
+        atomicAnd(&pend[a >> 5], ~(m << sh));
+        if (sh && (m >> (32u - sh))) atomicAnd(&pend[(a >> 5) + 1], ~(m >> (32u - sh)));
+    } else {
+        for (uint32_t w = a >> 5; w <= ((b - 1) >> 5); w++) atomicAnd(&pend[w], ~bits_mask(w, a, b));
+    }
 }
 __device__ __forceinline__ bool pend_any(const volatile uint32_t *pend, uint32_t a, uint32_t b) {
+    if (b - a <= 32u) {
+        const uint32_t m = b - a == 32u ? 0xFFFFFFFFu : (1u << (b - a)) - 1u;
+        return (__funnelshift_r(pend[a >> 5], pend[(a >> 5) + 1], a & 31u) & m) != 0;
+    }
     bool any = false;
     for (uint32_t w = a >> 5; w <= ((b - 1) >> 5); w++) any = any || (pend[w] & bits_mask(w, a, b)) != 0;
     return any;
@@ -469,7 +525,7 @@ __device__ __forceinline__ void flush_tile(const uint8_t *ring, uint8_t *outv, u
 
 __global__ void __launch_bounds__(kCopy2Threads, 12) lz4_copy2_kernel(Copy2Args a) {
     __shared__ __align__(16) uint8_t ring[kRing2];
-    __shared__ uint32_t pend[kTile2 / 32];
+    __shared__ uint32_t pend[kTile2 / 32 + 1];
     __shared__ CoopLit s_coop[kCopy2Threads];
     __shared__ Carry s_carry[2];
     __shared__ uint32_t s_ncoop[3], s_bulk[3], s_err[3];   // per-group flags, three slots in rotation (a fast warp is at most one group ahead)
@@ -494,7 +550,7 @@ __global__ void __launch_bounds__(kCopy2Threads, 12) lz4_copy2_kernel(Copy2Args 
     const uint32_t a0 = (uint32_t)((uintptr_t)out & 15u);
     uint8_t *outv = out - a0;                             // v-space: v = output position + a0; outv + v is 16-byte aligned at v % 16 == 0
     const uint64_t vlimit = (uint64_t)a0 + d.dcap;
-    for (uint32_t i = tid; i < kTile2 / 32; i += kCopy2Threads) pend[i] = 0;
+    for (uint32_t i = tid; i < kTile2 / 32 + 1; i += kCopy2Threads) pend[i] = 0;
     if (tid == 0) {
         s_ncoop[0] = s_ncoop[1] = s_ncoop[2] = 0; s_bulk[0] = s_bulk[1] = s_bulk[2] = 0;
         s_err[0] = s_err[1] = s_err[2] = 0xFFFFFFFFu; s_total = ~0ull; s_carry[0].tag = s_carry[1].tag = 0xFFFFFFFFu;
@@ -649,7 +705,9 @@ __global__ void __launch_bounds__(kCopy2Threads, 12) lz4_copy2_kernel(Copy2Args 
                     const int32_t s1 = s0 + (int32_t)(ovl ? off : mn);
                     if (s1 > 0) { sa = s0 > 0 ? (uint32_t)s0 : 0u; sb = (uint32_t)s1; }
                 }
+                uint32_t idle = 0;                                // turns in a row in which no lane of the warp could go
                 while (__any_sync(0xffffffffu, pending)) {
+                    const bool was = pending;
                     if (pending && mn <= kMatch2 && (sb <= sa || !pend_any(pend, sa, sb))) {
                         uint8_t *dp = ring + rb + lb;
                         if (s0 >= W0) {                           // the source is in the ring
@@ -709,6 +767,9 @@ __global__ void __launch_bounds__(kCopy2Threads, 12) lz4_copy2_kernel(Copy2Args 
                             atomicAnd(&pend[w], ~bits_mask(w, jlb, jlb + jmn));
                         if (lane == j) pending = false;
                     }
+                    // what this warp waits for is another warp's match: leave the issue slots to it
+                    if (__any_sync(0xffffffffu, was && !pending)) idle = 0;
+                    else { idle++; B2B_NANOSLEEP(idle < 4u ? 32u * idle : 128u); }
                 }
             }
             // ---- progress; a full tile leaves

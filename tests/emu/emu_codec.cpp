@@ -168,7 +168,8 @@ int emu_compress_frame(const uint8_t *src, uint32_t n, int shuffle, int64_t type
     return (int)status;
 }
 
-static uint32_t g_dst_misalign = 0;
+static uint32_t g_dst_misalign = 0, g_parse_grid = 1;
+void emu_set_parse_grid(uint32_t g) { g_parse_grid = g ? g : 1; }
 void emu_set_dst_misalign(uint32_t m) { g_dst_misalign = m & 15u; }
 
 // one frame through K4 (split = parse kernel + copy kernel, else the fused kernel) and the inverse filter,
@@ -210,8 +211,10 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         Parse2Args pp;
         pp.frames = a.frames; pp.frame_off = &frame_off; pp.fd = &fd; pp.nframes = 1; pp.chunk_base = &chunk_base;
         pp.total_chunks = &total_chunks; pp.table = tab.data(); pp.meta = cmeta.data(); pp.table_chunks = table_chunks;
-        emu::launch((uint32_t)std::max<uint64_t>(1, (total_chunks + kParse2Threads - 1) / kParse2Threads), kParse2Threads,
-                    [&] { lz4_chunk_parse_kernel(pp); });
+        std::vector<uint32_t> dead(table_chunks + 4, 0);
+        unsigned long long ticket = 0;
+        pp.dead = dead.data(); pp.ticket = &ticket;
+        emu::launch(g_parse_grid, kParse2Threads, [&] { lz4_chunk_parse_kernel(pp); });
         Stitch2Args sa;
         sa.frames = a.frames; sa.frame_off = &frame_off; sa.fd = &fd; sa.nframes = 1; sa.chunk_base = &chunk_base;
         sa.table = tab.data(); sa.meta = cmeta.data(); sa.desc = cdesc.data(); sa.last_chunk = &last_chunk;

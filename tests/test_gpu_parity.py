@@ -541,9 +541,9 @@ def test_indexed_frames_are_standard_and_decode_in_parallel(ctx, orc, torch_mod,
 
 
 def test_split_and_fused_decoders_agree(ctx, orc):
-    """K4 runs as parse kernel + copy kernel by default and as one fused kernel under option 104: on
-    a ragged batch of valid, truncated and corrupted frames both give the same status, length and bytes
-    (and the oracle's status)."""
+    """K4 has three variants behind option 104 (0 chunk-parallel decoder of lz4_decode2.cuh, 1 the fused one-warp-per-frame
+    kernel, 2 parse kernel + copy kernel; -1 = chosen by frame size): on a ragged batch of valid, truncated and
+    corrupted frames all give the same status, length and bytes (and the oracle's status)."""
     rng = np.random.default_rng(77)
     frames, caps = [], []
     for k, n in enumerate([1, 13, 305, 306, 307, 700, 4096, 65536, 70001, 300000, 1 << 20]):
@@ -564,14 +564,15 @@ def test_split_and_fused_decoders_agree(ctx, orc):
     cap = np.array(caps, dtype=np.uint64)
     doff = np.concatenate([[0], np.cumsum((cap[:-1] + 15) // 16 * 16)]).astype(np.uint64)
     res = []
-    for fused in (0, 1):
-        ctx.set_option(104, fused)
+    for variant in (0, 1, 2):
+        ctx.set_option(104, variant)
         try:
             out, olen, st = ctx.decompress_batch(blob, foff, flen, doff, int(doff[-1] + cap[-1]) + 64)
         finally:
-            ctx.set_option(104, 0)
+            ctx.set_option(104, -1)
         res.append((out.copy(), olen.copy(), st.copy()))
-    assert np.array_equal(res[0][2], res[1][2]) and np.array_equal(res[0][1], res[1][1])
+    for other in res[1:]:
+        assert np.array_equal(res[0][2], other[2]) and np.array_equal(res[0][1], other[1])
     for k, f in enumerate(frames):
         rc, ref = orc.decompress(f)
         assert int(res[0][2][k]) == rc, (k, int(res[0][2][k]), rc)
