@@ -714,42 +714,90 @@ def run_gpu(args):
     return 0 if ok else 1
 
 
+def pcie_ceiling(torch, dev, nbytes, world):
+    """Raw concurrent cudaMemcpyAsync H2D + D2H of pinned buffers on two streams (every rank at once): the box's
+    ceiling for the e2e leg, which moves (n + c) bytes each way per round trip."""
+    import torch.distributed as dist
+    h_a = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True); h_a.zero_()
+    h_b = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True); h_b.zero_()
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = 0.0
+    for it in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_a, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_b.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if it:
+            best = max(best, 2.0 * nbytes * world / float(dt.item()) / 1e9)
+    return best          # GB/s moved over PCIe, both directions and all ranks together
+
+
 def run_e2e(torch, pkg, ctx, args, dev, src, nf, total, world):
-    """Same round trip through the host-pointer batch API: pinned host in, pinned host out."""
+    """Same round trip through the host-pointer batch API, H2D and D2H inside the timed region: with pinned host
+    buffers (the headline `value`: DMA straight from / to the caller's memory) and with PAGEABLE ones (what a Go
+    caller of the reference API has: the library stages them through its pinned ring, csrc/host_staging.hpp)."""
     import torch.distributed as dist
     e_total = min(total, int(args.e2e_gib * 2**30)) // FRAME * FRAME
     e_nf = e_total // FRAME
-    h_src = torch.empty(e_total, dtype=torch.uint8, pin_memory=True)
-    h_src.copy_(src[:e_total])
-    h_comp = torch.empty(e_total + 32 * e_nf + 64, dtype=torch.uint8, pin_memory=True)
-    h_out = torch.empty(e_total, dtype=torch.uint8, pin_memory=True)
     offs = np.arange(e_nf, dtype=np.uint64) * FRAME
     lens = np.full(e_nf, FRAME, dtype=np.uint32)
-    a_src, a_comp, a_out = h_src.numpy(), h_comp.numpy(), h_out.numpy()
+    out = {}
+    for mem in ("pinned", "pageable"):
+        pin = mem == "pinned"
+        h_src = torch.empty(e_total, dtype=torch.uint8, pin_memory=pin)
+        h_src.copy_(src[:e_total])
+        h_comp = torch.empty(e_total + 32 * e_nf + 64, dtype=torch.uint8, pin_memory=pin)
+        h_out = torch.empty(e_total, dtype=torch.uint8, pin_memory=pin)
+        if not pin:
+            h_comp.zero_(); h_out.zero_()                    # the pages exist before the clock starts
+        a_src, a_comp, a_out = h_src.numpy(), h_comp.numpy(), h_out.numpy()
 
-    def step():
-        _, foff, flen, st, tot = ctx.compress_batch(a_src, offs, lens, pkg.Shuffle.Shuffle1, 4, dst=a_comp)
-        _, olen, st2 = ctx.decompress_batch(a_comp, foff, flen, offs, e_total, dst=a_out)
-        return tot, int(st.any()) + int(st2.any())
+        def step():
+            _, foff, flen, st, tot = ctx.compress_batch(a_src, offs, lens, pkg.Shuffle.Shuffle1, 4, dst=a_comp)
+            _, olen, st2 = ctx.decompress_batch(a_comp, foff, flen, offs, e_total, dst=a_out)
+            return tot, int(st.any()) + int(st2.any())
 
-    for _ in range(min(args.warmup, 2)):
-        step()
-    steps = max(1, min(args.steps, 3))
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        tot, bad = step()
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    dt = float(dt.item()) / steps
-    ok = bad == 0 and bool(torch.equal(h_out, h_src))
-    return {"value": e_total * world / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(e_total + tot),
-            "d2h_bytes_per_step": int(tot + e_total), "bytes_per_gpu": e_total, "ms_per_step": dt * 1e3, "verified": ok,
-            "api": "b2b_compress_batch + b2b_decompress_batch (host pointers, pinned)"}
+        for _ in range(min(args.warmup, 2)):
+            step()
+        steps = max(1, min(args.steps, 3))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tot, bad = step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item()) / steps
+        ok = bad == 0 and bool(torch.equal(h_out, h_src))
+        out[mem] = {"value": e_total * world / dt / 1e9, "ms_per_step": dt * 1e3, "verified": ok,
+                    "h2d": int(e_total + tot), "d2h": int(tot + e_total)}
+        del h_src, h_comp, h_out, a_src, a_comp, a_out
+    ceiling = pcie_ceiling(torch, dev, 1 << 30, world)
+    p = out["pinned"]
+    moved = (p["h2d"] + p["d2h"]) * world / (p["ms_per_step"] / 1e3) / 1e9
+    return {"value": p["value"], "unit": UNIT, "h2d_bytes_per_step": p["h2d"], "d2h_bytes_per_step": p["d2h"],
+            "bytes_per_gpu": e_total, "ms_per_step": p["ms_per_step"], "verified": p["verified"] and out["pageable"]["verified"],
+            "api": "b2b_compress_batch + b2b_decompress_batch (host pointers, pinned)",
+            "pageable": {"value": out["pageable"]["value"], "unit": UNIT, "ms_per_step": out["pageable"]["ms_per_step"],
+                         "of_pinned": out["pageable"]["value"] / p["value"],
+                         "note": "pageable caller buffers (what the Go API hands over), staged through the library's pinned ring "
+                                 "by host threads (csrc/host_staging.hpp)"},
+            "pcie_ceiling_gbs": ceiling, "pcie_moved_gbs": moved, "of_pcie_ceiling": moved / ceiling if ceiling else None,
+            "pcie_note": "ceiling = raw concurrent cudaMemcpyAsync H2D + D2H of 1 GiB pinned buffers on every rank at once "
+                         "(bytes moved per second, both directions); moved = what the pinned e2e leg moved per second"}
 
 
 def main():

@@ -22,6 +22,9 @@
 #include "scan.cuh"
 #include "lz4_decode2.cuh"
 #include "blocks.cuh"
+#include "host_staging.hpp"
+
+#include <sched.h>
 
 using namespace b2b;
 
@@ -74,6 +77,9 @@ struct b2b_ctx {
                                        // decoder (lz4_decode2.cuh: a frame is spread over many threads), 1 the first design's fused
                                        // kernel (one warp per frame), 2 the first design's parse kernel + copy kernel (one warp per frame)
     uint64_t opt_stage_bytes = 128ull << 20;
+    int opt_host_threads = 0;          // host threads that move pageable caller memory into / out of the pinned ring (0: automatic)
+    int opt_no_staging = 0;            // 1: pageable buffers go to cudaMemcpyAsync directly (synchronous, driver-staged), as in round 1
+    HostStaging *staging = nullptr;    // created when the first pageable buffer arrives
     uint64_t launches = 0;
     std::string last_err;
     // arena 0 is shared by every device-pointer call: a call on another stream than the previous one waits for it
@@ -177,6 +183,21 @@ void select_arena(b2b_ctx *ctx, int i) {
     ctx->arenas[ctx->cur_arena] = ctx->arena; ctx->arena_caps[ctx->cur_arena] = ctx->arena_cap;
     ctx->cur_arena = i;
     ctx->arena = ctx->arenas[i]; ctx->arena_cap = ctx->arena_caps[i];
+}
+
+// pinned staging of pageable caller buffers (host_staging.hpp); created on first use
+HostStaging *staging_of(b2b_ctx *ctx) {
+    if (!ctx->staging) {
+        int n = ctx->opt_host_threads;
+        if (n <= 0) {
+            cpu_set_t set;
+            int avail = (int)std::thread::hardware_concurrency();
+            if (sched_getaffinity(0, sizeof set, &set) == 0) avail = CPU_COUNT(&set);
+            n = std::max(1, std::min(8, avail / 2));
+        }
+        ctx->staging = new (std::nothrow) HostStaging(ctx->device, n - 1, ctx->s_in, ctx->s_out);
+    }
+    return ctx->staging;
 }
 
 // grow-only device staging buffer i of the host-pointer entry points
@@ -448,7 +469,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     // with the chunk-parallel decoder, whose parse runs on one thread per 8 KiB of stream and whose copy stage
     // gives a frame a whole CTA).
     int variant = ctx->opt_fused_decode;
-    if (variant < 0) variant = (max_orig > (512u << 10) || nframes < 4u * (uint32_t)ctx->sm_count) ? 0 : 2;
+    if (variant < 0) variant = max_orig > (512u << 10) ? 0 : 2;
     const bool v2 = !indexed && variant == 0;
     const bool split = !indexed && variant == 2;
     const uint64_t nrec_max = total_dst / 4 + (uint64_t)(kSeqSlack + 1) * nframes + 64;   // sum of dst_cap / 4 + slack
@@ -902,6 +923,8 @@ void b2b_destroy(b2b_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     fold_timings(ctx);
+    delete ctx->staging;               // joins its threads before the streams it uses go away
+    ctx->staging = nullptr;
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     select_arena(ctx, 0);
     for (int i = 0; i < 5; i++) if (ctx->arenas[i]) cudaFree(ctx->arenas[i]);
@@ -941,6 +964,15 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
         case 100: case 101: case 102: case 103: ctx->opt_tune[option - 100] = (uint32_t)value; return B2B_OK;
         case 104: if (value < -1 || value > 2) return B2B_EINVAL; ctx->opt_fused_decode = (int)value; return B2B_OK;
         case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (128ull << 20); return B2B_OK;
+        case B2B_OPT_HOST_THREADS:
+            if (value < 0 || value > 64) return B2B_EINVAL;
+            ctx->opt_host_threads = (int)value;
+            if (ctx->staging) { cudaDeviceSynchronize(); delete ctx->staging; ctx->staging = nullptr; }
+            return B2B_OK;
+        case B2B_OPT_NO_HOST_STAGING: ctx->opt_no_staging = value != 0; return B2B_OK;
+        case B2B_OPT_DECODER:
+            if (value < -1 || value > 2) return B2B_EINVAL;
+            ctx->opt_fused_decode = (int)value; return B2B_OK;
         default: return B2B_EINVAL;
     }
 }
@@ -1269,8 +1301,9 @@ int b2b_shuffle(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, const voi
 //   s_out   D2H of the chunk's bytes
 // The host only ever waits for a chunk's TABLES (one chunk behind the one it just launched), never
 // for a bulk copy, so H2D of chunk k+1, the kernels of chunk k and D2H of chunk k-1 overlap and
-// both PCIe directions stay busy.  Pinned caller buffers are DMA'd directly; pageable ones make
-// the bulk copies synchronous (still correct).
+// both PCIe directions stay busy.  Pinned caller buffers are DMA'd directly; pageable ones (what a Go
+// caller has) go through the context's pinned ring (host_staging.hpp), so they overlap the same way.
+constexpr uint64_t kStagingMinBytes = 16ull << 20;   // pageable batches below this go to cudaMemcpyAsync directly
 struct HostChunk { uint32_t f0, f1; uint64_t lo, hi; uint32_t max_len; uint64_t sum; };   // sum: bytes of all frames (> hi - lo when they overlap)
 
 static std::vector<HostChunk> split_chunks(const uint64_t *off, const uint32_t *len, uint32_t nframes,
@@ -1307,6 +1340,7 @@ static bool ranges_disjoint(const uint64_t *off, const uint32_t *len, uint32_t n
 }
 
 static int sync_pipeline(b2b_ctx *ctx, cudaError_t e, int rc) {
+    if (ctx->staging) { const cudaError_t es = ctx->staging->flush(); if (e == cudaSuccess) e = es; }
     const cudaError_t e1 = cudaStreamSynchronize(ctx->s_out), e2 = cudaStreamSynchronize(ctx->s_tab);
     cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < b2b_ctx::kSlots; i++) { const cudaError_t ek = cudaStreamSynchronize(ctx->s_k[i]); if (e3 == cudaSuccess) e3 = ek; }
@@ -1336,6 +1370,16 @@ static int host_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *sr
     int rc = B2B_OK;
     cudaError_t e = cudaSuccess;
     uint8_t *d_out[S] = {};
+    // pageable caller memory goes through the context's pinned ring (host_staging.hpp)
+    // (small batches are left to the driver: a thread hand-off costs more than it saves below a few MiB)
+    uint64_t batch_bytes = 0;
+    for (const HostChunk &c : chunks) batch_bytes += c.sum;
+    const bool stage_ok = !ctx->opt_no_staging && batch_bytes >= kStagingMinBytes;
+    const bool src_pageable = stage_ok && host_pointer_is_pageable(src);
+    const bool dst_pageable = stage_ok && host_pointer_is_pageable(dst);
+    HostStaging *stg = (src_pageable || dst_pageable) ? staging_of(ctx) : nullptr;
+    if ((src_pageable || dst_pageable) && !stg) return B2B_ECUDA;
+    uint64_t rec_ticket[S] = {};
     // table block of a chunk of n frames (same layout on the device and in the pinned block):
     //   [src_off u64 n][frame_off u64 n][src_len u32 n][frame_len u32 n][status u32 n][total u64]
     auto layout = [](uint32_t n, uint64_t &a8, uint64_t &a4) { a8 = align_up(8ull * n, 256); a4 = align_up(4ull * n, 256); };
@@ -1353,8 +1397,13 @@ static int host_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *sr
         const uint32_t *h_status = (const uint32_t *)(t + 2 * a8 + 2 * a4);
         const uint64_t h_total = *(const uint64_t *)(t + 2 * a8 + 3 * a4);
         if (running + h_total > dst_cap) return B2B_EDST_TOO_SMALL;
-        if (h_total) CU(ctx, cudaMemcpyAsync(hdst + running, d_out[slot], h_total, cudaMemcpyDeviceToHost, ctx->s_out));
-        CU(ctx, cudaEventRecord(ctx->ev_out_free[slot], ctx->s_out));
+        if (dst_pageable) {
+            if (h_total) stg->d2h(hdst + running, d_out[slot], h_total);
+            rec_ticket[slot] = stg->record(ctx->ev_out_free[slot]);
+        } else {
+            if (h_total) CU(ctx, cudaMemcpyAsync(hdst + running, d_out[slot], h_total, cudaMemcpyDeviceToHost, ctx->s_out));
+            CU(ctx, cudaEventRecord(ctx->ev_out_free[slot], ctx->s_out));
+        }
         for (uint32_t i = 0; i < n; i++) frame_off[c.f0 + i] = h_frame_off[i] + running;
         memcpy(frame_len + c.f0, h_frame_len, 4ull * n);
         memcpy(status + c.f0, h_status, 4ull * n);
@@ -1390,13 +1439,15 @@ static int host_compress_batch(b2b_ctx *ctx, const void *src, const uint64_t *sr
         memcpy(h_src_len, src_len + c.f0, 4ull * n);
         // H2D (the kernels that last read this slot's input must be done)
         if (k >= (size_t)S) e = cudaStreamWaitEvent(ctx->s_in, ctx->ev_in_free[slot], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, hsrc + c.lo, span, cudaMemcpyHostToDevice, ctx->s_in);
+        if (e == cudaSuccess) e = src_pageable ? stg->h2d(d_in, hsrc + c.lo, span)
+                                               : cudaMemcpyAsync(d_in, hsrc + c.lo, span, cudaMemcpyHostToDevice, ctx->s_in);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_src_off, h_src_off, 8ull * n, cudaMemcpyHostToDevice, ctx->s_in);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_src_len, h_src_len, 4ull * n, cudaMemcpyHostToDevice, ctx->s_in);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_ready[slot], ctx->s_in);
         // kernels (the D2H that last read this slot's output must be done)
         cudaStream_t sk = ctx->s_k[slot];
         if (e == cudaSuccess) e = cudaStreamWaitEvent(sk, ctx->ev_in_ready[slot], 0);
+        if (k >= (size_t)S && dst_pageable) stg->wait_recorded(rec_ticket[slot]);   // the drain thread has queued that chunk's copies
         if (e == cudaSuccess && k >= (size_t)S) e = cudaStreamWaitEvent(sk, ctx->ev_out_free[slot], 0);
         if (e != cudaSuccess) break;
         select_arena(ctx, 1 + slot);
@@ -1507,6 +1558,18 @@ static int host_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_
     std::vector<HostRun> out_runs[S];
     std::vector<uint64_t> dev_dst_off[S];
     uint8_t *d_out_slot[S] = {};
+    uint64_t batch_bytes = 0;
+    for (const Chunk &c : chunks) batch_bytes += c.out_bytes;
+    const bool stage_ok = !ctx->opt_no_staging && batch_bytes >= kStagingMinBytes;
+    const bool src_pageable = stage_ok && host_pointer_is_pageable(frames);
+    const bool dst_pageable = stage_ok && dst && host_pointer_is_pageable(dst);
+    HostStaging *stg = (src_pageable || dst_pageable) ? staging_of(ctx) : nullptr;
+    if ((src_pageable || dst_pageable) && !stg) return B2B_ECUDA;
+    uint64_t rec_ticket[S] = {};
+    auto d2h = [&](void *h, const void *dv, uint64_t len) -> cudaError_t {
+        if (dst_pageable) { stg->d2h(h, dv, len); return cudaSuccess; }
+        return cudaMemcpyAsync(h, dv, len, cudaMemcpyDeviceToHost, ctx->s_out);
+    };
     // table block: [frame_off u64 n][dst_off u64 n][frame_len u32 n][cap u32 n][out_len u32 n][status u32 n]
     auto retire = [&](size_t k) -> int {
         const Chunk &c = chunks[k];
@@ -1525,17 +1588,17 @@ static int host_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_
             for (uint32_t i = r.i0; i < r.i1 && whole; i++)
                 whole = h_status[i - c.i0] == B2B_OK && h_out_len[i - c.i0] == cap[F(i)];
             if (whole) {
-                if (r.len) CU(ctx, cudaMemcpyAsync(hdst + r.host, d_out_slot[slot] + r.dev, r.len, cudaMemcpyDeviceToHost, ctx->s_out));
+                if (r.len) CU(ctx, d2h(hdst + r.host, d_out_slot[slot] + r.dev, r.len));
                 continue;
             }
             for (uint32_t i = r.i0; i < r.i1; i++) {
                 const uint32_t st = h_status[i - c.i0], got = std::min(h_out_len[i - c.i0], cap[F(i)]);
                 if ((st == B2B_OK || st == B2B_ESIZE_MISMATCH) && got)
-                    CU(ctx, cudaMemcpyAsync(hdst + dst_off[F(i)], d_out_slot[slot] + dev_dst_off[slot][i - c.i0], got,
-                                            cudaMemcpyDeviceToHost, ctx->s_out));
+                    CU(ctx, d2h(hdst + dst_off[F(i)], d_out_slot[slot] + dev_dst_off[slot][i - c.i0], got));
             }
         }
-        CU(ctx, cudaEventRecord(ctx->ev_out_free[slot], ctx->s_out));
+        if (dst_pageable) rec_ticket[slot] = stg->record(ctx->ev_out_free[slot]);
+        else CU(ctx, cudaEventRecord(ctx->ev_out_free[slot], ctx->s_out));
         return B2B_OK;
     };
     size_t launched = 0, retired = 0;
@@ -1605,11 +1668,13 @@ static int host_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_
         }
         if (k >= (size_t)S) e = cudaStreamWaitEvent(ctx->s_in, ctx->ev_in_free[slot], 0);
         for (const HostRun &r : in_runs)
-            if (e == cudaSuccess && r.len) e = cudaMemcpyAsync(d_in + r.dev, hf + r.host, r.len, cudaMemcpyHostToDevice, ctx->s_in);
+            if (e == cudaSuccess && r.len) e = src_pageable ? stg->h2d(d_in + r.dev, hf + r.host, r.len)
+                                                            : cudaMemcpyAsync(d_in + r.dev, hf + r.host, r.len, cudaMemcpyHostToDevice, ctx->s_in);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab, h_tab, 2 * a8 + 2 * a4, cudaMemcpyHostToDevice, ctx->s_in);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_in_ready[slot], ctx->s_in);
         cudaStream_t sk = ctx->s_k[slot];
         if (e == cudaSuccess) e = cudaStreamWaitEvent(sk, ctx->ev_in_ready[slot], 0);
+        if (k >= (size_t)S && dst_pageable) stg->wait_recorded(rec_ticket[slot]);   // the drain thread has queued that chunk's copies
         if (e == cudaSuccess && k >= (size_t)S) e = cudaStreamWaitEvent(sk, ctx->ev_out_free[slot], 0);
         if (e != cudaSuccess) break;
         select_arena(ctx, 1 + slot);

@@ -114,7 +114,17 @@ enum {
      * shuffle, 5 for unshuffled input: the most recent occurrence of a 4-byte context is rarely the
      * longest one in text or low-entropy integers; the reference compressor hashes 6).  5 needs
      * B2B_OPT_HASH_LOG >= 11 and 6 needs >= 12 (smaller tables are raised to that). */
-    B2B_OPT_HASH_BYTES = 6
+    B2B_OPT_HASH_BYTES = 6,
+    /* host batch path, pageable caller buffers: host threads that move them into / out of the pinned staging
+     * ring (1..64; 0 = automatic: half of the CPUs this process may run on, at most 8) */
+    B2B_OPT_HOST_THREADS = 7,
+    /* 1: hand pageable buffers to cudaMemcpyAsync directly (synchronous, staged by the driver) instead of
+     * the library's pinned ring; for comparison only */
+    B2B_OPT_NO_HOST_STAGING = 8,
+    /* LZ4 decoder variant: -1 automatic (default: by frame size), 0 chunk-parallel (a frame is spread over
+     * many threads: large or few frames), 1 fused one-warp-per-frame kernel, 2 parse kernel + copy kernel
+     * (one warp per frame: thousands of small frames).  All give identical results. */
+    B2B_OPT_DECODER = 9
 };
 B2B_API int b2b_set_option(b2b_ctx *ctx, int option, int64_t value);
 /* pre-size the device scratch arena so that later calls do not allocate */

@@ -407,6 +407,69 @@ def test_ragged_batch_host_api(ctx, orc, stage):
         ctx.set_option(3, 0)
 
 
+def test_pageable_batches_go_through_the_pinned_ring(ctx, orc):
+    """Pageable caller buffers (numpy arrays here, Go slices in the drop-in) of more than 16 MiB are staged through
+    the library's pinned ring by host threads (csrc/host_staging.hpp), several pipeline chunks deep.  Same frames,
+    tables and bytes as the driver-staged path (option 8) and as pinned buffers; gapped and permuted output slots
+    keep the caller's bytes between them; a corrupt frame in the middle leaves its slot alone."""
+    import torch
+    sizes = [262144] * 90 + [1 << 20] * 9 + [13, 70001, 3 << 20, 999, 524288] * 3
+    rng = np.random.default_rng(5)
+    frames = []
+    for i, sz in enumerate(sizes):
+        frames.append(dg.smooth_f32((sz + 3) // 4, i)[:sz].copy() if i % 3 else dg.random_bytes(sz, i))
+    src = np.concatenate(frames)
+    assert src.size > (32 << 20)
+    lens = np.array(sizes, dtype=np.uint32)
+    offs = np.concatenate([[0], np.cumsum(lens[:-1].astype(np.uint64))]).astype(np.uint64)
+    ctx.set_option(3, 8 << 20)                                        # 8 MiB chunks: the ring turns over many times
+    try:
+        res = {}
+        for mode in ("staged", "driver", "pinned"):
+            ctx.set_option(8, 1 if mode == "driver" else 0)
+            if mode == "pinned":
+                h_src = torch.empty(src.size, dtype=torch.uint8, pin_memory=True).numpy(); h_src[:] = src
+                h_dst = torch.empty(src.size + 32 * len(sizes) + 64, dtype=torch.uint8, pin_memory=True).numpy()
+                dst, foff, flen, status, total = ctx.compress_batch(h_src, offs, lens, shuffle=1, typesize=4, dst=h_dst)
+            else:
+                dst, foff, flen, status, total = ctx.compress_batch(src, offs, lens, shuffle=1, typesize=4)
+            assert not status.any()
+            res[mode] = (dst[:total].copy(), foff.copy(), flen.copy())
+        for mode in ("driver", "pinned"):
+            assert np.array_equal(res["staged"][1], res[mode][1]) and np.array_equal(res["staged"][2], res[mode][2])
+            for f in range(len(sizes)):                               # (the padding between frames is not defined)
+                o, l = int(res["staged"][1][f]), int(res["staged"][2][f])
+                assert np.array_equal(res["staged"][0][o:o + l], res[mode][0][o:o + l]), (mode, f)
+        comp, foff, flen = res["staged"]
+        ctx.set_option(8, 0)
+        for f in (0, 1, 95, 100, 101, len(sizes) - 1):                # the oracle reads them
+            rc, back = orc.decompress(comp[int(foff[f]):int(foff[f]) + int(flen[f])])
+            assert rc == 0 and np.array_equal(back, frames[f]), f
+        out, out_len, st = ctx.decompress_batch(comp, foff, flen, offs, src.size)
+        assert not st.any() and np.array_equal(out_len, lens) and np.array_equal(out, src)
+        # gapped, permuted output slots into a pre-filled pageable buffer; one frame corrupted
+        order = rng.permutation(len(sizes))
+        gap = 40
+        doff = np.zeros(len(sizes), dtype=np.uint64)
+        pos = 7
+        for f in order:
+            doff[f] = pos; pos += sizes[f] + gap
+        broken = comp.copy()
+        broken[int(foff[50]) + 16:int(foff[50]) + int(flen[50])] ^= 0x5A
+        canvas = np.full(pos + 64, 0xEE, dtype=np.uint8)
+        out, out_len, st = ctx.decompress_batch(broken, foff, flen, doff, canvas.size, dst=canvas)
+        assert st[50] != 0 and not np.delete(st, 50).any()
+        want = np.full(canvas.size, 0xEE, dtype=np.uint8)
+        for f in range(len(sizes)):
+            if f != 50:
+                want[int(doff[f]):int(doff[f]) + sizes[f]] = frames[f]
+        keep = np.ones(canvas.size, dtype=bool)
+        keep[int(doff[50]):int(doff[50]) + sizes[50]] = False          # a failed frame's slot is unspecified only if it produced bytes
+        assert np.array_equal(out[keep], want[keep])
+    finally:
+        ctx.set_option(3, 0); ctx.set_option(8, 0)
+
+
 def _ragged_batch(ctx, orc):
     sizes = [32768, 65536, 1000, 131072, 13, 262144, 524288, 1, 99999, 2 << 20]
     frames = []
