@@ -187,6 +187,104 @@ __device__ __forceinline__ void shuffle_tile_generic(const uint8_t *__restrict__
     }
 }
 
+// ---- K1 staged tiles: any typesize up to kStageMaxT, any alignment, any element count ------------------
+// What the 16-byte fast path cannot take (T = 3, 5, 6, 7, 12, ...; frame bases that are not 16-byte aligned;
+// E % 16 != 0, i.e. most frame sizes that are not powers of two) used to go through shuffle_tile_generic:
+// byte-granular global accesses on both sides, 0.75 - 1.6 TB/s.  Here the CONTIGUOUS side of the transpose is
+// staged in shared memory and every global access is a 16-byte vector on a 16-byte boundary:
+//   * the contiguous side is loaded / stored from the aligned address below its first byte (the few bytes in
+//     front belong to the same 16-byte block, so the access stays inside the buffer);
+//   * on the plane side one thread owns one ALIGNED 16-byte vector of one plane segment: it gathers its 16
+//     bytes from (scatters them to) the staged elements at stride T; only the first and the last vector of a
+//     segment, which reach outside it, move single bytes.
+// Lanes run over the planes first, so the 32 lanes of a shared-memory access touch neighbouring bytes.
+constexpr uint32_t kStageTile = 16384;                             // bytes of one staged tile
+constexpr uint32_t kStageLin = kStageTile + 32;                    // + misalignment + over-read
+constexpr uint32_t kStageMaxT = 16;                                // (T = 32 measured no faster than the byte-granular path)
+
+// forward: elements [e0, e0 + ve) of the frame -> T plane segments
+__device__ __forceinline__ void shuffle_tile_staged(const uint8_t *__restrict__ s, uint8_t *__restrict__ d, uint64_t E,
+                                                    uint32_t T, uint64_t e0, uint32_t ve, uint8_t *lin) {
+    const uint32_t nb = ve * T;
+    const uint8_t *g0 = s + e0 * T;
+    const uint32_t mis = (uint32_t)((uintptr_t)g0 & 15u);
+    const uint32_t nvec = (mis + nb + 15u) >> 4;
+    for (uint32_t v = threadIdx.x; v < nvec; v += kFilterThreads)
+        *reinterpret_cast<uint4 *>(lin + 16u * v) = ldg128_stream(g0 - mis + 16ull * v);
+    __syncthreads();
+    const uint32_t d0 = (uint32_t)((uintptr_t)(d + e0) & 15u), dE = (uint32_t)(E & 15u);   // plane j starts at (d0 + j * dE) & 15
+    const uint32_t NV = (15u + ve + 15u) >> 4, items = NV * T;       // vectors a segment can touch
+    uint32_t v = threadIdx.x / T, j = threadIdx.x - v * T;
+    const uint32_t dv = kFilterThreads / T, dj = kFilterThreads - dv * T;
+    for (uint32_t idx = threadIdx.x; idx < items; idx += kFilterThreads) {
+        const uint32_t aj = (d0 + j * dE) & 15u;
+        const uint32_t lo = 16u * v, hi = lo + 16u;                   // this vector's bytes, counted from the aligned address
+        if (lo < aj + ve && hi > aj) {
+            uint8_t *gp = d + (uint64_t)j * E + e0 - aj;              // 16-byte aligned
+            if (lo >= aj && hi <= aj + ve) {
+                const uint8_t *p = lin + mis + (lo - aj) * T + j;     // element lo - aj, byte j
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    w[k] = (uint32_t)p[0] | ((uint32_t)p[T] << 8) | ((uint32_t)p[2u * T] << 16) | ((uint32_t)p[3u * T] << 24);
+                    p += 4u * T;
+                }
+                stg128_stream(gp + lo, make_uint4(w[0], w[1], w[2], w[3]));
+            } else {
+                for (uint32_t b = (lo > aj ? lo : aj); b < hi && b < aj + ve; b++) gp[b] = lin[mis + (b - aj) * T + j];
+            }
+        }
+        v += dv; j += dj;
+        if (j >= T) { j -= T; v++; }
+    }
+    __syncthreads();
+}
+
+// inverse: T plane segments [e0, e0 + ve) -> elements
+__device__ __forceinline__ void unshuffle_tile_staged(const uint8_t *__restrict__ s, uint8_t *__restrict__ d, uint64_t E,
+                                                      uint32_t T, uint64_t e0, uint32_t ve, uint8_t *lin) {
+    const uint32_t nb = ve * T;
+    uint8_t *g0 = d + e0 * T;
+    const uint32_t mis = (uint32_t)((uintptr_t)g0 & 15u);
+    const uint32_t s0 = (uint32_t)((uintptr_t)(s + e0) & 15u), sE = (uint32_t)(E & 15u);   // plane j starts at (s0 + j * sE) & 15
+    const uint32_t NV = (15u + ve + 15u) >> 4, items = NV * T;
+    uint32_t v = threadIdx.x / T, j = threadIdx.x - v * T;
+    const uint32_t dv = kFilterThreads / T, dj = kFilterThreads - dv * T;
+    for (uint32_t idx = threadIdx.x; idx < items; idx += kFilterThreads) {
+        const uint32_t aj = (s0 + j * sE) & 15u;
+        const uint32_t lo = 16u * v, hi = lo + 16u;
+        if (lo < aj + ve && hi > aj) {
+            const uint8_t *gp = s + (uint64_t)j * E + e0 - aj;        // 16-byte aligned
+            const uint4 x = ldg128_stream(gp + lo);
+            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+            if (lo >= aj && hi <= aj + ve) {
+                uint8_t *p = lin + mis + (lo - aj) * T + j;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    p[0] = (uint8_t)w[k]; p[T] = (uint8_t)(w[k] >> 8); p[2u * T] = (uint8_t)(w[k] >> 16); p[3u * T] = (uint8_t)(w[k] >> 24);
+                    p += 4u * T;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t b = lo + (uint32_t)k;
+                    if (b >= aj && b < aj + ve) lin[mis + (b - aj) * T + j] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+                }
+            }
+        }
+        v += dv; j += dj;
+        if (j >= T) { j -= T; v++; }
+    }
+    __syncthreads();
+    const uint32_t nvec = (mis + nb + 15u) >> 4;
+    for (uint32_t q = threadIdx.x; q < nvec; q += kFilterThreads) {
+        const uint32_t lo = 16u * q, hi = lo + 16u;
+        if (lo >= mis && hi <= mis + nb) stg128_stream(g0 - mis + lo, *reinterpret_cast<const uint4 *>(lin + lo));
+        else for (uint32_t b = (lo > mis ? lo : mis); b < hi && b < mis + nb; b++) (g0 - mis)[b] = lin[b];
+    }
+    __syncthreads();
+}
+
 // =========================================================================================
 // K2 fast groups: one thread owns one group of 8 elements (8*T contiguous bytes)
 // =========================================================================================
@@ -500,6 +598,7 @@ template <int T> struct BitSmemCfg {
 };
 constexpr uint32_t kFilterSmemBytes = BitSmemCfg<16>::kGroups * BitSmemCfg<16>::kStride;   // 18 432 >= both layouts
 static_assert(BitSmemCfg<8>::kGroups * BitSmemCfg<8>::kStride <= kFilterSmemBytes, "smem");
+static_assert(kStageLin <= kFilterSmemBytes, "smem");   // staged byte shuffle: the contiguous side of one tile
 
 // tile byte b (16-byte chunk) <-> its place in the padded rows
 template <int T> __device__ __forceinline__ uint32_t bit_smem_pos(uint32_t b) {
@@ -611,7 +710,17 @@ __global__ void __launch_bounds__(kFilterThreads, 6) filter_batch_kernel(FilterA
         else if (fast && T == 8) run_shuffle_fast<8>(s, d, E, tile0, tpf, inverse, smem);
         else if (fast && T == 2) run_shuffle_fast<2>(s, d, E, tile0, tpf, inverse, smem);
         else if (fast && T == 16) run_shuffle_fast<16>(s, d, E, tile0, tpf, inverse, smem);
-        else {
+        else if (T <= kStageMaxT) {
+            // everything else up to 16 bytes per element: staged through shared memory, aligned vectors on both sides
+            const uint64_t te = kStageTile / T;
+            const uint64_t ntiles = (E + te - 1) / te;
+            for (uint64_t t = tile0; t < ntiles; t += tpf) {
+                const uint64_t e0 = t * te;
+                const uint32_t ve = (uint32_t)(E - e0 < te ? E - e0 : te);
+                if (!inverse) shuffle_tile_staged(s, d, E, (uint32_t)T, e0, ve, smem);
+                else unshuffle_tile_staged(s, d, E, (uint32_t)T, e0, ve, smem);
+            }
+        } else {
             uint64_t te = kTileBytes / T;
             if (te == 0) te = 1;
             const uint64_t ntiles = (E + te - 1) / te;

@@ -94,7 +94,7 @@ static inline void __syncthreads() {
     const uint32_t g = c->gen;
     c->arrived++;
     while (c->gen == g) {
-        if (c->arrived == c->live) { c->arrived = 0; c->red[(g + 1) & 1] = 0; c->gen = g + 1; break; }
+        if (c->arrived == c->live) { c->arrived = 0; c->red[(g + 1) & 1] = 0; c->gen = g + 1; emu::n_collectives++; break; }
         emu::yield();
     }
 }
@@ -107,7 +107,7 @@ static inline int emu_syncthreads_reduce(int pred, int op) {
     if (pred) c->red[g & 1]++;
     c->arrived++;
     while (c->gen == g) {
-        if (c->arrived == c->live) { c->arrived = 0; c->red[(g + 1) & 1] = 0; c->gen = g + 1; break; }
+        if (c->arrived == c->live) { c->arrived = 0; c->red[(g + 1) & 1] = 0; c->gen = g + 1; emu::n_collectives++; break; }
         emu::yield();
     }
     const int n = (int)c->red[g & 1];
