@@ -553,7 +553,9 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         ca.frames = a.frames; ca.frame_off = d_frame_off; ca.fd = d_fd; ca.nframes = nframes; ca.dst = a.dst; ca.scratch = d_stage;
         ca.dst_off = d_dst_off; ca.chunk_base = d_chunk_base; ca.desc = d_cdesc; ca.last_chunk = d_last; ca.table = d_rec;
         ca.fallback = d_fallback; ca.out_len = d_out_len; ca.status = d_status; ca.meta = d_meta;
-        { LaunchTimer lt(ctx, K_COPY2, s); lz4_copy2_kernel<<<nframes, kCopy2Threads, 0, s>>>(ca); }
+        // stored (memcpy-flag) frames are split over gridDim.y CTAs: about one per MiB of the largest frame
+        const unsigned ny = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(64, ((uint64_t)max_orig + (1u << 20) - 1) >> 20));
+        { LaunchTimer lt(ctx, K_COPY2, s); lz4_copy2_kernel<<<dim3(nframes, ny), kCopy2Threads, 0, s>>>(ca); }
         CU(ctx, cudaGetLastError());
         a.only = d_fallback;
         { LaunchTimer lt(ctx, K_DECODE, s);

@@ -97,6 +97,20 @@ struct ChunkDesc {       // written by the stitch kernel
 // kEndBadA / kEndBadB: malformed (B: ll / lit are valid and inside the stream).  Written without early
 // returns: the callers keep the lanes of a warp converged across tokens (one vote per token), and only the
 // rare length-extension loops diverge.
+// Length bytes of a very long run (a 100 MB literal run has 400 000 of them): whole aligned 16-byte blocks of 0xFF
+// are taken at once.  Returns how many bytes were skipped (a multiple of 16); each adds 255.
+__device__ __forceinline__ uint32_t skip_ff_blocks(const uint8_t *__restrict__ s, uint32_t clen, uint32_t p) {
+    uint32_t n = 0;
+    if (((uintptr_t)(s + p) & 15u) == 0) {
+        while (p + n + 16u <= clen) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(s + p + n);
+            if ((v.x & v.y & v.z & v.w) != 0xFFFFFFFFu) break;
+            n += 16u;
+        }
+    }
+    return n;
+}
+
 __device__ __forceinline__ uint32_t tok_step(const uint8_t *__restrict__ s, uint32_t clen, uint32_t p, uint32_t &ll,
                                              uint32_t &lit, uint64_t &ml, uint32_t &next) {
     ll = 0; lit = p; ml = 0; next = p;
@@ -110,7 +124,10 @@ __device__ __forceinline__ uint32_t tok_step(const uint8_t *__restrict__ s, uint
             bool more = true;
             while (more) {
                 if (p >= clen) { kind = kEndBadA; more = false; }
-                else { const uint32_t b = s[p++]; l += b; more = b == 255u; }
+                else {
+                    const uint32_t b = s[p++]; l += b; more = b == 255u;
+                    if (more) { const uint32_t k = skip_ff_blocks(s, clen, p); p += k; l += 255ull * k; }
+                }
             }
         }
         if (kind == kEndCont && l > (uint64_t)(clen - p)) kind = kEndBadA;
@@ -126,7 +143,10 @@ __device__ __forceinline__ uint32_t tok_step(const uint8_t *__restrict__ s, uint
                     bool more = true;
                     while (more) {
                         if (p >= clen) { kind = kEndBadB; more = false; }
-                        else { const uint32_t b = s[p++]; m += b; more = b == 255u; }
+                        else {
+                            const uint32_t b = s[p++]; m += b; more = b == 255u;
+                            if (more) { const uint32_t k = skip_ff_blocks(s, clen, p); p += k; m += 255ull * k; }
+                        }
                     }
                     if (m > 0xFFFFFFFFull) kind = kEndBadB;
                 }
@@ -536,11 +556,14 @@ __global__ void __launch_bounds__(kCopy2Threads, 12) lz4_copy2_kernel(Copy2Args 
     const int lane = (int)(tid & 31u);
     const FrameDec d = a.fd[f];
     if (d.kind == 0 || a.fallback[f]) return;             // status is final (prep) / the fallback kernel's
+    if (blockIdx.y != 0 && d.kind != 1) return;           // only stored frames are shared between CTAs
     uint8_t *out = (d.mode ? a.scratch : a.dst) + a.dst_off[f];
     const uint8_t *fr = a.frames + a.frame_off[f];
-    if (d.kind == 1) {                                    // stored frame (memcpy flag, blosc.go:393-401)
-        cta_copy(out, fr + 16, d.plen);
-        if (tid == 0) {
+    if (d.kind == 1) {                                    // stored frame (memcpy flag, blosc.go:393-401): gridDim.y CTAs share it
+        const uint64_t slice = (((uint64_t)d.plen + gridDim.y - 1) / gridDim.y + 15ull) & ~15ull;
+        const uint64_t lo = (uint64_t)blockIdx.y * slice;
+        if (lo < d.plen) cta_copy(out + lo, fr + 16 + lo, d.plen - lo < slice ? d.plen - lo : slice);
+        if (tid == 0 && blockIdx.y == 0) {
             FrameMeta m; m.mode = d.mode; m.typesize = d.typesize;
             a.status[f] = kOk; a.out_len[f] = d.norig; a.meta[f] = m;
         }
@@ -596,7 +619,13 @@ __global__ void __launch_bounds__(kCopy2Threads, 12) lz4_copy2_kernel(Copy2Args 
                         uint32_t p = rc.x;
                         const uint32_t tok = src[p++];
                         ll = tok >> 4;
-                        if (ll == 15u) { uint32_t b; do { b = src[p++]; ll += b; } while (b == 255u); }
+                        if (ll == 15u) {
+                            uint32_t b;
+                            do {
+                                b = src[p++]; ll += b;
+                                if (b == 255u) { const uint32_t sk = skip_ff_blocks(src, d.plen, p); p += sk; ll += 255u * sk; }
+                            } while (b == 255u);
+                        }
                         lit = p;
                         vM = vL + ll;
                         ml = (uint64_t)(on - o) - ll;

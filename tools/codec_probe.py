@@ -12,6 +12,8 @@ from tools.perf_probe_lib import gen_f32
 pkg = entry.load_package()
 ctx = pkg.Context(0)
 ctx.set_option(pkg.OPT_KERNEL_TIMING, 1)
+if os.environ.get("PROBE_DECODER"):
+    ctx.set_option(pkg.OPT_DECODER, int(os.environ["PROBE_DECODER"]))      # -1 automatic, 0 chunk-parallel, 1 fused, 2 parse + copy
 s = torch.cuda.current_stream().cuda_stream
 size = int(os.environ.get("PROBE_BYTES", 2 << 30))
 which = os.environ.get("PROBE_CASES", "c3,c4,c5,text").split(",")
