@@ -37,7 +37,7 @@ MIN_HEADER_SIZE = 16
  EDATA_TOO_LARGE, ECOMPRESSION_FAILED, EDECOMPRESSION_FAILED, ECUDA, EUNSUPPORTED,
  EDST_TOO_SMALL, EINVAL) = range(13)
 OPT_REF_MEMCPY_QUIRK, OPT_FILTER_CTAS_PER_SM, OPT_HOST_STAGE_BYTES, OPT_HASH_LOG, OPT_KERNEL_TIMING, OPT_HASH_BYTES = 1, 2, 3, 4, 5, 6
-OPT_HOST_THREADS, OPT_NO_HOST_STAGING, OPT_DECODER = 7, 8, 9
+OPT_HOST_THREADS, OPT_NO_HOST_STAGING, OPT_DECODER, OPT_FUSE_UNSHUFFLE, OPT_DECODE_STREAMS = 7, 8, 9, 10, 11
 
 
 class Codec(enum.IntEnum):   # blosc.go:55-64

@@ -77,6 +77,12 @@ struct b2b_ctx {
                                        // decoder (lz4_decode2.cuh: a frame is spread over many threads), 1 the first design's fused
                                        // kernel (one warp per frame), 2 the first design's parse kernel + copy kernel (one warp per frame)
     uint64_t opt_stage_bytes = 128ull << 20;
+    int opt_decode_streams = 0;        // streams a large decompress batch is split over: 0 automatic (2), 1 none, 2..4
+    static constexpr int kSide = 3;
+    cudaStream_t s_side[kSide] = {};   // the extra streams of large device-pointer decompress batches
+    cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {};
+    int opt_fuse_unshuffle = 0;        // K4 (one warp per frame): 1 = the decoding warp also un-shuffles its frame (typesize 2 / 4).
+                                       // Measured neutral on C3 (decode +2.3 ms, separate pass -2.3 ms per 8 GiB: DESIGN.md section 4), so off
     int opt_host_threads = 0;          // host threads that move pageable caller memory into / out of the pinned ring (0: automatic)
     int opt_no_staging = 0;            // 1: pageable buffers go to cudaMemcpyAsync directly (synchronous, driver-staged), as in round 1
     HostStaging *staging = nullptr;    // created when the first pageable buffer arrives
@@ -509,7 +515,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     a.frame_len = d_frame_len; a.nframes = nframes; a.typesize_override = typesize_override;
     a.dst = static_cast<uint8_t *>(d_dst); a.scratch = d_stage; a.dst_off = d_dst_off;
     a.dst_cap = d_dst_cap; a.out_len = d_out_len; a.status = d_status; a.meta = d_meta;
-    a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr; a.only = nullptr;
+    a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr; a.only = nullptr; a.fuse_unshuffle = ctx->opt_fuse_unshuffle ? 1u : 0u;
     if (v2) {
         // prep -> K5 (chunks per frame) -> one thread per chunk parses -> one thread per frame stitches ->
         // one CTA per frame copies (lz4_decode2.cuh); frames the table has no room for (output slots that
@@ -577,14 +583,54 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         // parse kernel (28 registers, 48 warps per SM) -> one 8-byte record per sequence -> copy kernel
         rc = launch_scan(ctx, d_dst_cap, nframes, d_table_off, nullptr, kScanSeqSlots, scan_t, s);
         if (rc) return rc;
-        ParseArgs pa;
-        pa.frames = a.frames; pa.frame_off = d_frame_off; pa.frame_len = d_frame_len; pa.dst_cap = d_dst_cap;
-        pa.nframes = nframes; pa.table = d_table; pa.table_off = d_table_off; pa.nrec = d_nrec; pa.table_cap = nrec_max;
         a.table = d_table; a.table_off = d_table_off; a.nrec = d_nrec;
-        const unsigned grid = (nframes + kCodecWarps - 1) / kCodecWarps;
-        { LaunchTimer lt(ctx, K_PARSE, s); lz4_parse_kernel<<<grid, kCodecThreads, 0, s>>>(pa); }
-        CU(ctx, cudaGetLastError());
-        { LaunchTimer lt(ctx, K_DECODE, s); lz4_decode_kernel<true><<<grid, kCodecThreads, 0, s>>>(a); }
+        // Large batches run as TWO halves on two streams (the caller's and an internal one, forked and joined by
+        // events): every kernel here ends on a tail of warps that still walk their frames while most of the device
+        // idles, and the other half's kernels fill it (C3, 8 GiB: decompress 16.7 -> 15.3 ms).  The halves share the
+        // stage buffer and the record table (their frames' slots are disjoint); all tables are per frame.
+        const int want = ctx->opt_decode_streams == 0 ? 2 : ctx->opt_decode_streams;
+        const int parts = (nframes >= 2048 && ctx->cur_arena == 0) ? std::min(want, 1 + b2b_ctx::kSide) : 1;
+        const bool two = parts > 1;
+        if (two) {
+            CU(ctx, cudaEventRecord(ctx->ev_fork, s));
+            for (int i = 0; i + 1 < parts; i++) CU(ctx, cudaStreamWaitEvent(ctx->s_side[i], ctx->ev_fork, 0));
+        }
+        for (int part = 0; part < parts; part++) {
+            const uint32_t f0 = (uint32_t)(((uint64_t)nframes * part / parts + 3u) & ~3ull);
+            const uint32_t f1 = part + 1 == parts ? nframes : (uint32_t)(((uint64_t)nframes * (part + 1) / parts + 3u) & ~3ull);
+            const uint32_t n = f1 - f0;
+            cudaStream_t sp = part ? ctx->s_side[part - 1] : s;
+            ParseArgs pa;
+            pa.frames = a.frames; pa.frame_off = d_frame_off + f0; pa.frame_len = d_frame_len + f0; pa.dst_cap = d_dst_cap + f0;
+            pa.nframes = n; pa.table = d_table; pa.table_off = d_table_off + f0; pa.nrec = d_nrec + f0; pa.table_cap = nrec_max;
+            DecodeArgs ap = a;
+            ap.frame_off = d_frame_off + f0; ap.frame_len = d_frame_len + f0; ap.nframes = n; ap.dst_off = d_dst_off + f0;
+            ap.dst_cap = d_dst_cap + f0; ap.out_len = d_out_len + f0; ap.status = d_status + f0; ap.meta = d_meta + f0;
+            ap.table_off = d_table_off + f0; ap.nrec = d_nrec + f0;
+            const unsigned grid = (n + kCodecWarps - 1) / kCodecWarps;
+            { LaunchTimer lt(ctx, K_PARSE, sp); lz4_parse_kernel<<<grid, kCodecThreads, 0, sp>>>(pa); }
+            CU(ctx, cudaGetLastError());
+            { LaunchTimer lt(ctx, K_DECODE, sp); lz4_decode_kernel<true><<<grid, kCodecThreads, 0, sp>>>(ap); }
+            CU(ctx, cudaGetLastError());
+            if (two) {   // this half's un-shuffle follows on its own stream (the common tail below handles the one-stream case)
+                FilterArgs fh;
+                fh.src = d_stage; fh.dst = static_cast<uint8_t *>(d_dst);
+                fh.ft.off = d_dst_off + f0; fh.ft.len = d_out_len + f0; fh.ft.uniform_len = 0; fh.ft.nframes = n;
+                fh.ft.tiles_per_frame = tiles_for(max_orig, n, ctx);
+                fh.meta = d_meta + f0; fh.uniform = FrameMeta{0, 0}; fh.status = d_status + f0; fh.inverse = 1;
+                fh.copy_inactive = 0;
+                { LaunchTimer lt(ctx, K_FILTER, sp);
+                  filter_batch_kernel<<<(unsigned)((uint64_t)n * fh.ft.tiles_per_frame), kFilterThreads, 0, sp>>>(fh); }
+                CU(ctx, cudaGetLastError());
+            }
+        }
+        if (two) {
+            for (int i = 0; i + 1 < parts; i++) {
+                CU(ctx, cudaEventRecord(ctx->ev_join[i], ctx->s_side[i]));
+                CU(ctx, cudaStreamWaitEvent(s, ctx->ev_join[i], 0));
+            }
+            return B2B_OK;
+        }
     } else {
         LaunchTimer lt(ctx, K_DECODE, s);
         lz4_decode_kernel<false><<<(nframes + kCodecWarps - 1) / kCodecWarps, kCodecThreads, 0, s>>>(a);
@@ -908,6 +954,10 @@ int b2b_init(int device, b2b_ctx **out) {
               cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_tab, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_arena, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < b2b_ctx::kSide && ok; i++)
+        ok = cudaStreamCreateWithFlags(&ctx->s_side[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < b2b_ctx::kSlots && ok; i++)
         ok = cudaStreamCreateWithFlags(&ctx->s_k[i], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_in_ready[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -945,6 +995,11 @@ void b2b_destroy(b2b_ctx *ctx) {
     }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->ev_arena) cudaEventDestroy(ctx->ev_arena);
+    for (int i = 0; i < b2b_ctx::kSide; i++) {
+        if (ctx->s_side[i]) cudaStreamDestroy(ctx->s_side[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     delete ctx;
 }
 
@@ -972,6 +1027,10 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
             if (ctx->staging) { cudaDeviceSynchronize(); delete ctx->staging; ctx->staging = nullptr; }
             return B2B_OK;
         case B2B_OPT_NO_HOST_STAGING: ctx->opt_no_staging = value != 0; return B2B_OK;
+        case B2B_OPT_FUSE_UNSHUFFLE: ctx->opt_fuse_unshuffle = value != 0; return B2B_OK;
+        case B2B_OPT_DECODE_STREAMS:
+            if (value < 0 || value > 1 + b2b_ctx::kSide) return B2B_EINVAL;
+            ctx->opt_decode_streams = (int)value; return B2B_OK;
         case B2B_OPT_DECODER:
             if (value < -1 || value > 2) return B2B_EINVAL;
             ctx->opt_fused_decode = (int)value; return B2B_OK;

@@ -404,6 +404,7 @@ struct DecodeArgs {
     // fused kernel only: when not null, only the frames with only[f] != 0 are decoded (the frames the
     // chunk-parallel decoder of lz4_decode2.cuh had no table room for)
     const uint32_t *only;
+    uint32_t fuse_unshuffle;    // 1: a byte-shuffled frame (typesize 2 / 4, aligned) is un-shuffled by the warp that decoded it
 };
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t *p) {
@@ -421,6 +422,45 @@ __device__ __forceinline__ uint32_t check_header(const uint8_t *fr, uint32_t fle
     if (ver != 2) return kEInvalidVersion;
     if (ncomp > flen || ncomp < 16) return kEInvalidData;
     return kOk;
+}
+
+// ---- fused K1 epilogue (decompressBackend un-shuffles inside the same call, blosc.go:417-426) --------------
+// The warp that decoded a byte-shuffled frame into the stage buffer un-shuffles it straight into dst, while the
+// other warps of the SM are still decoding: the HBM-bound transpose runs under the issue-bound decode instead
+// of as a kernel of its own behind it.  Typesizes 2 and 4 with 16-byte aligned bases and E % 16 == 0 (every
+// frame of C3 / C5); anything else is left to filter_batch_kernel (meta keeps its mode).
+// One lane turns 16 elements per step: a 16-byte vector from each plane in, T vectors out.
+__device__ __forceinline__ void warp_unshuffle_frame(const uint8_t *sp, uint8_t *__restrict__ dp, uint32_t T, uint32_t E,
+                                                     uint32_t n, int lane) {
+    const uint32_t nq = E >> 4;
+    if (T == 4) {
+        for (uint32_t q = lane; q < nq; q += kWarp) {
+            const uint4 p0 = __ldcg(reinterpret_cast<const uint4 *>(sp + 16ull * q));
+            const uint4 p1 = __ldcg(reinterpret_cast<const uint4 *>(sp + (uint64_t)E + 16ull * q));
+            const uint4 p2 = __ldcg(reinterpret_cast<const uint4 *>(sp + 2ull * E + 16ull * q));
+            const uint4 p3 = __ldcg(reinterpret_cast<const uint4 *>(sp + 3ull * E + 16ull * q));
+            uint4 o;
+            uint8_t *d = dp + 64ull * q;
+            transpose4x4(p0.x, p1.x, p2.x, p3.x, o.x, o.y, o.z, o.w); stg128_stream(d, o);
+            transpose4x4(p0.y, p1.y, p2.y, p3.y, o.x, o.y, o.z, o.w); stg128_stream(d + 16, o);
+            transpose4x4(p0.z, p1.z, p2.z, p3.z, o.x, o.y, o.z, o.w); stg128_stream(d + 32, o);
+            transpose4x4(p0.w, p1.w, p2.w, p3.w, o.x, o.y, o.z, o.w); stg128_stream(d + 48, o);
+        }
+    } else {   // T == 2
+        for (uint32_t q = lane; q < nq; q += kWarp) {
+            const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(sp + 16ull * q));
+            const uint4 b = __ldcg(reinterpret_cast<const uint4 *>(sp + (uint64_t)E + 16ull * q));
+            uint8_t *d = dp + 32ull * q;
+            stg128_stream(d, make_uint4(prmt(a.x, b.x, 0x5140), prmt(a.x, b.x, 0x7362), prmt(a.y, b.y, 0x5140), prmt(a.y, b.y, 0x7362)));
+            stg128_stream(d + 16, make_uint4(prmt(a.z, b.z, 0x5140), prmt(a.z, b.z, 0x7362), prmt(a.w, b.w, 0x5140), prmt(a.w, b.w, 0x7362)));
+        }
+    }
+    for (uint32_t i = E * T + lane; i < n; i += kWarp) dp[i] = __ldcg(sp + i);   // the n % T bytes behind the last element
+}
+__device__ __forceinline__ bool unshuffle_fusable(const FrameMeta &m, const uint8_t *sp, const uint8_t *dp, uint32_t n) {
+    if (m.mode != 1 || (m.typesize != 4 && m.typesize != 2)) return false;
+    const uint32_t E = n / m.typesize;
+    return E >= 16 && (E & 15u) == 0 && ((((uintptr_t)sp) | ((uintptr_t)dp)) & 15u) == 0;
 }
 
 template <bool kSplit>
@@ -467,6 +507,15 @@ __global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_kernel(DecodeArgs
                 else if ((uint64_t)got != norig) { st = kESizeMismatch; produced = (uint32_t)got; }  // blosc.go:429-431
                 else produced = norig;
             }
+        }
+    }
+    if (st == kOk && a.fuse_unshuffle) {
+        const uint8_t *sp = a.scratch + a.dst_off[f];
+        uint8_t *dp = a.dst + a.dst_off[f];
+        if (unshuffle_fusable(m, sp, dp, norig)) {
+            __syncwarp();                                   // the frame is complete in the stage buffer
+            warp_unshuffle_frame(sp, dp, m.typesize, norig / m.typesize, norig, lane);
+            m.mode = 0; m.typesize = 0;                     // nothing left for filter_batch_kernel
         }
     }
     if (lane == 0) {

@@ -124,7 +124,16 @@ enum {
     /* LZ4 decoder variant: -1 automatic (default: by frame size), 0 chunk-parallel (a frame is spread over
      * many threads: large or few frames), 1 fused one-warp-per-frame kernel, 2 parse kernel + copy kernel
      * (one warp per frame: thousands of small frames).  All give identical results. */
-    B2B_OPT_DECODER = 9
+    B2B_OPT_DECODER = 9,
+    /* 1: in the one-warp-per-frame decoders the warp that decoded a byte-shuffled frame (typesize 2 or 4, 16-byte
+     * aligned slots, element count a multiple of 16) also un-shuffles it, instead of a separate pass over the
+     * batch; 0 (default): the separate pass.  Same results; measured equally fast on a B200 (the decoding warps
+     * are latency-bound and the device is fully occupied by them, so the transpose does not hide behind them). */
+    B2B_OPT_FUSE_UNSHUFFLE = 10,
+    /* device-pointer decompress batches of 2048 frames or more run as N parts on N streams (the caller's and
+     * internal ones, forked and joined with events, so the call still behaves as work on the caller's stream):
+     * 0 = automatic (2), 1 = one stream only, 2..4 = that many */
+    B2B_OPT_DECODE_STREAMS = 11
 };
 B2B_API int b2b_set_option(b2b_ctx *ctx, int option, int64_t value);
 /* pre-size the device scratch arena so that later calls do not allocate */

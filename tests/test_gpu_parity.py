@@ -644,6 +644,41 @@ def test_split_and_fused_decoders_agree(ctx, orc):
                 assert np.array_equal(out[int(doff[k]):int(doff[k]) + ref.size], ref), k
 
 
+def test_fused_unshuffle_epilogue_matches_the_separate_pass(ctx):
+    """Option 10: the decoding warp un-shuffles its own frame (typesize 2 / 4, aligned slots, E % 16 == 0) instead of
+    the separate filter pass; frames that do not qualify (other typesizes, odd sizes, bit shuffle) take the pass in
+    the same batch.  Same bytes either way."""
+    import torch
+    rng = np.random.default_rng(3)
+    specs = [(262144, 1, 4), (262144, 1, 2), (100000, 1, 4), (65536 + 64, 1, 4), (70001, 1, 4), (131072, 2, 4), (40000, 1, 8), (4096, 0, 1)] * 3
+    frames, datas = [], []
+    for i, (n, sh, T) in enumerate(specs):
+        data = dg.smooth_f32((n + 3) // 4, i)[:n].copy() if i % 2 else dg.lowent_i16((n + 1) // 2, i)[:n].copy()
+        datas.append(data)
+        frames.append(np.frombuffer(ctx.compress(data, 1, 5, sh, T), dtype=np.uint8).copy())
+    flen = np.array([f.size for f in frames], dtype=np.uint32)
+    foff = np.concatenate([[0], np.cumsum((flen[:-1].astype(np.uint64) + 15) // 16 * 16)]).astype(np.uint64)
+    blob = np.zeros(int(foff[-1] + flen[-1]) + 64, dtype=np.uint8)
+    for o, f in zip(foff, frames):
+        blob[int(o):int(o) + f.size] = f
+    cap = np.array([d.size for d in datas], dtype=np.uint64)
+    doff = np.concatenate([[0], np.cumsum((cap[:-1] + 15) // 16 * 16)]).astype(np.uint64)
+    outs = []
+    for fuse in (0, 1):
+        ctx.set_option(10, fuse)
+        try:
+            for variant in (1, 2):
+                ctx.set_option(104, variant)
+                out, olen, st = ctx.decompress_batch(blob, foff, flen, doff, int(doff[-1] + cap[-1]) + 64)
+                assert not st.any()
+                outs.append(out.copy())
+        finally:
+            ctx.set_option(10, 0); ctx.set_option(104, -1)
+    for k, d in enumerate(datas):
+        for out in outs:
+            assert np.array_equal(out[int(doff[k]):int(doff[k]) + d.size], d), k
+
+
 # ---- opt-in Blosc-1 multi-block frames (SURVEY 8(f) rank 3; oracle/blosc1_blocks.c, parity unpinned) ----
 from test_blocks_oracle import parse as b1_parse, walk_blocks as b1_walk  # noqa: E402
 

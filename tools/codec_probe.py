@@ -14,6 +14,10 @@ ctx = pkg.Context(0)
 ctx.set_option(pkg.OPT_KERNEL_TIMING, 1)
 if os.environ.get("PROBE_DECODER"):
     ctx.set_option(pkg.OPT_DECODER, int(os.environ["PROBE_DECODER"]))      # -1 automatic, 0 chunk-parallel, 1 fused, 2 parse + copy
+if os.environ.get("PROBE_ONESTREAM"):
+    ctx.set_option(pkg.OPT_DECODE_STREAMS, int(os.environ["PROBE_ONESTREAM"]))
+if os.environ.get("PROBE_FUSE"):
+    ctx.set_option(pkg.OPT_FUSE_UNSHUFFLE, int(os.environ["PROBE_FUSE"]))
 s = torch.cuda.current_stream().cuda_stream
 size = int(os.environ.get("PROBE_BYTES", 2 << 30))
 which = os.environ.get("PROBE_CASES", "c3,c4,c5,text").split(",")
