@@ -77,6 +77,8 @@ struct b2b_ctx {
                                        // decoder (lz4_decode2.cuh: a frame is spread over many threads), 1 the first design's fused
                                        // kernel (one warp per frame), 2 the first design's parse kernel + copy kernel (one warp per frame)
     uint64_t opt_stage_bytes = 128ull << 20;
+    int opt_persistent_decode = 0;     // (option 105) one-warp-per-frame decoders as persistent warps that take frames from a ticket: measured
+                                       // 3 % slower on one stream and neutral on two (the gain of the two streams is not a tail effect), so off
     int opt_decode_streams = 0;        // streams a large decompress batch is split over: 0 automatic (2), 1 none, 2..4
     static constexpr int kSide = 3;
     cudaStream_t s_side[kSide] = {};   // the extra streams of large device-pointer decompress batches
@@ -496,6 +498,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     FrameMeta *d_meta = ar.take<FrameMeta>(nframes);
     uint32_t *d_cap_eff = ar.take<uint32_t>(nframes);
     unsigned long long *d_ticket = ar.take<unsigned long long>(4);
+    unsigned long long *d_tickets = ar.take<unsigned long long>(2 * (1 + b2b_ctx::kSide));   // parse / copy tickets of every part
     clip_caps_kernel<<<(nframes + 255) / 256, 256, 0, s>>>(d_dst_off, d_dst_cap, total_dst, nframes, d_cap_eff);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
@@ -515,7 +518,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     a.frame_len = d_frame_len; a.nframes = nframes; a.typesize_override = typesize_override;
     a.dst = static_cast<uint8_t *>(d_dst); a.scratch = d_stage; a.dst_off = d_dst_off;
     a.dst_cap = d_dst_cap; a.out_len = d_out_len; a.status = d_status; a.meta = d_meta;
-    a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr; a.only = nullptr; a.fuse_unshuffle = ctx->opt_fuse_unshuffle ? 1u : 0u;
+    a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr; a.only = nullptr; a.fuse_unshuffle = ctx->opt_fuse_unshuffle ? 1u : 0u; a.ticket = nullptr;
     if (v2) {
         // prep -> K5 (chunks per frame) -> one thread per chunk parses -> one thread per frame stitches ->
         // one CTA per frame copies (lz4_decode2.cuh); frames the table has no room for (output slots that
@@ -607,10 +610,18 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
             ap.frame_off = d_frame_off + f0; ap.frame_len = d_frame_len + f0; ap.nframes = n; ap.dst_off = d_dst_off + f0;
             ap.dst_cap = d_dst_cap + f0; ap.out_len = d_out_len + f0; ap.status = d_status + f0; ap.meta = d_meta + f0;
             ap.table_off = d_table_off + f0; ap.nrec = d_nrec + f0;
-            const unsigned grid = (n + kCodecWarps - 1) / kCodecWarps;
-            { LaunchTimer lt(ctx, K_PARSE, sp); lz4_parse_kernel<<<grid, kCodecThreads, 0, sp>>>(pa); }
+            // persistent warps that take frames from a ticket (no warp idles behind the slowest frame of its CTA, no
+            // tail of half-empty SMs at the end of a launch) once there are more frames than resident warps
+            const unsigned full = (n + kCodecWarps - 1) / kCodecWarps;
+            const bool persistent = ctx->opt_persistent_decode && full > (unsigned)ctx->sm_count * 12u;
+            unsigned long long *tk = d_tickets + 2 * part;
+            if (persistent) CU(ctx, cudaMemsetAsync(tk, 0, 16, sp));
+            pa.ticket = persistent ? tk : nullptr; ap.ticket = persistent ? tk + 1 : nullptr;
+            { LaunchTimer lt(ctx, K_PARSE, sp);
+              lz4_parse_kernel<<<persistent ? (unsigned)ctx->sm_count * 12u : full, kCodecThreads, 0, sp>>>(pa); }
             CU(ctx, cudaGetLastError());
-            { LaunchTimer lt(ctx, K_DECODE, sp); lz4_decode_kernel<true><<<grid, kCodecThreads, 0, sp>>>(ap); }
+            { LaunchTimer lt(ctx, K_DECODE, sp);
+              lz4_decode_kernel<true><<<persistent ? (unsigned)ctx->sm_count * 8u : full, kCodecThreads, 0, sp>>>(ap); }
             CU(ctx, cudaGetLastError());
             if (two) {   // this half's un-shuffle follows on its own stream (the common tail below handles the one-stream case)
                 FilterArgs fh;
@@ -1028,6 +1039,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
             return B2B_OK;
         case B2B_OPT_NO_HOST_STAGING: ctx->opt_no_staging = value != 0; return B2B_OK;
         case B2B_OPT_FUSE_UNSHUFFLE: ctx->opt_fuse_unshuffle = value != 0; return B2B_OK;
+        case 105: ctx->opt_persistent_decode = value != 0; return B2B_OK;
         case B2B_OPT_DECODE_STREAMS:
             if (value < 0 || value > 1 + b2b_ctx::kSide) return B2B_EINVAL;
             ctx->opt_decode_streams = (int)value; return B2B_OK;

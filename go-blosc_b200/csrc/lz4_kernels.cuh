@@ -405,6 +405,7 @@ struct DecodeArgs {
     // chunk-parallel decoder of lz4_decode2.cuh had no table room for)
     const uint32_t *only;
     uint32_t fuse_unshuffle;    // 1: a byte-shuffled frame (typesize 2 / 4, aligned) is un-shuffled by the warp that decoded it
+    unsigned long long *ticket; // not null: persistent warps, frames handed out in order (zero before the launch)
 };
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t *p) {
@@ -463,12 +464,9 @@ __device__ __forceinline__ bool unshuffle_fusable(const FrameMeta &m, const uint
     return E >= 16 && (E & 15u) == 0 && ((((uintptr_t)sp) | ((uintptr_t)dp)) & 15u) == 0;
 }
 
+// one frame, one warp
 template <bool kSplit>
-__global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_kernel(DecodeArgs a) {
-    __shared__ SeqTable seq_tables[kCodecWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t f = blockIdx.x * kCodecWarps + warp;
-    if (f >= a.nframes) return;
+__device__ __forceinline__ void warp_decode_frame(const DecodeArgs &a, uint32_t f, SeqTable *seq_table, int lane) {
     if (!kSplit && a.only && !a.only[f]) return;
     const uint8_t *fr = a.frames + a.frame_off[f];
     const uint32_t flen = a.frame_len[f];
@@ -501,7 +499,7 @@ __global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_kernel(DecodeArgs
             } else {
                 const uint32_t dcap = cap < norig ? cap : norig;
                 const int64_t got = kSplit ? warp_lz4_copy(fr + 16, plen, out, dcap, a.table + a.table_off[f], a.nrec[f], lane)
-                                           : warp_lz4_decode(fr + 16, plen, out, dcap, &seq_tables[warp], lane);
+                                           : warp_lz4_decode(fr + 16, plen, out, dcap, seq_table, lane);
                 if (got == -1) st = kEDecompressionFailed;            // blosc.go:410-413
                 else if (got == -2) st = dcap == norig ? kEDecompressionFailed : kEDstTooSmall;
                 else if ((uint64_t)got != norig) { st = kESizeMismatch; produced = (uint32_t)got; }  // blosc.go:429-431
@@ -523,6 +521,28 @@ __global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_kernel(DecodeArgs
         a.status[f] = st;
         a.out_len[f] = produced;
         a.meta[f] = m;
+    }
+}
+
+// With a ticket (zero before the launch) the warps are persistent and take the next frame as soon as they are done
+// with one: no warp waits for the slowest frame of its CTA, and the launch does not end on a tail of half-empty
+// SMs.  Without one, warp w of CTA b takes frame 4 b + w.
+template <bool kSplit>
+__global__ void __launch_bounds__(kCodecThreads, 8) lz4_decode_kernel(DecodeArgs a) {
+    __shared__ SeqTable seq_tables[kCodecWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!a.ticket) {
+        const uint32_t f = blockIdx.x * kCodecWarps + warp;
+        if (f < a.nframes) warp_decode_frame<kSplit>(a, f, &seq_tables[warp], lane);
+        return;
+    }
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.ticket, 1ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= a.nframes) break;
+        warp_decode_frame<kSplit>(a, (uint32_t)t, &seq_tables[warp], lane);
+        __syncwarp();
     }
 }
 
@@ -549,6 +569,7 @@ struct ParseArgs {
     const uint64_t *table_off;  // first record of frame f (exclusive scan of dst_cap / 4 + kSeqSlack)
     uint32_t *nrec;             // records written for frame f (~0: no room in the table, decode without it)
     uint64_t table_cap;         // records the table can hold in all
+    unsigned long long *ticket = nullptr;   // not null: persistent warps (zero before the launch)
 };
 
 // the sequence records of one LZ4 block; returns how many were written (room >= 15)
@@ -604,10 +625,7 @@ __device__ __forceinline__ uint32_t warp_lz4_parse(const uint8_t *__restrict__ s
     return n;
 }
 
-__global__ void __launch_bounds__(kCodecThreads, 12) lz4_parse_kernel(ParseArgs a) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t f = blockIdx.x * kCodecWarps + warp;
-    if (f >= a.nframes) return;
+__device__ __forceinline__ void warp_parse_frame(const ParseArgs &a, uint32_t f, int lane) {
     const uint8_t *fr = a.frames + a.frame_off[f];
     uint32_t flags = 0, codec = 0, tsz = 0, norig = 0, ncomp = 0;
     const uint32_t st = check_header(fr, a.frame_len[f], flags, codec, tsz, norig, ncomp);
@@ -619,6 +637,23 @@ __global__ void __launch_bounds__(kCodecThreads, 12) lz4_parse_kernel(ParseArgs 
     }
     const uint32_t n = warp_lz4_parse(fr + 16, ncomp - 16, a.table + a.table_off[f], room, lane);
     if (lane == 0) a.nrec[f] = n;
+}
+
+__global__ void __launch_bounds__(kCodecThreads, 12) lz4_parse_kernel(ParseArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!a.ticket) {
+        const uint32_t f = blockIdx.x * kCodecWarps + warp;
+        if (f < a.nframes) warp_parse_frame(a, f, lane);
+        return;
+    }
+    for (;;) {                                                  // persistent warps (see lz4_decode_kernel)
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.ticket, 1ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= a.nframes) break;
+        warp_parse_frame(a, (uint32_t)t, lane);
+        __syncwarp();
+    }
 }
 
 // ---- the same two halves over a table of bare LZ4 streams (the blocks of blocks.cuh) ----------------

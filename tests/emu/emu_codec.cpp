@@ -192,7 +192,7 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
     a.frames = (const uint8_t *)p_fr; a.frame_off = &frame_off; a.frame_len = &len; a.nframes = 1;
     a.typesize_override = typesize_override; a.dst = (uint8_t *)p_dst; a.scratch = (uint8_t *)p_stage; a.dst_off = &dst_off;
     a.dst_cap = &cap_eff; a.out_len = &out; a.status = &status; a.meta = &meta;
-    a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr; a.only = nullptr; a.fuse_unshuffle = 1;
+    a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr; a.only = nullptr; a.fuse_unshuffle = 1; a.ticket = nullptr;
     if (split == 2) {
         // chunk-parallel decoder (lz4_decode2.cuh): prep -> K5 -> chunk parse -> stitch -> tile copy (+ fallback)
         FrameDec fd;

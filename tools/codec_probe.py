@@ -16,6 +16,8 @@ if os.environ.get("PROBE_DECODER"):
     ctx.set_option(pkg.OPT_DECODER, int(os.environ["PROBE_DECODER"]))      # -1 automatic, 0 chunk-parallel, 1 fused, 2 parse + copy
 if os.environ.get("PROBE_ONESTREAM"):
     ctx.set_option(pkg.OPT_DECODE_STREAMS, int(os.environ["PROBE_ONESTREAM"]))
+if os.environ.get("PROBE_PERSIST"):
+    ctx.set_option(105, int(os.environ["PROBE_PERSIST"]))
 if os.environ.get("PROBE_FUSE"):
     ctx.set_option(pkg.OPT_FUSE_UNSHUFFLE, int(os.environ["PROBE_FUSE"]))
 s = torch.cuda.current_stream().cuda_stream
