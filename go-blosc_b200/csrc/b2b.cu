@@ -77,6 +77,7 @@ struct b2b_ctx {
                                        // decoder (lz4_decode2.cuh: a frame is spread over many threads), 1 the first design's fused
                                        // kernel (one warp per frame), 2 the first design's parse kernel + copy kernel (one warp per frame)
     uint64_t opt_stage_bytes = 128ull << 20;
+    int opt_encode_ctas = 0;           // (option 106) persistent encoder CTAs per SM, 0 = as many as fit
     int opt_persistent_decode = 0;     // (option 105) one-warp-per-frame decoders as persistent warps that take frames from a ticket: measured
                                        // 3 % slower on one stream and neutral on two (the gain of the two streams is not a tail effect), so off
     int opt_decode_streams = 0;        // streams a large decompress batch is split over: 0 automatic (2), 1 none, 2..4
@@ -302,7 +303,8 @@ int launch_encode(b2b_ctx *ctx, const EncodeArgs &e, bool unshuffled, cudaStream
     const uint64_t warps = (uint64_t)e.nframes * e.segs_grid;
     const size_t smem = (size_t)kEncWarps * sizeof(uint32_t) << hl;
     // persistent CTAs: as many as fit on the device (warps pull items from the ticket)
-    const uint64_t per_sm = hl <= 10 ? 7 : hl == 11 ? 5 : hl == 12 ? 2 : 1;   // __launch_bounds__ of the kernel
+    uint64_t per_sm = hl <= 10 ? 7 : hl == 11 ? 5 : hl == 12 ? 2 : 1;   // __launch_bounds__ of the kernel
+    if (ctx->opt_encode_ctas > 0 && (uint64_t)ctx->opt_encode_ctas < per_sm) per_sm = (uint64_t)ctx->opt_encode_ctas;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((warps + kEncWarps - 1) / kEncWarps,
                                                                      (uint64_t)ctx->sm_count * per_sm));
     CU(ctx, cudaMemsetAsync(e.ticket, 0, 8, s));
@@ -1040,6 +1042,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
         case B2B_OPT_NO_HOST_STAGING: ctx->opt_no_staging = value != 0; return B2B_OK;
         case B2B_OPT_FUSE_UNSHUFFLE: ctx->opt_fuse_unshuffle = value != 0; return B2B_OK;
         case 105: ctx->opt_persistent_decode = value != 0; return B2B_OK;
+        case 106: ctx->opt_encode_ctas = (int)std::max<int64_t>(0, value); return B2B_OK;
         case B2B_OPT_DECODE_STREAMS:
             if (value < 0 || value > 1 + b2b_ctx::kSide) return B2B_EINVAL;
             ctx->opt_decode_streams = (int)value; return B2B_OK;

@@ -146,6 +146,48 @@ def test_shuffle_whole_buffer_1gib_vs_torch(ctx, torch_mod, T):
     assert torch.equal(back, src) and not torch.equal(dst, src)
 
 
+@pytest.mark.parametrize("T", [2, 4, 16, 3])
+def test_shuffle_whole_buffer_4gib(ctx, orc, torch_mod, T):
+    """Config C2 at its full size: ONE 4 GiB buffer (T = 2: 2^31 elements per plane, where a 32-bit index would wrap;
+    T = 3: the staged path with E % 16 != 0 planes).  The byte shuffle is compared with torch's own transpose over the
+    whole buffer, both filters with the oracle on windows at the start, across the 2^31 / 2^32 marks and at the end,
+    and the inverses must return the input."""
+    torch = torch_mod
+    n = (1 << 32) if T != 3 else (1 << 32) - 4                        # a multiple of T
+    E = n // T
+    g = torch.Generator(device="cuda"); g.manual_seed(100 + T)
+    src = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    dst = torch.empty_like(src)
+    s = torch.cuda.current_stream().cuda_stream
+    ctx.shuffle_dev(1, False, T, src, dst, n, s)
+    torch.cuda.synchronize()
+    ref_ok = True
+    for j in range(T):                                                 # plane by plane: no 4 GiB temporary
+        ref_ok = ref_ok and bool(torch.equal(dst[j * E:(j + 1) * E], src[j::T]))
+    assert ref_ok
+    W = 1 << 20
+    for e0 in (0, E // 2 - W // 2, E - W):                             # element windows against the oracle's loop
+        win = src[e0 * T:(e0 + W) * T].cpu().numpy()
+        want = orc.shuffle(win, T)
+        for j in (0, T - 1):
+            assert np.array_equal(dst[j * E + e0:j * E + e0 + W].cpu().numpy(), want[j * W:(j + 1) * W]), (e0, j)
+    ctx.shuffle_dev(1, True, T, dst, src, n, s)                        # back into src: compare with a regenerated copy
+    g.manual_seed(100 + T)
+    again = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    torch.cuda.synchronize()
+    assert torch.equal(src, again)
+    ctx.shuffle_dev(2, False, T, src, dst, n, s)                       # bit shuffle: groups of 8 elements are local
+    torch.cuda.synchronize()
+    G = 8 * T
+    for b0 in (0, (1 << 31) - 4 * G, (n // G - 4096) * G):
+        b0 -= b0 % G
+        win = src[b0:b0 + 4096 * G].cpu().numpy()
+        assert np.array_equal(dst[b0:b0 + 4096 * G].cpu().numpy(), orc.bitshuffle(win, T)), b0
+    ctx.shuffle_dev(2, True, T, dst, again, n, s)
+    torch.cuda.synchronize()
+    assert torch.equal(again, src)
+
+
 def test_golden_fixtures_on_gpu(ctx, orc):
     import make_golden
     with open(GOLDEN) as f:

@@ -20,6 +20,8 @@ parts = int(os.environ.get("PROBE_PARTS", 2))
 class Half:
     def __init__(self, lo, hi):
         self.ctx = pkg.Context(0)
+        if os.environ.get("PROBE_ENC_CTAS"):
+            self.ctx.set_option(106, int(os.environ["PROBE_ENC_CTAS"]))
         self.stream = torch.cuda.Stream()
         self.s = self.stream.cuda_stream
         self.n = hi - lo
