@@ -21,6 +21,7 @@
 #include "lz4_kernels.cuh"
 #include "scan.cuh"
 #include "lz4_decode2.cuh"
+#include "lz4_decode3.cuh"
 #include "blocks.cuh"
 #include "host_staging.hpp"
 
@@ -29,13 +30,13 @@
 using namespace b2b;
 
 enum KernelId { K_FILTER = 0, K_ENCODE, K_DECODE, K_SCAN, K_PACK, K_INFO, K_FINALIZE, K_PARSE,
-                K_BLOCKS_META, K_BLOCKS_PACK, K_BLOCKS_DECODE, K_PREP2, K_PARSE2, K_STITCH2, K_COPY2, K_COUNT };
+                K_BLOCKS_META, K_BLOCKS_PACK, K_BLOCKS_DECODE, K_PREP2, K_PARSE2, K_STITCH2, K_COPY2, K_LANE, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"filter_batch_kernel", "lz4_encode_kernel", "lz4_decode_kernel",
                                                   "scan_offsets_kernel", "pack_frames_kernel", "frame_info_kernel",
                                                   "finalize_frames_kernel", "lz4_parse_kernel",
                                                   "blocks_meta_kernels", "blocks_pack_kernel", "blocks_decode_kernel",
                                                   "frame_prep_kernel", "lz4_chunk_parse_kernel", "lz4_stitch_kernel",
-                                                  "lz4_copy2_kernel"};
+                                                  "lz4_copy2_kernel", "lz4_lane_decode_kernel"};
 
 struct TimedLaunch { int id; cudaEvent_t a, b; };
 
@@ -73,7 +74,8 @@ struct b2b_ctx {
     int opt_hash_log = 0;              // 0: automatic (launch_encode)
     int opt_hash_bytes = 0;            // 0: automatic
     uint32_t opt_tune[4] = {0, 0, 0, 0};   // encoder experiment knobs (0: built-in default)
-    int opt_fused_decode = -1;         // K4 variant: -1 automatic (by frame size, see decompress_batch_dev_locked), 0 chunk-parallel
+    int opt_fused_decode = -1;         // K4 variant: -1 automatic (by the batch's shape, see decompress_batch_dev_locked), 3 one lane per
+                                       // frame (lz4_decode3.cuh), 0 chunk-parallel
                                        // decoder (lz4_decode2.cuh: a frame is spread over many threads), 1 the first design's fused
                                        // kernel (one warp per frame), 2 the first design's parse kernel + copy kernel (one warp per frame)
     uint64_t opt_stage_bytes = 128ull << 20;
@@ -479,9 +481,14 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     // with the chunk-parallel decoder, whose parse runs on one thread per 8 KiB of stream and whose copy stage
     // gives a frame a whole CTA).
     int variant = ctx->opt_fused_decode;
-    if (variant < 0) variant = max_orig > (512u << 10) ? 0 : 2;
+    // A third arrangement gives every frame ONE LANE (lz4_decode3.cuh): 32 scalar decoders in lockstep per warp.  It
+    // needs tens of thousands of frames to fill the device and each of them is decoded at the latency of one
+    // thread, so it only pays for very many very small frames (2^20 frames of 1 KiB: 222 against 158 GB/s; 4 KiB: 367
+    // against 348; 16 KiB: 297 against 590; C3's 256 KiB frames: 58 ms against 13.7 ms per 8 GiB).
+    if (variant < 0) variant = max_orig > (512u << 10) ? 0 : (max_orig <= 4096u && nframes >= 65536u) ? 3 : 2;
     const bool v2 = !indexed && variant == 0;
     const bool split = !indexed && variant == 2;
+    const bool lanes = !indexed && variant == 3;
     const uint64_t nrec_max = total_dst / 4 + (uint64_t)(kSeqSlack + 1) * nframes + 64;   // sum of dst_cap / 4 + slack
     // chunk-parallel decoder: an LZ4 block that decodes to n bytes has at most n + n / 255 + 16 bytes (longer ones
     // are refused by the prep kernel), so the chunks of a batch are bounded by its output size
@@ -644,6 +651,10 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
             }
             return B2B_OK;
         }
+    } else if (lanes) {
+        // one lane per frame (lz4_decode3.cuh): no table, no parse kernel
+        LaunchTimer lt(ctx, K_LANE, s);
+        lz4_lane_decode_kernel<<<(nframes + kLaneThreads - 1) / kLaneThreads, kLaneThreads, 0, s>>>(a);
     } else {
         LaunchTimer lt(ctx, K_DECODE, s);
         lz4_decode_kernel<false><<<(nframes + kCodecWarps - 1) / kCodecWarps, kCodecThreads, 0, s>>>(a);
@@ -1032,7 +1043,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
             if (value != 0 && (value < 4 || value > 6)) return B2B_EINVAL;
             ctx->opt_hash_bytes = (int)value; return B2B_OK;
         case 100: case 101: case 102: case 103: ctx->opt_tune[option - 100] = (uint32_t)value; return B2B_OK;
-        case 104: if (value < -1 || value > 2) return B2B_EINVAL; ctx->opt_fused_decode = (int)value; return B2B_OK;
+        case 104: if (value < -1 || value > 3) return B2B_EINVAL; ctx->opt_fused_decode = (int)value; return B2B_OK;
         case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (128ull << 20); return B2B_OK;
         case B2B_OPT_HOST_THREADS:
             if (value < 0 || value > 64) return B2B_EINVAL;
@@ -1047,7 +1058,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
             if (value < 0 || value > 1 + b2b_ctx::kSide) return B2B_EINVAL;
             ctx->opt_decode_streams = (int)value; return B2B_OK;
         case B2B_OPT_DECODER:
-            if (value < -1 || value > 2) return B2B_EINVAL;
+            if (value < -1 || value > 3) return B2B_EINVAL;
             ctx->opt_fused_decode = (int)value; return B2B_OK;
         default: return B2B_EINVAL;
     }

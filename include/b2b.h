@@ -121,9 +121,10 @@ enum {
     /* 1: hand pageable buffers to cudaMemcpyAsync directly (synchronous, staged by the driver) instead of
      * the library's pinned ring; for comparison only */
     B2B_OPT_NO_HOST_STAGING = 8,
-    /* LZ4 decoder variant: -1 automatic (default: by frame size), 0 chunk-parallel (a frame is spread over
-     * many threads: large or few frames), 1 fused one-warp-per-frame kernel, 2 parse kernel + copy kernel
-     * (one warp per frame: thousands of small frames).  All give identical results. */
+    /* LZ4 decoder variant: -1 automatic (default: by the batch's shape), 0 chunk-parallel (a frame is spread over
+     * many threads: frames over 512 KiB), 1 fused one-warp-per-frame kernel, 2 parse kernel + copy kernel (one warp
+     * per frame: thousands of small frames), 3 one lane per frame (2^16 frames or more of at most 4 KiB).  All give
+     * identical results. */
     B2B_OPT_DECODER = 9,
     /* 1: in the one-warp-per-frame decoders the warp that decoded a byte-shuffled frame (typesize 2 or 4, 16-byte
      * aligned slots, element count a multiple of 16) also un-shuffles it, instead of a separate pass over the

@@ -30,6 +30,7 @@ inline void tr(int tag, int64_t a, int64_t b, int64_t c, int64_t d, int64_t e) {
 #include "../../go-blosc_b200/csrc/lz4_kernels.cuh"
 #include "../../go-blosc_b200/csrc/scan.cuh"
 #include "../../go-blosc_b200/csrc/lz4_decode2.cuh"
+#include "../../go-blosc_b200/csrc/lz4_decode3.cuh"
 
 using namespace b2b;
 
@@ -193,7 +194,9 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
     a.typesize_override = typesize_override; a.dst = (uint8_t *)p_dst; a.scratch = (uint8_t *)p_stage; a.dst_off = &dst_off;
     a.dst_cap = &cap_eff; a.out_len = &out; a.status = &status; a.meta = &meta;
     a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr; a.only = nullptr; a.fuse_unshuffle = 1; a.ticket = nullptr;
-    if (split == 2) {
+    if (split == 3) {
+        emu::launch(1, kLaneThreads, [&] { lz4_lane_decode_kernel(a); });
+    } else if (split == 2) {
         // chunk-parallel decoder (lz4_decode2.cuh): prep -> K5 -> chunk parse -> stitch -> tile copy (+ fallback)
         FrameDec fd;
         uint32_t plen_eff = 0, last_chunk = 0, fallback = 0;

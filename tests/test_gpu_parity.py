@@ -647,7 +647,7 @@ def test_indexed_frames_are_standard_and_decode_in_parallel(ctx, orc, torch_mod,
 
 def test_split_and_fused_decoders_agree(ctx, orc):
     """K4 has three variants behind option 104 (0 chunk-parallel decoder of lz4_decode2.cuh, 1 the fused one-warp-per-frame
-    kernel, 2 parse kernel + copy kernel; -1 = chosen by frame size): on a ragged batch of valid, truncated and
+    kernel, 2 parse kernel + copy kernel, 3 one lane per frame of lz4_decode3.cuh; -1 = chosen by the batch's shape): on a ragged batch of valid, truncated and
     corrupted frames all give the same status, length and bytes (and the oracle's status)."""
     rng = np.random.default_rng(77)
     frames, caps = [], []
@@ -669,7 +669,7 @@ def test_split_and_fused_decoders_agree(ctx, orc):
     cap = np.array(caps, dtype=np.uint64)
     doff = np.concatenate([[0], np.cumsum((cap[:-1] + 15) // 16 * 16)]).astype(np.uint64)
     res = []
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         ctx.set_option(104, variant)
         try:
             out, olen, st = ctx.decompress_batch(blob, foff, flen, doff, int(doff[-1] + cap[-1]) + 64)
@@ -684,6 +684,66 @@ def test_split_and_fused_decoders_agree(ctx, orc):
         if rc == 0:
             for out, _, _ in res:
                 assert np.array_equal(out[int(doff[k]):int(doff[k]) + ref.size], ref), k
+
+
+def test_many_tiny_frames_take_the_lane_decoder(ctx, orc):
+    """70 000 frames of 1..3000 bytes in one batch: the automatic choice decodes them one LANE per frame
+    (lz4_decode3.cuh).  Same status, length and bytes as one warp per frame, also for truncated and corrupted frames;
+    a sample is checked against the oracle."""
+    rng = np.random.default_rng(21)
+    base = {k: v for k, v in dg.corpus(3000).items()}
+    kinds = list(base)
+    nfr = 70000
+    sizes = rng.integers(1, 3001, nfr)
+    sizes[:64] = np.arange(1, 65)
+    src_frames, shapes = [], []
+    # compress a few hundred distinct frames on the GPU, then repeat them (the batch is about the decoder)
+    distinct = []
+    for i in range(400):
+        n = int(sizes[i]); kind = kinds[i % len(kinds)]
+        sh, T = [(1, 4), (0, 1), (2, 8), (1, 2)][i % 4]
+        data = base[kind][:n].copy()
+        fr = np.frombuffer(ctx.compress(data, 1, 5, sh, T), dtype=np.uint8).copy()
+        distinct.append((fr, data, True))
+        if fr.size > 24 and not fr[2] & 2:
+            m = fr.copy(); m[int(rng.integers(16, m.size))] ^= np.uint8(rng.integers(1, 256)); distinct.append((m, data, False))
+            cut = int(rng.integers(17, fr.size)); t = fr[:cut].copy(); t[12:16] = np.frombuffer(struct.pack("<I", cut), dtype=np.uint8)
+            distinct.append((t, data, False))
+    pick = rng.integers(0, len(distinct), nfr)
+    frames = [distinct[k][0] for k in pick]
+    caps = np.array([distinct[k][1].size for k in pick], dtype=np.uint64)
+    flen = np.array([f.size for f in frames], dtype=np.uint32)
+    foff = np.concatenate([[0], np.cumsum((flen[:-1].astype(np.uint64) + 15) // 16 * 16)]).astype(np.uint64)
+    blob = np.zeros(int(foff[-1] + flen[-1]) + 64, dtype=np.uint8)
+    for o, f in zip(foff, frames):
+        blob[int(o):int(o) + f.size] = f
+    doff = np.concatenate([[0], np.cumsum((caps[:-1] + 15) // 16 * 16 + 16)]).astype(np.uint64)      # a gap behind every slot
+    doff[1::5] += 3                                                   # some slots are not 16-byte aligned
+    total = int(doff[-1] + caps[-1]) + 64
+    res = []
+    for variant in (-1, 3, 2):
+        ctx.set_option(104, variant)
+        try:
+            out, olen, st = ctx.decompress_batch(blob, foff, flen, doff, total)
+        finally:
+            ctx.set_option(104, -1)
+        res.append((out.copy(), olen.copy(), st.copy()))
+    for other in res[1:]:
+        assert np.array_equal(res[0][2], other[2]) and np.array_equal(res[0][1], other[1])
+    ok = res[0][2] == 0
+    assert ok.sum() > nfr // 2 and (~ok).sum() > 1000
+    for k in np.nonzero(ok)[0][::97]:
+        want, clean = distinct[pick[k]][1], distinct[pick[k]][2]
+        a0 = res[0][0][int(doff[k]):int(doff[k]) + want.size]
+        for out, _, _ in res[1:]:
+            assert np.array_equal(out[int(doff[k]):int(doff[k]) + want.size], a0), k
+        if clean:
+            assert np.array_equal(a0, want), k
+    for k in list(range(0, nfr, 701)):
+        rc, ref = orc.decompress(frames[k])                           # (a flipped literal byte still decodes: compare with the oracle)
+        assert int(res[0][2][k]) == rc, (k, int(res[0][2][k]), rc)
+        if rc == 0:
+            assert np.array_equal(res[0][0][int(doff[k]):int(doff[k]) + ref.size], ref), k
 
 
 def test_fused_unshuffle_epilogue_matches_the_separate_pass(ctx):

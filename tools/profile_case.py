@@ -17,6 +17,8 @@ T = int(os.environ.get("PROBE_T", 4))
 hl = int(os.environ.get("PROBE_HASHLOG", 0))
 iters = int(os.environ.get("PROBE_ITERS", 2))
 ctx.set_option(pkg.OPT_HASH_LOG, hl)
+if os.environ.get("PROBE_DECODER"):
+    ctx.set_option(pkg.OPT_DECODER, int(os.environ["PROBE_DECODER"]))
 fl = 262144
 nf = size // fl
 src = gen_f32(size // 4) if T != 8 else gen_f32(size // 4, f64=True)
