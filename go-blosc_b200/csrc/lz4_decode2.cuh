@@ -460,7 +460,10 @@ __global__ void __launch_bounds__(64) lz4_stitch_kernel(Stitch2Args a) {
 }
 
 // ---- copy: one CTA per frame, one thread per sequence ---------------------------------------------------------
-constexpr int kCopy2Threads = 128;
+#ifndef B2B_COPY2_THREADS
+#define B2B_COPY2_THREADS 128
+#endif
+constexpr int kCopy2Threads = B2B_COPY2_THREADS;
 constexpr uint32_t kTile2 = 4096;                 // output bytes of one tile
 constexpr uint32_t kRing2 = 2 * kTile2;           // the tile being filled + the one before it
 constexpr uint32_t kLit2 = 64;                    // longest literal run a thread copies by itself
@@ -543,7 +546,7 @@ __device__ __forceinline__ void flush_tile(const uint8_t *ring, uint8_t *outv, u
     }
 }
 
-__global__ void __launch_bounds__(kCopy2Threads, 12) lz4_copy2_kernel(Copy2Args a) {
+__global__ void __launch_bounds__(kCopy2Threads, 1536 / kCopy2Threads) lz4_copy2_kernel(Copy2Args a) {
     __shared__ __align__(16) uint8_t ring[kRing2];
     __shared__ uint32_t pend[kTile2 / 32 + 1];
     __shared__ CoopLit s_coop[kCopy2Threads];
