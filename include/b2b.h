@@ -141,10 +141,12 @@ B2B_API int b2b_set_option(b2b_ctx *ctx, int option, int64_t value);
 B2B_API int b2b_reserve(b2b_ctx *ctx, uint64_t total_uncompressed_bytes, uint32_t nframes);
 /* number of kernel launches issued through this ctx since creation (bench's gpu_launches) */
 B2B_API uint64_t b2b_launch_count(b2b_ctx *ctx);
-/* per-kernel launch counts and (with B2B_OPT_KERNEL_TIMING) summed device time; kernel = 0..10:
+/* per-kernel launch counts and (with B2B_OPT_KERNEL_TIMING) summed device time; kernel = 0..15:
  * filter, lz4 encode, lz4 decode (copy half), offsets scan, pack, frame info, finalize, lz4 parse
- * (decode's parse half), block-frame tables, block-frame pack, block-frame decode; B2B_EINVAL
- * beyond.  Synchronises pending events. */
+ * (decode's parse half), block-frame tables, block-frame pack, block-frame decode, then the chunk-parallel
+ * decoder's frame prep, chunk parse, stitch and copy engine, and the lane decoder; B2B_EINVAL beyond.
+ * Synchronises pending events.  Times are event spans on the launching stream: kernels of a decompress batch
+ * that runs on two streams overlap (B2B_OPT_DECODE_STREAMS = 1 gives exclusive times). */
 B2B_API int b2b_kernel_stats(b2b_ctx *ctx, int kernel, const char **name, uint64_t *launches,
                              double *total_ms);
 B2B_API int b2b_kernel_stats_reset(b2b_ctx *ctx);
