@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -49,7 +50,7 @@ __attribute__((target("avx2"))) static inline void stream_copy_avx2(uint8_t *d, 
 #endif
 static inline void stream_copy(void *d, const void *s, size_t n) {
 #if defined(__x86_64__)
-    static const bool avx2 = __builtin_cpu_supports("avx2");
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("B2B_STAGE_MEMCPY");
     if (avx2 && n >= 4096) { stream_copy_avx2((uint8_t *)d, (const uint8_t *)s, n); return; }
 #endif
     memcpy(d, s, n);
@@ -114,11 +115,13 @@ private:
 
 class HostStaging {
 public:
-    static constexpr size_t kBlock = 8u << 20;
+    size_t kBlock = 8u << 20;          // bytes of one staging block (B2B_STAGE_BLOCK_MB overrides: experiments)
     static constexpr int kRing = 3;
 
     HostStaging(int device, int nthreads, cudaStream_t s_in, cudaStream_t s_out)
-        : device_(device), pool_(nthreads), s_in_(s_in), s_out_(s_out) {}
+        : device_(device), pool_(nthreads), s_in_(s_in), s_out_(s_out) {
+        if (const char *e = getenv("B2B_STAGE_BLOCK_MB")) { const long v = atol(e); if (v >= 1 && v <= 256) kBlock = (size_t)v << 20; }
+    }
     ~HostStaging() {
         { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
         cv_.notify_all();
