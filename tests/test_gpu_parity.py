@@ -746,6 +746,48 @@ def test_many_tiny_frames_take_the_lane_decoder(ctx, orc):
             assert np.array_equal(res[0][0][int(doff[k]):int(doff[k]) + ref.size], ref), k
 
 
+def test_garbage_payloads_get_the_oracle_status_from_every_decoder(ctx, orc):
+    """Valid headers in front of payloads that are not LZ4 at all (random bytes, 0xFF runs, a valid stream spliced into
+    garbage), 1 KiB .. 3 MiB: every K4 variant must end with the oracle's status and never write outside its slot
+    (the chunk-parallel decoder sees chunks whose speculative chains die, stitch re-parses, long bogus length runs)."""
+    rng = np.random.default_rng(99)
+    good = np.frombuffer(ctx.compress(dg.smooth_f32(200000, 5), 1, 5, 1, 4), dtype=np.uint8)
+    frames = []
+    for i, n in enumerate([1024, 5000, 70000, 600000, 1 << 20, 3 << 20] * 4):
+        kind = i % 4
+        if kind == 0:
+            payload = rng.integers(0, 256, n, dtype=np.uint8)
+        elif kind == 1:
+            payload = rng.integers(0, 256, n, dtype=np.uint8); payload[n // 3:n // 3 + min(n // 4, 300000)] = 0xFF
+        elif kind == 2:
+            payload = np.concatenate([good[16:16 + min(n // 2, good.size - 16)], rng.integers(0, 256, n - min(n // 2, good.size - 16), dtype=np.uint8)])
+        else:
+            payload = np.zeros(n, dtype=np.uint8); payload[::7] = rng.integers(0, 256, payload[::7].size, dtype=np.uint8)
+        norig = int(rng.integers(n, 4 * n))
+        hdr = np.frombuffer(struct.pack("<BBBBIII", 2, 1, [0, 1, 4, 0][i % 4], 4, norig, norig, 16 + payload.size), dtype=np.uint8)
+        frames.append(np.concatenate([hdr, payload]))
+    flen = np.array([f.size for f in frames], dtype=np.uint32)
+    foff = np.concatenate([[0], np.cumsum((flen[:-1].astype(np.uint64) + 15) // 16 * 16)]).astype(np.uint64)
+    blob = np.zeros(int(foff[-1] + flen[-1]) + 64, dtype=np.uint8)
+    for o, f in zip(foff, frames):
+        blob[int(o):int(o) + f.size] = f
+    caps = np.array([int.from_bytes(f[4:8].tobytes(), "little") for f in frames], dtype=np.uint64)
+    doff = np.concatenate([[0], np.cumsum((caps[:-1] + 15) // 16 * 16 + 32)]).astype(np.uint64)
+    total = int(doff[-1] + caps[-1]) + 64
+    want = [orc.decompress(f)[0] for f in frames]
+    for variant in (0, 1, 2, 3):
+        ctx.set_option(104, variant)
+        try:
+            canvas = np.full(total, 0xC3, dtype=np.uint8)
+            out, olen, st = ctx.decompress_batch(blob, foff, flen, doff, total, dst=canvas)
+        finally:
+            ctx.set_option(104, -1)
+        assert [int(x) for x in st] == want, (variant, [int(x) for x in st], want)
+        for k in range(len(frames)):                                   # the gaps behind the slots keep the caller's bytes
+            end = int(doff[k] + caps[k])
+            assert (out[end:end + 32] == 0xC3).all(), (variant, k)
+
+
 def test_fused_unshuffle_epilogue_matches_the_separate_pass(ctx):
     """Option 10: the decoding warp un-shuffles its own frame (typesize 2 / 4, aligned slots, E % 16 == 0) instead of
     the separate filter pass; frames that do not qualify (other typesizes, odd sizes, bit shuffle) take the pass in
