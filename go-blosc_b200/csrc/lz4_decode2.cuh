@@ -66,7 +66,8 @@ enum : uint32_t {
 };
 
 struct FrameDec {
-    uint32_t kind;       // 0: nothing to decode (status final), 1: stored (memcpy flag), 2: LZ4 block
+    uint32_t kind;       // 0: nothing to decode (status final), 1: stored (memcpy flag), 2: LZ4 block, 3: LZ4 block left to the
+                         // one-warp-per-frame kernel (small against its output)
     uint32_t plen;       // payload bytes
     uint32_t norig;      // NBytesOrig
     uint32_t dcap;       // min(capacity, NBytesOrig)
@@ -231,7 +232,11 @@ __global__ void frame_prep_kernel(Prep2Args a) {
                 // runs over the capacity or is malformed, whichever comes first
                 const uint64_t bound = (uint64_t)d.dcap + d.dcap / 255u + 16u;
                 if ((uint64_t)d.plen > bound) st = d.dcap == norig ? kEDecompressionFailed : kEDstTooSmall;
-                else d.kind = 2;
+                // A frame whose block is small against its output (long runs, sparse arrays: ratio under 0.3) is a few
+                // thousand sequences however large it is: one warp walks that faster than a CTA walks the frame's tiles
+                // (4 MiB frames of a sparse int32 array: 35 -> 197 GB/s), so it goes to the one-warp-per-frame kernel
+                // that runs behind the copy engine (kind 3; the stitch kernel flags it).
+                else d.kind = 10ull * d.plen < 3ull * norig ? 3u : 2u;
             }
         }
     }
@@ -374,6 +379,7 @@ __global__ void __launch_bounds__(64) lz4_stitch_kernel(Stitch2Args a) {
         d = a.fd[f];
         plen = d.plen;
         nch = (plen + kChunkBytes - 1) / kChunkBytes;
+        if (d.kind == 3) a.fallback[f] = 1;
         if (d.kind == 2 && nch != 0) {
             cb = a.chunk_base[f];
             if (cb + nch > a.table_chunks) a.fallback[f] = 1;
@@ -546,7 +552,7 @@ __device__ __forceinline__ void flush_tile(const uint8_t *ring, uint8_t *outv, u
     }
 }
 
-__global__ void __launch_bounds__(kCopy2Threads, 1536 / kCopy2Threads) lz4_copy2_kernel(Copy2Args a) {
+__global__ void __launch_bounds__(kCopy2Threads, 1024 / kCopy2Threads) lz4_copy2_kernel(Copy2Args a) {
     __shared__ __align__(16) uint8_t ring[kRing2];
     __shared__ uint32_t pend[kTile2 / 32 + 1];
     __shared__ CoopLit s_coop[kCopy2Threads];
@@ -661,6 +667,11 @@ __global__ void __launch_bounds__(kCopy2Threads, 1536 / kCopy2Threads) lz4_copy2
             // stream to the output
             const bool bulk = lit_ok && vL <= T0 && vM >= T1 + kTile2;
             if (bulk) { s_bulk[slot] = (uint32_t)((vM - T0) / kTile2); s_bulk_src[slot] = src + lit + (uint32_t)(T0 - vL); }
+            // the same for a periodic match (a run of zeros, a repeated 2 / 4 / 8 / 16-byte element) that began at least
+            // 16 bytes before this tile and covers it and the next one: every aligned 16-byte vector of it equals the
+            // 16 bytes in front of the tile
+            const bool mbulk = match_ok && off <= 16u && (off & (off - 1u)) == 0u && vM + 16u <= T0 && vE >= T1 + kTile2;
+            if (mbulk) { s_bulk[slot] = 0x80000000u | (uint32_t)((vE - T0) / kTile2); s_bulk_src[slot] = nullptr; }
             // ---- literals: no ordering, the source is the stream
             if (lit_ok && lb > la && !bulk) {
                 const uint32_t n = lb - la;
@@ -673,7 +684,7 @@ __global__ void __launch_bounds__(kCopy2Threads, 1536 / kCopy2Threads) lz4_copy2
                     s_coop[cs].dst = rb + la; s_coop[cs].n = n; s_coop[cs].src = sp;
                 }
             }
-            const bool mine = match_ok && mb > lb;
+            const bool mine = match_ok && mb > lb && !mbulk;
             if (mine) pend_set(pend, lb, mb);
             if (have && !fin && vL < T1) {                        // at most one record starts in the tile and ends behind it
                 Carry &c = s_carry[it & 1u];
@@ -686,9 +697,16 @@ __global__ void __launch_bounds__(kCopy2Threads, 1536 / kCopy2Threads) lz4_copy2
             if (tid == 0) { s_ncoop[(it + 2u) % 3u] = 0; s_bulk[(it + 2u) % 3u] = 0; s_err[(it + 2u) % 3u] = 0xFFFFFFFFu; }
             const uint32_t gerr = s_err[slot];
             if (gerr != 0xFFFFFFFFu) { code = gerr & 3u; break; }
-            const uint32_t nbulk = s_bulk[slot];
+            const uint32_t nbulk = s_bulk[slot] & 0x7FFFFFFFu;
             if (nbulk) {
-                cta_copy(outv + T0, s_bulk_src[slot], (uint64_t)nbulk * kTile2);
+                if (s_bulk[slot] & 0x80000000u) {
+                    const uint4 pat = W0 <= -16 ? *reinterpret_cast<const uint4 *>(ring + ((rb - 16u) & (kRing2 - 1u)))
+                                                : __ldcg(reinterpret_cast<const uint4 *>(outv + (T0 - 16u)));
+                    const uint64_t nvec = (uint64_t)nbulk * (kTile2 / 16u);
+                    for (uint64_t q = tid; q < nvec; q += kCopy2Threads) stg128(outv + T0 + 16ull * q, pat);
+                } else {
+                    cta_copy(outv + T0, s_bulk_src[slot], (uint64_t)nbulk * kTile2);
+                }
                 T0 += (uint64_t)nbulk * kTile2;
                 W0 = 0;                                           // the ring holds nothing of what was just written
                 __syncthreads();                                  // the copy is visible to later match reads of the CTA
@@ -787,11 +805,24 @@ __global__ void __launch_bounds__(kCopy2Threads, 1536 / kCopy2Threads) lz4_copy2
                         uint8_t *dp = ring + rb + jlb;
                         uint32_t rem = jov ? (jskip + (uint32_t)lane) % joff : 0u;   // place of my byte inside the period
                         const uint32_t step = jov ? 32u % joff : 0u;
-                        for (uint32_t q = lane; q < jmn; q += 32) {
+                        // a run / short period (1, 2, 4, 8, 16 bytes): once 16 bytes of it stand at an aligned place, every
+                        // further aligned 16-byte vector of the match is that same vector
+                        uint32_t bytewise = jmn;
+                        const bool vec = jov && joff <= 16u && (joff & (joff - 1u)) == 0u && jmn >= 64u;
+                        if (vec) bytewise = ((16u - (jlb & 15u)) & 15u) + 16u;
+                        for (uint32_t q = lane; q < bytewise; q += 32) {
                             const int32_t sp = js0 + (int32_t)(jov ? rem : q);
                             dp[q] = sp >= W0 ? ring[(rb + (uint32_t)sp) & (kRing2 - 1u)] : __ldcg(outv + (T0 + (int64_t)sp));
                             rem += step;
                             if (rem >= joff) rem -= joff;
+                        }
+                        if (vec) {
+                            __syncwarp();
+                            const uint4 pat = *reinterpret_cast<const uint4 *>(dp + bytewise - 16u);
+                            const uint32_t nvec = (jmn - bytewise) >> 4;
+                            for (uint32_t q = lane; q < nvec; q += 32) *reinterpret_cast<uint4 *>(dp + bytewise + 16u * q) = pat;
+                            const uint32_t done = bytewise + 16u * nvec;
+                            if (done + (uint32_t)lane < jmn) dp[done + lane] = dp[bytewise - 16u + lane];   // < 16 bytes behind the last vector
                         }
                         __threadfence_block();
                         __syncwarp();
