@@ -1393,19 +1393,36 @@ int b2b_shuffle(b2b_ctx *ctx, int mode, int inverse, int64_t typesize, const voi
 constexpr uint64_t kStagingMinBytes = 16ull << 20;   // pageable batches below this go to cudaMemcpyAsync directly
 struct HostChunk { uint32_t f0, f1; uint64_t lo, hi; uint32_t max_len; uint64_t sum; };   // sum: bytes of all frames (> hi - lo when they overlap)
 
+// Chunk sizes ramp up at the start of a batch and down at its end (stage / 4, stage / 2, stage, ..., stage / 2,
+// stage / 4): nothing overlaps the first chunk's H2D or the last chunk's kernels and D2H, so those are kept short.
+static uint64_t chunk_target(uint64_t done, uint64_t total, uint64_t stage) {
+    const uint64_t left = total - done;
+    uint64_t t = stage;
+    if (done == 0) t = stage / 4;
+    else if (done < stage) t = stage / 2;
+    if (left <= stage / 4 + stage / 8) return left;
+    if (left <= stage) t = std::min(t, left > stage / 2 ? left - stage / 4 : left);
+    else if (left <= 2 * stage) t = std::min(t, stage / 2 + (left - stage) / 2);
+    return std::max<uint64_t>(t, 1);
+}
+
 static std::vector<HostChunk> split_chunks(const uint64_t *off, const uint32_t *len, uint32_t nframes,
                                            uint64_t stage_bytes) {
     std::vector<HostChunk> out;
+    uint64_t total = 0, done = 0;
+    for (uint32_t i = 0; i < nframes; i++) total += len[i];
     uint32_t f = 0;
     while (f < nframes) {
         HostChunk c{f, f, ~0ull, 0, 0, 0};
         uint64_t bytes = 0;
-        while (c.f1 < nframes && (c.f1 == c.f0 || bytes + len[c.f1] <= stage_bytes)) {
+        const uint64_t target = chunk_target(done, total, stage_bytes);
+        while (c.f1 < nframes && (c.f1 == c.f0 || bytes + len[c.f1] <= target)) {
             c.lo = std::min(c.lo, off[c.f1]); c.hi = std::max(c.hi, off[c.f1] + len[c.f1]);
             c.max_len = std::max(c.max_len, len[c.f1]);
             bytes += len[c.f1]; c.f1++;
         }
         c.sum = bytes;
+        done += bytes;
         out.push_back(c);
         f = c.f1;
     }
@@ -1632,11 +1649,15 @@ static int host_decompress_batch(b2b_ctx *ctx, const void *frames, const uint64_
     // chunks by OUTPUT bytes (the larger side), in processing order
     struct Chunk { uint32_t i0, i1, max_cap; uint64_t out_bytes; };
     std::vector<Chunk> chunks;
+    uint64_t cap_total = 0, cap_done = 0;
+    for (uint32_t i = 0; i < nframes; i++) cap_total += cap[i];
     for (uint32_t i = 0; i < nframes;) {
         Chunk c{i, i, 0, 0};
-        while (c.i1 < nframes && (c.i1 == c.i0 || c.out_bytes + cap[F(c.i1)] <= ctx->opt_stage_bytes)) {
+        const uint64_t target = chunk_target(cap_done, cap_total, ctx->opt_stage_bytes);   // ramp up / down like split_chunks
+        while (c.i1 < nframes && (c.i1 == c.i0 || c.out_bytes + cap[F(c.i1)] <= target)) {
             c.out_bytes += cap[F(c.i1)]; c.max_cap = std::max(c.max_cap, cap[F(c.i1)]); c.i1++;
         }
+        cap_done += c.out_bytes;
         chunks.push_back(c);
         i = c.i1;
     }
