@@ -335,10 +335,11 @@ class Context:
     def kernel_stats(self) -> dict:
         """{kernel name: (launches, total device ms)}; times need OPT_KERNEL_TIMING."""
         out = {}
-        for k in range(16):
+        for k in range(64):
             name, n, ms = C.c_char_p(), C.c_uint64(0), C.c_double(0)
-            if lib().b2b_kernel_stats(self._h, k, C.byref(name), C.byref(n), C.byref(ms)) == 0:
-                out[name.value.decode()] = (int(n.value), float(ms.value))
+            if lib().b2b_kernel_stats(self._h, k, C.byref(name), C.byref(n), C.byref(ms)) != 0:
+                break                                               # B2B_EINVAL beyond the last kernel id
+            out[name.value.decode()] = (int(n.value), float(ms.value))
         return out
 
     def kernel_stats_reset(self):

@@ -22,6 +22,7 @@
 #include "scan.cuh"
 #include "lz4_decode2.cuh"
 #include "lz4_decode3.cuh"
+#include "lz4_decode4.cuh"
 #include "blocks.cuh"
 #include "host_staging.hpp"
 
@@ -30,13 +31,16 @@
 using namespace b2b;
 
 enum KernelId { K_FILTER = 0, K_ENCODE, K_DECODE, K_SCAN, K_PACK, K_INFO, K_FINALIZE, K_PARSE,
-                K_BLOCKS_META, K_BLOCKS_PACK, K_BLOCKS_DECODE, K_PREP2, K_PARSE2, K_STITCH2, K_COPY2, K_LANE, K_COUNT };
+                K_BLOCKS_META, K_BLOCKS_PACK, K_BLOCKS_DECODE, K_PREP2, K_PARSE2, K_STITCH2, K_COPY2, K_LANE,
+                K_JUMP_MAP, K_JUMP_ROUND, K_JUMP_GATHER, K_JUMP_LONG, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"filter_batch_kernel", "lz4_encode_kernel", "lz4_decode_kernel",
                                                   "scan_offsets_kernel", "pack_frames_kernel", "frame_info_kernel",
                                                   "finalize_frames_kernel", "lz4_parse_kernel",
                                                   "blocks_meta_kernels", "blocks_pack_kernel", "blocks_decode_kernel",
                                                   "frame_prep_kernel", "lz4_chunk_parse_kernel", "lz4_stitch_kernel",
-                                                  "lz4_copy2_kernel", "lz4_lane_decode_kernel"};
+                                                  "lz4_copy2_kernel", "lz4_lane_decode_kernel",
+                                                  "lz4_jump_map_kernel", "lz4_jump_round_kernel", "lz4_jump_gather_kernel",
+                                                  "lz4_jump_long_kernel"};
 
 struct TimedLaunch { int id; cudaEvent_t a, b; };
 
@@ -485,8 +489,18 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     // needs tens of thousands of frames to fill the device and each of them is decoded at the latency of one
     // thread, so it only pays for very many very small frames (2^20 frames of 1 KiB: 222 against 158 GB/s; 4 KiB: 367
     // against 348; 16 KiB: 297 against 590; C3's 256 KiB frames: 58 ms against 13.7 ms per 8 GiB).
+    // A fourth arrangement (lz4_decode4.cuh) takes the ORDER out of a frame: every output byte gets a source index and
+    // pointer jumping resolves the match chains, so one large frame is spread over the whole device instead of one CTA
+    // (one 256 MiB frame: 0.35 GB/s in stream order).  It costs 4 bytes of scratch and tens of bytes of traffic per output
+    // byte, so it is only chosen when the frames are too few to fill the device in stream order.
+    const bool want_jump = variant == 4;
+    if (variant == 4) variant = 0;
     if (variant < 0) variant = max_orig > (512u << 10) ? 0 : (max_orig <= 4096u && nframes >= 65536u) ? 3 : 2;
     const bool v2 = !indexed && variant == 0;
+    const bool jump = v2 && nframes <= 64 && total_dst < 0xFFFF0000ull &&
+                      (want_jump || (ctx->opt_fused_decode < 0 && total_dst <= 24ull * max_orig));
+    const uint32_t jump_bpf = max_orig / kJumpBlock + 1;
+    const uint32_t jump_long_cap = (uint32_t)(total_dst / kJumpLong) + nframes + 16;
     const bool split = !indexed && variant == 2;
     const bool lanes = !indexed && variant == 3;
     const uint64_t nrec_max = total_dst / 4 + (uint64_t)(kSeqSlack + 1) * nframes + 64;   // sum of dst_cap / 4 + slack
@@ -499,7 +513,10 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
                           (v2 ? align_up(sizeof(FrameDec) * (uint64_t)nframes, 256) + 3 * align_up(4ull * nframes, 256) +
                                 align_up(8ull * nframes, 256) + scan_scratch_bytes(nframes) +
                                 align_up(8ull * kChunkSlot * table_chunks, 256) + 2 * align_up(32ull * table_chunks, 256) +
-                                align_up(4ull * table_chunks + 16, 256) + 2048 : 0);
+                                align_up(4ull * table_chunks + 16, 256) + 2048 : 0) +
+                          (jump ? align_up(4ull * total_dst + 64, 256) + 2 * align_up(4ull * nframes, 256) +
+                                  align_up(sizeof(JumpLong) * (uint64_t)jump_long_cap, 256) + 512 +
+                                  align_up((uint64_t)nframes * jump_bpf, 256) + 1024 : 0);
     int rc = ensure_arena(ctx, need);
     if (rc) return rc;
     Arena ar(ctx);
@@ -547,6 +564,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         pa.frames = a.frames; pa.frame_off = d_frame_off; pa.frame_len = d_frame_len; pa.dst_cap = d_dst_cap;
         pa.nframes = nframes; pa.typesize_override = typesize_override; pa.fd = d_fd; pa.plen_eff = d_plen;
         pa.out_len = d_out_len; pa.status = d_status; pa.meta = d_meta;
+        pa.keep_sparse = jump ? 1u : 0u;
         { LaunchTimer lt(ctx, K_PREP2, s); frame_prep_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(pa); }
         CU(ctx, cudaGetLastError());
         rc = launch_scan(ctx, d_plen, nframes, d_chunk_base, d_total_chunks, kScanChunks, scan_c, s);
@@ -567,7 +585,41 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         sa.table_chunks = table_chunks;
         { LaunchTimer lt(ctx, K_STITCH2, s); lz4_stitch_kernel<<<(nframes + 63) / 64, 64, 0, s>>>(sa); }
         CU(ctx, cudaGetLastError());
+        uint32_t *d_jump_state = nullptr;
+        if (jump) {
+            // select -> map (+ long runs) -> check -> jump rounds -> gather; what it refuses (state 2) is the tile engine's
+            JumpArgs ja;
+            ja.frames = a.frames; ja.frame_off = d_frame_off; ja.fd = d_fd; ja.nframes = nframes; ja.dst = a.dst; ja.scratch = d_stage;
+            ja.dst_off = d_dst_off; ja.chunk_base = d_chunk_base; ja.total_chunks = d_total_chunks; ja.table_chunks = table_chunks;
+            ja.desc = d_cdesc; ja.last_chunk = d_last; ja.table = d_rec; ja.fallback = d_fallback;
+            ja.S = ar.take<uint32_t>(total_dst + 16);
+            ja.state = d_jump_state = ar.take<uint32_t>(nframes);
+            ja.total = ar.take<uint32_t>(nframes);
+            ja.longq = ar.take<JumpLong>(jump_long_cap); ja.long_cap = jump_long_cap;
+            ja.nlong = ar.take<uint32_t>(1 + kJumpRounds); ja.changed = ja.nlong + 1;
+            ja.blockdone = ar.take<uint8_t>((uint64_t)nframes * jump_bpf); ja.blocks_per_frame = jump_bpf;
+            ja.blocks_grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(jump_bpf, (uint64_t)ctx->sm_count * 8 / nframes));
+            ja.out_len = d_out_len; ja.status = d_status; ja.meta = d_meta;
+            CU(ctx, cudaMemsetAsync(ja.blockdone, 0, (uint64_t)nframes * jump_bpf, s));
+            lz4_jump_select_kernel<<<(nframes + 63) / 64, 64, 0, s>>>(ja);
+            ctx->launches++;
+            CU(ctx, cudaGetLastError());
+            const unsigned mgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(table_chunks, (uint64_t)ctx->sm_count * 8));
+            { LaunchTimer lt(ctx, K_JUMP_MAP, s); lz4_jump_map_kernel<<<mgrid, kJumpThreads, 0, s>>>(ja); }
+            { LaunchTimer lt(ctx, K_JUMP_LONG, s);
+              lz4_jump_long_kernel<<<(unsigned)ctx->sm_count * 4, kJumpThreads, 0, s>>>(ja);
+              lz4_jump_check_kernel<<<(nframes + 63) / 64, 64, 0, s>>>(ja); }
+            ctx->launches += 1;
+            CU(ctx, cudaGetLastError());
+            { LaunchTimer lt(ctx, K_JUMP_ROUND, s);
+              for (uint32_t r = 0; r < kJumpRounds; r++) lz4_jump_round_kernel<<<nframes * ja.blocks_grid, kJumpThreads, 0, s>>>(ja, r); }
+            ctx->launches += kJumpRounds - 1;
+            CU(ctx, cudaGetLastError());
+            { LaunchTimer lt(ctx, K_JUMP_GATHER, s); lz4_jump_gather_kernel<<<nframes * ja.blocks_grid, kJumpThreads, 0, s>>>(ja); }
+            CU(ctx, cudaGetLastError());
+        }
         Copy2Args ca;
+        ca.jump_state = d_jump_state;
         ca.frames = a.frames; ca.frame_off = d_frame_off; ca.fd = d_fd; ca.nframes = nframes; ca.dst = a.dst; ca.scratch = d_stage;
         ca.dst_off = d_dst_off; ca.chunk_base = d_chunk_base; ca.desc = d_cdesc; ca.last_chunk = d_last; ca.table = d_rec;
         ca.fallback = d_fallback; ca.out_len = d_out_len; ca.status = d_status; ca.meta = d_meta;
@@ -1043,7 +1095,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
             if (value != 0 && (value < 4 || value > 6)) return B2B_EINVAL;
             ctx->opt_hash_bytes = (int)value; return B2B_OK;
         case 100: case 101: case 102: case 103: ctx->opt_tune[option - 100] = (uint32_t)value; return B2B_OK;
-        case 104: if (value < -1 || value > 3) return B2B_EINVAL; ctx->opt_fused_decode = (int)value; return B2B_OK;
+        case 104: if (value < -1 || value > 4) return B2B_EINVAL; ctx->opt_fused_decode = (int)value; return B2B_OK;
         case B2B_OPT_HOST_STAGE_BYTES: ctx->opt_stage_bytes = value > 0 ? (uint64_t)value : (128ull << 20); return B2B_OK;
         case B2B_OPT_HOST_THREADS:
             if (value < 0 || value > 64) return B2B_EINVAL;
@@ -1058,7 +1110,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
             if (value < 0 || value > 1 + b2b_ctx::kSide) return B2B_EINVAL;
             ctx->opt_decode_streams = (int)value; return B2B_OK;
         case B2B_OPT_DECODER:
-            if (value < -1 || value > 3) return B2B_EINVAL;
+            if (value < -1 || value > 4) return B2B_EINVAL;
             ctx->opt_fused_decode = (int)value; return B2B_OK;
         default: return B2B_EINVAL;
     }

@@ -199,6 +199,7 @@ struct Prep2Args {
     uint32_t *plen_eff;     // payload bytes of the frames that hold an LZ4 block, else 0 (input of the chunk scan)
     uint32_t *out_len, *status;
     FrameMeta *meta;
+    uint32_t keep_sparse = 0;   // 1: frames that are small against their output stay with this decoder (kind 2), see below
 };
 
 __global__ void frame_prep_kernel(Prep2Args a) {
@@ -236,7 +237,8 @@ __global__ void frame_prep_kernel(Prep2Args a) {
                 // thousand sequences however large it is: one warp walks that faster than a CTA walks the frame's tiles
                 // (4 MiB frames of a sparse int32 array: 35 -> 197 GB/s), so it goes to the one-warp-per-frame kernel
                 // that runs behind the copy engine (kind 3; the stitch kernel flags it).
-                else d.kind = 10ull * d.plen < 3ull * norig ? 3u : 2u;
+                // (not when the pointer-jumping engine of lz4_decode4.cuh follows: it does not care about sequence lengths)
+                else d.kind = (!a.keep_sparse && 10ull * d.plen < 3ull * norig) ? 3u : 2u;
             }
         }
     }
@@ -489,6 +491,7 @@ struct Copy2Args {
     const uint32_t *fallback;
     uint32_t *out_len, *status;
     FrameMeta *meta;
+    const uint32_t *jump_state = nullptr;   // frames with state 1 were decoded by the pointer-jumping engine (lz4_decode4.cuh)
 };
 
 struct CoopLit { uint32_t dst, n; const uint8_t *src; };
@@ -565,6 +568,7 @@ __global__ void __launch_bounds__(kCopy2Threads, 1024 / kCopy2Threads) lz4_copy2
     const int lane = (int)(tid & 31u);
     const FrameDec d = a.fd[f];
     if (d.kind == 0 || a.fallback[f]) return;             // status is final (prep) / the fallback kernel's
+    if (a.jump_state && a.jump_state[f] == 1) return;     // decoded by the pointer-jumping engine
     if (blockIdx.y != 0 && d.kind != 1) return;           // only stored frames are shared between CTAs
     uint8_t *out = (d.mode ? a.scratch : a.dst) + a.dst_off[f];
     const uint8_t *fr = a.frames + a.frame_off[f];

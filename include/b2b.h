@@ -123,8 +123,11 @@ enum {
     B2B_OPT_NO_HOST_STAGING = 8,
     /* LZ4 decoder variant: -1 automatic (default: by the batch's shape), 0 chunk-parallel (a frame is spread over
      * many threads: frames over 512 KiB), 1 fused one-warp-per-frame kernel, 2 parse kernel + copy kernel (one warp
-     * per frame: thousands of small frames), 3 one lane per frame (2^16 frames or more of at most 4 KiB).  All give
-     * identical results. */
+     * per frame: thousands of small frames), 3 one lane per frame (2^16 frames or more of at most 4 KiB), 4 the
+     * chunk-parallel parse followed by pointer jumping over per-byte source indices (a FEW LARGE frames, e.g. the one
+     * frame of b2b_decompress: the frame is spread over the whole device; needs 4 bytes of scratch per output byte,
+     * at most 64 frames and under 4 GiB of output per call, otherwise 0 is used; automatic when the batch's output
+     * is at most 24 times its largest frame).  All give identical results. */
     B2B_OPT_DECODER = 9,
     /* 1: in the one-warp-per-frame decoders the warp that decoded a byte-shuffled frame (typesize 2 or 4, 16-byte
      * aligned slots, element count a multiple of 16) also un-shuffles it, instead of a separate pass over the
@@ -141,10 +144,11 @@ B2B_API int b2b_set_option(b2b_ctx *ctx, int option, int64_t value);
 B2B_API int b2b_reserve(b2b_ctx *ctx, uint64_t total_uncompressed_bytes, uint32_t nframes);
 /* number of kernel launches issued through this ctx since creation (bench's gpu_launches) */
 B2B_API uint64_t b2b_launch_count(b2b_ctx *ctx);
-/* per-kernel launch counts and (with B2B_OPT_KERNEL_TIMING) summed device time; kernel = 0..15:
+/* per-kernel launch counts and (with B2B_OPT_KERNEL_TIMING) summed device time; kernel = 0..19:
  * filter, lz4 encode, lz4 decode (copy half), offsets scan, pack, frame info, finalize, lz4 parse
  * (decode's parse half), block-frame tables, block-frame pack, block-frame decode, then the chunk-parallel
- * decoder's frame prep, chunk parse, stitch and copy engine, and the lane decoder; B2B_EINVAL beyond.
+ * decoder's frame prep, chunk parse, stitch and copy engine, the lane decoder, and the pointer-jumping
+ * decoder's map, rounds, gather and long-run (+ check) launches; B2B_EINVAL beyond.
  * Synchronises pending events.  Times are event spans on the launching stream: kernels of a decompress batch
  * that runs on two streams overlap (B2B_OPT_DECODE_STREAMS = 1 gives exclusive times). */
 B2B_API int b2b_kernel_stats(b2b_ctx *ctx, int kernel, const char **name, uint64_t *launches,

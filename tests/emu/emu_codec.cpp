@@ -31,6 +31,7 @@ inline void tr(int tag, int64_t a, int64_t b, int64_t c, int64_t d, int64_t e) {
 #include "../../go-blosc_b200/csrc/scan.cuh"
 #include "../../go-blosc_b200/csrc/lz4_decode2.cuh"
 #include "../../go-blosc_b200/csrc/lz4_decode3.cuh"
+#include "../../go-blosc_b200/csrc/lz4_decode4.cuh"
 
 using namespace b2b;
 
@@ -170,6 +171,8 @@ int emu_compress_frame(const uint8_t *src, uint32_t n, int shuffle, int64_t type
 }
 
 static uint32_t g_dst_misalign = 0, g_parse_grid = 1;
+static uint32_t g_jump_taken = 0;
+uint32_t emu_jump_taken() { return g_jump_taken; }     // frames the pointer-jumping engine decoded itself (state 1) so far
 void emu_set_parse_grid(uint32_t g) { g_parse_grid = g ? g : 1; }
 void emu_set_dst_misalign(uint32_t m) { g_dst_misalign = m & 15u; }
 
@@ -196,7 +199,8 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
     a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr; a.only = nullptr; a.fuse_unshuffle = 1; a.ticket = nullptr;
     if (split == 3) {
         emu::launch(1, kLaneThreads, [&] { lz4_lane_decode_kernel(a); });
-    } else if (split == 2) {
+    } else if (split == 2 || split == 4) {
+        // split 4: the pointer-jumping engine (lz4_decode4.cuh) in front of the tile copy engine
         // chunk-parallel decoder (lz4_decode2.cuh): prep -> K5 -> chunk parse -> stitch -> tile copy (+ fallback)
         FrameDec fd;
         uint32_t plen_eff = 0, last_chunk = 0, fallback = 0;
@@ -204,7 +208,7 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         Prep2Args pa;
         pa.frames = a.frames; pa.frame_off = &frame_off; pa.frame_len = &len; pa.dst_cap = &cap_eff; pa.nframes = 1;
         pa.typesize_override = typesize_override; pa.fd = &fd; pa.plen_eff = &plen_eff; pa.out_len = &out; pa.status = &status;
-        pa.meta = &meta;
+        pa.meta = &meta; pa.keep_sparse = split == 4 ? 1u : 0u;
         emu::launch(1, 128, [&] { frame_prep_kernel(pa); });
         run_scan(&plen_eff, 1, &chunk_base, &total_chunks, kScanChunks);
         const uint64_t table_chunks = (uint64_t)cap / kChunkBytes + (uint64_t)cap / (255ull * kChunkBytes) + 2 + 16;
@@ -223,7 +227,33 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         sa.table = tab.data(); sa.meta = cmeta.data(); sa.desc = cdesc.data(); sa.last_chunk = &last_chunk;
         sa.fallback = &fallback; sa.table_chunks = table_chunks;
         emu::launch(1, 128, [&] { lz4_stitch_kernel(sa); });
+        uint32_t jstate = 0, jtotal = 0;
+        std::vector<uint32_t> jS;
+        std::vector<JumpLong> jq;
+        std::vector<uint8_t> jdone;
+        uint32_t jctl[1 + kJumpRounds];
+        if (split == 4) {
+            JumpArgs ja;
+            ja.frames = a.frames; ja.frame_off = &frame_off; ja.fd = &fd; ja.nframes = 1; ja.dst = a.dst; ja.scratch = a.scratch;
+            ja.dst_off = &dst_off; ja.chunk_base = &chunk_base; ja.total_chunks = &total_chunks; ja.table_chunks = table_chunks;
+            ja.desc = cdesc.data(); ja.last_chunk = &last_chunk; ja.table = tab.data(); ja.fallback = &fallback;
+            jS.assign((uint64_t)cap + 64, 0xDEADBEEFu); ja.S = jS.data();
+            ja.state = &jstate; ja.total = &jtotal;
+            ja.long_cap = cap / kJumpLong + 1 + 16; jq.resize(ja.long_cap); ja.longq = jq.data();
+            ja.nlong = jctl; ja.changed = jctl + 1;
+            ja.blocks_per_frame = cap / kJumpBlock + 1; jdone.assign(ja.blocks_per_frame, 0); ja.blockdone = jdone.data();
+            ja.blocks_grid = g_parse_grid > 1 ? 3 : 1;
+            ja.out_len = &out; ja.status = &status; ja.meta = &meta;
+            emu::launch(1, 64, [&] { lz4_jump_select_kernel(ja); });
+            emu::launch(g_parse_grid > 1 ? 3 : 1, kJumpThreads, [&] { lz4_jump_map_kernel(ja); });
+            emu::launch(g_parse_grid > 1 ? 3 : 1, kJumpThreads, [&] { lz4_jump_long_kernel(ja); });
+            emu::launch(1, 64, [&] { lz4_jump_check_kernel(ja); });
+            for (uint32_t r = 0; r < kJumpRounds; r++) emu::launch(ja.blocks_grid, kJumpThreads, [&] { lz4_jump_round_kernel(ja, r); });
+            emu::launch(ja.blocks_grid, kJumpThreads, [&] { lz4_jump_gather_kernel(ja); });
+            if (jstate == 1) g_jump_taken++;
+        }
         Copy2Args ca;
+        ca.jump_state = split == 4 ? &jstate : nullptr;
         ca.frames = a.frames; ca.frame_off = &frame_off; ca.fd = &fd; ca.nframes = 1; ca.dst = a.dst; ca.scratch = a.scratch;
         ca.dst_off = &dst_off; ca.chunk_base = &chunk_base; ca.desc = cdesc.data(); ca.last_chunk = &last_chunk;
         ca.table = tab.data(); ca.fallback = &fallback; ca.out_len = &out; ca.status = &status; ca.meta = &meta;

@@ -775,7 +775,7 @@ def test_garbage_payloads_get_the_oracle_status_from_every_decoder(ctx, orc):
     doff = np.concatenate([[0], np.cumsum((caps[:-1] + 15) // 16 * 16 + 32)]).astype(np.uint64)
     total = int(doff[-1] + caps[-1]) + 64
     want = [orc.decompress(f)[0] for f in frames]
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2, 3, 4):
         ctx.set_option(104, variant)
         try:
             canvas = np.full(total, 0xC3, dtype=np.uint8)
@@ -1298,3 +1298,92 @@ def test_allgather_sizes_through_the_c_abi(ctx, torch_mod):
         assert torch.equal(all_off[1:], want[:-1]) and int(total.item()) == int(want[-1].item())
     finally:
         comm.close()
+
+
+def test_jump_decoder_few_large_frames(ctx, orc):
+    """K4's fourth arrangement (lz4_decode4.cuh; option 9 = 4, and the automatic choice for batches of few large
+    frames): chunk-parallel parse, then every output byte resolves its own source by pointer jumping.  Batches of at
+    most 64 frames between 600 KiB and 6 MiB -- every corpus kind and filter, frames of the GPU encoder and of the
+    oracle, flipped bytes, truncations, a capacity one byte short -- in permuted, gapped, unaligned slots: status,
+    length and bytes equal the chunk-parallel decoder's (variant 0) and the oracle's, the gaps keep the caller's
+    bytes, and the engine really ran (its kernels are counted)."""
+    rng = np.random.default_rng(404)
+    frames, caps = [], []
+    sizes = [600 << 10, (1 << 20) + 13, 3 << 20, (6 << 20) + 5]
+    kinds = ("smooth_f32", "lowent_i16", "text", "random", "zeros", "period3")
+    for k, n in enumerate(sizes):
+        for j, kind in enumerate(kinds):
+            data = dg.corpus(n)[kind]
+            sh, T = [(1, 4), (0, 1), (2, 8), (1, 2)][(k + j) % 4]
+            fr = np.frombuffer(ctx.compress(data, 1, 5, sh, T), dtype=np.uint8).copy()
+            frames.append(fr); caps.append(n)
+            if k == 0:
+                rc, ref = orc.compress(data, orc.LZ4, 5, sh, T)
+                frames.append(np.asarray(ref, dtype=np.uint8).copy()); caps.append(n)
+            if fr.size > 4096 and not fr[2] & 2 and k < 2:
+                m = fr.copy(); m[int(rng.integers(16, m.size))] ^= np.uint8(rng.integers(1, 256)); frames.append(m); caps.append(n)
+                if k == 0:
+                    cut = int(rng.integers(17, fr.size)); t = fr[:cut].copy(); t[12:16] = np.frombuffer(struct.pack("<I", cut), dtype=np.uint8)
+                    frames.append(t); caps.append(n)
+    frames.append(frames[0].copy()); caps.append(caps[0] - 1)            # capacity one byte short: ErrDstTooSmall-like status
+    assert len(frames) <= 64
+    order = rng.permutation(len(frames))
+    flen = np.array([f.size for f in frames], dtype=np.uint32)
+    foff = np.concatenate([[0], np.cumsum((flen[:-1].astype(np.uint64) + 15) // 16 * 16)]).astype(np.uint64)
+    blob = np.zeros(int(foff[-1] + flen[-1]) + 64, dtype=np.uint8)
+    for o, f in zip(foff, frames):
+        blob[int(o):int(o) + f.size] = f
+    cap = np.array(caps, dtype=np.uint64)
+    doff = np.zeros(len(frames), dtype=np.uint64)
+    pos = 0
+    for idx in order:                                                     # permuted slots, 48-byte gaps, some unaligned
+        doff[idx] = pos + (3 if idx % 4 == 1 else 0)
+        pos = int(doff[idx] + cap[idx] + 48 + 15) // 16 * 16
+    total = pos + 64
+    # the device-pointer call (one batch, one stream) so that the batch is not cut into pipeline chunks
+    import torch
+    d_blob = torch.from_numpy(blob).cuda(); d_foff = torch.from_numpy(foff.astype(np.int64)).cuda()
+    d_flen = torch.from_numpy(flen.astype(np.int32)).cuda(); d_doff = torch.from_numpy(doff.astype(np.int64)).cuda()
+    d_cap = torch.from_numpy(cap.astype(np.uint32).astype(np.int32)).cuda()
+    res = []
+    for variant in (4, 0, -1):
+        ctx.set_option(9, variant)
+        ctx.kernel_stats_reset()
+        try:
+            d_out = torch.full((total,), 0xC3, dtype=torch.uint8, device="cuda")
+            d_olen = torch.zeros(len(frames), dtype=torch.int32, device="cuda"); d_st = torch.zeros(len(frames), dtype=torch.int32, device="cuda")
+            ctx.decompress_batch_dev(d_blob, d_foff, d_flen, len(frames), 0, d_out, d_doff, d_cap, total, int(cap.max()), d_olen, d_st)
+            torch.cuda.synchronize()
+        finally:
+            ctx.set_option(9, -1)
+        ran = ctx.kernel_stats().get("lz4_jump_map_kernel", (0, 0))[0]
+        assert (ran > 0) == (variant != 0), (variant, ran)               # 80 MiB in 46 frames of <= 6 MiB: also the automatic choice
+        res.append((d_out.cpu().numpy(), d_olen.cpu().numpy().astype(np.uint32), d_st.cpu().numpy().astype(np.uint32)))
+    for other in res[1:]:
+        assert np.array_equal(res[0][2], other[2]) and np.array_equal(res[0][1], other[1])
+    nok = 0
+    for k, f in enumerate(frames):
+        rc, ref = orc.decompress(f) if caps[k] >= int.from_bytes(f[4:8].tobytes(), "little") else (11, None)
+        assert int(res[0][2][k]) == rc, (k, int(res[0][2][k]), rc)
+        end = int(doff[k] + cap[k])
+        for out, _, _ in res:
+            assert (out[end:end + 45] == 0xC3).all(), k
+            if rc == 0:
+                assert np.array_equal(out[int(doff[k]):int(doff[k]) + ref.size], ref), k
+        nok += rc == 0
+    assert nok >= len(sizes) * len(kinds)
+
+
+def test_jump_decoder_is_the_automatic_choice_for_one_large_frame(ctx):
+    """b2b_decompress of ONE frame (what decompressBackend binds, blosc.go:291-303): 48 MiB of float32 behind a byte
+    shuffle, of text without a filter and of a sparse array (a frame that is small against its output) come back
+    exactly, through the pointer-jumping engine."""
+    n = 48 << 20
+    for kind, sh, T in (("smooth_f32", 1, 4), ("text", 0, 1), ("zeros", 1, 4), ("lowent_i16", 2, 2)):
+        data = dg.corpus(n)[kind]
+        fr = ctx.compress(data, 1, 5, sh, T)
+        ctx.kernel_stats_reset()
+        back = np.frombuffer(ctx.decompress(fr), dtype=np.uint8)
+        assert np.array_equal(back, data), kind
+        if not (fr[2] & 2):
+            assert ctx.kernel_stats()["lz4_jump_map_kernel"][0] > 0, kind

@@ -31,9 +31,11 @@ for size in [int(x) for x in os.environ.get("PROBE_BYTES", str(256 << 20)).split
         ctx.compress_batch_dev(src, d_off, d_len, 1, size, min(size, 2**32 - 1), sh, T, d_c, cap, d_foff, d_flen, d_st, d_tot, s)
         b.record(); torch.cuda.synchronize()
         print(f"{size >> 20} MiB frame, {name}: compress {size / a.elapsed_time(b) / 1e6:.1f} GB/s, ratio {int(d_tot.item()) / size:.4f}, status {int(d_st.item())}", flush=True)
-        for variant in (0, 2):
+        for variant in [int(v) for v in os.environ.get('PROBE_VARIANTS', '4,-1,0').split(',')]:
             ctx.set_option(pkg.OPT_DECODER, variant)
+            ctx.decompress_batch_dev(d_c, d_foff, d_flen, 1, 0, d_out, d_off, d_len, size, min(size, 2**32 - 1), d_olen, d_st, s)   # (grows the arena)
             d_out.zero_()
+            torch.cuda.synchronize()
             ctx.kernel_stats_reset()
             a.record()
             ctx.decompress_batch_dev(d_c, d_foff, d_flen, 1, 0, d_out, d_off, d_len, size, min(size, 2**32 - 1), d_olen, d_st, s)
