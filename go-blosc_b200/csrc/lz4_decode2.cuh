@@ -100,9 +100,22 @@ struct ChunkDesc {       // written by the stitch kernel
 // rare length-extension loops diverge.
 // Length bytes of a very long run (a 100 MB literal run has 400 000 of them): whole aligned 16-byte blocks of 0xFF
 // are taken at once.  Returns how many bytes were skipped (a multiple of 16); each adds 255.
+// A run of R literals has R / 255 length bytes (the incompressible byte plane of ONE 1 GiB frame: a million of them) and
+// one thread walks them, so the walk must not pay a memory round trip per 16 bytes: 64 bytes per step with the lines
+// 1 KiB ahead already on their way to L1 (one 256 MiB frame: chunk parse 8.0 -> and map 5.5 ms -> see DESIGN).
 __device__ __forceinline__ uint32_t skip_ff_blocks(const uint8_t *__restrict__ s, uint32_t clen, uint32_t p) {
     uint32_t n = 0;
     if (((uintptr_t)(s + p) & 15u) == 0) {
+        while (p + n + 64u <= clen) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(s + p + n);
+#if defined(__CUDA_ARCH__)
+            if (p + n + 1152u <= clen) asm volatile("prefetch.global.L1 [%0];" ::"l"(s + p + n + 1024u));
+#endif
+            const uint4 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
+            if (((v0.x & v0.y & v0.z & v0.w) & (v1.x & v1.y & v1.z & v1.w) & (v2.x & v2.y & v2.z & v2.w) &
+                 (v3.x & v3.y & v3.z & v3.w)) != 0xFFFFFFFFu) break;
+            n += 64u;
+        }
         while (p + n + 16u <= clen) {
             const uint4 v = *reinterpret_cast<const uint4 *>(s + p + n);
             if ((v.x & v.y & v.z & v.w) != 0xFFFFFFFFu) break;
@@ -368,8 +381,17 @@ struct Stitch2Args {
 // A state machine per lane, one small step per turn, so that the lanes of a warp stay together whatever their
 // frames need: 0 look at the next chunk, 1 walk from the true position towards the speculative chain, 2 write the
 // records that walk found missing (or the whole chunk), 3 done.
-__global__ void __launch_bounds__(64) lz4_stitch_kernel(Stitch2Args a) {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+// kWarpPerFrame: the same walk with a whole WARP per frame (few, large frames: one 1 GiB frame has 10^5 chunks and a
+// thread that adopts them one dependent load at a time needs 40 ms).  All lanes run the state machine redundantly (same
+// loads, same stores), and the common step -- adopt the next chunk -- is taken 32 chunks at a time: lane i looks at chunk
+// k + i, the leading lanes whose entry equals the exit of the chunk before them (and whose chain simply runs into the
+// next chunk) are adopted together, output bases from a warp prefix sum; the first chunk that is anything else
+// (a wrong entry, a token that jumps over chunks, the end of the chain, the capacity) goes through the scalar steps.
+template <bool kWarpPerFrame>
+__device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t f = kWarpPerFrame ? gt >> 5 : gt;
+    const uint32_t lane = threadIdx.x & 31u;
     int mode = 3;
     FrameDec d; d.kind = 0; d.plen = 0; d.dcap = 0;
     uint32_t plen = 0, nch = 0;
@@ -406,8 +428,41 @@ __global__ void __launch_bounds__(64) lz4_stitch_kernel(Stitch2Args a) {
         if (mode == 0) {
             k = e / kChunkBytes;
             if (k >= nch) k = nch - 1;
-            for (uint32_t q = knext; q < k; q++) a.desc[cb + q].count = 0;    // chunks inside one long token
+            if (kWarpPerFrame) { for (uint32_t q = knext + lane; q < k; q += 32) a.desc[cb + q].count = 0; }
+            else { for (uint32_t q = knext; q < k; q++) a.desc[cb + q].count = 0; }   // chunks inside one long token
             knext = k + 1;
+            bool took = false;
+            if (kWarpPerFrame) {
+                const uint32_t ki = k + lane;
+                ChunkMeta mi; mi.entry = 0xFFFFFFFFu; mi.exit = 0; mi.count = 0; mi.end = kEndDead; mi.out = 0;
+                if (ki < nch) mi = a.meta[cb + ki];
+                uint32_t prev_exit = __shfl_up_sync(0xffffffffu, mi.exit, 1);
+                if (lane == 0) prev_exit = e;
+                unsigned long long incl = mi.out;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, dd);
+                    if ((int)lane >= dd) incl += t;
+                }
+                const uint32_t nk = mi.exit / kChunkBytes < nch ? mi.exit / kChunkBytes : nch - 1;
+                const bool reg = ki + 1 < nch && mi.entry == prev_exit && mi.end == kEndCont && nk == ki + 1 &&
+                                 op + (long long)incl <= (long long)d.dcap;
+                const uint32_t irr = ~__ballot_sync(0xffffffffu, reg);
+                const uint32_t r = irr ? (uint32_t)__ffs((int)irr) - 1u : 32u;
+                if (r > 0) {
+                    if (lane < r) {
+                        ChunkDesc Di;
+                        Di.base_a = 0; Di.base_b = op + (long long)(incl - mi.out); Di.start = kChunkHead; Di.count = mi.count;
+                        Di.split = 0; Di.end = kEndCont;
+                        a.desc[cb + ki] = Di;
+                    }
+                    op += (long long)__shfl_sync(0xffffffffu, incl, (int)r - 1);
+                    e = __shfl_sync(0xffffffffu, mi.exit, (int)r - 1);
+                    knext = k + r;
+                    took = true;
+                }
+            }
+            if (took) continue;
             m = a.meta[cb + k];
             slot = a.table + (cb + k) * kChunkSlot;
             cend = k + 1 == nch ? plen + 1 : (k + 1) * kChunkBytes;
@@ -466,6 +521,9 @@ __global__ void __launch_bounds__(64) lz4_stitch_kernel(Stitch2Args a) {
         }
     }
 }
+
+__global__ void __launch_bounds__(64) lz4_stitch_kernel(Stitch2Args a) { stitch_body<false>(a); }
+__global__ void __launch_bounds__(64) lz4_stitch_warp_kernel(Stitch2Args a) { stitch_body<true>(a); }
 
 // ---- copy: one CTA per frame, one thread per sequence ---------------------------------------------------------
 #ifndef B2B_COPY2_THREADS

@@ -924,26 +924,56 @@ __device__ __forceinline__ uint32_t cta_put_token(uint8_t *dst, uint32_t lt, uin
     return 2 + full;
 }
 
-// segment s of frame f's LZ4 block, assembled at its place in `out` (the start of the block) by the whole CTA
+// bytes a token with lt literals takes before the literals
+__device__ __forceinline__ uint32_t token_hdr_bytes(uint32_t lt) { return 1u + len_ext_bytes(lt); }
+
+// segment s of frame f's LZ4 block, assembled at its place in `out` (the start of the block) by the whole CTA.
+// Every segment moves exactly the input bytes it OWNS: a literal run that crosses segment boundaries (the trailing
+// literals of a segment, whole segments without a match -- the incompressible byte planes of a shuffled frame --
+// and the leading literals of the segment that closes the run) is copied piecewise by its owners, each of which
+// finds the run's place from the closing segment's entry.  (Round 1 let the closing segment copy the whole run:
+// in ONE large frame that is a single CTA moving half the frame -- 256 MiB: 12.7 of 14.9 ms.)
 __device__ __forceinline__ void cta_pack_lz4_segment(const PackArgs &a, uint32_t f, uint32_t s, uint32_t n,
                                                      uint32_t nseg, uint64_t base, uint8_t *out) {
+    __shared__ uint32_t s_closer;
     const uint32_t B = s * kSegBytes;
+    const uint32_t L = n - B < kSegBytes ? n - B : kSegBytes;
     const uint8_t *frame = a.in + a.src_off[f];
     const SegMeta m = a.meta[base + s];
     if (m.info & 0x100u) {
         const SegPlace pl = a.place[base + s];
         uint8_t *d = out + pl.out_off;
         const uint32_t hdr = cta_put_token(d, pl.lit_total, m.info & 15u);
-        // carried + leading literals are one contiguous input range ending at the match start
-        cta_copy(d + hdr, frame + ((uint64_t)B + m.first_ll - pl.lit_total), pl.lit_total);
+        // my own leading literals close the run; the segment body follows them
+        cta_copy(d + hdr + (pl.lit_total - m.first_ll), frame + B, m.first_ll);
         cta_copy(d + hdr + pl.lit_total, a.comp + a.comp_off[f] + (uint64_t)s * kSegSlot, m.body_len);
     }
-    if (s == nseg - 1) {                                  // closing token: the last literals
-        const uint32_t lf = a.final_ll[f];
-        uint8_t *d = out + a.final_off[f];
-        const uint32_t hdr = cta_put_token(d, lf, 0);
-        cta_copy(d + hdr, frame + (n - lf), lf);
+    if (s == nseg - 1) cta_put_token(out + a.final_off[f], a.final_ll[f], 0);      // closing token: the last literals
+    // my trailing literals (the whole segment when it has no match) open or continue the run that the next
+    // segment with a match closes -- or the closing token
+    const uint32_t mine = (m.info & 0x100u) ? m.trail_ll : L;
+    if (mine == 0) return;                                        // (uniform: m is the same for every thread)
+    __syncthreads();
+    if (threadIdx.x == 0) s_closer = nseg;
+    __syncthreads();
+    for (uint32_t b0 = s + 1; b0 < nseg; b0 += blockDim.x) {
+        const uint32_t idx = b0 + threadIdx.x;
+        if (idx < nseg && (a.meta[base + idx].info & 0x100u)) atomicMin(&s_closer, idx);
+        __syncthreads();
+        if (s_closer < nseg) break;
     }
+    const uint32_t c = s_closer;
+    uint32_t tok_off, lt, run_in0;                                // the run: its token, its literals, where they start in the input
+    if (c < nseg) {
+        const SegPlace pc = a.place[base + c];
+        tok_off = pc.out_off; lt = pc.lit_total;
+        run_in0 = c * kSegBytes + a.meta[base + c].first_ll - lt;
+    } else {
+        tok_off = a.final_off[f]; lt = a.final_ll[f];
+        run_in0 = n - lt;
+    }
+    const uint32_t in0 = B + L - mine;
+    cta_copy(out + tok_off + token_hdr_bytes(lt) + (in0 - run_in0), frame + in0, mine);
 }
 
 __global__ void __launch_bounds__(kFilterThreads, 8) pack_frames_kernel(PackArgs a) {

@@ -226,7 +226,8 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         sa.frames = a.frames; sa.frame_off = &frame_off; sa.fd = &fd; sa.nframes = 1; sa.chunk_base = &chunk_base;
         sa.table = tab.data(); sa.meta = cmeta.data(); sa.desc = cdesc.data(); sa.last_chunk = &last_chunk;
         sa.fallback = &fallback; sa.table_chunks = table_chunks;
-        emu::launch(1, 128, [&] { lz4_stitch_kernel(sa); });
+        if (split == 4) emu::launch(1, 64, [&] { lz4_stitch_warp_kernel(sa); });      // a warp per frame, 32 chunks per step
+        else emu::launch(1, 128, [&] { lz4_stitch_kernel(sa); });
         uint32_t jstate = 0, jtotal = 0;
         std::vector<uint32_t> jS;
         std::vector<JumpLong> jq;

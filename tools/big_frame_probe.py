@@ -27,10 +27,12 @@ for size in [int(x) for x in os.environ.get("PROBE_BYTES", str(256 << 20)).split
     for sh, T, name in ((1, 4, "Shuffle1 T=4"), (0, 1, "NoShuffle")):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.compress_batch_dev(src, d_off, d_len, 1, size, min(size, 2**32 - 1), sh, T, d_c, cap, d_foff, d_flen, d_st, d_tot, s)
+        ctx.kernel_stats_reset()
         a.record()
         ctx.compress_batch_dev(src, d_off, d_len, 1, size, min(size, 2**32 - 1), sh, T, d_c, cap, d_foff, d_flen, d_st, d_tot, s)
         b.record(); torch.cuda.synchronize()
-        print(f"{size >> 20} MiB frame, {name}: compress {size / a.elapsed_time(b) / 1e6:.1f} GB/s, ratio {int(d_tot.item()) / size:.4f}, status {int(d_st.item())}", flush=True)
+        per = ", ".join(f"{k.replace('_kernel', '')} {v[1]:.2f}ms" for k, v in ctx.kernel_stats().items() if v[0] and v[1] > 0.05)
+        print(f"{size >> 20} MiB frame, {name}: compress {a.elapsed_time(b):.2f} ms = {size / a.elapsed_time(b) / 1e6:.1f} GB/s, ratio {int(d_tot.item()) / size:.4f}, status {int(d_st.item())} | {per}", flush=True)
         for variant in [int(v) for v in os.environ.get('PROBE_VARIANTS', '4,-1,0').split(',')]:
             ctx.set_option(pkg.OPT_DECODER, variant)
             ctx.decompress_batch_dev(d_c, d_foff, d_flen, 1, 0, d_out, d_off, d_len, size, min(size, 2**32 - 1), d_olen, d_st, s)   # (grows the arena)
