@@ -579,6 +579,14 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
                                                                           (uint64_t)ctx->sm_count * 12));
         { LaunchTimer lt(ctx, K_PARSE2, s); lz4_chunk_parse_kernel<<<pgrid, kParse2Threads, 0, s>>>(pp); }
         CU(ctx, cudaGetLastError());
+        {   // mis-speculated chunks are repaired all at once, on the exit of the chunk before them (lz4_decode2.cuh)
+            Repair2Args ra;
+            ra.frames = a.frames; ra.frame_off = d_frame_off; ra.fd = d_fd; ra.nframes = nframes; ra.chunk_base = d_chunk_base;
+            ra.total_chunks = d_total_chunks; ra.table = d_rec; ra.meta = d_cmeta; ra.table_chunks = table_chunks;
+            LaunchTimer lt(ctx, K_STITCH2, s);
+            lz4_chunk_repair_kernel<<<(unsigned)((table_chunks + 127) / 128), 128, 0, s>>>(ra);
+        }
+        CU(ctx, cudaGetLastError());
         Stitch2Args sa;
         sa.frames = a.frames; sa.frame_off = d_frame_off; sa.fd = d_fd; sa.nframes = nframes; sa.chunk_base = d_chunk_base;
         sa.table = d_rec; sa.meta = d_cmeta; sa.desc = d_cdesc; sa.last_chunk = d_last; sa.fallback = d_fallback;

@@ -81,6 +81,9 @@ struct ChunkMeta {       // written by the parse kernel
     uint32_t count;      // records (without the closing one)
     uint32_t end;        // kEnd*
     uint32_t out;        // output bytes of those records
+    // written by the repair kernel (zero after the parse): the chain that enters at pad[0] -- the exit of the chunk before --
+    // meets the speculative one at its record j after mc tokens of its own, which now stand in front of record j;
+    // pad[1] = 0x80000000 | mc << 12 | j, pad[2] = output bytes of the chunk on that chain
     uint32_t pad[3];
 };
 
@@ -101,20 +104,25 @@ struct ChunkDesc {       // written by the stitch kernel
 // Length bytes of a very long run (a 100 MB literal run has 400 000 of them): whole aligned 16-byte blocks of 0xFF
 // are taken at once.  Returns how many bytes were skipped (a multiple of 16); each adds 255.
 // A run of R literals has R / 255 length bytes (the incompressible byte plane of ONE 1 GiB frame: a million of them) and
-// one thread walks them, so the walk must not pay a memory round trip per 16 bytes: 64 bytes per step with the lines
-// 1 KiB ahead already on their way to L1 (one 256 MiB frame: chunk parse 8.0 -> and map 5.5 ms -> see DESIGN).
-__device__ __forceinline__ uint32_t skip_ff_blocks(const uint8_t *__restrict__ s, uint32_t clen, uint32_t p) {
+// one thread walks them, so the walk must not pay a memory round trip per 16 bytes (one 256 MiB frame: chunk parse 8.0 ->
+// 4.1 ms).  Not inlined: its registers are only paid for where a run is that long.
+__device__ __noinline__ uint32_t skip_ff_blocks(const uint8_t *__restrict__ s, uint32_t clen, uint32_t p) {
     uint32_t n = 0;
     if (((uintptr_t)(s + p) & 15u) == 0) {
-        while (p + n + 64u <= clen) {
-            const uint4 *q = reinterpret_cast<const uint4 *>(s + p + n);
-#if defined(__CUDA_ARCH__)
-            if (p + n + 1152u <= clen) asm volatile("prefetch.global.L1 [%0];" ::"l"(s + p + n + 1024u));
-#endif
-            const uint4 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
-            if (((v0.x & v0.y & v0.z & v0.w) & (v1.x & v1.y & v1.z & v1.w) & (v2.x & v2.y & v2.z & v2.w) &
-                 (v3.x & v3.y & v3.z & v3.w)) != 0xFFFFFFFFu) break;
-            n += 64u;
+        // 64 bytes per step, the next step's loads already in flight while this step's are tested
+        if (p + n + 64u <= clen) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(s + p);
+            uint4 c0 = q[0], c1 = q[1], c2 = q[2], c3 = q[3];
+            for (;;) {
+                const bool more = p + n + 128u <= clen;
+                uint4 d0 = c0, d1 = c1, d2 = c2, d3 = c3;
+                if (more) { const uint4 *qn = reinterpret_cast<const uint4 *>(s + p + n + 64u); d0 = qn[0]; d1 = qn[1]; d2 = qn[2]; d3 = qn[3]; }
+                if (((c0.x & c0.y & c0.z & c0.w) & (c1.x & c1.y & c1.z & c1.w) & (c2.x & c2.y & c2.z & c2.w) &
+                     (c3.x & c3.y & c3.z & c3.w)) != 0xFFFFFFFFu) break;
+                n += 64u;
+                if (!more) break;
+                c0 = d0; c1 = d1; c2 = d2; c3 = d3;
+            }
         }
         while (p + n + 16u <= clen) {
             const uint4 v = *reinterpret_cast<const uint4 *>(s + p + n);
@@ -363,6 +371,86 @@ __global__ void __launch_bounds__(kParse2Threads, 12) lz4_chunk_parse_kernel(Par
     }
 }
 
+// ---- repair: one thread per chunk ---------------------------------------------------------------------------------
+// A chunk whose speculative chain did not start where the chain of the chunk before it ends is repaired by walking
+// from that exit until the two chains meet (the stitch kernel's own rule).  The stitch kernel does this where the TRUE
+// chain arrives, one chunk after the other; here every such chunk is repaired at once, on the assumption that the
+// chunk before it ends where its speculative chain ends -- true whenever that chain was right or was itself repaired
+// by merging, which is the case the stitch kernel then only has to confirm (entry == pad[0]); where the assumption
+// was wrong the stitch kernel ignores the result and repairs as before.
+struct Repair2Args {
+    const uint8_t *frames;
+    const uint64_t *frame_off;
+    const FrameDec *fd;
+    uint32_t nframes;
+    const uint64_t *chunk_base;
+    const uint64_t *total_chunks;
+    uint2 *table;
+    ChunkMeta *meta;
+    uint64_t table_chunks;
+};
+
+__global__ void __launch_bounds__(128) lz4_chunk_repair_kernel(Repair2Args a) {
+    uint64_t total = *a.total_chunks;
+    if (total > a.table_chunks) total = a.table_chunks;
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0 || g >= total) return;
+    uint32_t lo = 0, hi = a.nframes;                          // last frame whose first chunk is <= g
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (a.chunk_base[mid] <= g) lo = mid; else hi = mid;
+    }
+    const uint32_t f = lo;
+    const FrameDec d = a.fd[f];
+    const uint32_t k = (uint32_t)(g - a.chunk_base[f]);
+    const uint32_t plen = d.plen, nch = (plen + kChunkBytes - 1) / kChunkBytes;
+    if (d.kind != 2 || k == 0 || k >= nch) return;
+    const ChunkMeta prev = a.meta[g - 1], m = a.meta[g];
+    if (prev.entry == 0xFFFFFFFFu || prev.end != kEndCont) return;           // no chain runs out of the chunk before
+    const uint32_t e = prev.exit;
+    if ((e / kChunkBytes < nch ? e / kChunkBytes : nch - 1) != k || m.entry == e) return;
+    const uint32_t sc = m.entry == 0xFFFFFFFFu ? 0u : m.count;
+    if (sc == 0) return;                                                      // nothing to meet: the stitch kernel re-parses
+    const uint8_t *s = a.frames + a.frame_off[f] + 16;
+    uint2 *slot = a.table + g * kChunkSlot;
+    const uint32_t cend = k + 1 == nch ? plen + 1 : (k + 1) * kChunkBytes;
+    uint32_t pos = e, j = 0, mc = 0, spec_tok = slot[kChunkHead].x;
+    uint64_t rel = 0;
+    for (;;) {
+        if (pos >= cend) return;
+        if (spec_tok < pos) {
+            if (++j >= sc) return;
+            spec_tok = slot[kChunkHead + j].x;
+        } else if (spec_tok == pos) {
+            if (mc > kChunkHead + j) return;                                  // no room in front of record j
+            break;
+        } else {
+            Walk t; t.pos = pos; t.n = 0; t.end = kEndCont; t.rel = 0;
+            const bool go = walk_step<false>(s, plen, t, nullptr);
+            mc++;
+            if (!go || rel + t.rel > 0xFFFFFFFFull) return;                   // the chain ends inside the chunk
+            rel += t.rel; pos = t.pos;
+        }
+    }
+    const uint64_t out_alt = rel + (uint64_t)(m.out - slot[kChunkHead + j].y);
+    if (out_alt > 0xFFFFFFFFull || mc >= 4096u || j >= 4096u) return;
+    Walk w; w.pos = e; w.n = 0; w.end = kEndCont; w.rel = 0;
+    uint2 *dstrec = slot + kChunkHead + j - mc;
+    while (w.n < mc && w.pos < cend) { if (!walk_step<true>(s, plen, w, dstrec)) return; }
+    ChunkMeta r = m;
+    r.pad[0] = e; r.pad[1] = 0x80000000u | (mc << 12) | j; r.pad[2] = (uint32_t)out_alt;
+    a.meta[g] = r;
+}
+
+// descriptor of a chunk adopted on its repaired chain (pad[] of its meta), output so far = op
+__device__ __forceinline__ ChunkDesc repaired_desc(const ChunkMeta &m, long long op) {
+    const uint32_t j = m.pad[1] & 0xFFFu, mc = (m.pad[1] >> 12) & 0xFFFu;
+    ChunkDesc D;
+    D.base_a = op; D.base_b = op + ((long long)m.pad[2] - (long long)m.out);
+    D.start = kChunkHead + j - mc; D.count = mc + (m.count - j); D.split = mc; D.end = m.end;
+    return D;
+}
+
 // ---- stitch: one thread per frame ----------------------------------------------------------------------------
 struct Stitch2Args {
     const uint8_t *frames;
@@ -421,7 +509,7 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
     Walk w; w.pos = 0; w.n = 0; w.end = kEndCont; w.rel = 0;
     uint2 *dstrec = nullptr;
     uint32_t limit = 0;
-    bool full = false;
+    bool full = false, prev_full = false;
     while (__any_sync(0xffffffffu, mode != 3)) {
         ChunkDesc D; D.count = 0xFFFFFFFFu;                   // set: a descriptor is ready this turn
         uint32_t endk = kEndCont;
@@ -438,28 +526,32 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
                 if (ki < nch) mi = a.meta[cb + ki];
                 uint32_t prev_exit = __shfl_up_sync(0xffffffffu, mi.exit, 1);
                 if (lane == 0) prev_exit = e;
-                unsigned long long incl = mi.out;
+                const bool alt = mi.entry != prev_exit && (mi.pad[1] >> 31) != 0 && mi.pad[0] == prev_exit;   // repaired chain
+                const uint32_t my_out = alt ? mi.pad[2] : mi.out;
+                unsigned long long incl = my_out;
 #pragma unroll
                 for (int dd = 1; dd < 32; dd <<= 1) {
                     const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, dd);
                     if ((int)lane >= dd) incl += t;
                 }
                 const uint32_t nk = mi.exit / kChunkBytes < nch ? mi.exit / kChunkBytes : nch - 1;
-                const bool reg = ki + 1 < nch && mi.entry == prev_exit && mi.end == kEndCont && nk == ki + 1 &&
+                const bool reg = ki + 1 < nch && (mi.entry == prev_exit || alt) && mi.end == kEndCont && nk == ki + 1 &&
                                  op + (long long)incl <= (long long)d.dcap;
                 const uint32_t irr = ~__ballot_sync(0xffffffffu, reg);
                 const uint32_t r = irr ? (uint32_t)__ffs((int)irr) - 1u : 32u;
+                if (lane == 0) { B2B_STAT(22, 1); B2B_STAT(23, r); }
                 if (r > 0) {
                     if (lane < r) {
                         ChunkDesc Di;
-                        Di.base_a = 0; Di.base_b = op + (long long)(incl - mi.out); Di.start = kChunkHead; Di.count = mi.count;
+                        Di.base_a = 0; Di.base_b = op + (long long)(incl - my_out); Di.start = kChunkHead; Di.count = mi.count;
                         Di.split = 0; Di.end = kEndCont;
+                        if (alt) Di = repaired_desc(mi, op + (long long)(incl - my_out));
                         a.desc[cb + ki] = Di;
                     }
                     op += (long long)__shfl_sync(0xffffffffu, incl, (int)r - 1);
                     e = __shfl_sync(0xffffffffu, mi.exit, (int)r - 1);
                     knext = k + r;
-                    took = true;
+                    took = true; prev_full = false;
                 }
             }
             if (took) continue;
@@ -468,7 +560,20 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
             cend = k + 1 == nch ? plen + 1 : (k + 1) * kChunkBytes;
             if (m.entry == e) {
                 D.base_a = 0; D.base_b = op; D.start = kChunkHead; D.count = m.count; D.split = 0; D.end = m.end;
-                op += m.out; e = m.exit; endk = m.end;
+                op += m.out; e = m.exit; endk = m.end; prev_full = false;
+            } else if ((m.pad[1] >> 31) != 0 && m.pad[0] == e) {          // repaired for exactly this entry (repair kernel)
+                D = repaired_desc(m, op);
+                op += m.pad[2]; e = m.exit; endk = m.end; prev_full = false;
+            } else if (prev_full) {
+                // the chunk before this one had to be re-parsed as a whole and this one is wrong again: two chains that
+                // run side by side without meeting (sequences of one fixed length, e.g. token + offset + one length byte
+                // in the sign / exponent plane of a smooth field: whatever starts off phase stays off phase).  Looking for
+                // the meeting point first would walk the chunk twice.
+                B2B_STAT(20, 1); B2B_STAT(21, 1);
+                full = true;
+                w.pos = e; w.n = 0; w.end = kEndCont; w.rel = 0;
+                limit = 0xFFFFFFFFu; dstrec = slot + kChunkHead;
+                mode = 2;
             } else {
                 B2B_STAT(20, 1);
                 sc = m.entry == 0xFFFFFFFFu ? 0u : m.count;
@@ -504,7 +609,9 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
                     dstrec[w.n] = make_uint2(w.pos, (uint32_t)w.rel);
                     D.base_a = 0; D.base_b = op; D.start = kChunkHead; D.count = w.n; D.split = 0; D.end = w.end;
                     op += (long long)w.rel; e = w.pos; endk = w.end;
+                    prev_full = true;
                 } else {
+                    prev_full = false;
                     // mc records in front of spec[j]; they count from the true position (base_a)
                     const uint32_t spec_rel = slot[kChunkHead + j].y;
                     D.base_a = op; D.base_b = op + (long long)rel - (long long)spec_rel;

@@ -83,6 +83,9 @@ __global__ void lz4_jump_select_kernel(JumpArgs a) {
     a.total[f] = 0xFFFFFFFFu;
 }
 
+// length bytes behind a token whose nibble is 15 for the length v >= 15
+__device__ __forceinline__ uint32_t len_ext_bytes_dec(uint32_t v) { return (v - 15u) / 255u + 1u; }
+
 // source index of byte m of a match that starts at output position oM: a match that overlaps itself repeats the
 // `off` bytes in front of it
 __device__ __forceinline__ uint32_t jump_match_src(uint32_t oM, uint32_t off, bool ovl, uint32_t m) {
@@ -131,7 +134,15 @@ __global__ void __launch_bounds__(kJumpThreads) lz4_jump_map_kernel(JumpArgs a) 
                     uint32_t p = rc.x;
                     const uint32_t tok = src[p++];
                     ll = tok >> 4;
-                    if (ll == 15u) {
+                    const uint64_t span = (uint64_t)(on - o);         // output bytes of the sequence: ll + ml
+                    if (ll == 15u && span >= 4096u && (kind == kEndFinal || (tok & 15u) != 15u) &&
+                        span >= (kind == kEndFinal ? 15u : (tok & 15u) + 4u + 15u)) {
+                        // A long run: its length follows from the record table (the parse walked and checked every length
+                        // byte: 255, ..., 255, last) -- the closing token is all literals, and a match nibble under 15 is
+                        // the whole match length -- so a million length bytes are not walked a second time by one thread
+                        ll = (uint32_t)(span - (kind == kEndFinal ? 0u : (tok & 15u) + 4u));
+                        p += len_ext_bytes_dec(ll);
+                    } else if (ll == 15u) {
                         uint32_t b;
                         do {
                             b = src[p++]; ll += b;

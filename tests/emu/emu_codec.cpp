@@ -57,6 +57,7 @@ template <int HL, int HB, bool PH = false> void run_encode(const EncodeArgs &e, 
 
 extern "C" {
 
+void emu_stat_reset() { for (auto &c : b2b_emu_stats::counters) c = 0; }
 void emu_trace(int on) { b2b_emu_stats::trace_on = on != 0; b2b_emu_stats::trace.clear(); }
 uint64_t emu_trace_len(void) { return b2b_emu_stats::trace.size(); }
 const int64_t *emu_trace_data(void) { return b2b_emu_stats::trace.data(); }
@@ -222,6 +223,12 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         unsigned long long ticket = 0;
         pp.dead = dead.data(); pp.ticket = &ticket;
         emu::launch(g_parse_grid, kParse2Threads, [&] { lz4_chunk_parse_kernel(pp); });
+        {
+            Repair2Args ra;
+            ra.frames = a.frames; ra.frame_off = &frame_off; ra.fd = &fd; ra.nframes = 1; ra.chunk_base = &chunk_base;
+            ra.total_chunks = &total_chunks; ra.table = tab.data(); ra.meta = cmeta.data(); ra.table_chunks = table_chunks;
+            emu::launch((uint32_t)((table_chunks + 127) / 128), 128, [&] { lz4_chunk_repair_kernel(ra); });
+        }
         Stitch2Args sa;
         sa.frames = a.frames; sa.frame_off = &frame_off; sa.fd = &fd; sa.nframes = 1; sa.chunk_base = &chunk_base;
         sa.table = tab.data(); sa.meta = cmeta.data(); sa.desc = cdesc.data(); sa.last_chunk = &last_chunk;
