@@ -86,6 +86,7 @@ struct b2b_ctx {
     int opt_encode_ctas = 0;           // (option 106) persistent encoder CTAs per SM, 0 = as many as fit
     int opt_persistent_decode = 0;     // (option 105) one-warp-per-frame decoders as persistent warps that take frames from a ticket: measured
                                        // 3 % slower on one stream and neutral on two (the gain of the two streams is not a tail effect), so off
+    uint32_t opt_jump_min_bytes = 0;   // (option 107) batches of at most 4 frames: frames over this size take the chunk-parallel parse (0: 192 KiB; one 256 KiB frame 1.55 -> 1.22 ms, one 64 KiB frame 0.43 -> 0.81 ms)
     int opt_decode_streams = 0;        // streams a large decompress batch is split over: 0 automatic (2), 1 none, 2..4
     static constexpr int kSide = 3;
     cudaStream_t s_side[kSide] = {};   // the extra streams of large device-pointer decompress batches
@@ -495,7 +496,10 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     // byte, so it is only chosen when the frames are too few to fill the device in stream order.
     const bool want_jump = variant == 4;
     if (variant == 4) variant = 0;
-    if (variant < 0) variant = max_orig > (512u << 10) ? 0 : (max_orig <= 4096u && nframes >= 65536u) ? 3 : 2;
+    // (a handful of frames is latency, not throughput: there the chunk-parallel parse + pointer jumping already pays for
+    // frames over opt_jump_min_bytes)
+    const uint32_t v2_min = nframes <= 4 ? (ctx->opt_jump_min_bytes ? ctx->opt_jump_min_bytes : (192u << 10)) : (512u << 10);
+    if (variant < 0) variant = max_orig > v2_min ? 0 : (max_orig <= 4096u && nframes >= 65536u) ? 3 : 2;
     const bool v2 = !indexed && variant == 0;
     const bool jump = v2 && nframes <= 64 && total_dst < 0xFFFF0000ull &&
                       (want_jump || (ctx->opt_fused_decode < 0 && total_dst <= 24ull * max_orig));
@@ -623,8 +627,11 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
             ctx->launches += 1;
             CU(ctx, cudaGetLastError());
             { LaunchTimer lt(ctx, K_JUMP_ROUND, s);
-              for (uint32_t r = 0; r < kJumpRounds; r++) lz4_jump_round_kernel<<<nframes * ja.blocks_grid, kJumpThreads, 0, s>>>(ja, r); }
-            ctx->launches += kJumpRounds - 1;
+              // a chain is shorter than the frame: ceil(log2(largest frame)) rounds resolve every one (the unused ones are not launched)
+              uint32_t rounds = 1;
+              while (rounds < kJumpRounds && (1ull << rounds) < (uint64_t)max_orig) rounds++;
+              for (uint32_t r = 0; r < rounds; r++) lz4_jump_round_kernel<<<nframes * ja.blocks_grid, kJumpThreads, 0, s>>>(ja, r);
+              ctx->launches += rounds - 1; }
             CU(ctx, cudaGetLastError());
             { LaunchTimer lt(ctx, K_JUMP_GATHER, s); lz4_jump_gather_kernel<<<nframes * ja.blocks_grid, kJumpThreads, 0, s>>>(ja); }
             CU(ctx, cudaGetLastError());
@@ -1116,6 +1123,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
         case B2B_OPT_NO_HOST_STAGING: ctx->opt_no_staging = value != 0; return B2B_OK;
         case B2B_OPT_FUSE_UNSHUFFLE: ctx->opt_fuse_unshuffle = value != 0; return B2B_OK;
         case 105: ctx->opt_persistent_decode = value != 0; return B2B_OK;
+        case 107: ctx->opt_jump_min_bytes = (uint32_t)std::max<int64_t>(0, value); return B2B_OK;
         case 106: ctx->opt_encode_ctas = (int)std::max<int64_t>(0, value); return B2B_OK;
         case B2B_OPT_DECODE_STREAMS:
             if (value < 0 || value > 1 + b2b_ctx::kSide) return B2B_EINVAL;

@@ -109,20 +109,15 @@ struct ChunkDesc {       // written by the stitch kernel
 __device__ __noinline__ uint32_t skip_ff_blocks(const uint8_t *__restrict__ s, uint32_t clen, uint32_t p) {
     uint32_t n = 0;
     if (((uintptr_t)(s + p) & 15u) == 0) {
-        // 64 bytes per step, the next step's loads already in flight while this step's are tested
-        if (p + n + 64u <= clen) {
-            const uint4 *q = reinterpret_cast<const uint4 *>(s + p);
-            uint4 c0 = q[0], c1 = q[1], c2 = q[2], c3 = q[3];
-            for (;;) {
-                const bool more = p + n + 128u <= clen;
-                uint4 d0 = c0, d1 = c1, d2 = c2, d3 = c3;
-                if (more) { const uint4 *qn = reinterpret_cast<const uint4 *>(s + p + n + 64u); d0 = qn[0]; d1 = qn[1]; d2 = qn[2]; d3 = qn[3]; }
-                if (((c0.x & c0.y & c0.z & c0.w) & (c1.x & c1.y & c1.z & c1.w) & (c2.x & c2.y & c2.z & c2.w) &
-                     (c3.x & c3.y & c3.z & c3.w)) != 0xFFFFFFFFu) break;
-                n += 64u;
-                if (!more) break;
-                c0 = d0; c1 = d1; c2 = d2; c3 = d3;
-            }
+        while (p + n + 128u <= clen) {                        // a cache line per step, its eight loads in flight together
+            const uint4 *q = reinterpret_cast<const uint4 *>(s + p + n);
+            const uint4 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3], v4 = q[4], v5 = q[5], v6 = q[6], v7 = q[7];
+            const uint32_t lo = (v0.x & v0.y & v0.z & v0.w) & (v1.x & v1.y & v1.z & v1.w) & (v2.x & v2.y & v2.z & v2.w) &
+                                (v3.x & v3.y & v3.z & v3.w);
+            const uint32_t hi = (v4.x & v4.y & v4.z & v4.w) & (v5.x & v5.y & v5.z & v5.w) & (v6.x & v6.y & v6.z & v6.w) &
+                                (v7.x & v7.y & v7.z & v7.w);
+            if ((lo & hi) != 0xFFFFFFFFu) break;
+            n += 128u;
         }
         while (p + n + 16u <= clen) {
             const uint4 v = *reinterpret_cast<const uint4 *>(s + p + n);
@@ -604,6 +599,8 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
         } else if (mode == 2) {
             bool fin = !(w.pos < cend && w.n < limit);
             if (!fin) fin = !walk_step<true>(s, plen, w, dstrec);
+            // (a warp per frame has nobody to stay in step with: the whole walk in one turn, without the state machine around it)
+            if (kWarpPerFrame) while (!fin) { fin = !(w.pos < cend && w.n < limit); if (!fin) fin = !walk_step<true>(s, plen, w, dstrec); }
             if (fin) {
                 if (full) {
                     dstrec[w.n] = make_uint2(w.pos, (uint32_t)w.rel);
