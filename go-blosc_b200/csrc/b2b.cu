@@ -445,7 +445,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     fa.index = d_index; fa.segs_per_frame = segs_per_frame;
     fa.comp_off = d_comp_off; fa.comp_cap = comp_bytes; fa.seg_cap = max_segs_total;
     fa.src_off = d_src_off; fa.src_cap = filtered ? total_src : ~0ull;
-    { LaunchTimer lt(ctx, K_FINALIZE, s); finalize_frames_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(fa); }
+    { LaunchTimer lt(ctx, K_FINALIZE, s); finalize_frames_kernel<<<(unsigned)(((uint64_t)nframes * 32 + 127) / 128), 128, 0, s>>>(fa); }
     CU(ctx, cudaGetLastError());
 
     rc = launch_scan(ctx, d_frame_len, nframes, d_frame_off, d_total_out, kScanAlign16, scan_c, s);
@@ -851,7 +851,7 @@ int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *
     fa.index = nullptr; fa.segs_per_frame = 0;
     fa.comp_off = comp_off; fa.comp_cap = comp_bytes; fa.seg_cap = max_segs_total;
     fa.src_off = blk_off; fa.src_cap = filtered ? total_src : ~0ull;
-    { LaunchTimer lt(ctx, K_FINALIZE, s); finalize_frames_kernel<<<(nslots + 127) / 128, 128, 0, s>>>(fa); }
+    { LaunchTimer lt(ctx, K_FINALIZE, s); finalize_frames_kernel<<<(unsigned)(((uint64_t)nslots * 32 + 127) / 128), 128, 0, s>>>(fa); }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemsetAsync(comp_len + nslots, 0, 4, s));
     rc = launch_scan(ctx, comp_len, nslots + 1, blk_pos, nullptr, kScanStream, scan_c, s);

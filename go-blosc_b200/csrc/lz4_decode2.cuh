@@ -82,7 +82,7 @@ struct ChunkMeta {       // written by the parse kernel
     uint32_t end;        // kEnd*
     uint32_t out;        // output bytes of those records
     // written by the repair kernel (zero after the parse): the chain that enters at pad[0] -- the exit of the chunk before --
-    // meets the speculative one at its record j after mc tokens of its own, which now stand in front of record j;
+    // meets the speculative one at its record j after mc tokens of its own, which now stand at the end of the head-room;
     // pad[1] = 0x80000000 | mc << 12 | j, pad[2] = output bytes of the chunk on that chain
     uint32_t pad[3];
 };
@@ -90,11 +90,18 @@ struct ChunkMeta {       // written by the parse kernel
 struct ChunkDesc {       // written by the stitch kernel
     long long base_a;    // absolute output position of relative position 0, records [0, split)
     long long base_b;    // the same for records [split, count]
-    uint32_t start;      // first record, relative to the chunk slot
+    uint32_t start;      // bits 0..15: first record, relative to the chunk slot; bits 16..31: slots skipped between record
+                         // split - 1 and record split (a chunk adopted on its repaired chain: its own tokens stand in the
+                         // head-room, the speculative records from the meeting point on where the parse put them)
     uint32_t count;      // 0: no token of the true chain starts in this chunk
     uint32_t split;
     uint32_t end;
 };
+
+// record i of a chunk (i <= count: the closing record included)
+__device__ __forceinline__ uint2 desc_rec(const uint2 *slot, const ChunkDesc &D, uint32_t i) {
+    return slot[(D.start & 0xFFFFu) + i + (i >= D.split ? D.start >> 16 : 0u)];
+}
 
 // ---- one token, one thread ----------------------------------------------------------------------------
 // kEndCont: a sequence (ll literals at lit, ml match bytes, next token at next); kEndFinal: closing token;
@@ -372,7 +379,9 @@ __global__ void __launch_bounds__(kParse2Threads, 12) lz4_chunk_parse_kernel(Par
 // chain arrives, one chunk after the other; here every such chunk is repaired at once, on the assumption that the
 // chunk before it ends where its speculative chain ends -- true whenever that chain was right or was itself repaired
 // by merging, which is the case the stitch kernel then only has to confirm (entry == pad[0]); where the assumption
-// was wrong the stitch kernel ignores the result and repairs as before.
+// was wrong the stitch kernel ignores the result and repairs as before.  The repair's own tokens go into the head-room
+// in front of the chunk's records and nowhere else: the speculative records must stay whole, they are what the stitch
+// kernel adopts or searches when the assumption does not hold.
 struct Repair2Args {
     const uint8_t *frames;
     const uint64_t *frame_off;
@@ -417,7 +426,7 @@ __global__ void __launch_bounds__(128) lz4_chunk_repair_kernel(Repair2Args a) {
             if (++j >= sc) return;
             spec_tok = slot[kChunkHead + j].x;
         } else if (spec_tok == pos) {
-            if (mc > kChunkHead + j) return;                                  // no room in front of record j
+            if (mc > kChunkHead) return;                                      // no room in the head-room
             break;
         } else {
             Walk t; t.pos = pos; t.n = 0; t.end = kEndCont; t.rel = 0;
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(128) lz4_chunk_repair_kernel(Repair2Args a) {
     const uint64_t out_alt = rel + (uint64_t)(m.out - slot[kChunkHead + j].y);
     if (out_alt > 0xFFFFFFFFull || mc >= 4096u || j >= 4096u) return;
     Walk w; w.pos = e; w.n = 0; w.end = kEndCont; w.rel = 0;
-    uint2 *dstrec = slot + kChunkHead + j - mc;
+    uint2 *dstrec = slot + kChunkHead - mc;       // the head-room only: the speculative records stay whole (they are the truth if the assumption is not)
     while (w.n < mc && w.pos < cend) { if (!walk_step<true>(s, plen, w, dstrec)) return; }
     ChunkMeta r = m;
     r.pad[0] = e; r.pad[1] = 0x80000000u | (mc << 12) | j; r.pad[2] = (uint32_t)out_alt;
@@ -442,7 +451,7 @@ __device__ __forceinline__ ChunkDesc repaired_desc(const ChunkMeta &m, long long
     const uint32_t j = m.pad[1] & 0xFFFu, mc = (m.pad[1] >> 12) & 0xFFFu;
     ChunkDesc D;
     D.base_a = op; D.base_b = op + ((long long)m.pad[2] - (long long)m.out);
-    D.start = kChunkHead + j - mc; D.count = mc + (m.count - j); D.split = mc; D.end = m.end;
+    D.start = (kChunkHead - mc) | (j << 16); D.count = mc + (m.count - j); D.split = mc; D.end = m.end;
     return D;
 }
 
@@ -764,7 +773,7 @@ __global__ void __launch_bounds__(kCopy2Threads, 1024 / kCopy2Threads) lz4_copy2
     for (uint32_t k = 0; code == 0 && k <= last; k++) {
         const ChunkDesc D = a.desc[cb + k];
         if (D.count == 0) continue;
-        const uint2 *rec = a.table + (cb + k) * kChunkSlot + D.start;
+        const uint2 *rec = a.table + (cb + k) * kChunkSlot;
         uint32_t r = 0;
         while (r < D.count) {
             it++;
@@ -783,7 +792,7 @@ __global__ void __launch_bounds__(kCopy2Threads, 1024 / kCopy2Threads) lz4_copy2
                     lit_ok = (c.flags & 1u) != 0; match_ok = (c.flags & 2u) != 0; err = c.flags >> 2;
                     vM = vL + ll; vE = vM + ml;
                 } else {
-                    const uint2 rc = rec[i], nx = rec[i + 1];
+                    const uint2 rc = desc_rec(rec, D, i), nx = desc_rec(rec, D, i + 1);
                     const long long o = (i < D.split ? D.base_a : D.base_b) + (long long)rc.y;
                     const long long on = (i + 1 < D.split ? D.base_a : D.base_b) + (long long)nx.y;
                     const uint32_t kind = i + 1 == D.count ? D.end : (uint32_t)kEndCont;

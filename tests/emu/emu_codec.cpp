@@ -9,6 +9,8 @@
 #include "cuda_runtime.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace b2b_emu_stats {
@@ -227,7 +229,7 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
             Repair2Args ra;
             ra.frames = a.frames; ra.frame_off = &frame_off; ra.fd = &fd; ra.nframes = 1; ra.chunk_base = &chunk_base;
             ra.total_chunks = &total_chunks; ra.table = tab.data(); ra.meta = cmeta.data(); ra.table_chunks = table_chunks;
-            emu::launch((uint32_t)((table_chunks + 127) / 128), 128, [&] { lz4_chunk_repair_kernel(ra); });
+            if (!getenv("EMU_NO_REPAIR")) emu::launch((uint32_t)((table_chunks + 127) / 128), 128, [&] { lz4_chunk_repair_kernel(ra); });
         }
         Stitch2Args sa;
         sa.frames = a.frames; sa.frame_off = &frame_off; sa.fd = &fd; sa.nframes = 1; sa.chunk_base = &chunk_base;
@@ -235,6 +237,15 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         sa.fallback = &fallback; sa.table_chunks = table_chunks;
         if (split == 4) emu::launch(1, 64, [&] { lz4_stitch_warp_kernel(sa); });      // a warp per frame, 32 chunks per step
         else emu::launch(1, 128, [&] { lz4_stitch_kernel(sa); });
+        if (getenv("EMU_DUMP_DESC"))
+            for (uint64_t q = 0; q < total_chunks; q++)
+                fprintf(stderr, "desc %llu: a=%lld b=%lld start=%u count=%u split=%u end=%u | meta entry=%u exit=%u count=%u out=%u pad=%u %x %u\n",
+                        (unsigned long long)q, cdesc[q].base_a, cdesc[q].base_b, cdesc[q].start, cdesc[q].count, cdesc[q].split, cdesc[q].end,
+                        cmeta[q].entry, cmeta[q].exit, cmeta[q].count, cmeta[q].out, cmeta[q].pad[0], cmeta[q].pad[1], cmeta[q].pad[2]);
+        if (getenv("EMU_DUMP_REC"))
+            for (uint64_t q = 0; q < total_chunks; q++)
+                for (uint32_t i = 0; i <= cdesc[q].count && cdesc[q].count; i++)
+                    fprintf(stderr, "rec %llu %u: %u %u\n", (unsigned long long)q, i, desc_rec(&tab[q * kChunkSlot], cdesc[q], i).x, desc_rec(&tab[q * kChunkSlot], cdesc[q], i).y);
         uint32_t jstate = 0, jtotal = 0;
         std::vector<uint32_t> jS;
         std::vector<JumpLong> jq;

@@ -160,3 +160,20 @@ def test_emulated_decoder_status_words_on_mutants(emu, orc):
             assert st == rc, (st, rc, m[:16].tobytes().hex())
             if rc == 0:
                 assert np.array_equal(out, want)
+
+
+def test_emulated_chunk_repair_keeps_the_speculative_records(emu, orc):
+    """300 000-byte frames of the oracle's compressor over the adversarial inputs (copies of far-back chunks, runs, strip
+    periods): 30-odd parse chunks each, a third of them entered off the speculative chain.  The repair kernel repairs such
+    chunks on an ASSUMED entry; when the assumption is wrong the stitch kernel adopts or searches the chunk's speculative
+    records, which the repair must therefore have left alone (a first version wrote its tokens over them: status 0 and
+    3 105 wrong bytes on `copies`).  Both users of the record table: tile copy engine (2) and pointer jumping (4)."""
+    n = 300000
+    adv = dg.strip_adversarial(n, seed=n)
+    for name in ("copies", "runs", "period61", "period4096"):
+        data = adv[name]
+        for sh, T in ((0, 1), (1, 4)):
+            rc, fr = orc.compress(data, orc.LZ4, 5, sh, T)
+            for split in (2, 4):
+                st, out = emu.decompress(np.asarray(fr, dtype=np.uint8), n, split)
+                assert st == 0 and np.array_equal(out, data), (name, sh, T, split)
