@@ -90,18 +90,11 @@ struct ChunkMeta {       // written by the parse kernel
 struct ChunkDesc {       // written by the stitch kernel
     long long base_a;    // absolute output position of relative position 0, records [0, split)
     long long base_b;    // the same for records [split, count]
-    uint32_t start;      // bits 0..15: first record, relative to the chunk slot; bits 16..31: slots skipped between record
-                         // split - 1 and record split (a chunk adopted on its repaired chain: its own tokens stand in the
-                         // head-room, the speculative records from the meeting point on where the parse put them)
+    uint32_t start;      // first record, relative to the chunk slot
     uint32_t count;      // 0: no token of the true chain starts in this chunk
     uint32_t split;
     uint32_t end;
 };
-
-// record i of a chunk (i <= count: the closing record included)
-__device__ __forceinline__ uint2 desc_rec(const uint2 *slot, const ChunkDesc &D, uint32_t i) {
-    return slot[(D.start & 0xFFFFu) + i + (i >= D.split ? D.start >> 16 : 0u)];
-}
 
 // ---- one token, one thread ----------------------------------------------------------------------------
 // kEndCont: a sequence (ll literals at lit, ml match bytes, next token at next); kEndFinal: closing token;
@@ -446,12 +439,15 @@ __global__ void __launch_bounds__(128) lz4_chunk_repair_kernel(Repair2Args a) {
     a.meta[g] = r;
 }
 
-// descriptor of a chunk adopted on its repaired chain (pad[] of its meta), output so far = op
-__device__ __forceinline__ ChunkDesc repaired_desc(const ChunkMeta &m, long long op) {
+// A chunk is adopted on its repaired chain (pad[] of its meta; output so far = op).  Only now is it certain that the
+// speculative records in front of the meeting point are dead, so only now do the repair's tokens move from the head-room
+// to their place in front of record j: the copy engines read a chunk's records as one run.
+__device__ __forceinline__ ChunkDesc adopt_repaired(uint2 *slot, const ChunkMeta &m, long long op) {
     const uint32_t j = m.pad[1] & 0xFFFu, mc = (m.pad[1] >> 12) & 0xFFFu;
+    if (j != 0) for (uint32_t q = mc; q-- > 0;) slot[kChunkHead + j - mc + q] = slot[kChunkHead - mc + q];   // (moves up: last first)
     ChunkDesc D;
     D.base_a = op; D.base_b = op + ((long long)m.pad[2] - (long long)m.out);
-    D.start = (kChunkHead - mc) | (j << 16); D.count = mc + (m.count - j); D.split = mc; D.end = m.end;
+    D.start = kChunkHead + j - mc; D.count = mc + (m.count - j); D.split = mc; D.end = m.end;
     return D;
 }
 
@@ -549,7 +545,7 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
                         ChunkDesc Di;
                         Di.base_a = 0; Di.base_b = op + (long long)(incl - my_out); Di.start = kChunkHead; Di.count = mi.count;
                         Di.split = 0; Di.end = kEndCont;
-                        if (alt) Di = repaired_desc(mi, op + (long long)(incl - my_out));
+                        if (alt) Di = adopt_repaired(a.table + (cb + ki) * kChunkSlot, mi, op + (long long)(incl - my_out));
                         a.desc[cb + ki] = Di;
                     }
                     op += (long long)__shfl_sync(0xffffffffu, incl, (int)r - 1);
@@ -566,7 +562,7 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
                 D.base_a = 0; D.base_b = op; D.start = kChunkHead; D.count = m.count; D.split = 0; D.end = m.end;
                 op += m.out; e = m.exit; endk = m.end; prev_full = false;
             } else if ((m.pad[1] >> 31) != 0 && m.pad[0] == e) {          // repaired for exactly this entry (repair kernel)
-                D = repaired_desc(m, op);
+                D = adopt_repaired(slot, m, op);
                 op += m.pad[2]; e = m.exit; endk = m.end; prev_full = false;
             } else if (prev_full) {
                 // the chunk before this one had to be re-parsed as a whole and this one is wrong again: two chains that
@@ -773,7 +769,7 @@ __global__ void __launch_bounds__(kCopy2Threads, 1024 / kCopy2Threads) lz4_copy2
     for (uint32_t k = 0; code == 0 && k <= last; k++) {
         const ChunkDesc D = a.desc[cb + k];
         if (D.count == 0) continue;
-        const uint2 *rec = a.table + (cb + k) * kChunkSlot;
+        const uint2 *rec = a.table + (cb + k) * kChunkSlot + D.start;
         uint32_t r = 0;
         while (r < D.count) {
             it++;
@@ -792,7 +788,7 @@ __global__ void __launch_bounds__(kCopy2Threads, 1024 / kCopy2Threads) lz4_copy2
                     lit_ok = (c.flags & 1u) != 0; match_ok = (c.flags & 2u) != 0; err = c.flags >> 2;
                     vM = vL + ll; vE = vM + ml;
                 } else {
-                    const uint2 rc = desc_rec(rec, D, i), nx = desc_rec(rec, D, i + 1);
+                    const uint2 rc = rec[i], nx = rec[i + 1];
                     const long long o = (i < D.split ? D.base_a : D.base_b) + (long long)rc.y;
                     const long long on = (i + 1 < D.split ? D.base_a : D.base_b) + (long long)nx.y;
                     const uint32_t kind = i + 1 == D.count ? D.end : (uint32_t)kEndCont;

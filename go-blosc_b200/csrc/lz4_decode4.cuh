@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kJumpThreads) lz4_jump_map_kernel(JumpArgs a) 
         const ChunkDesc D = a.desc[g];
         if (D.count == 0) continue;
         const FrameDec d = a.fd[f];
-        const uint2 *rec = a.table + g * kChunkSlot;
+        const uint2 *rec = a.table + g * kChunkSlot + D.start;
         const uint32_t X = (uint32_t)a.dst_off[f];
         uint8_t *out = (d.mode ? a.scratch : a.dst) + a.dst_off[f];
         const uint8_t *__restrict__ src = a.frames + a.frame_off[f] + 16;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kJumpThreads) lz4_jump_map_kernel(JumpArgs a) 
             bool ovl = false;
             if (i < D.count) {
                 // the record's place and its token: the checks of lz4_copy2_kernel, in the same order
-                const uint2 rc = desc_rec(rec, D, i), nx = desc_rec(rec, D, i + 1);
+                const uint2 rc = rec[i], nx = rec[i + 1];
                 const long long o = (i < D.split ? D.base_a : D.base_b) + (long long)rc.y;
                 const long long on = (i + 1 < D.split ? D.base_a : D.base_b) + (long long)nx.y;
                 const uint32_t kind = i + 1 == D.count ? D.end : (uint32_t)kEndCont;

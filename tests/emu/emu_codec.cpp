@@ -245,7 +245,7 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         if (getenv("EMU_DUMP_REC"))
             for (uint64_t q = 0; q < total_chunks; q++)
                 for (uint32_t i = 0; i <= cdesc[q].count && cdesc[q].count; i++)
-                    fprintf(stderr, "rec %llu %u: %u %u\n", (unsigned long long)q, i, desc_rec(&tab[q * kChunkSlot], cdesc[q], i).x, desc_rec(&tab[q * kChunkSlot], cdesc[q], i).y);
+                    fprintf(stderr, "rec %llu %u: %u %u\n", (unsigned long long)q, i, tab[q * kChunkSlot + cdesc[q].start + i].x, tab[q * kChunkSlot + cdesc[q].start + i].y);
         uint32_t jstate = 0, jtotal = 0;
         std::vector<uint32_t> jS;
         std::vector<JumpLong> jq;

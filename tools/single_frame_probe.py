@@ -30,6 +30,11 @@ for n in [int(x) for x in os.environ.get("PROBE_SIZES", "16384,65536,262144,1048
         dt = (time.perf_counter() - t0) / reps
         line += f"  decompress[min={thr}] {1e6 * dt:9.0f} us ({n / dt / 1e9:6.2f} GB/s)"
     ctx.set_option(107, 0)
+    ctx.set_option(pkg.OPT_KERNEL_TIMING, 1); ctx.kernel_stats_reset()
+    for _ in range(5):
+        back = ctx.decompress(fr)
+    st = ctx.kernel_stats(); ctx.set_option(pkg.OPT_KERNEL_TIMING, 0)
+    line += "\n      decompress kernels (us): " + ", ".join(f"{k.replace('_kernel', '').replace('lz4_', '')} {1e3 * v[1] / 5:.0f}" for k, v in st.items() if v[0])
     t0 = time.perf_counter()
     for _ in range(5):
         fr = ctx.compress(data, 1, 5, 1, 4)
