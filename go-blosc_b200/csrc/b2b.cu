@@ -580,7 +580,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         pp.dead = d_dead; pp.ticket = reinterpret_cast<unsigned long long *>(d_dead + ((table_chunks + 1) & ~1ull));
         CU(ctx, cudaMemsetAsync(d_dead, 0, 4ull * (table_chunks + 4), s));
         const unsigned pgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((table_chunks + kParse2Threads - 1) / kParse2Threads,
-                                                                          (uint64_t)ctx->sm_count * 12));
+                                                                          (uint64_t)ctx->sm_count * B2B_PARSE2_CTAS));
         { LaunchTimer lt(ctx, K_PARSE2, s); lz4_chunk_parse_kernel<<<pgrid, kParse2Threads, 0, s>>>(pp); }
         CU(ctx, cudaGetLastError());
         {   // mis-speculated chunks are repaired all at once, on the exit of the chunk before them (lz4_decode2.cuh)

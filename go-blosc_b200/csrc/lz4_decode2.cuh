@@ -282,6 +282,9 @@ struct Parse2Args {
 };
 
 constexpr int kParse2Threads = 128;
+#ifndef B2B_PARSE2_CTAS
+#define B2B_PARSE2_CTAS 8       // 64 registers (at 12 CTAs / 40 registers the walk spilled 528 bytes into its token loop)
+#endif
 
 // Persistent lanes: every lane walks one chunk at a time, one token per turn, in lockstep with the other lanes of
 // its warp (a vote per turn keeps them converged whatever the tokens are); a lane that is done takes the next
@@ -289,7 +292,7 @@ constexpr int kParse2Threads = 128;
 // chunks (a long literal run: the incompressible byte planes of a shuffled frame) flags those chunks, and whoever
 // holds them stops walking what can only be the inside of that run.  The flag may come from a speculative chain
 // that is itself wrong; the stitch kernel re-parses such a chunk, so it costs time, never correctness.
-__global__ void __launch_bounds__(kParse2Threads, 12) lz4_chunk_parse_kernel(Parse2Args a) {
+__global__ void __launch_bounds__(kParse2Threads, B2B_PARSE2_CTAS) lz4_chunk_parse_kernel(Parse2Args a) {
     uint64_t total = *a.total_chunks;
     if (total > a.table_chunks) total = a.table_chunks;
     const int lane = (int)(threadIdx.x & 31u);
