@@ -86,6 +86,7 @@ struct b2b_ctx {
     int opt_encode_ctas = 0;           // (option 106) persistent encoder CTAs per SM, 0 = as many as fit
     int opt_persistent_decode = 0;     // (option 105) one-warp-per-frame decoders as persistent warps that take frames from a ticket: measured
                                        // 3 % slower on one stream and neutral on two (the gain of the two streams is not a tail effect), so off
+    int opt_no_small_chunks = 0;       // (option 108) 1: 8 KiB parse chunks also for a handful of small frames
     uint32_t opt_jump_min_bytes = 0;   // (option 107) batches of at most 4 frames: frames over this size take the chunk-parallel parse (0: 192 KiB; one 256 KiB frame 1.55 -> 1.22 ms, one 64 KiB frame 0.43 -> 0.81 ms)
     int opt_decode_streams = 0;        // streams a large decompress batch is split over: 0 automatic (2), 1 none, 2..4
     static constexpr int kSide = 3;
@@ -510,13 +511,17 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
     const uint64_t nrec_max = total_dst / 4 + (uint64_t)(kSeqSlack + 1) * nframes + 64;   // sum of dst_cap / 4 + slack
     // chunk-parallel decoder: an LZ4 block that decodes to n bytes has at most n + n / 255 + 16 bytes (longer ones
     // are refused by the prep kernel), so the chunks of a batch are bounded by its output size
-    const uint64_t table_chunks = total_dst / kChunkBytes + total_dst / (255ull * kChunkBytes) + 2ull * nframes + 16;
+    // (a handful of frames of a few MiB: 1 KiB chunks -- the parse is one thread per chunk and its slowest chunk is the
+    // latency of the call: one 1 MiB frame 1.35 -> see DESIGN section 4; large frames keep 8 KiB, the stitch walks the chunks)
+    const uint32_t cshift = (jump && nframes <= 4 && max_orig <= (32u << 20) && !ctx->opt_no_small_chunks) ? kChunkShiftSmall : kChunkShift;
+    const uint64_t cbytes = 1ull << cshift, cslot = chunk_slot_records(cshift);
+    const uint64_t table_chunks = total_dst / cbytes + total_dst / (255ull * cbytes) + 2ull * nframes + 16;
     const uint64_t need = align_up(total_dst + 64, 256) + align_up(8ull * nframes, 256) + align_up(4ull * nframes, 256) + 8192 +
                           (split ? align_up(8 * nrec_max, 256) + align_up(8ull * nframes, 256) +
                                    align_up(4ull * nframes, 256) + scan_scratch_bytes(nframes) + 1024 : 0) +
                           (v2 ? align_up(sizeof(FrameDec) * (uint64_t)nframes, 256) + 3 * align_up(4ull * nframes, 256) +
                                 align_up(8ull * nframes, 256) + scan_scratch_bytes(nframes) +
-                                align_up(8ull * kChunkSlot * table_chunks, 256) + 2 * align_up(32ull * table_chunks, 256) +
+                                align_up(8ull * cslot * table_chunks, 256) + 2 * align_up(32ull * table_chunks, 256) +
                                 align_up(4ull * table_chunks + 16, 256) + 2048 : 0) +
                           (jump ? align_up(4ull * total_dst + 64, 256) + 2 * align_up(4ull * nframes, 256) +
                                   align_up(sizeof(JumpLong) * (uint64_t)jump_long_cap, 256) + 512 +
@@ -560,7 +565,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         uint64_t *d_chunk_base = ar.take<uint64_t>(nframes);
         uint64_t *d_total_chunks = ar.take<uint64_t>(1);
         uint8_t *scan_c = ar.take<uint8_t>(scan_scratch_bytes(nframes));
-        uint2 *d_rec = ar.take<uint2>((uint64_t)kChunkSlot * table_chunks);
+        uint2 *d_rec = ar.take<uint2>(cslot * table_chunks);
         ChunkMeta *d_cmeta = ar.take<ChunkMeta>(table_chunks);
         ChunkDesc *d_cdesc = ar.take<ChunkDesc>(table_chunks);
         uint32_t *d_dead = ar.take<uint32_t>(table_chunks + 4);      // + the parse ticket behind it
@@ -571,12 +576,12 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         pa.keep_sparse = jump ? 1u : 0u;
         { LaunchTimer lt(ctx, K_PREP2, s); frame_prep_kernel<<<(nframes + 127) / 128, 128, 0, s>>>(pa); }
         CU(ctx, cudaGetLastError());
-        rc = launch_scan(ctx, d_plen, nframes, d_chunk_base, d_total_chunks, kScanChunks, scan_c, s);
+        rc = launch_scan(ctx, d_plen, nframes, d_chunk_base, d_total_chunks, cshift == kChunkShift ? kScanChunks : kScanChunksSmall, scan_c, s);
         if (rc) return rc;
         Parse2Args pp;
         pp.frames = a.frames; pp.frame_off = d_frame_off; pp.fd = d_fd; pp.nframes = nframes;
         pp.chunk_base = d_chunk_base; pp.total_chunks = d_total_chunks; pp.table = d_rec; pp.meta = d_cmeta;
-        pp.table_chunks = table_chunks;
+        pp.table_chunks = table_chunks; pp.chunk_shift = cshift;
         pp.dead = d_dead; pp.ticket = reinterpret_cast<unsigned long long *>(d_dead + ((table_chunks + 1) & ~1ull));
         CU(ctx, cudaMemsetAsync(d_dead, 0, 4ull * (table_chunks + 4), s));
         const unsigned pgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((table_chunks + kParse2Threads - 1) / kParse2Threads,
@@ -586,7 +591,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         {   // mis-speculated chunks are repaired all at once, on the exit of the chunk before them (lz4_decode2.cuh)
             Repair2Args ra;
             ra.frames = a.frames; ra.frame_off = d_frame_off; ra.fd = d_fd; ra.nframes = nframes; ra.chunk_base = d_chunk_base;
-            ra.total_chunks = d_total_chunks; ra.table = d_rec; ra.meta = d_cmeta; ra.table_chunks = table_chunks;
+            ra.total_chunks = d_total_chunks; ra.table = d_rec; ra.meta = d_cmeta; ra.table_chunks = table_chunks; ra.chunk_shift = cshift;
             LaunchTimer lt(ctx, K_STITCH2, s);
             lz4_chunk_repair_kernel<<<(unsigned)((table_chunks + 127) / 128), 128, 0, s>>>(ra);
         }
@@ -594,7 +599,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         Stitch2Args sa;
         sa.frames = a.frames; sa.frame_off = d_frame_off; sa.fd = d_fd; sa.nframes = nframes; sa.chunk_base = d_chunk_base;
         sa.table = d_rec; sa.meta = d_cmeta; sa.desc = d_cdesc; sa.last_chunk = d_last; sa.fallback = d_fallback;
-        sa.table_chunks = table_chunks;
+        sa.table_chunks = table_chunks; sa.chunk_shift = cshift;
         // few frames: a warp per frame that adopts 32 chunks per step (one 1 GiB frame: 40 ms with one thread)
         { LaunchTimer lt(ctx, K_STITCH2, s);
           if (jump || nframes <= 256) lz4_stitch_warp_kernel<<<(nframes * 32 + 63) / 64, 64, 0, s>>>(sa);
@@ -614,7 +619,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
             ja.nlong = ar.take<uint32_t>(1 + kJumpRounds); ja.changed = ja.nlong + 1;
             ja.blockdone = ar.take<uint8_t>((uint64_t)nframes * jump_bpf); ja.blocks_per_frame = jump_bpf;
             ja.blocks_grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(jump_bpf, (uint64_t)ctx->sm_count * 8 / nframes));
-            ja.out_len = d_out_len; ja.status = d_status; ja.meta = d_meta;
+            ja.out_len = d_out_len; ja.status = d_status; ja.meta = d_meta; ja.chunk_shift = cshift;
             CU(ctx, cudaMemsetAsync(ja.blockdone, 0, (uint64_t)nframes * jump_bpf, s));
             lz4_jump_select_kernel<<<(nframes + 63) / 64, 64, 0, s>>>(ja);
             ctx->launches++;
@@ -637,7 +642,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
             CU(ctx, cudaGetLastError());
         }
         Copy2Args ca;
-        ca.jump_state = d_jump_state;
+        ca.jump_state = d_jump_state; ca.chunk_shift = cshift;
         ca.frames = a.frames; ca.frame_off = d_frame_off; ca.fd = d_fd; ca.nframes = nframes; ca.dst = a.dst; ca.scratch = d_stage;
         ca.dst_off = d_dst_off; ca.chunk_base = d_chunk_base; ca.desc = d_cdesc; ca.last_chunk = d_last; ca.table = d_rec;
         ca.fallback = d_fallback; ca.out_len = d_out_len; ca.status = d_status; ca.meta = d_meta;
@@ -1123,6 +1128,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
         case B2B_OPT_NO_HOST_STAGING: ctx->opt_no_staging = value != 0; return B2B_OK;
         case B2B_OPT_FUSE_UNSHUFFLE: ctx->opt_fuse_unshuffle = value != 0; return B2B_OK;
         case 105: ctx->opt_persistent_decode = value != 0; return B2B_OK;
+        case 108: ctx->opt_no_small_chunks = value != 0; return B2B_OK;
         case 107: ctx->opt_jump_min_bytes = (uint32_t)std::max<int64_t>(0, value); return B2B_OK;
         case 106: ctx->opt_encode_ctas = (int)std::max<int64_t>(0, value); return B2B_OK;
         case B2B_OPT_DECODE_STREAMS:

@@ -53,6 +53,11 @@ constexpr uint32_t kChunkWarm = 1024;                   // bytes walked before t
 constexpr uint32_t kChunkHead = 64;                     // free records in front of a chunk's records (stitch prefix)
 constexpr uint32_t kChunkCap = kChunkBytes / 3 + 3;     // a token that opens a match takes >= 3 bytes
 constexpr uint32_t kChunkSlot = kChunkHead + kChunkCap + 1;   // records per chunk slot (+ the closing record)
+// The chunk size is a launch parameter (chunk_shift in the argument structs, 13 = the 8 KiB above unless the host says
+// otherwise): a handful of frames of a few MiB are latency, not throughput, and there the host asks for 1 KiB chunks --
+// eight times as many threads, each with an eighth of the serial walk (b2b.cu).
+constexpr uint32_t kChunkShift = 13, kChunkShiftSmall = 10;
+__host__ __device__ __forceinline__ uint32_t chunk_slot_records(uint32_t shift) { return kChunkHead + ((1u << shift) / 3u + 3u) + 1u; }
 
 // how a chain of tokens ended
 enum : uint32_t {
@@ -109,6 +114,14 @@ struct ChunkDesc {       // written by the stitch kernel
 __device__ __noinline__ uint32_t skip_ff_blocks(const uint8_t *__restrict__ s, uint32_t clen, uint32_t p) {
     uint32_t n = 0;
     if (((uintptr_t)(s + p) & 15u) == 0) {
+        while (p + n + 512u <= clen) {                        // four cache lines per step: as many loads in flight as registers allow
+            const uint4 *q = reinterpret_cast<const uint4 *>(s + p + n);
+            uint32_t acc = 0xFFFFFFFFu;
+#pragma unroll
+            for (int i = 0; i < 32; i++) { const uint4 v = q[i]; acc &= v.x & v.y & v.z & v.w; }
+            if (acc != 0xFFFFFFFFu) break;
+            n += 512u;
+        }
         while (p + n + 128u <= clen) {                        // a cache line per step, its eight loads in flight together
             const uint4 *q = reinterpret_cast<const uint4 *>(s + p + n);
             const uint4 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3], v4 = q[4], v5 = q[5], v6 = q[6], v7 = q[7];
@@ -178,8 +191,37 @@ struct Walk { uint32_t pos, n, end; uint64_t rel; };
 
 // one step of a walk: the token at w.pos; record (kEmit) at out[w.n].  Returns false when the chain ended
 // (w.end says how).  rel counts output bytes from the start of the walk and never passes 2^32 - 1.
+//
+// Fast path: a token whose two lengths take at most one length byte each and whose sequence ends at least one byte
+// before the end of the stream -- practically every token -- is stepped over with the few instructions it needs.  A walk
+// is ONE dependent instruction stream (a thread of the parse kernel, a warp of the stitch kernel), so its speed is its
+// instruction count: the general tok_step (64-bit lengths, every malformed case, length-byte loops) cost about a
+// microsecond per token, which was the latency of every call with few frames.  Anything else -- longer lengths, the last
+// sequences of a stream, anything malformed, a position counter near 2^32 -- takes the general path, so the result is
+// the same by construction.
 template <bool kEmit>
 __device__ __forceinline__ bool walk_step(const uint8_t *__restrict__ s, uint32_t clen, Walk &w, uint2 *out) {
+    {
+        const uint32_t p = w.pos;
+        if (p + 1u < clen && w.rel < 0xFFFF0000ull) {             // the token and a possible length byte exist
+            const uint32_t tok = s[p];
+            uint32_t l = tok >> 4, q = p + 1u;
+            bool ok = true;
+            if (l == 15u) { const uint32_t b = s[q]; ok = b != 255u; l += b; q++; }
+            const uint32_t e = q + l;                             // literals [q, e), offset [e, e + 2), a length byte at e + 2
+            if (ok && e + 3u <= clen) {
+                uint32_t m = tok & 15u, nx = e + 2u;
+                if (m == 15u) { const uint32_t b = s[nx]; ok = b != 255u; m += b; nx++; }
+                if (ok) {
+                    if (kEmit) out[w.n] = make_uint2(p, (uint32_t)w.rel);
+                    w.n++;
+                    w.rel += l + m + 4u;                          // <= 269 + 273: far from 2^32 (checked above)
+                    w.pos = nx;
+                    return true;
+                }
+            }
+        }
+    }
     uint32_t ll, lit, next; uint64_t ml;
     const uint32_t kind = tok_step(s, clen, w.pos, ll, lit, ml, next);
     if (kEmit) out[w.n] = make_uint2(w.pos, (uint32_t)w.rel);
@@ -279,6 +321,7 @@ struct Parse2Args {
     uint64_t table_chunks;          // chunks the table has room for
     uint32_t *dead;                 // one word per chunk, zero before launch: "inside a long literal run, do not walk"
     unsigned long long *ticket;     // zero before launch: next chunk to hand out
+    uint32_t chunk_shift = kChunkShift;
 };
 
 constexpr int kParse2Threads = 128;
@@ -295,6 +338,7 @@ constexpr int kParse2Threads = 128;
 __global__ void __launch_bounds__(kParse2Threads, B2B_PARSE2_CTAS) lz4_chunk_parse_kernel(Parse2Args a) {
     uint64_t total = *a.total_chunks;
     if (total > a.table_chunks) total = a.table_chunks;
+    const uint32_t CSH = a.chunk_shift, CB = 1u << CSH, CS = chunk_slot_records(CSH);
     const int lane = (int)(threadIdx.x & 31u);
     ChunkMeta m; m.pad[0] = m.pad[1] = m.pad[2] = 0;
     m.entry = 0xFFFFFFFFu; m.exit = 0; m.count = 0; m.end = kEndDead; m.out = 0;
@@ -324,15 +368,15 @@ __global__ void __launch_bounds__(kParse2Threads, B2B_PARSE2_CTAS) lz4_chunk_par
                     const uint32_t f = lo;
                     k = (uint32_t)(g - a.chunk_base[f]);
                     plen = a.fd[f].plen;
-                    nch = (plen + kChunkBytes - 1) / kChunkBytes;
+                    nch = (uint32_t)(((uint64_t)plen + CB - 1) >> CSH);
                     m.entry = 0xFFFFFFFFu; m.exit = 0; m.count = 0; m.end = kEndDead; m.out = 0;
                     w.n = 0; w.end = kEndCont; w.rel = 0;
                     if (a.fd[f].kind == 2 && k < nch && !__ldcg(a.dead + g)) {
                         s = a.frames + a.frame_off[f] + 16;
-                        cbeg = k * kChunkBytes;
-                        cend = k + 1 == nch ? plen + 1 : cbeg + kChunkBytes;   // the last chunk owns position plen
+                        cbeg = k << CSH;
+                        cend = k + 1 == nch ? plen + 1 : cbeg + CB;   // the last chunk owns position plen
                         w.pos = cbeg > kChunkWarm ? cbeg - kChunkWarm : 0u;
-                        rec = a.table + g * kChunkSlot + kChunkHead;
+                        rec = a.table + g * CS + kChunkHead;
                         phase = w.pos < cbeg ? 0 : 1;
                         if (phase == 1) m.entry = w.pos;
                     } else {
@@ -352,9 +396,9 @@ __global__ void __launch_bounds__(kParse2Threads, B2B_PARSE2_CTAS) lz4_chunk_par
             }
         } else if (phase == 1) {
             const bool go = walk_step<true>(s, plen, w, rec);
-            if (go && w.pos >= cbeg + 2 * kChunkBytes) {
+            if (go && w.pos >= cbeg + 2 * CB) {
                 // this token covers the chunks up to the one that holds w.pos: nothing starts inside them
-                const uint32_t k1 = w.pos / kChunkBytes < nch ? w.pos / kChunkBytes : nch;
+                const uint32_t k1 = (w.pos >> CSH) < nch ? (w.pos >> CSH) : nch;
                 for (uint32_t j = k + 1; j < k1; j++) a.dead[g + (j - k)] = 1u;
             }
             if (!go || w.pos >= cend) {
@@ -388,11 +432,13 @@ struct Repair2Args {
     uint2 *table;
     ChunkMeta *meta;
     uint64_t table_chunks;
+    uint32_t chunk_shift = kChunkShift;
 };
 
 __global__ void __launch_bounds__(128) lz4_chunk_repair_kernel(Repair2Args a) {
     uint64_t total = *a.total_chunks;
     if (total > a.table_chunks) total = a.table_chunks;
+    const uint32_t CSH = a.chunk_shift, CB = 1u << CSH, CS = chunk_slot_records(CSH);
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0 || g >= total) return;
     uint32_t lo = 0, hi = a.nframes;                          // last frame whose first chunk is <= g
@@ -403,17 +449,17 @@ __global__ void __launch_bounds__(128) lz4_chunk_repair_kernel(Repair2Args a) {
     const uint32_t f = lo;
     const FrameDec d = a.fd[f];
     const uint32_t k = (uint32_t)(g - a.chunk_base[f]);
-    const uint32_t plen = d.plen, nch = (plen + kChunkBytes - 1) / kChunkBytes;
+    const uint32_t plen = d.plen, nch = (uint32_t)(((uint64_t)plen + CB - 1) >> CSH);
     if (d.kind != 2 || k == 0 || k >= nch) return;
     const ChunkMeta prev = a.meta[g - 1], m = a.meta[g];
     if (prev.entry == 0xFFFFFFFFu || prev.end != kEndCont) return;           // no chain runs out of the chunk before
     const uint32_t e = prev.exit;
-    if ((e / kChunkBytes < nch ? e / kChunkBytes : nch - 1) != k || m.entry == e) return;
+    if (((e >> CSH) < nch ? (e >> CSH) : nch - 1) != k || m.entry == e) return;
     const uint32_t sc = m.entry == 0xFFFFFFFFu ? 0u : m.count;
     if (sc == 0) return;                                                      // nothing to meet: the stitch kernel re-parses
     const uint8_t *s = a.frames + a.frame_off[f] + 16;
-    uint2 *slot = a.table + g * kChunkSlot;
-    const uint32_t cend = k + 1 == nch ? plen + 1 : (k + 1) * kChunkBytes;
+    uint2 *slot = a.table + g * CS;
+    const uint32_t cend = k + 1 == nch ? plen + 1 : (k + 1) << CSH;
     uint32_t pos = e, j = 0, mc = 0, spec_tok = slot[kChunkHead].x;
     uint64_t rel = 0;
     for (;;) {
@@ -467,6 +513,7 @@ struct Stitch2Args {
     uint32_t *last_chunk;           // last chunk with a descriptor (~0: the frame has no chunk)
     uint32_t *fallback;             // 1: no room in the table, the frame is decoded by the first design's kernel
     uint64_t table_chunks;
+    uint32_t chunk_shift = kChunkShift;
 };
 
 // A state machine per lane, one small step per turn, so that the lanes of a warp stay together whatever their
@@ -483,6 +530,7 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t f = kWarpPerFrame ? gt >> 5 : gt;
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t CSH = a.chunk_shift, CB = 1u << CSH, CS = chunk_slot_records(CSH);
     int mode = 3;
     FrameDec d; d.kind = 0; d.plen = 0; d.dcap = 0;
     uint32_t plen = 0, nch = 0;
@@ -493,7 +541,7 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
         a.last_chunk[f] = 0xFFFFFFFFu;
         d = a.fd[f];
         plen = d.plen;
-        nch = (plen + kChunkBytes - 1) / kChunkBytes;
+        nch = (uint32_t)(((uint64_t)plen + CB - 1) >> CSH);
         if (d.kind == 3) a.fallback[f] = 1;
         if (d.kind == 2 && nch != 0) {
             cb = a.chunk_base[f];
@@ -517,7 +565,7 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
         ChunkDesc D; D.count = 0xFFFFFFFFu;                   // set: a descriptor is ready this turn
         uint32_t endk = kEndCont;
         if (mode == 0) {
-            k = e / kChunkBytes;
+            k = e >> CSH;
             if (k >= nch) k = nch - 1;
             if (kWarpPerFrame) { for (uint32_t q = knext + lane; q < k; q += 32) a.desc[cb + q].count = 0; }
             else { for (uint32_t q = knext; q < k; q++) a.desc[cb + q].count = 0; }   // chunks inside one long token
@@ -537,7 +585,7 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
                     const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, dd);
                     if ((int)lane >= dd) incl += t;
                 }
-                const uint32_t nk = mi.exit / kChunkBytes < nch ? mi.exit / kChunkBytes : nch - 1;
+                const uint32_t nk = (mi.exit >> CSH) < nch ? (mi.exit >> CSH) : nch - 1;
                 const bool reg = ki + 1 < nch && (mi.entry == prev_exit || alt) && mi.end == kEndCont && nk == ki + 1 &&
                                  op + (long long)incl <= (long long)d.dcap;
                 const uint32_t irr = ~__ballot_sync(0xffffffffu, reg);
@@ -548,7 +596,7 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
                         ChunkDesc Di;
                         Di.base_a = 0; Di.base_b = op + (long long)(incl - my_out); Di.start = kChunkHead; Di.count = mi.count;
                         Di.split = 0; Di.end = kEndCont;
-                        if (alt) Di = adopt_repaired(a.table + (cb + ki) * kChunkSlot, mi, op + (long long)(incl - my_out));
+                        if (alt) Di = adopt_repaired(a.table + (cb + ki) * CS, mi, op + (long long)(incl - my_out));
                         a.desc[cb + ki] = Di;
                     }
                     op += (long long)__shfl_sync(0xffffffffu, incl, (int)r - 1);
@@ -559,8 +607,8 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
             }
             if (took) continue;
             m = a.meta[cb + k];
-            slot = a.table + (cb + k) * kChunkSlot;
-            cend = k + 1 == nch ? plen + 1 : (k + 1) * kChunkBytes;
+            slot = a.table + (cb + k) * CS;
+            cend = k + 1 == nch ? plen + 1 : (k + 1) << CSH;
             if (m.entry == e) {
                 D.base_a = 0; D.base_b = op; D.start = kChunkHead; D.count = m.count; D.split = 0; D.end = m.end;
                 op += m.out; e = m.exit; endk = m.end; prev_full = false;
@@ -662,6 +710,7 @@ struct Copy2Args {
     uint32_t *out_len, *status;
     FrameMeta *meta;
     const uint32_t *jump_state = nullptr;   // frames with state 1 were decoded by the pointer-jumping engine (lz4_decode4.cuh)
+    uint32_t chunk_shift = kChunkShift;
 };
 
 struct CoopLit { uint32_t dst, n; const uint8_t *src; };
@@ -772,7 +821,7 @@ __global__ void __launch_bounds__(kCopy2Threads, 1024 / kCopy2Threads) lz4_copy2
     for (uint32_t k = 0; code == 0 && k <= last; k++) {
         const ChunkDesc D = a.desc[cb + k];
         if (D.count == 0) continue;
-        const uint2 *rec = a.table + (cb + k) * kChunkSlot + D.start;
+        const uint2 *rec = a.table + (cb + k) * chunk_slot_records(a.chunk_shift) + D.start;
         uint32_t r = 0;
         while (r < D.count) {
             it++;

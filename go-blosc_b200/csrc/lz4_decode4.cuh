@@ -69,6 +69,7 @@ struct JumpArgs {
     uint32_t *changed;          // [kJumpRounds]: round r found something to do
     uint32_t *out_len, *status;
     FrameMeta *meta;
+    uint32_t chunk_shift = kChunkShift;
 };
 
 // ---- select: which frames this engine takes ------------------------------------------------------------------
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kJumpThreads) lz4_jump_map_kernel(JumpArgs a) 
         const ChunkDesc D = a.desc[g];
         if (D.count == 0) continue;
         const FrameDec d = a.fd[f];
-        const uint2 *rec = a.table + g * kChunkSlot + D.start;
+        const uint2 *rec = a.table + g * chunk_slot_records(a.chunk_shift) + D.start;
         const uint32_t X = (uint32_t)a.dst_off[f];
         uint8_t *out = (d.mode ? a.scratch : a.dst) + a.dst_off[f];
         const uint8_t *__restrict__ src = a.frames + a.frame_off[f] + 16;

@@ -24,7 +24,8 @@ enum ScanOp : int {
     kScanSegCount = 3,   // number of 64 KiB segments of the frame
     kScanSeqSlots = 4,   // sequence records of the split decoder for a frame of capacity x
     kScanStream = 5,     // x ? x + 4 : 0     a stream of a Blosc-1 block behind its int32 size (blocks.cuh)
-    kScanChunks = 6      // ceil(x / 8192)     parse chunks of an LZ4 block of x bytes (lz4_decode2.cuh)
+    kScanChunks = 6,     // ceil(x / 8192)     parse chunks of an LZ4 block of x bytes (lz4_decode2.cuh)
+    kScanChunksSmall = 7 // ceil(x / 1024)     the same with 1 KiB chunks (a handful of frames: b2b.cu)
 };
 
 __device__ __forceinline__ uint64_t scan_apply(int op, uint32_t x) {
@@ -34,6 +35,7 @@ __device__ __forceinline__ uint64_t scan_apply(int op, uint32_t x) {
     if (op == kScanSeqSlots) return (uint64_t)(x / 4u) + kSeqSlack;
     if (op == kScanStream) return x ? (uint64_t)x + 4ull : 0ull;
     if (op == kScanChunks) return ((uint64_t)x + 8191ull) / 8192ull;
+    if (op == kScanChunksSmall) return ((uint64_t)x + 1023ull) / 1024ull;
     return x;
 }
 

@@ -202,7 +202,10 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
     a.table = nullptr; a.table_off = nullptr; a.nrec = nullptr; a.only = nullptr; a.fuse_unshuffle = 1; a.ticket = nullptr;
     if (split == 3) {
         emu::launch(1, kLaneThreads, [&] { lz4_lane_decode_kernel(a); });
-    } else if (split == 2 || split == 4) {
+    } else if (split == 2 || split == 4 || split == 5) {
+        // split 5: split 4 with 1 KiB parse chunks
+        const bool jumping = split >= 4;
+        const uint32_t cshift = split == 5 ? kChunkShiftSmall : kChunkShift;
         // split 4: the pointer-jumping engine (lz4_decode4.cuh) in front of the tile copy engine
         // chunk-parallel decoder (lz4_decode2.cuh): prep -> K5 -> chunk parse -> stitch -> tile copy (+ fallback)
         FrameDec fd;
@@ -211,16 +214,17 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         Prep2Args pa;
         pa.frames = a.frames; pa.frame_off = &frame_off; pa.frame_len = &len; pa.dst_cap = &cap_eff; pa.nframes = 1;
         pa.typesize_override = typesize_override; pa.fd = &fd; pa.plen_eff = &plen_eff; pa.out_len = &out; pa.status = &status;
-        pa.meta = &meta; pa.keep_sparse = split == 4 ? 1u : 0u;
+        pa.meta = &meta; pa.keep_sparse = jumping ? 1u : 0u;
         emu::launch(1, 128, [&] { frame_prep_kernel(pa); });
-        run_scan(&plen_eff, 1, &chunk_base, &total_chunks, kScanChunks);
-        const uint64_t table_chunks = (uint64_t)cap / kChunkBytes + (uint64_t)cap / (255ull * kChunkBytes) + 2 + 16;
-        std::vector<uint2> tab(table_chunks * kChunkSlot);
+        run_scan(&plen_eff, 1, &chunk_base, &total_chunks, cshift == kChunkShift ? kScanChunks : kScanChunksSmall);
+        const uint64_t table_chunks = ((uint64_t)cap >> cshift) + ((uint64_t)cap / 255ull >> cshift) + 2 + 16;
+        const uint32_t kSlotRecs = chunk_slot_records(cshift);
+        std::vector<uint2> tab(table_chunks * kSlotRecs);
         std::vector<ChunkMeta> cmeta(table_chunks);
         std::vector<ChunkDesc> cdesc(table_chunks);
         Parse2Args pp;
         pp.frames = a.frames; pp.frame_off = &frame_off; pp.fd = &fd; pp.nframes = 1; pp.chunk_base = &chunk_base;
-        pp.total_chunks = &total_chunks; pp.table = tab.data(); pp.meta = cmeta.data(); pp.table_chunks = table_chunks;
+        pp.total_chunks = &total_chunks; pp.table = tab.data(); pp.meta = cmeta.data(); pp.table_chunks = table_chunks; pp.chunk_shift = cshift;
         std::vector<uint32_t> dead(table_chunks + 4, 0);
         unsigned long long ticket = 0;
         pp.dead = dead.data(); pp.ticket = &ticket;
@@ -228,14 +232,14 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         {
             Repair2Args ra;
             ra.frames = a.frames; ra.frame_off = &frame_off; ra.fd = &fd; ra.nframes = 1; ra.chunk_base = &chunk_base;
-            ra.total_chunks = &total_chunks; ra.table = tab.data(); ra.meta = cmeta.data(); ra.table_chunks = table_chunks;
+            ra.total_chunks = &total_chunks; ra.table = tab.data(); ra.meta = cmeta.data(); ra.table_chunks = table_chunks; ra.chunk_shift = cshift;
             if (!getenv("EMU_NO_REPAIR")) emu::launch((uint32_t)((table_chunks + 127) / 128), 128, [&] { lz4_chunk_repair_kernel(ra); });
         }
         Stitch2Args sa;
         sa.frames = a.frames; sa.frame_off = &frame_off; sa.fd = &fd; sa.nframes = 1; sa.chunk_base = &chunk_base;
         sa.table = tab.data(); sa.meta = cmeta.data(); sa.desc = cdesc.data(); sa.last_chunk = &last_chunk;
-        sa.fallback = &fallback; sa.table_chunks = table_chunks;
-        if (split == 4) emu::launch(1, 64, [&] { lz4_stitch_warp_kernel(sa); });      // a warp per frame, 32 chunks per step
+        sa.fallback = &fallback; sa.table_chunks = table_chunks; sa.chunk_shift = cshift;
+        if (jumping) emu::launch(1, 64, [&] { lz4_stitch_warp_kernel(sa); });      // a warp per frame, 32 chunks per step
         else emu::launch(1, 128, [&] { lz4_stitch_kernel(sa); });
         if (getenv("EMU_DUMP_DESC"))
             for (uint64_t q = 0; q < total_chunks; q++)
@@ -245,14 +249,14 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         if (getenv("EMU_DUMP_REC"))
             for (uint64_t q = 0; q < total_chunks; q++)
                 for (uint32_t i = 0; i <= cdesc[q].count && cdesc[q].count; i++)
-                    fprintf(stderr, "rec %llu %u: %u %u\n", (unsigned long long)q, i, tab[q * kChunkSlot + cdesc[q].start + i].x, tab[q * kChunkSlot + cdesc[q].start + i].y);
+                    fprintf(stderr, "rec %llu %u: %u %u\n", (unsigned long long)q, i, tab[q * kSlotRecs + cdesc[q].start + i].x, tab[q * kSlotRecs + cdesc[q].start + i].y);
         uint32_t jstate = 0, jtotal = 0;
         std::vector<uint32_t> jS;
         std::vector<JumpLong> jq;
         std::vector<uint8_t> jdone;
         uint32_t jctl[1 + kJumpRounds];
-        if (split == 4) {
-            JumpArgs ja;
+        if (jumping) {
+            JumpArgs ja; ja.chunk_shift = cshift;
             ja.frames = a.frames; ja.frame_off = &frame_off; ja.fd = &fd; ja.nframes = 1; ja.dst = a.dst; ja.scratch = a.scratch;
             ja.dst_off = &dst_off; ja.chunk_base = &chunk_base; ja.total_chunks = &total_chunks; ja.table_chunks = table_chunks;
             ja.desc = cdesc.data(); ja.last_chunk = &last_chunk; ja.table = tab.data(); ja.fallback = &fallback;
@@ -272,7 +276,7 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
             if (jstate == 1) g_jump_taken++;
         }
         Copy2Args ca;
-        ca.jump_state = split == 4 ? &jstate : nullptr;
+        ca.jump_state = jumping ? &jstate : nullptr; ca.chunk_shift = cshift;
         ca.frames = a.frames; ca.frame_off = &frame_off; ca.fd = &fd; ca.nframes = 1; ca.dst = a.dst; ca.scratch = a.scratch;
         ca.dst_off = &dst_off; ca.chunk_base = &chunk_base; ca.desc = cdesc.data(); ca.last_chunk = &last_chunk;
         ca.table = tab.data(); ca.fallback = &fallback; ca.out_len = &out; ca.status = &status; ca.meta = &meta;

@@ -1378,8 +1378,9 @@ def test_jump_decoder_is_the_automatic_choice_for_one_large_frame(ctx):
     """b2b_decompress of ONE frame (what decompressBackend binds, blosc.go:291-303): 48 MiB of float32 behind a byte
     shuffle, of text without a filter and of a sparse array (a frame that is small against its output) come back
     exactly, through the pointer-jumping engine."""
-    n = 48 << 20
-    for kind, sh, T in (("smooth_f32", 1, 4), ("text", 0, 1), ("zeros", 1, 4), ("lowent_i16", 2, 2)):
+    for n, kind, sh, T in ((48 << 20, "smooth_f32", 1, 4), (48 << 20, "text", 0, 1), (48 << 20, "zeros", 1, 4), (48 << 20, "lowent_i16", 2, 2),
+                           ((3 << 20) + 7, "smooth_f32", 1, 4), ((3 << 20) + 7, "text", 0, 1), (700001, "lowent_i16", 1, 2), (700001, "period3", 0, 1)):
+        # (frames of at most 32 MiB in a call of at most four: 1 KiB parse chunks)
         data = dg.corpus(n)[kind]
         fr = ctx.compress(data, 1, 5, sh, T)
         ctx.kernel_stats_reset()

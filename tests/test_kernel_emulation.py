@@ -110,13 +110,13 @@ def test_emulated_encoder_frames_decode_through_the_oracle(emu, orc, name, make,
     rc, ref = orc.compress(data, orc.LZ4, 5, sh, T)
     assert fr[:12].tobytes() == ref[:12].tobytes()
     assert bool(fr[2] & 2) == bool(ref[2] & 2), "memcpy decision differs from the oracle's"
-    for split in (0, 1, 2, 3, 4):
+    for split in (0, 1, 2, 3, 4, 5):
         taken = emu.lib.emu_jump_taken()
         st, out = emu.decompress(fr, data.size, split)
         assert st == 0 and np.array_equal(out, data)
         st, out = emu.decompress(ref, data.size, split)
         assert st == 0 and np.array_equal(out, data)
-        if split == 4 and not (fr[2] & 2):      # the pointer-jumping engine decoded both itself (no hand-over to the tile engine)
+        if split in (4, 5) and not (fr[2] & 2):      # the pointer-jumping engine decoded both itself (no hand-over to the tile engine)
             assert emu.lib.emu_jump_taken() == taken + 2
 
 
@@ -155,7 +155,7 @@ def test_emulated_decoder_status_words_on_mutants(emu, orc):
         rc, want = orc.decompress(m)
         norig = int.from_bytes(m[4:8].tobytes(), "little") if m.size >= 16 else 0
         cap = min(norig, 255 * m.size + 64)
-        for split in (0, 1, 2, 3, 4):
+        for split in (0, 1, 2, 3, 4, 5):
             st, out = emu.decompress(m, cap, split)
             assert st == rc, (st, rc, m[:16].tobytes().hex())
             if rc == 0:
@@ -174,6 +174,6 @@ def test_emulated_chunk_repair_keeps_the_speculative_records(emu, orc):
         data = adv[name]
         for sh, T in ((0, 1), (1, 4)):
             rc, fr = orc.compress(data, orc.LZ4, 5, sh, T)
-            for split in (2, 4):
+            for split in (2, 4, 5):
                 st, out = emu.decompress(np.asarray(fr, dtype=np.uint8), n, split)
                 assert st == 0 and np.array_equal(out, data), (name, sh, T, split)
