@@ -86,6 +86,7 @@ struct b2b_ctx {
     int opt_encode_ctas = 0;           // (option 106) persistent encoder CTAs per SM, 0 = as many as fit
     int opt_persistent_decode = 0;     // (option 105) one-warp-per-frame decoders as persistent warps that take frames from a ticket: measured
                                        // 3 % slower on one stream and neutral on two (the gain of the two streams is not a tail effect), so off
+    int opt_parse_ctas = 0;            // (option 109) chunk-parse CTAs per SM (0: as many as fit)
     int opt_no_small_chunks = 0;       // (option 108) 1: 8 KiB parse chunks also for a handful of small frames
     uint32_t opt_jump_min_bytes = 0;   // (option 107) batches of at most 4 frames: frames over this size take the chunk-parallel parse (0: 192 KiB; one 256 KiB frame 1.55 -> 1.22 ms, one 64 KiB frame 0.43 -> 0.81 ms)
     int opt_decode_streams = 0;        // streams a large decompress batch is split over: 0 automatic (2), 1 none, 2..4
@@ -585,7 +586,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         pp.dead = d_dead; pp.ticket = reinterpret_cast<unsigned long long *>(d_dead + ((table_chunks + 1) & ~1ull));
         CU(ctx, cudaMemsetAsync(d_dead, 0, 4ull * (table_chunks + 4), s));
         const unsigned pgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((table_chunks + kParse2Threads - 1) / kParse2Threads,
-                                                                          (uint64_t)ctx->sm_count * B2B_PARSE2_CTAS));
+                                                                          (uint64_t)ctx->sm_count * (ctx->opt_parse_ctas > 0 ? std::min(ctx->opt_parse_ctas, B2B_PARSE2_CTAS) : B2B_PARSE2_CTAS)));
         { LaunchTimer lt(ctx, K_PARSE2, s); lz4_chunk_parse_kernel<<<pgrid, kParse2Threads, 0, s>>>(pp); }
         CU(ctx, cudaGetLastError());
         {   // mis-speculated chunks are repaired all at once, on the exit of the chunk before them (lz4_decode2.cuh)
@@ -1128,6 +1129,7 @@ int b2b_set_option(b2b_ctx *ctx, int option, int64_t value) {
         case B2B_OPT_NO_HOST_STAGING: ctx->opt_no_staging = value != 0; return B2B_OK;
         case B2B_OPT_FUSE_UNSHUFFLE: ctx->opt_fuse_unshuffle = value != 0; return B2B_OK;
         case 105: ctx->opt_persistent_decode = value != 0; return B2B_OK;
+        case 109: ctx->opt_parse_ctas = (int)std::max<int64_t>(0, value); return B2B_OK;
         case 108: ctx->opt_no_small_chunks = value != 0; return B2B_OK;
         case 107: ctx->opt_jump_min_bytes = (uint32_t)std::max<int64_t>(0, value); return B2B_OK;
         case 106: ctx->opt_encode_ctas = (int)std::max<int64_t>(0, value); return B2B_OK;

@@ -12,6 +12,8 @@ from tools.perf_probe_lib import gen_f32
 pkg = entry.load_package()
 ctx = pkg.Context(0)
 ctx.set_option(pkg.OPT_KERNEL_TIMING, 1)
+if os.environ.get("PROBE_PARSE_CTAS"):
+    ctx.set_option(109, int(os.environ["PROBE_PARSE_CTAS"]))
 s = torch.cuda.current_stream().cuda_stream
 for size in [int(x) for x in os.environ.get("PROBE_BYTES", str(256 << 20)).split(",")]:
     src = gen_f32(size // 4)
