@@ -189,33 +189,57 @@ __device__ __forceinline__ uint32_t tok_step(const uint8_t *__restrict__ s, uint
 
 struct Walk { uint32_t pos, n, end; uint64_t rel; };
 
+// Eight stream bytes from position p as one little-endian word: two ALIGNED 8-byte loads and a funnel shift.  The lanes of
+// a warp walk 32 different chunks, so every byte load is 32 cache-line lookups; a token, its length bytes and the next
+// field's length bytes taken byte by byte were ~17 such loads per turn, and the turn time was the LSU working through
+// them.  Reads the two aligned words that cover [p, p + 8): up to 7 bytes before p and 15 behind it.
+__device__ __forceinline__ uint64_t walk_window8(const uint8_t *__restrict__ s, uint32_t p) {
+    const uintptr_t a = (uintptr_t)(s + p);
+    const uint64_t *q = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
+    const uint32_t sh = 8u * (uint32_t)(a & 7u);
+    const uint64_t lo = q[0], hi = q[1];
+    return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+}
+// A length field whose nibble was 15: its length bytes are bytes first .. 7 of the window w (255, ..., 255, last).  v grows
+// by their sum; returns the bytes taken, 0 when the field does not end inside the window (the caller takes the general
+// path).  The first byte that is not 0xFF is found with one find-first-set on the inverted word: a walk is a serial
+// instruction stream, and a loop over the bytes was most of its instructions.
+__device__ __forceinline__ uint32_t walk_len_ext(uint64_t w, uint32_t first, uint32_t &v) {
+    const uint64_t t = (~w) >> (8u * first);              // byte i: zero iff length byte i is 0xFF (zeros come in at the top)
+    if (t == 0) return 0u;
+    const uint32_t idx = (uint32_t)(__ffsll((long long)t) - 1) >> 3;
+    v += 255u * idx + ((uint32_t)(w >> (8u * (first + idx))) & 0xFFu);
+    return idx + 1u;
+}
+
 // one step of a walk: the token at w.pos; record (kEmit) at out[w.n].  Returns false when the chain ended
 // (w.end says how).  rel counts output bytes from the start of the walk and never passes 2^32 - 1.
 //
-// Fast path: a token whose two lengths take at most one length byte each and whose sequence ends at least one byte
-// before the end of the stream -- practically every token -- is stepped over with the few instructions it needs.  A walk
-// is ONE dependent instruction stream (a thread of the parse kernel, a warp of the stitch kernel), so its speed is its
-// instruction count: the general tok_step (64-bit lengths, every malformed case, length-byte loops) cost about a
-// microsecond per token, which was the latency of every call with few frames.  Anything else -- longer lengths, the last
-// sequences of a stream, anything malformed, a position counter near 2^32 -- takes the general path, so the result is
-// the same by construction.
+// Fast path: a token whose two lengths take at most seven / eight length bytes each (lengths up to ~2 000) and whose
+// sequence ends at least 24 bytes before the end of the stream -- practically every token -- is stepped over with two
+// round trips to memory: an 8-byte window with the token and its length bytes, then one with the match's length bytes.  A walk is ONE dependent chain (a thread of
+// the parse kernel among 31 others in lockstep, a warp of the stitch kernel) and the general tok_step pays a round trip per
+// length byte; with 32 lanes per warp some lane had a match of several hundred bytes nearly every turn (the sign /
+// exponent plane of a smooth field: 1.7 us per token).  Anything else -- longer lengths, the last sequences of a stream,
+// anything malformed, a position counter near 2^32 -- takes the general path, so the result is the same by construction.
 template <bool kEmit>
 __device__ __forceinline__ bool walk_step(const uint8_t *__restrict__ s, uint32_t clen, Walk &w, uint2 *out) {
     {
         const uint32_t p = w.pos;
-        if (p + 1u < clen && w.rel < 0xFFFF0000ull) {             // the token and a possible length byte exist
-            const uint32_t tok = s[p];
+        if (p + 24u <= clen && w.rel < 0xFFFF0000ull) {           // the token's window lies inside the stream
+            const uint64_t w0 = walk_window8(s, p);               // token and up to seven length bytes
+            const uint32_t tok = (uint32_t)w0 & 0xFFu;
             uint32_t l = tok >> 4, q = p + 1u;
             bool ok = true;
-            if (l == 15u) { const uint32_t b = s[q]; ok = b != 255u; l += b; q++; }
-            const uint32_t e = q + l;                             // literals [q, e), offset [e, e + 2), a length byte at e + 2
-            if (ok && e + 3u <= clen) {
+            if (l == 15u) { const uint32_t k = walk_len_ext(w0, 1u, l); ok = k != 0u; q += k; }
+            const uint32_t e = q + l;                             // literals [q, e), offset [e, e + 2), length bytes from e + 2
+            if (ok && e + 26u <= clen) {
                 uint32_t m = tok & 15u, nx = e + 2u;
-                if (m == 15u) { const uint32_t b = s[nx]; ok = b != 255u; m += b; nx++; }
+                if (m == 15u) { const uint32_t k = walk_len_ext(walk_window8(s, nx), 0u, m); ok = k != 0u; nx += k; }
                 if (ok) {
                     if (kEmit) out[w.n] = make_uint2(p, (uint32_t)w.rel);
                     w.n++;
-                    w.rel += l + m + 4u;                          // <= 269 + 273: far from 2^32 (checked above)
+                    w.rel += l + m + 4u;                          // <= 2 * (15 + 8 * 255) + 4: far from 2^32 (checked above)
                     w.pos = nx;
                     return true;
                 }

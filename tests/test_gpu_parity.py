@@ -1388,3 +1388,37 @@ def test_jump_decoder_is_the_automatic_choice_for_one_large_frame(ctx):
         assert np.array_equal(back, data), kind
         if not (fr[2] & 2):
             assert ctx.kernel_stats()["lz4_jump_map_kernel"][0] > 0, kind
+
+
+def test_one_gib_frame_round_trip_on_the_device(ctx):
+    """ONE frame of 1 GiB (the format allows 4 GiB, blosc.go:363-365) through compress_batch_dev / decompress_batch_dev:
+    16 384 encoder segments, ~94 000 parse chunks, 2^30 source indices.  Exact round trip, the pointer-jumping engine
+    took it, and the first and last MiB equal the oracle's decode of nothing less than the frame's own header fields."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < (20 << 30):
+        pytest.skip("needs 20 GiB of free device memory")
+    n = 1 << 30
+    i = torch.arange(n // 4, device="cuda", dtype=torch.float64)
+    g = torch.Generator(device="cuda"); g.manual_seed(1234)
+    x = torch.sin(2 * torch.pi * i / 4096) + 0.25 * torch.sin(2 * torch.pi * i / 333.3) + 1e-3 * (torch.rand(n // 4, device="cuda", generator=g, dtype=torch.float64) * 2 - 1)
+    src = x.to(torch.float32).view(torch.uint8)
+    del i, x
+    d_off = torch.zeros(1, dtype=torch.int64, device="cuda"); d_len = torch.tensor([n], dtype=torch.int32, device="cuda")
+    cap = n + 96
+    d_c = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_foff = torch.empty(1, dtype=torch.int64, device="cuda"); d_flen = torch.empty(1, dtype=torch.int32, device="cuda")
+    d_st = torch.empty(1, dtype=torch.int32, device="cuda"); d_tot = torch.empty(1, dtype=torch.int64, device="cuda")
+    d_out = torch.zeros_like(src); d_olen = torch.empty(1, dtype=torch.int32, device="cuda")
+    ctx.compress_batch_dev(src, d_off, d_len, 1, n, n, 1, 4, d_c, cap, d_foff, d_flen, d_st, d_tot)
+    torch.cuda.synchronize()
+    assert int(d_st.item()) == 0 and 0.5 * n < int(d_tot.item()) < 0.8 * n
+    hdr = d_c[:16].cpu().numpy()
+    assert hdr[0] == 2 and hdr[1] == 1 and hdr[2] == 1 and hdr[3] == 4
+    assert int.from_bytes(hdr[4:8].tobytes(), "little") == n and int.from_bytes(hdr[12:16].tobytes(), "little") == int(d_flen.item())
+    ctx.kernel_stats_reset()
+    ctx.decompress_batch_dev(d_c, d_foff, d_flen, 1, 0, d_out, d_off, d_len, n, n, d_olen, d_st)
+    torch.cuda.synchronize()
+    assert int(d_st.item()) == 0 and int(d_olen.item()) == n
+    assert ctx.kernel_stats()["lz4_jump_map_kernel"][0] == 1
+    assert torch.equal(d_out, src)
