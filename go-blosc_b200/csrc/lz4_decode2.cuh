@@ -349,6 +349,7 @@ struct Parse2Args {
 };
 
 constexpr int kParse2Threads = 128;
+constexpr int kWalkBurst = 8;           // tokens a parse lane walks between two votes of its warp
 #ifndef B2B_PARSE2_CTAS
 #define B2B_PARSE2_CTAS 8       // 64 registers (at 12 CTAs / 40 registers the walk spilled 528 bytes into its token loop)
 #endif
@@ -409,8 +410,17 @@ __global__ void __launch_bounds__(kParse2Threads, B2B_PARSE2_CTAS) lz4_chunk_par
                 }
             }
         }
+        // Up to kWalkBurst tokens per turn: the vote, the ticket logic and the phase dispatch around a token cost as many
+        // instructions as the token itself, and a walk is as fast as its instruction stream is short (ncu on a frame of the
+        // sign / exponent plane alone: 130 instructions per token at 12 cycles each).  The lanes still meet every turn.
         if (phase == 0) {
-            if (!walk_step<false>(s, plen, w, nullptr)) { phase = 2; a.meta[g] = m; }   // the speculative chain died before the chunk
+            bool alive = true;
+#pragma unroll 1
+            for (int r = 0; r < kWalkBurst; r++) {
+                alive = walk_step<false>(s, plen, w, nullptr);
+                if (!alive || w.pos >= cbeg) break;
+            }
+            if (!alive) { phase = 2; a.meta[g] = m; }   // the speculative chain died before the chunk
             else if (w.pos >= cbeg) {
                 // (a token that jumps over whole chunks from the warm-up zone says nothing certain: no flags)
                 m.entry = w.pos; m.exit = w.pos; m.end = kEndCont;
@@ -419,7 +429,12 @@ __global__ void __launch_bounds__(kParse2Threads, B2B_PARSE2_CTAS) lz4_chunk_par
                 else { if (w.pos < cend) { m.entry = 0xFFFFFFFFu; m.end = kEndDead; } phase = 2; a.meta[g] = m; }
             }
         } else if (phase == 1) {
-            const bool go = walk_step<true>(s, plen, w, rec);
+            bool go = true;
+#pragma unroll 1
+            for (int r = 0; r < kWalkBurst; r++) {
+                go = walk_step<true>(s, plen, w, rec);
+                if (!go || w.pos >= cend || (w.n & 31u) == 0u) break;     // (w.pos >= cbeg + 2 * CB implies w.pos >= cend)
+            }
             if (go && w.pos >= cbeg + 2 * CB) {
                 // this token covers the chunks up to the one that holds w.pos: nothing starts inside them
                 const uint32_t k1 = (w.pos >> CSH) < nch ? (w.pos >> CSH) : nch;
