@@ -522,7 +522,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
                                    align_up(4ull * nframes, 256) + scan_scratch_bytes(nframes) + 1024 : 0) +
                           (v2 ? align_up(sizeof(FrameDec) * (uint64_t)nframes, 256) + 3 * align_up(4ull * nframes, 256) +
                                 align_up(8ull * nframes, 256) + scan_scratch_bytes(nframes) +
-                                align_up(8ull * cslot * table_chunks, 256) + 2 * align_up(32ull * table_chunks, 256) +
+                                align_up(8ull * cslot * (table_chunks + nframes), 256) + 2 * align_up(32ull * table_chunks, 256) +
                                 align_up(4ull * table_chunks + 16, 256) + 2048 : 0) +
                           (jump ? align_up(4ull * total_dst + 64, 256) + 2 * align_up(4ull * nframes, 256) +
                                   align_up(sizeof(JumpLong) * (uint64_t)jump_long_cap, 256) + 512 +
@@ -566,7 +566,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         uint64_t *d_chunk_base = ar.take<uint64_t>(nframes);
         uint64_t *d_total_chunks = ar.take<uint64_t>(1);
         uint8_t *scan_c = ar.take<uint8_t>(scan_scratch_bytes(nframes));
-        uint2 *d_rec = ar.take<uint2>(cslot * table_chunks);
+        uint2 *d_rec = ar.take<uint2>(cslot * (table_chunks + nframes));   // + one spare slot per frame (warp stitch)
         ChunkMeta *d_cmeta = ar.take<ChunkMeta>(table_chunks);
         ChunkDesc *d_cdesc = ar.take<ChunkDesc>(table_chunks);
         uint32_t *d_dead = ar.take<uint32_t>(table_chunks + 4);      // + the parse ticket behind it
@@ -600,7 +600,7 @@ int decompress_batch_dev_locked(b2b_ctx *ctx, const void *d_frames, const uint64
         Stitch2Args sa;
         sa.frames = a.frames; sa.frame_off = d_frame_off; sa.fd = d_fd; sa.nframes = nframes; sa.chunk_base = d_chunk_base;
         sa.table = d_rec; sa.meta = d_cmeta; sa.desc = d_cdesc; sa.last_chunk = d_last; sa.fallback = d_fallback;
-        sa.table_chunks = table_chunks; sa.chunk_shift = cshift;
+        sa.table_chunks = table_chunks; sa.chunk_shift = cshift; sa.scratch = d_rec + cslot * table_chunks;
         // few frames: a warp per frame that adopts 32 chunks per step (one 1 GiB frame: 40 ms with one thread)
         { LaunchTimer lt(ctx, K_STITCH2, s);
           if (jump || nframes <= 256) lz4_stitch_warp_kernel<<<(nframes * 32 + 63) / 64, 64, 0, s>>>(sa);

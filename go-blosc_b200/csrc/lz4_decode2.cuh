@@ -530,9 +530,9 @@ __global__ void __launch_bounds__(128) lz4_chunk_repair_kernel(Repair2Args a) {
 // A chunk is adopted on its repaired chain (pad[] of its meta; output so far = op).  Only now is it certain that the
 // speculative records in front of the meeting point are dead, so only now do the repair's tokens move from the head-room
 // to their place in front of record j: the copy engines read a chunk's records as one run.
-__device__ __forceinline__ ChunkDesc adopt_repaired(uint2 *slot, const ChunkMeta &m, long long op) {
+__device__ __forceinline__ ChunkDesc adopt_repaired(uint2 *slot, const ChunkMeta &m, long long op, bool move = true) {
     const uint32_t j = m.pad[1] & 0xFFFu, mc = (m.pad[1] >> 12) & 0xFFFu;
-    if (j != 0) for (uint32_t q = mc; q-- > 0;) slot[kChunkHead + j - mc + q] = slot[kChunkHead - mc + q];   // (moves up: last first)
+    if (move && j != 0) for (uint32_t q = mc; q-- > 0;) slot[kChunkHead + j - mc + q] = slot[kChunkHead - mc + q];   // (moves up: last first)
     ChunkDesc D;
     D.base_a = op; D.base_b = op + ((long long)m.pad[2] - (long long)m.out);
     D.start = kChunkHead + j - mc; D.count = mc + (m.count - j); D.split = mc; D.end = m.end;
@@ -553,6 +553,7 @@ struct Stitch2Args {
     uint32_t *fallback;             // 1: no room in the table, the frame is decoded by the first design's kernel
     uint64_t table_chunks;
     uint32_t chunk_shift = kChunkShift;
+    uint2 *scratch = nullptr;       // warp per frame: one spare chunk slot per frame (records of a walk whose place is not known yet)
 };
 
 // A state machine per lane, one small step per turn, so that the lanes of a warp stay together whatever their
@@ -652,8 +653,42 @@ __device__ __forceinline__ void stitch_body(const Stitch2Args &a) {
                 D.base_a = 0; D.base_b = op; D.start = kChunkHead; D.count = m.count; D.split = 0; D.end = m.end;
                 op += m.out; e = m.exit; endk = m.end; prev_full = false;
             } else if ((m.pad[1] >> 31) != 0 && m.pad[0] == e) {          // repaired for exactly this entry (repair kernel)
-                D = adopt_repaired(slot, m, op);
+                D = adopt_repaired(slot, m, op, !kWarpPerFrame || lane == 0);   // (the move overlaps itself: one lane does it)
+                if (kWarpPerFrame) __syncwarp();
                 op += m.pad[2]; e = m.exit; endk = m.end; prev_full = false;
+            } else if (kWarpPerFrame && a.scratch) {
+                // One walk from the true entry does both jobs: it looks for the speculative chain AND keeps its tokens (in
+                // the frame's spare slot), so that neither outcome walks the chunk a second time -- the records move to
+                // their place, 32 lanes wide, when the walk knows where that is.  (One 1 GiB frame: 17 chunks of the
+                // sign / exponent plane never meet their speculative chain, 2 000 tokens each; search + re-parse was 17 of
+                // the kernel's 19 ms.)
+                B2B_STAT(20, 1);
+                sc = m.entry == 0xFFFFFFFFu ? 0u : m.count;
+                j = 0; spec_tok = sc ? slot[kChunkHead].x : 0xFFFFFFFFu;
+                uint2 *tmp = a.scratch + (uint64_t)f * CS;
+                w.pos = e; w.n = 0; w.end = kEndCont; w.rel = 0;
+                bool merged = false;
+                for (;;) {
+                    if (w.pos >= cend) break;
+                    if (j < sc && spec_tok < w.pos) { j++; spec_tok = j < sc ? slot[kChunkHead + j].x : 0xFFFFFFFFu; continue; }
+                    if (j < sc && spec_tok == w.pos && w.n <= kChunkHead + j) { merged = true; break; }
+                    if (!walk_step<true>(s, plen, w, tmp)) break;          // the chain ends inside the chunk
+                }
+                __syncwarp();                                              // every lane is done reading the speculative records
+                if (merged) {
+                    const uint32_t nmine = w.n, spec_rel = slot[kChunkHead + j].y;
+                    for (uint32_t q = lane; q < nmine; q += 32) slot[kChunkHead + j - nmine + q] = tmp[q];
+                    D.base_a = op; D.base_b = op + (long long)w.rel - (long long)spec_rel;
+                    D.start = kChunkHead + j - nmine; D.count = nmine + (m.count - j); D.split = nmine; D.end = m.end;
+                    op += (long long)w.rel + (long long)(m.out - spec_rel);
+                    e = m.exit; endk = m.end; prev_full = false;
+                } else {
+                    B2B_STAT(21, 1);
+                    for (uint32_t q = lane; q < w.n; q += 32) slot[kChunkHead + q] = tmp[q];
+                    slot[kChunkHead + w.n] = make_uint2(w.pos, (uint32_t)w.rel);
+                    D.base_a = 0; D.base_b = op; D.start = kChunkHead; D.count = w.n; D.split = 0; D.end = w.end;
+                    op += (long long)w.rel; e = w.pos; endk = w.end; prev_full = true;
+                }
             } else if (prev_full) {
                 // the chunk before this one had to be re-parsed as a whole and this one is wrong again: two chains that
                 // run side by side without meeting (sequences of one fixed length, e.g. token + offset + one length byte

@@ -219,7 +219,7 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         run_scan(&plen_eff, 1, &chunk_base, &total_chunks, cshift == kChunkShift ? kScanChunks : kScanChunksSmall);
         const uint64_t table_chunks = ((uint64_t)cap >> cshift) + ((uint64_t)cap / 255ull >> cshift) + 2 + 16;
         const uint32_t kSlotRecs = chunk_slot_records(cshift);
-        std::vector<uint2> tab(table_chunks * kSlotRecs);
+        std::vector<uint2> tab((table_chunks + 1) * kSlotRecs);   // + the frame's spare slot (warp stitch)
         std::vector<ChunkMeta> cmeta(table_chunks);
         std::vector<ChunkDesc> cdesc(table_chunks);
         Parse2Args pp;
@@ -238,7 +238,7 @@ int emu_decompress_frame(const uint8_t *frame, uint32_t len, int64_t typesize_ov
         Stitch2Args sa;
         sa.frames = a.frames; sa.frame_off = &frame_off; sa.fd = &fd; sa.nframes = 1; sa.chunk_base = &chunk_base;
         sa.table = tab.data(); sa.meta = cmeta.data(); sa.desc = cdesc.data(); sa.last_chunk = &last_chunk;
-        sa.fallback = &fallback; sa.table_chunks = table_chunks; sa.chunk_shift = cshift;
+        sa.fallback = &fallback; sa.table_chunks = table_chunks; sa.chunk_shift = cshift; sa.scratch = tab.data() + table_chunks * kSlotRecs;
         if (jumping) emu::launch(1, 64, [&] { lz4_stitch_warp_kernel(sa); });      // a warp per frame, 32 chunks per step
         else emu::launch(1, 128, [&] { lz4_stitch_kernel(sa); });
         if (getenv("EMU_DUMP_DESC"))
