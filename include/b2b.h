@@ -126,8 +126,8 @@ enum {
      * per frame: thousands of small frames), 3 one lane per frame (2^16 frames or more of at most 4 KiB), 4 the
      * chunk-parallel parse followed by pointer jumping over per-byte source indices (a FEW LARGE frames, e.g. the one
      * frame of b2b_decompress: the frame is spread over the whole device; needs 4 bytes of scratch per output byte,
-     * at most 64 frames and under 4 GiB of output per call, otherwise 0 is used; automatic when the batch's output
-     * is at most 24 times its largest frame).  All give identical results. */
+     * at most 256 frames and under 4 GiB of output per call, otherwise 0 is used; automatic when the batch's output
+     * is at most 128 times its largest frame).  All give identical results. */
     B2B_OPT_DECODER = 9,
     /* 1: in the one-warp-per-frame decoders the warp that decoded a byte-shuffled frame (typesize 2 or 4, 16-byte
      * aligned slots, element count a multiple of 16) also un-shuffles it, instead of a separate pass over the
