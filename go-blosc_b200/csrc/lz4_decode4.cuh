@@ -63,7 +63,7 @@ struct JumpArgs {
     JumpLong *longq;
     uint32_t *nlong;
     uint32_t long_cap;
-    uint8_t *blockdone;         // [nframes][blocks_per_frame]
+    uint8_t *blockdone;         // [nframes][blocks_per_frame]: 1 every byte points at a literal, 2 every byte IS a literal
     uint32_t blocks_per_frame;
     uint32_t blocks_grid;       // CTAs per frame of the rounds / the gather (they stride over the frame's blocks)
     uint32_t *changed;          // [kJumpRounds]: round r found something to do
@@ -241,6 +241,10 @@ __global__ void __launch_bounds__(kJumpThreads) lz4_jump_long_kernel(JumpArgs a)
             if (it.kind == 0) {
                 cta_copy(out + it.pos + m0, src + it.src + m0, cnt);
                 for (uint32_t i = threadIdx.x; i < cnt; i += kJumpThreads) a.S[X + it.pos + m0 + i] = X + it.pos + m0 + i;
+                // blocks that lie wholly inside this slice hold literals only: nothing to resolve, nothing to gather (the
+                // incompressible byte planes of a shuffled frame are half of it)
+                const uint32_t b_lo = (it.pos + m0 + kJumpBlock - 1) / kJumpBlock, b_hi = (it.pos + m0 + cnt) / kJumpBlock;
+                for (uint32_t b = b_lo + threadIdx.x; b < b_hi; b += kJumpThreads) a.blockdone[(uint64_t)it.frame * a.blocks_per_frame + b] = 2;
             } else {
                 const bool ovl = it.src < it.len;
                 for (uint32_t i = threadIdx.x; i < cnt; i += kJumpThreads)
@@ -314,7 +318,9 @@ __global__ void __launch_bounds__(kJumpThreads) lz4_jump_gather_kernel(JumpArgs 
     const uint32_t X = (uint32_t)a.dst_off[f];
     uint8_t *out = (a.fd[f].mode ? a.scratch : a.dst) + a.dst_off[f];
     const uint32_t nb = (total + kJumpBlock - 1) / kJumpBlock;
+    const uint8_t *done = a.blockdone + (uint64_t)f * a.blocks_per_frame;
     for (uint32_t b = b0; b < nb; b += a.blocks_grid) {
+        if (done[b] == 2) continue;                          // literals only (lz4_jump_long_kernel)
         const uint32_t base = b * kJumpBlock;
         const uint32_t n = total - base < kJumpBlock ? total - base : kJumpBlock;
         const uint32_t *Sb = a.S + X + base;
