@@ -391,7 +391,7 @@ int compress_batch_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *d
     const uint64_t comp_bytes = comp_scratch_bytes(total_src, nframes);
     const uint64_t max_segs_total = total_src / kSegBytes + nframes + 1;
     const uint64_t need = (filtered ? align_up(total_src + 64, 256) : 0) + align_up(comp_bytes, 256) +
-                          align_up(16 * max_segs_total, 256) + align_up(8 * max_segs_total, 256) +
+                          align_up(16 * max_segs_total, 256) + align_up(16 * max_segs_total, 256) +
                           8 * align_up(8ull * nframes, 256) + 3 * scan_scratch_bytes(nframes) + 8192;
     int rc = ensure_arena(ctx, need);
     if (rc) return rc;
@@ -783,7 +783,7 @@ int compress_blocks_dev_locked(b2b_ctx *ctx, const void *d_src, const uint64_t *
     const uint64_t comp_bytes = comp_scratch_bytes(total_src, nslots);
     const uint64_t max_segs_total = total_src / kSegBytes + nslots + 1;
     const uint64_t need = (filtered ? align_up(total_src + 64, 256) : 0) + align_up(comp_bytes, 256) +
-                          align_up(16 * max_segs_total, 256) + align_up(8 * max_segs_total, 256) +
+                          align_up(16 * max_segs_total, 256) + align_up(16 * max_segs_total, 256) +
                           12 * align_up(8ull * (nslots + 1), 256) + 4 * align_up(8ull * nframes, 256) +
                           3 * scan_scratch_bytes(nslots + 1) + 2 * scan_scratch_bytes(nframes) + 16384;
     int rc = ensure_arena(ctx, need);

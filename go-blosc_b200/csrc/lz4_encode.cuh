@@ -55,6 +55,9 @@ struct SegMeta {
 struct SegPlace {
     uint32_t out_off;    // payload offset of this segment's (merged) first token
     uint32_t lit_total;  // literals of that token: carried ones + first_ll
+    uint32_t trail_dst;  // payload offset of the literals this segment hands on: its trailing literals, or (no match) all of
+                         // it.  They lie inside the literal run of the next token, whichever segment holds that
+    uint32_t pad;
 };
 
 __host__ __device__ __forceinline__ uint32_t seg_count(uint32_t n) { return (n + kSegBytes - 1) / kSegBytes; }
@@ -848,6 +851,17 @@ struct FinalizeArgs {
     uint64_t src_cap = ~0ull;
 };
 
+// segments [lo, hi) of a frame learn that the token in front of their literal run takes hdr bytes (four loads in flight)
+__device__ __forceinline__ void fix_trail_dst(SegPlace *place, uint32_t lo, uint32_t hi, uint32_t hdr, uint32_t lane) {
+    for (uint32_t q = lo + lane; q < hi; q += 128) {
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = q + 32u * u < hi ? place[q + 32u * u].trail_dst : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (q + 32u * u < hi) place[q + 32u * u].trail_dst = v[u] + hdr;
+    }
+}
+
 // One WARP per frame: the walk over the segments is a serial recurrence (where a segment's first token goes depends
 // on everything before it), but its cost was the dependent load of one summary per step -- one thread walking the
 // 16 384 segments of a 1 GiB frame took 2.6 ms, as long as the encoder.  The lanes load 32 summaries at once, every
@@ -871,12 +885,18 @@ __global__ void finalize_frames_kernel(FinalizeArgs a) {
         const uint32_t nseg = seg_count(n);
         const uint64_t base = a.seg_base[f];
         uint64_t out = 0, carry = 0;
+        // the literal run that is open: its token will stand at payload offset `out` (fixed until the run closes), its
+        // literals come from the segments run_first .. (trailing literals of a segment with a match, then whole segments
+        // without one); where a segment's share starts inside the run is known at once, the token's length bytes in
+        // front of it only when the run closes -- they are added then (to the lanes of this group, and in memory to the
+        // segments of earlier groups: the incompressible planes of one large frame are a run of a thousand segments)
+        uint32_t run_first = 0;
         if (a.index) for (uint32_t s = nseg + lane; s < a.segs_per_frame; s += 32) a.index[ibase + s] = ~0ull;
         for (uint32_t s0 = 0; s0 < nseg; s0 += 32) {
             const uint32_t s = s0 + lane;
             SegMeta m; m.first_ll = 0; m.body_len = 0; m.trail_ll = 0; m.info = 0;
             if (s < nseg) m = a.meta[base + s];
-            SegPlace pl; pl.out_off = 0; pl.lit_total = 0;
+            SegPlace pl; pl.out_off = 0; pl.lit_total = 0; pl.trail_dst = 0; pl.pad = 0;
             uint64_t idx = ~0ull;
             const uint32_t cnt = nseg - s0 < 32u ? nseg - s0 : 32u;
             for (uint32_t j = 0; j < cnt; j++) {
@@ -884,14 +904,21 @@ __global__ void finalize_frames_kernel(FinalizeArgs a) {
                 const uint32_t body = __shfl_sync(0xffffffffu, m.body_len, (int)j), trail = __shfl_sync(0xffffffffu, m.trail_ll, (int)j);
                 if (info & 0x100u) {
                     const uint64_t lt = carry + first;
+                    const uint32_t hdr = 1u + len_ext_bytes((uint32_t)lt);
+                    // the run closes: its contributors learn where the literals start
+                    if (s >= run_first && lane < j) pl.trail_dst += hdr;
+                    if (run_first < s0) fix_trail_dst(a.place + base, run_first, s0, hdr, lane);
                     if (lane == j) {
                         pl.out_off = (uint32_t)(out > 0xFFFFFFFFull ? 0xFFFFFFFFull : out);
                         pl.lit_total = (uint32_t)lt;
                         idx = (uint64_t)pl.out_off | (((uint64_t)(s0 + j) * kSegBytes + first - lt) << 32);
                     }
-                    out += 1ull + len_ext_bytes((uint32_t)lt) + lt + body;
+                    out += 1ull + hdr - 1u + lt + body;
                     carry = trail;
+                    run_first = s0 + j;                   // its trailing literals open the next run, at its very start
+                    if (lane == j) pl.trail_dst = (uint32_t)out;
                 } else {
+                    if (lane == j) pl.trail_dst = (uint32_t)(out + carry);
                     carry += trail;                       // no match: the whole segment is carried
                 }
             }
@@ -899,6 +926,12 @@ __global__ void finalize_frames_kernel(FinalizeArgs a) {
                 a.place[base + s] = pl;
                 if (a.index && s < a.segs_per_frame) a.index[ibase + s] = idx;
             }
+            __threadfence_block();
+            __syncwarp();                                 // (the stores above are read-modify-written by other lanes when a run closes)
+        }
+        {   // the closing token closes the last run
+            const uint32_t hdr = 1u + len_ext_bytes((uint32_t)carry);
+            fix_trail_dst(a.place + base, run_first, nseg, hdr, lane);
         }
         if (lane == 0) {
             a.final_ll[f] = (uint32_t)carry;
@@ -949,12 +982,11 @@ __device__ __forceinline__ uint32_t token_hdr_bytes(uint32_t lt) { return 1u + l
 // segment s of frame f's LZ4 block, assembled at its place in `out` (the start of the block) by the whole CTA.
 // Every segment moves exactly the input bytes it OWNS: a literal run that crosses segment boundaries (the trailing
 // literals of a segment, whole segments without a match -- the incompressible byte planes of a shuffled frame --
-// and the leading literals of the segment that closes the run) is copied piecewise by its owners, each of which
-// finds the run's place from the closing segment's entry.  (Round 1 let the closing segment copy the whole run:
+// and the leading literals of the segment that closes the run) is copied piecewise by its owners; the finalize pass
+// gives every segment the place of its share (SegPlace.trail_dst).  (Round 1 let the closing segment copy the whole run:
 // in ONE large frame that is a single CTA moving half the frame -- 256 MiB: 12.7 of 14.9 ms.)
 __device__ __forceinline__ void cta_pack_lz4_segment(const PackArgs &a, uint32_t f, uint32_t s, uint32_t n,
                                                      uint32_t nseg, uint64_t base, uint8_t *out) {
-    __shared__ uint32_t s_closer;
     const uint32_t B = s * kSegBytes;
     const uint32_t L = n - B < kSegBytes ? n - B : kSegBytes;
     const uint8_t *frame = a.in + a.src_off[f];
@@ -968,31 +1000,12 @@ __device__ __forceinline__ void cta_pack_lz4_segment(const PackArgs &a, uint32_t
         cta_copy(d + hdr + pl.lit_total, a.comp + a.comp_off[f] + (uint64_t)s * kSegSlot, m.body_len);
     }
     if (s == nseg - 1) cta_put_token(out + a.final_off[f], a.final_ll[f], 0);      // closing token: the last literals
-    // my trailing literals (the whole segment when it has no match) open or continue the run that the next
-    // segment with a match closes -- or the closing token
+    // my trailing literals (the whole segment when it has no match) open or continue the literal run of the next token:
+    // the finalize pass has worked out where they go
     const uint32_t mine = (m.info & 0x100u) ? m.trail_ll : L;
-    if (mine == 0) return;                                        // (uniform: m is the same for every thread)
-    __syncthreads();
-    if (threadIdx.x == 0) s_closer = nseg;
-    __syncthreads();
-    for (uint32_t b0 = s + 1; b0 < nseg; b0 += blockDim.x) {
-        const uint32_t idx = b0 + threadIdx.x;
-        if (idx < nseg && (a.meta[base + idx].info & 0x100u)) atomicMin(&s_closer, idx);
-        __syncthreads();
-        if (s_closer < nseg) break;
-    }
-    const uint32_t c = s_closer;
-    uint32_t tok_off, lt, run_in0;                                // the run: its token, its literals, where they start in the input
-    if (c < nseg) {
-        const SegPlace pc = a.place[base + c];
-        tok_off = pc.out_off; lt = pc.lit_total;
-        run_in0 = c * kSegBytes + a.meta[base + c].first_ll - lt;
-    } else {
-        tok_off = a.final_off[f]; lt = a.final_ll[f];
-        run_in0 = n - lt;
-    }
-    const uint32_t in0 = B + L - mine;
-    cta_copy(out + tok_off + token_hdr_bytes(lt) + (in0 - run_in0), frame + in0, mine);
+    if (mine == 0) return;
+    const uint32_t dst_off = a.place[base + s].trail_dst;
+    cta_copy(out + dst_off, frame + (B + L - mine), mine);
 }
 
 __global__ void __launch_bounds__(kFilterThreads, 8) pack_frames_kernel(PackArgs a) {
