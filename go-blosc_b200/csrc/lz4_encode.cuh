@@ -35,6 +35,9 @@
 #ifndef B2B_TRACE
 #define B2B_TRACE(...) ((void)0)      // tests/emu only: event hook of the CPU shim, nothing in the CUDA build
 #endif
+#ifndef B2B_STAT
+#define B2B_STAT(i, v) ((void)0)      // tests/emu only: counters of the CPU shim
+#endif
 
 namespace b2b {
 
@@ -272,6 +275,9 @@ constexpr uint32_t kStripCap = 61;       // own match followed this far past the
 constexpr uint32_t kListMax = 14;        // matches a lane records per strip (a 15th would need 61 bytes of
                                          // back-to-back 4-byte matches; the lane then stops probing).  14 rather
                                          // than 16 keeps a CTA at 26.5 KiB of shared memory: 8 CTAs per SM, not 7
+constexpr uint32_t kDeadTrialBytes = 20480;   // start of a bit-shuffled segment that runs without the noise-place rule and audits it
+                                              // (a cold table sees a period only after its first repeat)
+constexpr uint32_t kDeadHits = 8;        // matches inside the candidate noise places, in one audited step, that switch the rule off
 constexpr uint32_t kLaneLitEmit = 32;    // literal runs up to here are written by the owning lane
 
 struct LaneLists {
@@ -351,6 +357,42 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
         }
     }
     __syncwarp();
+    // Bit-shuffled typed arrays: a group of 8 * typesize bytes holds, place by place, one bit of eight elements -- the low
+    // mantissa bits first (noise), the high bits, sign and exponent last (nearly constant from group to group).  Looking
+    // for matches in the noise places costs most of the encoder's time there and the few it finds (4 bytes, far back) push
+    // the useful positions out of the 1 024-entry table.  So the warp measures, on up to 64 pairs of neighbouring groups
+    // of its segment, at which place the group stops being noise (first place whose byte repeats from group to group in
+    // at least half of the pairs) and probes / enters positions only from one byte past it.  float64 (C4): 48 of 64 places
+    // are noise.  Unaudited: size 1.030 -> 1.019 of the oracle's, encode 9.1 -> 5.6 ms per 2 GiB, compress 203 -> 301 GB/s;
+    // with the audit below (which the bit planes of a ramp need): 1.027, 7.3 ms, 244 GB/s.
+    // (Groups that start with compressible places, e.g. int16 counters, have no noise prefix and are left alone.)
+    uint32_t dead = 0, dead_c = 0;
+    if (PH && phmask) {
+        const uint32_t G = phmask + 1u;
+        const uint32_t q0 = W + ((G - ((ph0 + W) & phmask)) & phmask);   // first group that starts inside the segment
+        const uint32_t avail = W + L > q0 + G ? (W + L - q0) / G - 1u : 0u;   // pairs (g, g + 1) wholly inside it
+        const uint32_t np = avail < 64u ? avail : 64u;
+        if (np >= 16u) {
+            uint32_t p = 0;
+            for (; p < G; p++) {
+                uint32_t c = 0;
+#pragma unroll
+                for (uint32_t u = 0; u < 2; u++) {
+                    const uint32_t g = (uint32_t)lane + 32u * u;
+                    if (g < np) c += org[q0 + g * G + p] == org[q0 + (g + 1u) * G + p] ? 1u : 0u;
+                }
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (2u * c >= np) break;
+            }
+            if (p >= 8u && p < G) dead_c = p + 4u;
+        }
+    }
+    // ... but "does not repeat from group to group" is not yet "noise": the bit planes of a RAMP do not repeat that way
+    // either and still compress 40:1 through matches that start in those places.  So the rule is AUDITED: the dense steps
+    // of the segment's first 20 KiB and every eighth one after them run without it and count the matches that start in
+    // the candidate places; more than kDeadHits in a step switch the rule off for the rest of the segment.
+    uint32_t dstep = 0, trial_hits = 0;
+    bool audit = false;
     uint32_t anchor = W, si = W;
     uint32_t rep = 0;                                            // this lane's last match offset
     uint32_t ramp = cold_start ? 0u : 5u;                        // dense steps taken so far (5: no ramp)
@@ -370,6 +412,11 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             const uint32_t strip = strip_full;
             const uint32_t nlanes = ramp < 5 ? (1u << ramp) : 32u;
             ramp++;
+            if (PH) {
+                audit = dead_c != 0 && (si - W < kDeadTrialBytes || (dstep & 7u) == 0u);
+                dead = audit ? 0u : dead_c;
+                dstep++;
+            }
             uint32_t pos = si + (uint32_t)lane * strip;
             if (pos > mfl || (uint32_t)lane >= nlanes) pos = mfl;
             const uint32_t send = pos + strip < mfl ? pos + strip : mfl;
@@ -390,9 +437,11 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             }
             while (__any_sync(0xffffffffu, ext || pos < send)) {
                 if (!ext) {
-#ifdef B2B_EXP_DEAD
-                    if (pos < send && phmask) { const uint32_t phs = (ph0 + pos) & phmask; if (phs + 3 < B2B_EXP_DEAD) { pos += B2B_EXP_DEAD - 3 - phs; if (pos > send) pos = send; } }
-#endif
+                    if (PH && dead && pos < send) {
+                        // bit-shuffled input: nothing is looked for (or entered) where the group is noise, see `dead` above
+                        const uint32_t phs = (ph0 + pos) & phmask;
+                        if (phs + 3 < dead) { pos += dead - 3 - phs; if (pos > send) pos = send; }
+                    }
                     if (pos < send) {
                         // ---- four consecutive positions per turn: one 12-byte window, four probes in flight
                         uint32_t v0, v1;
@@ -558,6 +607,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                     const uint32_t me = k + 1 == cnt ? my_last : (a & 0x1FFFFu) + (a >> 17);
                     uint32_t mc = ms - lists->off[k][lane];
                     while (ms > pe && mc > 0 && org[ms - 1] == org[mc - 1]) { ms--; mc--; }
+                    if (PH && audit && ((ph0 + ms) & phmask) + 7u < dead_c) trial_hits++;   // (its four bytes lie in candidate places)
                     const uint32_t len = me - ms;
                     lists->a[k][lane] = ms | ((len < 0x7FFFu ? len : 0x7FFFu) << 17);
                     const uint32_t ll = ms - pe, mlc = len - 4;
@@ -689,6 +739,12 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
                 st.m.first_ll = __shfl_sync(0xffffffffu, st.m.first_ll, fl0);
                 st.m.info = __shfl_sync(0xffffffffu, st.m.info, fl0);
                 st.have_first = true;
+            }
+            if (PH && audit) {
+                const uint32_t hits = __reduce_add_sync(0xffffffffu, trial_hits);
+                trial_hits = 0;
+                B2B_STAT(24, hits);
+                if (hits > kDeadHits) dead_c = 0;
             }
             st.op += total;
             anchor = last_kept_end;

@@ -289,12 +289,13 @@ def test_compressed_size_within_one_percent_of_oracle(ctx, orc):
         report[name] = (mine, int(ref.size), mine / ref.size)
     print("\ncompressed size gpu vs oracle:", json.dumps(report, indent=1))
     # north_star bar: within 1% of the reference (here: of the restated compressor).  Met on C1/C3/C5.
-    # Not met on the bit-shuffled C4 field (1.030): the oracle's second match of a 64-byte group comes from
-    # up to 64 KiB back (half of them from more than 1 KiB), which needs its 2^16-entry table and 6-byte hash
-    # (a scalar greedy parse with this kernel's 2^10 entries and 4-byte hash gives the same 1.03; DESIGN.md
-    # section 4 has the sweep), and a table of that reach does not fit a warp's share of shared memory.
+    # The bit-shuffled C4 field is at 1.027 (round 1: 1.036, round 2 first half: 1.030): the encoder measures where a
+    # bit-shuffle group stops being noise and, after auditing that on the segment's first 20 KiB and every eighth step, neither
+    # probes nor enters positions before it (lz4_encode.cuh, `dead`; without the audit 1.019, but the bit planes of a ramp
+    # then triple).  The rest is the oracle's second match of a 64-byte group, which comes from up to 64 KiB back and needs
+    # its 2^16-entry table and 6-byte hash.  The 1 % bar is still missed, and the bound says so.
     # Unshuffled input (not a BASELINE config) runs with a 2^12 table and a 5-byte hash by default.
-    bound = {"C4 smooth f64 + BitShuffle T=8": 1.032, "text NoShuffle": 1.09, "f32 i*0.001 + Shuffle T=4": 1.01,
+    bound = {"C4 smooth f64 + BitShuffle T=8": 1.03, "text NoShuffle": 1.09, "f32 i*0.001 + Shuffle T=4": 1.01,
              "lowent int16 NoShuffle": 1.06}
     for name, (mine, ref, ratio) in report.items():
         assert mine <= ref * bound.get(name, 1.01) + 16, (name, mine, ref)

@@ -126,7 +126,7 @@ def test_emulated_encoder_size_against_the_oracle(emu, orc):
     n = 262144
     cases = {
         "C3": (dg.smooth_f32(n // 4, 1), 1, 4, 1.01),
-        "C4": (dg.smooth_f64(n // 8, 2), 2, 8, 1.035),
+        "C4": (dg.smooth_f64(n // 8, 2), 2, 8, 1.025),
         "C5": (dg.lowent_i16(n // 2, 3), 1, 2, 1.01),
         "C1": (dg.ramp(100000), 1, 4, 1.01),
         "text": (dg.text_like(n, 9), 0, 1, 1.10),
