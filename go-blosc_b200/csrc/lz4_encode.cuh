@@ -277,6 +277,7 @@ constexpr uint32_t kListMax = 14;        // matches a lane records per strip (a 
                                          // than 16 keeps a CTA at 26.5 KiB of shared memory: 8 CTAs per SM, not 7
 constexpr uint32_t kDeadTrialBytes = 20480;   // start of a bit-shuffled segment that runs without the noise-place rule and audits it
                                               // (a cold table sees a period only after its first repeat)
+constexpr uint32_t kDeadTrialWarm = 6144;     // the same for a segment that starts from its predecessor's warm-up window (periods up to 4 KiB are in the table)
 constexpr uint32_t kDeadHits = 8;        // matches inside the candidate noise places, in one audited step, that switch the rule off
 constexpr uint32_t kLaneLitEmit = 32;    // literal runs up to here are written by the owning lane
 
@@ -364,7 +365,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
     // of its segment, at which place the group stops being noise (first place whose byte repeats from group to group in
     // at least half of the pairs) and probes / enters positions only from one byte past it.  float64 (C4): 48 of 64 places
     // are noise.  Unaudited: size 1.030 -> 1.019 of the oracle's, encode 9.1 -> 5.6 ms per 2 GiB, compress 203 -> 301 GB/s;
-    // with the audit below (which the bit planes of a ramp need): 1.027, 7.3 ms, 244 GB/s.
+    // with the audit below (which the bit planes of a ramp need): 1.026, 6.8 ms, 271 GB/s in the bench's 16 GiB run.
     // (Groups that start with compressible places, e.g. int16 counters, have no noise prefix and are left alone.)
     uint32_t dead = 0, dead_c = 0;
     if (PH && phmask) {
@@ -389,7 +390,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
     }
     // ... but "does not repeat from group to group" is not yet "noise": the bit planes of a RAMP do not repeat that way
     // either and still compress 40:1 through matches that start in those places.  So the rule is AUDITED: the dense steps
-    // of the segment's first 20 KiB and every eighth one after them run without it and count the matches that start in
+    // of the segment's first 20 KiB (6 KiB when the table starts warm) and every eighth one after them run without it and count the matches that start in
     // the candidate places; more than kDeadHits in a step switch the rule off for the rest of the segment.
     uint32_t dstep = 0, trial_hits = 0;
     bool audit = false;
@@ -413,7 +414,7 @@ __device__ __forceinline__ SegMeta warp_encode_segment(const uint8_t *__restrict
             const uint32_t nlanes = ramp < 5 ? (1u << ramp) : 32u;
             ramp++;
             if (PH) {
-                audit = dead_c != 0 && (si - W < kDeadTrialBytes || (dstep & 7u) == 0u);
+                audit = dead_c != 0 && (si - W < (cold_start ? kDeadTrialBytes : kDeadTrialWarm) || (dstep & 7u) == 0u);
                 dead = audit ? 0u : dead_c;
                 dstep++;
             }
